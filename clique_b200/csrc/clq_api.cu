@@ -1,0 +1,643 @@
+// clq_api.cu -- host side of libclq: context, device buffers, stream slots, kernel dispatch (C ABI of include/clq.h).
+// There is no CPU path in this file: every alignment result is produced by the kernels in clq_kernels.cuh.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "clq_kernels.cuh"
+
+using namespace clq;
+
+namespace {
+
+struct Cfg { int G, C; };
+// wavefront geometries: G lanes per pair x C columns per lane (stripe width W = G*C)
+const Cfg kCfgs[] = {{8, 16}, {8, 24}, {8, 40}, {16, 24}, {32, 16}, {32, 32}};
+constexpr int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    DevBuf read_bytes, read_off, fixed_ref, order, results, scores, cand_mask, single_ref, ref_of_read, votes;
+    DevBuf cigar_pool, bits, cig_scratch, col_scratch;
+    DevBuf counters;                 // [0..3] task counters (u32, padded to 8 B each), [4] cigar cursor, [5] cells
+    unsigned long long* h_counters = nullptr;  // pinned mirror
+    uint32_t n_reads = 0;
+    uint64_t n_read_bytes = 0;
+    uint32_t max_len = 0, min_len = 0;
+    bool have_order = false, have_fixed = false;
+    int state = 0;  // 0 empty, 1 uploaded, 2 launched, 3 downloaded
+    uint32_t flags = 0;
+    clq_stats_t stats = {};
+    int n_dp = 0;
+    bool launched = false;
+};
+
+}  // namespace
+
+struct clq_ctx {
+    int device = 0;
+    int sm_count = 0;
+    clq_limits_t lim = {};
+    std::string err;
+    DevBuf ref_bytes, ref_off, kmer_keys, kmer_owner;
+    std::vector<uint8_t> h_ref_bytes;
+    std::vector<uint64_t> h_ref_off;
+    uint32_t n_refs = 0, max_ref_len = 0;
+    uint32_t kmer_k = 0, kmer_skip = 0, n_keys = 0;
+    std::vector<Slot> slots;
+    int force_cfg = -1;
+    int64_t max_scratch_bytes = 48ll << 30;
+};
+
+namespace {
+
+int32_t fail(clq_ctx* c, int32_t code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CU(c, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(c, CLQ_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+int32_t ensure(clq_ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return CLQ_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = std::max<size_t>(bytes, 256);
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) return fail(c, CLQ_E_NOMEM, std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+    b.cap = want;
+    return CLQ_OK;
+}
+
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+template <int G, int C, bool TB, bool FIN>
+cudaError_t launch_one(const KParams& p, int sm_count, size_t smem, cudaStream_t st, int* grid_out, bool query_only) {
+    auto kern = gotoh_kernel<G, C, TB, FIN>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int nb = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (nb < 1) return cudaErrorLaunchOutOfResources;
+    int grid = nb * sm_count;
+    if (*grid_out > 0) grid = std::min(grid, *grid_out);  // caller-imposed cap (scratch budget)
+    *grid_out = grid;
+    if (query_only) return cudaSuccess;
+    kern<<<grid, kThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <bool TB, bool FIN>
+cudaError_t launch_cfg(int cfg, const KParams& p, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
+    switch (cfg) {
+        case 0: return launch_one<8, 16, TB, FIN>(p, sm, smem, st, grid, q);
+        case 1: return launch_one<8, 24, TB, FIN>(p, sm, smem, st, grid, q);
+        case 2: return launch_one<8, 40, TB, FIN>(p, sm, smem, st, grid, q);
+        case 3: return launch_one<16, 24, TB, FIN>(p, sm, smem, st, grid, q);
+        case 4: return launch_one<32, 16, TB, FIN>(p, sm, smem, st, grid, q);
+        default: return launch_one<32, 32, TB, FIN>(p, sm, smem, st, grid, q);
+    }
+}
+
+cudaError_t launch_any(int cfg, bool tb, bool fin, const KParams& p, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
+    if (tb) return fin ? launch_cfg<true, true>(cfg, p, sm, smem, st, grid, q) : launch_cfg<true, false>(cfg, p, sm, smem, st, grid, q);
+    return fin ? launch_cfg<false, true>(cfg, p, sm, smem, st, grid, q) : launch_cfg<false, false>(cfg, p, sm, smem, st, grid, q);
+}
+
+int pick_cfg(const clq_ctx* c, uint32_t max_len) {
+    if (c->force_cfg >= 0 && c->force_cfg < kNumCfgs) return c->force_cfg;
+    for (int i = 0; i < kNumCfgs; i++)
+        if ((uint32_t)(kCfgs[i].G * kCfgs[i].C) >= max_len) return i;
+    return kNumCfgs - 1;
+}
+
+bool is_integral(double v) { return v == std::floor(v) && std::fabs(v) < 2.0e8; }
+
+Slot* get_slot(clq_ctx* c, int32_t slot) {
+    if (!c || slot < 0 || slot >= (int32_t)c->slots.size()) return nullptr;
+    return &c->slots[slot];
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t clq_version(void) { return CLQ_VERSION; }
+
+const char* clq_strerror(int32_t code) {
+    switch (code) {
+        case CLQ_OK: return "ok";
+        case CLQ_READ_TOO_LONG: return "read too long";
+        case CLQ_SCORING_NOT_REPRESENTABLE: return "scoring not representable as scaled integers";
+        case CLQ_TRACEBACK_DIVERGED: return "traceback diverged (reference would not terminate)";
+        case CLQ_CIGAR_POOL_FULL: return "cigar pool full";
+        case CLQ_NO_CANDIDATE: return "no candidate reference";
+        case CLQ_E_INVALID: return "invalid argument";
+        case CLQ_E_CUDA: return "CUDA error";
+        case CLQ_E_NOMEM: return "out of device memory";
+        case CLQ_E_LIMIT: return "batch exceeds context limits";
+        case CLQ_E_STATE: return "call out of order for this slot";
+        case CLQ_E_UNSUPPORTED: return "unsupported mode";
+        default: return "unknown";
+    }
+}
+
+int32_t clq_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int32_t clq_affine_from_f64(double match_score, double mismatch_score, double special_character_score, double gap_open,
+                            double gap_extend, double final_gap_multiplier, clq_affine_t* out) {
+    if (!out) return CLQ_E_INVALID;
+    if (!(gap_open < 0.0)) return CLQ_SCORING_NOT_REPRESENTABLE;
+    for (int scale = 1; scale <= 64; scale *= 2) {
+        const double s = (double)scale;
+        const double v[10] = {match_score * s,
+                              mismatch_score * s,
+                              special_character_score * s,
+                              (gap_open + gap_extend) * s,
+                              gap_extend * s,
+                              (gap_open + gap_extend * final_gap_multiplier) * s,
+                              (gap_extend * final_gap_multiplier) * s,
+                              (gap_open * final_gap_multiplier) * s,
+                              (gap_extend * final_gap_multiplier) * s,
+                              -100000.0 * s};
+        bool ok = true;
+        for (double x : v) ok = ok && is_integral(x);
+        if (!ok) continue;
+        out->scale = scale;
+        out->match = (int32_t)v[0]; out->mismatch = (int32_t)v[1]; out->special = (int32_t)v[2];
+        out->oe_in = (int32_t)v[3]; out->e_in = (int32_t)v[4];
+        out->oe_fin = (int32_t)v[5]; out->e_fin = (int32_t)v[6];
+        out->b0 = (int32_t)v[7]; out->b1 = (int32_t)v[8];
+        out->max_neg = (int32_t)v[9];
+        return CLQ_OK;
+    }
+    return CLQ_SCORING_NOT_REPRESENTABLE;
+}
+
+int32_t clq_host_alloc(size_t bytes, void** out) {
+    if (!out) return CLQ_E_INVALID;
+    cudaError_t e = cudaHostAlloc(out, std::max<size_t>(bytes, 64), cudaHostAllocDefault);
+    return e == cudaSuccess ? CLQ_OK : CLQ_E_CUDA;
+}
+
+int32_t clq_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? CLQ_OK : CLQ_E_CUDA; }
+
+int32_t clq_ctx_create(int32_t device, const clq_limits_t* limits, clq_ctx** out) {
+    if (!out || !limits) return CLQ_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return CLQ_E_CUDA;
+    clq_ctx* c = new clq_ctx();
+    c->device = device;
+    c->lim = *limits;
+    if (c->lim.n_slots < 1) c->lim.n_slots = 1;
+    if (c->lim.n_slots > 4) c->lim.n_slots = 4;
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return CLQ_E_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return CLQ_E_CUDA; }
+    c->sm_count = prop.multiProcessorCount;
+    c->slots.resize(c->lim.n_slots);
+    for (auto& s : c->slots) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { clq_ctx_destroy(c); return CLQ_E_CUDA; }
+        for (auto& e : s.ev) cudaEventCreate(&e);
+        if (cudaHostAlloc((void**)&s.h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) { clq_ctx_destroy(c); return CLQ_E_CUDA; }
+        if (ensure(c, s.counters, 8 * sizeof(unsigned long long)) != CLQ_OK) { clq_ctx_destroy(c); return CLQ_E_NOMEM; }
+    }
+    *out = c;
+    return CLQ_OK;
+}
+
+void clq_ctx_destroy(clq_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto& s : c->slots) {
+        if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+        for (auto& e : s.ev) if (e) cudaEventDestroy(e);
+        for (DevBuf* b : {&s.read_bytes, &s.read_off, &s.fixed_ref, &s.order, &s.results, &s.scores, &s.cand_mask, &s.single_ref,
+                          &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.counters})
+            release(*b);
+        if (s.h_counters) cudaFreeHost(s.h_counters);
+    }
+    release(c->ref_bytes); release(c->ref_off); release(c->kmer_keys); release(c->kmer_owner);
+    delete c;
+}
+
+const char* clq_ctx_last_error(const clq_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int32_t clq_set_option(clq_ctx* c, const char* key, int64_t value) {
+    if (!c || !key) return CLQ_E_INVALID;
+    if (!strcmp(key, "force_cfg")) { c->force_cfg = (int)value; return CLQ_OK; }
+    if (!strcmp(key, "max_scratch_bytes")) { c->max_scratch_bytes = value; return CLQ_OK; }
+    return fail(c, CLQ_E_INVALID, std::string("unknown option ") + key);
+}
+
+int32_t clq_refs_set(clq_ctx* c, uint32_t n_refs, const uint8_t* bytes, const uint64_t* off) {
+    if (!c || (n_refs && (!bytes || !off))) return CLQ_E_INVALID;
+    if (n_refs > c->lim.max_refs) return fail(c, CLQ_E_LIMIT, "too many references");
+    const uint64_t total = n_refs ? off[n_refs] : 0;
+    if (total > c->lim.max_ref_bytes) return fail(c, CLQ_E_LIMIT, "reference bytes exceed limit");
+    CU(c, cudaSetDevice(c->device));
+    c->h_ref_bytes.assign(bytes, bytes + total);
+    c->h_ref_off.assign(off, off + n_refs + 1);
+    if (!n_refs) c->h_ref_off.assign(1, 0);
+    c->n_refs = n_refs;
+    c->max_ref_len = 0;
+    for (uint32_t r = 0; r < n_refs; r++) {
+        if (off[r + 1] < off[r]) return fail(c, CLQ_E_INVALID, "reference offsets must be non-decreasing");
+        c->max_ref_len = std::max<uint32_t>(c->max_ref_len, (uint32_t)(off[r + 1] - off[r]));
+    }
+    int32_t rc;
+    if ((rc = ensure(c, c->ref_bytes, total + 16)) != CLQ_OK) return rc;
+    if ((rc = ensure(c, c->ref_off, (n_refs + 1) * sizeof(uint64_t))) != CLQ_OK) return rc;
+    for (auto& s : c->slots) CU(c, cudaStreamSynchronize(s.stream));
+    if (total) CU(c, cudaMemcpy(c->ref_bytes.p, bytes, total, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->ref_off.p, c->h_ref_off.data(), (n_refs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    c->n_keys = 0;
+    c->kmer_k = 0;
+    return CLQ_OK;
+}
+
+// ReferenceManager::unique_kmers (reference/fasta_reference.rs:159-202): upper-case, windows(k).step_by(skip),
+// consecutive run-length dedup, k-mer unique <=> its run counts over all references sum to exactly 1.
+int32_t clq_kmer_index_set(clq_ctx* c, uint32_t k, uint32_t skip) {
+    if (!c || k == 0 || skip == 0) return CLQ_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    struct Ent { const uint8_t* p; uint32_t ref, count; };
+    std::vector<uint8_t> up(c->h_ref_bytes.size() + 1);
+    for (size_t i = 0; i < c->h_ref_bytes.size(); i++) {
+        uint8_t ch = c->h_ref_bytes[i];
+        up[i] = (ch >= 'a' && ch <= 'z') ? ch - 32 : ch;
+    }
+    std::vector<Ent> ents;
+    for (uint32_t r = 0; r < c->n_refs; r++) {
+        const uint8_t* s = up.data() + c->h_ref_off[r];
+        const size_t len = (size_t)(c->h_ref_off[r + 1] - c->h_ref_off[r]);
+        const uint8_t* run = nullptr;
+        uint32_t cnt = 0;
+        for (size_t pos = 0; pos + k <= len; pos += skip) {
+            const uint8_t* w = s + pos;
+            if (run && memcmp(run, w, k) == 0) cnt++;
+            else {
+                if (run) ents.push_back({run, r, cnt});
+                run = w;
+                cnt = 1;
+            }
+        }
+        if (run) ents.push_back({run, r, cnt});
+    }
+    std::sort(ents.begin(), ents.end(), [k](const Ent& a, const Ent& b) {
+        int cmp = memcmp(a.p, b.p, k);
+        return cmp ? cmp < 0 : a.ref < b.ref;
+    });
+    std::vector<uint8_t> keys;
+    std::vector<uint32_t> owner;
+    for (size_t i = 0; i < ents.size();) {
+        size_t j = i;
+        uint64_t tot = 0;
+        while (j < ents.size() && memcmp(ents[j].p, ents[i].p, k) == 0) { tot += ents[j].count; j++; }
+        if (tot == 1) {
+            keys.insert(keys.end(), ents[i].p, ents[i].p + k);
+            owner.push_back(ents[i].ref);
+        }
+        i = j;
+    }
+    int32_t rc;
+    if ((rc = ensure(c, c->kmer_keys, keys.size() + 16)) != CLQ_OK) return rc;
+    if ((rc = ensure(c, c->kmer_owner, (owner.size() + 1) * sizeof(uint32_t))) != CLQ_OK) return rc;
+    if (!keys.empty()) {
+        CU(c, cudaMemcpy(c->kmer_keys.p, keys.data(), keys.size(), cudaMemcpyHostToDevice));
+        CU(c, cudaMemcpy(c->kmer_owner.p, owner.data(), owner.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    c->kmer_k = k;
+    c->kmer_skip = skip;
+    c->n_keys = (uint32_t)owner.size();
+    return CLQ_OK;
+}
+
+int32_t clq_upload(clq_ctx* c, int32_t slot, uint32_t n_reads, const uint8_t* read_bytes, const uint64_t* read_off,
+                   const int32_t* fixed_ref) {
+    Slot* s = get_slot(c, slot);
+    if (!s || (n_reads && (!read_off))) return CLQ_E_INVALID;
+    if (n_reads > c->lim.max_reads) return fail(c, CLQ_E_LIMIT, "too many reads for one batch");
+    const uint64_t total = n_reads ? read_off[n_reads] - read_off[0] : 0;
+    if (total > c->lim.max_read_bytes) return fail(c, CLQ_E_LIMIT, "read bytes exceed limit");
+    if (total && !read_bytes) return CLQ_E_INVALID;
+    if (n_reads && read_off[0] != 0) return fail(c, CLQ_E_INVALID, "read_off[0] must be 0");
+    CU(c, cudaSetDevice(c->device));
+    int32_t rc;
+    if ((rc = ensure(c, s->read_bytes, total + 16)) != CLQ_OK) return rc;
+    if ((rc = ensure(c, s->read_off, ((size_t)n_reads + 1) * sizeof(uint64_t))) != CLQ_OK) return rc;
+    if ((rc = ensure(c, s->results, ((size_t)n_reads + 1) * sizeof(clq_result_t))) != CLQ_OK) return rc;
+    if ((rc = ensure(c, s->ref_of_read, ((size_t)n_reads + 1) * sizeof(int32_t))) != CLQ_OK) return rc;
+    // host pass over the offsets: length range + (when lengths vary) a longest-first processing order
+    uint32_t mx = 0, mn = 0xffffffffu;
+    for (uint32_t i = 0; i < n_reads; i++) {
+        if (read_off[i + 1] < read_off[i]) return fail(c, CLQ_E_INVALID, "read offsets must be non-decreasing");
+        const uint64_t l = read_off[i + 1] - read_off[i];
+        if (l >= c->lim.max_read_len) continue;  // dropped on the device with CLQ_READ_TOO_LONG
+        mx = std::max<uint32_t>(mx, (uint32_t)l);
+        mn = std::min<uint32_t>(mn, (uint32_t)l);
+    }
+    if (mn == 0xffffffffu) mn = 0;
+    s->max_len = mx;
+    s->min_len = mn;
+    s->have_order = false;
+    static thread_local std::vector<uint32_t> order, bucket;
+    if (n_reads && mx > mn + mn / 8 + 16) {
+        const uint32_t nb = mx / 16 + 2;
+        bucket.assign(nb + 1, 0);
+        auto key = [&](uint32_t i) -> uint32_t {
+            const uint64_t l = read_off[i + 1] - read_off[i];
+            const uint32_t b = l >= c->lim.max_read_len ? 0 : (uint32_t)l / 16 + 1;
+            return nb - 1 - std::min(b, nb - 1);  // longest first
+        };
+        for (uint32_t i = 0; i < n_reads; i++) bucket[key(i) + 1]++;
+        for (uint32_t b = 0; b < nb; b++) bucket[b + 1] += bucket[b];
+        order.resize(n_reads);
+        for (uint32_t i = 0; i < n_reads; i++) order[bucket[key(i)]++] = i;
+        if ((rc = ensure(c, s->order, (size_t)n_reads * sizeof(uint32_t))) != CLQ_OK) return rc;
+        CU(c, cudaMemcpyAsync(s->order.p, order.data(), (size_t)n_reads * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+        CU(c, cudaStreamSynchronize(s->stream));  // `order` is a reused host vector
+        s->have_order = true;
+    }
+    uint64_t h2d = 0;
+    if (total) {
+        CU(c, cudaMemcpyAsync(s->read_bytes.p, read_bytes + read_off[0], total, cudaMemcpyHostToDevice, s->stream));
+        h2d += total;
+    }
+    if (n_reads) {
+        CU(c, cudaMemcpyAsync(s->read_off.p, read_off, ((size_t)n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+        h2d += ((size_t)n_reads + 1) * sizeof(uint64_t);
+    }
+    s->have_fixed = false;
+    if (fixed_ref && n_reads) {
+        if ((rc = ensure(c, s->fixed_ref, (size_t)n_reads * sizeof(int32_t))) != CLQ_OK) return rc;
+        CU(c, cudaMemcpyAsync(s->fixed_ref.p, fixed_ref, (size_t)n_reads * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+        h2d += (size_t)n_reads * sizeof(int32_t);
+        s->have_fixed = true;
+    }
+    if (s->have_order) h2d += (size_t)n_reads * sizeof(uint32_t);
+    s->n_reads = n_reads;
+    s->n_read_bytes = total;
+    s->stats = clq_stats_t{};
+    s->launched = false;
+    s->stats.h2d_bytes = h2d;
+    s->state = 1;
+    return CLQ_OK;
+}
+
+int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags, double match_threshold) {
+    Slot* s = get_slot(c, slot);
+    if (!s || !scoring) return CLQ_E_INVALID;
+    if (s->state < 1) return fail(c, CLQ_E_STATE, "clq_launch before clq_upload");
+    if (flags & CLQ_CONVEX) return fail(c, CLQ_E_UNSUPPORTED, "convex (two-piece) mode is not built yet");
+    const uint32_t band = flags & CLQ_BAND_MASK;
+    const uint32_t search = flags & CLQ_SEARCH_MASK;
+    if (band > CLQ_BAND_READLEN) return fail(c, CLQ_E_UNSUPPORTED, "explicit bandwidth is not supported (the hot path never passes one)");
+    if (search == CLQ_SEARCH_FIXED && !s->have_fixed && s->n_reads) return fail(c, CLQ_E_INVALID, "CLQ_SEARCH_FIXED needs fixed_ref");
+    if (search == CLQ_SEARCH_QUICK && c->kmer_k == 0) return fail(c, CLQ_E_STATE, "CLQ_SEARCH_QUICK needs clq_kmer_index_set");
+    if (search > CLQ_SEARCH_QUICK) return CLQ_E_INVALID;
+    const clq_affine_t sc = *(const clq_affine_t*)scoring;
+    if (!(sc.oe_in - sc.e_in < 0) || sc.scale < 1) return fail(c, CLQ_SCORING_NOT_REPRESENTABLE, "gap_open must be negative");
+    CU(c, cudaSetDevice(c->device));
+    const bool fin = sc.oe_fin != sc.oe_in || sc.e_fin != sc.e_in;
+    const bool score_only = (flags & CLQ_SCORE_ONLY) != 0;
+    const uint32_t n = s->n_reads;
+    const int cfg = pick_cfg(c, s->max_len);
+    const int G = kCfgs[cfg].G, C = kCfgs[cfg].C, W = G * C, GPW = 32 / G;
+    const uint32_t L1max = c->max_ref_len, L2max = s->max_len;
+    const uint32_t ns_max = std::max<uint32_t>(1, (L2max + W - 1) / W);
+    const uint32_t ref_sm_stride = (L1max + 15) / 16 * 16 + 16;
+    const size_t smem = (size_t)(kThreads / 32) * GPW * ref_sm_stride;
+    if (smem > 200 * 1024) return fail(c, CLQ_E_LIMIT, "references too long for this geometry's shared-memory staging");
+
+    KParams p = {};
+    p.ref_bytes = (const uint8_t*)c->ref_bytes.p;
+    p.ref_off = (const uint64_t*)c->ref_off.p;
+    p.n_refs = c->n_refs;
+    p.read_bytes = (const uint8_t*)s->read_bytes.p;
+    p.read_off = (const uint64_t*)s->read_off.p;
+    p.n_reads = n;
+    p.order = s->have_order ? (const uint32_t*)s->order.p : nullptr;
+    p.sc = sc;
+    p.band_mode = band;
+    p.max_read_len = c->lim.max_read_len;
+    p.ref_sm_stride = ref_sm_stride;
+    p.results = (clq_result_t*)s->results.p;
+    unsigned long long* ctr = (unsigned long long*)s->counters.p;
+    p.cigar_cursor = ctr + 4;
+    p.cells = ctr + 5;
+
+    // grid + scratch sizing (per resident group)
+    int grid_tb = 0, grid_sc = 0;
+    cudaError_t ce;
+    if ((ce = launch_any(cfg, true, fin, p, c->sm_count, smem, s->stream, &grid_tb, true)) != cudaSuccess)
+        return fail(c, CLQ_E_CUDA, std::string("occupancy(tb): ") + cudaGetErrorString(ce));
+    if ((ce = launch_any(cfg, false, fin, p, c->sm_count, smem, s->stream, &grid_sc, true)) != cudaSuccess)
+        return fail(c, CLQ_E_CUDA, std::string("occupancy(score): ") + cudaGetErrorString(ce));
+    const uint64_t bits_stride = (uint64_t)ns_max * (L1max + G) * G * (C / 8);
+    const uint32_t cig_stride = L1max + L2max + 8;
+    const uint32_t col_stride = L1max + 8;
+    const uint64_t per_group = bits_stride * 4 + (uint64_t)cig_stride * 4 + (uint64_t)col_stride * 16;
+    if (!score_only) {
+        const uint64_t groups_per_cta = (uint64_t)(kThreads / 32) * GPW;
+        const uint64_t max_ctas = std::max<uint64_t>(1, (uint64_t)c->max_scratch_bytes / (per_group * groups_per_cta));
+        if ((uint64_t)grid_tb > max_ctas) grid_tb = (int)max_ctas;
+    }
+    const uint64_t groups_tb = (uint64_t)grid_tb * (kThreads / 32) * GPW;
+    const uint64_t groups_sc = (uint64_t)grid_sc * (kThreads / 32) * GPW;
+    int32_t rc;
+    if (!score_only) {
+        if ((rc = ensure(c, s->bits, groups_tb * bits_stride * 4)) != CLQ_OK) return rc;
+        if ((rc = ensure(c, s->cig_scratch, groups_tb * cig_stride * 4)) != CLQ_OK) return rc;
+        if ((rc = ensure(c, s->cigar_pool, (size_t)c->lim.cigar_pool_ops * 4 + 16)) != CLQ_OK) return rc;
+    }
+    if ((rc = ensure(c, s->col_scratch, std::max(groups_tb, groups_sc) * col_stride * 16)) != CLQ_OK) return rc;
+    p.bits = (uint32_t*)s->bits.p;
+    p.bits_stride = bits_stride;
+    p.cig_scratch = (uint32_t*)s->cig_scratch.p;
+    p.cig_stride = cig_stride;
+    p.col_scratch = (int32_t*)s->col_scratch.p;
+    p.col_stride = col_stride;
+    p.cigar_pool = (uint32_t*)s->cigar_pool.p;
+    p.cigar_cap = c->lim.cigar_pool_ops;
+
+    s->flags = flags;
+    s->stats.launches = 0;
+    s->stats.dp_launches = 0;
+    s->n_dp = 0;
+    CU(c, cudaMemsetAsync(s->counters.p, 0, 8 * sizeof(unsigned long long), s->stream));
+    CU(c, cudaEventRecord(s->ev[0], s->stream));
+
+    const int32_t* ref_of_read = nullptr;
+    if (search == CLQ_SEARCH_FIXED) {
+        ref_of_read = (const int32_t*)s->fixed_ref.p;
+    } else if (n) {
+        const uint32_t nrefs = c->n_refs;
+        const uint32_t mask_words = (nrefs + 31) / 32;
+        const uint32_t* cand = nullptr;
+        const int32_t* single = nullptr;
+        if (search == CLQ_SEARCH_QUICK && nrefs) {
+            if ((rc = ensure(c, s->votes, (size_t)n * nrefs * 4)) != CLQ_OK) return rc;
+            if ((rc = ensure(c, s->cand_mask, (size_t)n * mask_words * 4)) != CLQ_OK) return rc;
+            if ((rc = ensure(c, s->single_ref, (size_t)n * 4)) != CLQ_OK) return rc;
+            kmer_vote_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(
+                p.read_bytes, p.read_off, n, (const uint8_t*)c->kmer_keys.p, (const uint32_t*)c->kmer_owner.p, c->n_keys, c->kmer_k,
+                c->kmer_skip, nrefs, match_threshold, (uint32_t*)s->votes.p, (uint32_t*)s->cand_mask.p, mask_words, (int32_t*)s->single_ref.p);
+            CU(c, cudaGetLastError());
+            s->stats.launches++;
+            cand = (const uint32_t*)s->cand_mask.p;
+            single = (const int32_t*)s->single_ref.p;
+        }
+        if (nrefs) {
+            if ((rc = ensure(c, s->scores, (size_t)n * nrefs * 4)) != CLQ_OK) return rc;
+            KParams q = p;
+            q.all_pairs = 1;
+            q.n_tasks = n * nrefs;
+            if ((uint64_t)n * nrefs > 0xfffffff0ull) return fail(c, CLQ_E_LIMIT, "reads x references exceeds 2^32 tasks per batch");
+            q.cand_mask = cand;
+            q.mask_words = mask_words;
+            q.scores = (int32_t*)s->scores.p;
+            q.task_counter = (unsigned int*)(ctr + 0);
+            CU(c, cudaEventRecord(s->ev[1], s->stream));
+            int g = grid_sc;
+            if ((ce = launch_any(cfg, false, fin, q, c->sm_count, smem, s->stream, &g, false)) != cudaSuccess)
+                return fail(c, CLQ_E_CUDA, std::string("score kernel: ") + cudaGetErrorString(ce));
+            CU(c, cudaEventRecord(s->ev[2], s->stream));
+            s->stats.launches++;
+            s->stats.dp_launches++;
+            s->n_dp |= 1;
+        }
+        select_best_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>((const int32_t*)s->scores.p, n, nrefs, cand, mask_words,
+                                                                   (int32_t*)s->ref_of_read.p, single);
+        CU(c, cudaGetLastError());
+        s->stats.launches++;
+        ref_of_read = (const int32_t*)s->ref_of_read.p;
+    }
+    if (n) {
+        KParams q = p;
+        q.all_pairs = 0;
+        q.n_tasks = n;
+        q.ref_of_read = ref_of_read;
+        q.task_counter = (unsigned int*)(ctr + 1);
+        CU(c, cudaEventRecord(s->ev[3], s->stream));
+        int g = score_only ? grid_sc : grid_tb;
+        if ((ce = launch_any(cfg, !score_only, fin, q, c->sm_count, smem, s->stream, &g, false)) != cudaSuccess)
+            return fail(c, CLQ_E_CUDA, std::string("traceback kernel: ") + cudaGetErrorString(ce));
+        CU(c, cudaEventRecord(s->ev[4], s->stream));
+        s->stats.launches++;
+        s->stats.dp_launches++;
+        s->n_dp |= 2;
+    }
+    CU(c, cudaEventRecord(s->ev[5], s->stream));
+    s->launched = true;
+    s->state = 2;
+    return CLQ_OK;
+}
+
+int32_t clq_download(clq_ctx* c, int32_t slot) {
+    Slot* s = get_slot(c, slot);
+    if (!s) return CLQ_E_INVALID;
+    if (s->state < 2) return fail(c, CLQ_E_STATE, "clq_download before clq_launch");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpyAsync(s->h_counters, s->counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    s->state = 3;
+    return CLQ_OK;
+}
+
+int32_t clq_sync(clq_ctx* c, int32_t slot) {
+    Slot* s = get_slot(c, slot);
+    if (!s) return CLQ_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(s->stream));
+    return CLQ_OK;
+}
+
+int32_t clq_slot_stats(clq_ctx* c, int32_t slot, clq_stats_t* out) {
+    Slot* s = get_slot(c, slot);
+    if (!s || !out) return CLQ_E_INVALID;
+    if (!s->launched) return fail(c, CLQ_E_STATE, "no launch on this slot");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    CU(c, cudaEventElapsedTime(&ms, s->ev[0], s->ev[5]));
+    s->stats.kernel_ms = ms;
+    float dp = 0.f;
+    if (s->n_dp & 1) { CU(c, cudaEventElapsedTime(&ms, s->ev[1], s->ev[2])); dp += ms; }
+    if (s->n_dp & 2) { CU(c, cudaEventElapsedTime(&ms, s->ev[3], s->ev[4])); dp += ms; }
+    s->stats.dp_ms = dp;
+    unsigned long long cells = 0;
+    CU(c, cudaMemcpy(&cells, (unsigned long long*)s->counters.p + 5, sizeof(cells), cudaMemcpyDeviceToHost));
+    s->stats.cells = cells;
+    *out = s->stats;
+    return CLQ_OK;
+}
+
+int32_t clq_wait(clq_ctx* c, int32_t slot, clq_result_t* results, uint32_t* cigar_pool, uint64_t cigar_cap, uint64_t* cigar_used) {
+    Slot* s = get_slot(c, slot);
+    if (!s) return CLQ_E_INVALID;
+    if (s->state < 2) return fail(c, CLQ_E_STATE, "clq_wait before clq_launch");
+    int32_t rc;
+    if (s->state < 3 && (rc = clq_download(c, slot)) != CLQ_OK) return rc;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(s->stream));
+    const uint64_t cursor = s->h_counters[4];
+    const uint64_t used = std::min<uint64_t>(cursor, c->lim.cigar_pool_ops);
+    s->stats.cells = s->h_counters[5];
+    uint64_t d2h = 8 * sizeof(unsigned long long);
+    if (results && s->n_reads) {
+        CU(c, cudaMemcpyAsync(results, s->results.p, (size_t)s->n_reads * sizeof(clq_result_t), cudaMemcpyDeviceToHost, s->stream));
+        d2h += (size_t)s->n_reads * sizeof(clq_result_t);
+    }
+    const bool has_pool = !(s->flags & CLQ_SCORE_ONLY);
+    if (cigar_used) *cigar_used = has_pool ? used : 0;
+    if (has_pool && used) {
+        if (!cigar_pool || used > cigar_cap) {
+            CU(c, cudaStreamSynchronize(s->stream));
+            return fail(c, CLQ_E_LIMIT, "caller's CIGAR buffer is smaller than the ops produced");
+        }
+        CU(c, cudaMemcpyAsync(cigar_pool, s->cigar_pool.p, used * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+        d2h += used * sizeof(uint32_t);
+    }
+    CU(c, cudaStreamSynchronize(s->stream));
+    s->stats.d2h_bytes = d2h;
+    s->state = 1;  // inputs stay resident: the slot can be launched again
+    return CLQ_OK;
+}
+
+int32_t clq_submit(clq_ctx* c, int32_t slot, uint32_t n_reads, const uint8_t* read_bytes, const uint64_t* read_off,
+                   const int32_t* fixed_ref, const void* scoring, uint32_t flags, double match_threshold) {
+    int32_t rc;
+    if ((rc = clq_upload(c, slot, n_reads, read_bytes, read_off, fixed_ref)) != CLQ_OK) return rc;
+    if ((rc = clq_launch(c, slot, scoring, flags, match_threshold)) != CLQ_OK) return rc;
+    return clq_download(c, slot);
+}
+
+}  // extern "C"

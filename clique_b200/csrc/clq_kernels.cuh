@@ -1,0 +1,463 @@
+// clq_kernels.cuh -- sm_100a kernels of libclq: batched global affine-gap Gotoh alignment.
+//
+// One G-lane sub-warp group aligns one (read, reference) pair as an anti-diagonal wavefront:
+// lane l owns C consecutive read columns in registers, the reference streams past row by row from shared
+// memory, lane l works on row x = t - l at step t, and the right-edge values of a lane's stripe travel to the
+// next lane with __shfl_up_sync.  Reads longer than G*C columns are processed in column stripes whose boundary
+// column is parked in a small global scratch.  With TB the kernel also records 4 direction bits per cell
+// (coalesced, one G*C/8-word row per step), walks them back on one lane and emits the run-length CIGAR.
+//
+// Arithmetic restated from the reference (file:line relative to rust_cmd/src/ of mckennalab/clique):
+//   update_3d_score                alignment/alignment_matrix.rs:618-665
+//   three_way_max_and_direction    alignment/alignment_matrix.rs:671-683   (ties: Diag > Left > Up)
+//   boundary init + f64 band       alignment/alignment_matrix.rs:385-424
+//   perform_3d_global_traceback    alignment/alignment_matrix.rs:941-1086  (start layer = last max)
+//   simplify_cigar_string          alignment_manager.rs:386-423
+//   match_mismatch                 alignment/scoring_functions.rs:100-102
+//
+// Value recurrence used here (identical values because gap_open < 0 makes E+le >= E+x1):
+//   M = B[x-1,y-1] + m,  E = max(E[x-1,y] + le, B[x-1,y] + x1),  F = max(F[x,y-1] + le, B[x,y-1] + x1),
+//   B = max(M, E, F).
+// Direction bits per cell (x,y), enough to replay all three traceback layers exactly:
+//   A    (2 bits) = argmax(M,E,F) with priority M > F > E  (0=M 1=E 2=F; 3 marks a band-skipped "stale" cell)
+//   ext1 (1 bit)  = E[x,y] extended E[x-1,y] (strictly better than opening)          -> T1 = Up
+//   ext2 (1 bit)  = F[x,y] extended F[x,y-1] (>= the E-open, > the M-open)            -> T2 = Left
+//   T0[x,y] = A[x-1,y-1];  T1[x,y] = ext1 ? Up : (A[x-1,y]==F ? Left : Diag);  T2[x,y] = ext2 ? Left : (A[x,y-1]==E ? Up : Diag)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/clq.h"
+
+namespace clq {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int kThreads = 128;  // 4 warps per CTA
+
+struct KParams {
+    const uint8_t* ref_bytes;
+    const uint64_t* ref_off;
+    uint32_t n_refs;
+    const uint8_t* read_bytes;
+    const uint64_t* read_off;
+    uint32_t n_reads;
+    const uint32_t* order;       // processing order over reads (nullptr = identity)
+    const int32_t* ref_of_read;  // per-read reference (pair mode); < 0 => no candidate
+    uint32_t n_tasks;
+    uint32_t all_pairs;          // 1: task = (read, ref) over every reference, output -> scores
+    const uint32_t* cand_mask;   // all_pairs: optional candidate bitmask, mask_words per read
+    uint32_t mask_words;
+    int32_t* scores;             // [n_reads * n_refs]
+    clq_result_t* results;       // [n_reads]
+    clq_affine_t sc;
+    uint32_t band_mode;
+    uint32_t max_read_len;
+    uint32_t ref_sm_stride;      // bytes of shared memory per group
+    uint32_t* bits;              // traceback bits scratch
+    uint64_t bits_stride;        // words per group
+    uint32_t* cig_scratch;
+    uint32_t cig_stride;         // ops per group
+    int32_t* col_scratch;        // stripe boundary column: 4 arrays of col_stride per group
+    uint32_t col_stride;
+    uint32_t* cigar_pool;
+    uint64_t cigar_cap;
+    unsigned long long* cigar_cursor;
+    unsigned int* task_counter;
+    unsigned long long* cells;
+};
+
+__device__ __forceinline__ bool is_special(int c) { return c == 'N' || c < 58; }
+
+// rows 1..K whose band skips the last column (f64 centre, alignment/alignment_matrix.rs:413-417)
+__device__ inline int stale_rows(int L1, int L2, uint32_t band_mode) {
+    long long bw = band_mode == CLQ_BAND_READLEN ? L2 : (L1 > L2 ? L1 : L2);
+    long long lim = (long long)L2 - bw;
+    if (lim < 0) return 0;
+    int K = 0;
+    for (int x = 1; x <= L1; x++) {
+        long long yc = (long long)(((double)x / (double)(L1 + 1)) * (double)(L2 + 1));
+        if (yc <= lim) K = x; else break;
+    }
+    return K;
+}
+
+// One wavefront step of one lane: C cells of row x.
+template <int C, bool TB, bool FIN, bool LAST>
+__device__ __forceinline__ void row_step(int (&E)[C], int (&B)[C], const int (&bq)[C], uint32_t (&w)[C / 8],
+                                         int& Fl, int& El, int& Ml, int& Bl, int diag, int rcode, int mt, int mm,
+                                         const clq_affine_t& sc, bool own_last, int jL, int& capM, int& capE, int& capF) {
+    const int x1row = LAST ? sc.oe_fin : sc.oe_in;
+    const int lerow = LAST ? sc.e_fin : sc.e_in;
+#pragma unroll
+    for (int k = 0; k < C / 8; k++) w[k] = 0;
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+        int m = (bq[j] == rcode) ? mt : mm;
+        if (bq[j] & 0x100) m = sc.special;
+        int x1c = x1row, lec = lerow;
+        if (FIN && !LAST) {
+            if (own_last && j == jL) { x1c = sc.oe_fin; lec = sc.e_fin; }
+        }
+        const int Mv = diag + m;
+        const int Eext = E[j] + lec, Eopen = B[j] + x1c;
+        const int Ev = max(Eext, Eopen);
+        const int Fext = Fl + lec, Fopen = Bl + x1c;
+        const int Fv = max(Fext, Fopen);
+        const int Pv = max(Mv, Fv);
+        const int Bv = max(Pv, Ev);
+        if (TB) {
+            const bool ext1 = Eext > Eopen;
+            const bool ext2 = (Fext >= El + x1c) && (Fext > Ml + x1c);
+            const uint32_t a = (Pv >= Ev) ? ((Mv >= Fv) ? 0u : 2u) : 1u;
+            const uint32_t nib = a | (ext1 ? 4u : 0u) | (ext2 ? 8u : 0u);
+            w[j >> 3] |= nib << (4 * (j & 7));
+        }
+        diag = B[j];
+        E[j] = Ev;
+        B[j] = Bv;
+        Fl = Fv; Bl = Bv; El = Ev; Ml = Mv;
+        if (LAST) {
+            if (own_last && j == jL) { capM = Mv; capE = Ev; capF = Fv; }
+        }
+    }
+}
+
+template <int G, int C, bool TB, bool FIN>
+__global__ void __launch_bounds__(kThreads) gotoh_kernel(const KParams p) {
+    static_assert(C % 8 == 0, "C must be a multiple of 8 (4 direction bits per cell, whole words per lane)");
+    extern __shared__ uint8_t smem[];
+    constexpr int GPW = 32 / G;
+    constexpr int W = G * C;
+    constexpr int WPL = C / 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gl = lane % G, gw = lane / G;
+    const int wpb = blockDim.x >> 5;
+    const uint32_t ggid = (blockIdx.x * wpb + warp) * GPW + gw;
+    uint8_t* ref_sm = smem + (size_t)(warp * GPW + gw) * p.ref_sm_stride;
+    uint32_t* bits_g = TB ? p.bits + (size_t)ggid * p.bits_stride : nullptr;
+    uint32_t* cig_g = TB ? p.cig_scratch + (size_t)ggid * p.cig_stride : nullptr;
+    int32_t* col_g = p.col_scratch + (size_t)ggid * 4 * p.col_stride;
+    const clq_affine_t sc = p.sc;
+    int staged_ref = -1;
+
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(p.task_counter, (unsigned)GPW);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= p.n_tasks) break;
+        const uint32_t task = base + gw;
+        bool valid = task < p.n_tasks;
+        uint32_t ridx = 0;
+        int ref = -1;
+        if (valid) {
+            if (p.all_pairs) {
+                const uint32_t q = task / p.n_refs;
+                ref = (int)(task - q * p.n_refs);
+                ridx = p.order ? p.order[q] : q;
+                if (p.cand_mask && !((p.cand_mask[(size_t)ridx * p.mask_words + (ref >> 5)] >> (ref & 31)) & 1u)) valid = false;
+            } else {
+                ridx = p.order ? p.order[task] : task;
+                ref = p.ref_of_read[ridx];
+            }
+        }
+        int L1 = 0, L2 = 0;
+        const uint8_t* refp = nullptr;
+        const uint8_t* readp = nullptr;
+        uint32_t status = CLQ_OK;
+        if (valid) {
+            const uint64_t r0 = p.read_off[ridx];
+            L2 = (int)(p.read_off[ridx + 1] - r0);
+            readp = p.read_bytes + r0;
+            if ((uint32_t)L2 >= p.max_read_len) status = CLQ_READ_TOO_LONG;
+            else if (ref < 0 || (uint32_t)ref >= p.n_refs) status = CLQ_NO_CANDIDATE;
+            else {
+                const uint64_t f0 = p.ref_off[ref];
+                L1 = (int)(p.ref_off[ref + 1] - f0);
+                refp = p.ref_bytes + f0;
+            }
+        }
+        const bool ok = valid && status == CLQ_OK;
+        const bool run = ok && L1 > 0 && L2 > 0;
+
+        if (run && ref != staged_ref) {
+            for (int i = gl; i < L1; i += G) ref_sm[i] = refp[i];
+            staged_ref = ref;
+        }
+        __syncwarp();
+
+        const int K = run ? stale_rows(L1, L2, p.band_mode) : 0;
+        const int NS = run ? (L2 + W - 1) / W : 0;
+        const int NSmax = __reduce_max_sync(FULL, NS);
+        const int T = run ? L1 + G - 1 : 0;
+        const int Tmax = __reduce_max_sync(FULL, T);
+        // the lane / register that own column L2 in the last stripe
+        const int cL = run ? (L2 - 1) - (NS - 1) * W : 0;
+        const int lL = cL / C, jL = cL - lL * C;
+        int capM = 0, capE = 0, capF = 0;
+
+        for (int s = 0; s < NSmax; s++) {
+            const bool act_s = run && s < NS;
+            const bool own_last = act_s && s == NS - 1 && gl == lL;
+            const int y0 = s * W + gl * C;  // columns y0+1 .. y0+C
+            int E[C], B[C], bq[C];
+            uint32_t w[WPL];
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                const int y = y0 + j + 1;
+                int code = 0x400;  // padding column: never equal, not special
+                if (act_s && y <= L2) {
+                    const int c = readp[y - 1];
+                    code = is_special(c) ? (c | 0x100) : c;
+                }
+                bq[j] = code;
+                E[j] = B[j] = sc.b0 + y * sc.b1;  // row 0: S[0,y] = (MAXNEG, g(y), g(y))
+            }
+            int prevBl = (y0 == 0) ? 0 : sc.b0 + y0 * sc.b1;  // B[0, y0]
+            int oF = 0, oE = 0, oM = 0, oB = 0;
+            // stripe boundary column (left edge of lane 0 when s > 0), prefetched one row ahead
+            int nF = 0, nE = 0, nM = 0, nB = 0;
+            if (s > 0 && gl == 0 && act_s) {
+                nF = col_g[1]; nE = col_g[p.col_stride + 1]; nM = col_g[2 * p.col_stride + 1]; nB = col_g[3 * p.col_stride + 1];
+            }
+            int rnext = act_s ? ref_sm[0] : 0;  // every lane starts at row 1 (lane gl at step t = 1 + gl)
+
+            for (int t = 1; t <= Tmax; t++) {
+                const int x = t - gl;
+                int Fl = __shfl_up_sync(FULL, oF, 1, G);
+                int Bl = __shfl_up_sync(FULL, oB, 1, G);
+                int El = 0, Ml = 0;
+                if (TB) {
+                    El = __shfl_up_sync(FULL, oE, 1, G);
+                    Ml = __shfl_up_sync(FULL, oM, 1, G);
+                }
+                const bool act = act_s && x >= 1 && x <= L1;
+                if (act) {
+                    if (gl == 0) {
+                        if (s == 0) {
+                            Fl = El = Bl = sc.b0 + x * sc.b1;  // S[x,0] = (MAXNEG, g(x), g(x))
+                            Ml = sc.max_neg;
+                        } else {
+                            Fl = nF; El = nE; Ml = nM; Bl = nB;
+                            if (x < L1) {
+                                nF = col_g[x + 1]; nE = col_g[p.col_stride + x + 1];
+                                nM = col_g[2 * p.col_stride + x + 1]; nB = col_g[3 * p.col_stride + x + 1];
+                            }
+                        }
+                    }
+                    const int r = rnext;
+                    if (x < L1) rnext = ref_sm[x];
+                    const bool rsp = is_special(r);
+                    const int rcode = rsp ? 0x200 : r;
+                    const int mt = rsp ? sc.special : sc.match;
+                    const int mm = rsp ? sc.special : sc.mismatch;
+                    const int BlIn = Bl;
+                    if (x == L1)
+                        row_step<C, TB, FIN, true>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, rcode, mt, mm, sc, own_last, jL, capM, capE, capF);
+                    else
+                        row_step<C, TB, FIN, false>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, rcode, mt, mm, sc, own_last, jL, capM, capE, capF);
+                    prevBl = BlIn;
+                    oF = Fl; oE = El; oM = Ml; oB = Bl;
+                    if (K > 0 && own_last && x <= K) {
+                        // band-skipped cell (x, L2): fresh-matrix state (0,0,0) / Up(0)
+#pragma unroll
+                        for (int j = 0; j < C; j++)
+                            if (j == jL) { E[j] = 0; B[j] = 0; }
+                        if (TB) {
+#pragma unroll
+                            for (int k = 0; k < WPL; k++)
+                                if (k == (jL >> 3)) w[k] |= 3u << (4 * (jL & 7));
+                        }
+                        if (jL == C - 1) { oF = 0; oE = 0; oM = 0; oB = 0; }
+                        if (x == L1) { capM = 0; capE = 0; capF = 0; }
+                    }
+                    if (TB) {
+                        uint32_t* dst = bits_g + ((size_t)(s * T + (t - 1)) * G + gl) * WPL;
+#pragma unroll
+                        for (int k = 0; k < WPL; k++) dst[k] = w[k];
+                    }
+                    if (gl == G - 1 && s < NS - 1) {
+                        col_g[x] = oF; col_g[p.col_stride + x] = oE; col_g[2 * p.col_stride + x] = oM; col_g[3 * p.col_stride + x] = oB;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- final cell: score + start layer = LAST maximum of (M, E, F)  (alignment/alignment_matrix.rs:963-972) ----
+        const int src = gw * G + lL;
+        capM = __shfl_sync(FULL, capM, src);
+        capE = __shfl_sync(FULL, capE, src);
+        capF = __shfl_sync(FULL, capF, src);
+        int score = 0, z = 0;
+        if (run) {
+            score = capM; z = 0;
+            if (capE >= score) { score = capE; z = 1; }
+            if (capF >= score) { score = capF; z = 2; }
+        } else if (ok) {
+            const int n = L1 > L2 ? L1 : L2;
+            if (n > 0) { score = sc.b0 + n * sc.b1; z = 2; }
+        }
+
+        if (!TB) {
+            if (valid && gl == 0) {
+                if (p.all_pairs) p.scores[(size_t)ridx * p.n_refs + ref] = ok ? score : INT32_MIN;
+                else {
+                    clq_result_t r;
+                    r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = 0; r.cigar_len = 0; r.status = status;
+                    p.results[ridx] = r;
+                }
+                if (run) atomicAdd(p.cells, (unsigned long long)L1 * (unsigned long long)L2);
+            }
+            continue;
+        }
+
+        // ---- traceback walk on the group's lane 0 ----
+        int nops = 0, cpos = 0;
+        if (ok && gl == 0) {
+            int x = L1, y = L2;
+            cpos = (int)p.cig_stride;
+            uint32_t cur_op = 3, cur_len = 0;
+            auto emit = [&](uint32_t op, uint32_t n) {
+                if (op == cur_op) cur_len += n;
+                else {
+                    if (cur_len) cig_g[--cpos] = (cur_len << 4) | cur_op;
+                    cur_op = op; cur_len = n;
+                }
+            };
+            auto nibble = [&](int xx, int yy) -> uint32_t {
+                int c = yy - 1;
+                const int s = c / W;
+                c -= s * W;
+                const int ln = c / C, j = c - ln * C;
+                const size_t idx = ((size_t)(s * T + (xx + ln - 1)) * G + ln) * WPL + (j >> 3);
+                return (bits_g[idx] >> (4 * (j & 7))) & 15u;
+            };
+            uint32_t nib = (x > 0 && y > 0) ? nibble(x, y) : 0;
+            while (x > 0 && y > 0) {
+                if ((nib & 3u) == 3u) { status = CLQ_TRACEBACK_DIVERGED; break; }
+                const uint32_t old = nib;
+                if (z == 0) { emit(CLQ_OP_M, 1); x--; y--; }
+                else if (z == 1) { emit(CLQ_OP_D, 1); x--; }
+                else { emit(CLQ_OP_I, 1); y--; }
+                if (x == 0 || y == 0) break;
+                nib = nibble(x, y);
+                const uint32_t a = nib & 3u;
+                if (z == 0) z = (a == 1u) ? 1 : (a == 2u ? 2 : 0);
+                else if (z == 1) z = (old & 4u) ? 1 : (a == 2u ? 2 : 0);
+                else z = (old & 8u) ? 2 : (a == 1u ? 1 : 0);
+            }
+            if (status == CLQ_OK) {
+                if (x > 0) emit(CLQ_OP_D, (uint32_t)x);
+                if (y > 0) emit(CLQ_OP_I, (uint32_t)y);
+            }
+            if (cur_len) cig_g[--cpos] = (cur_len << 4) | cur_op;
+            nops = (int)p.cig_stride - cpos;
+            if (status != CLQ_OK) nops = 0;
+        }
+        // ---- copy the CIGAR into the pool (group-cooperative) ----
+        unsigned long long off = 0;
+        if (ok && gl == 0 && nops > 0) {
+            off = atomicAdd(p.cigar_cursor, (unsigned long long)nops);
+            if (off + (unsigned long long)nops > p.cigar_cap) { status = CLQ_CIGAR_POOL_FULL; nops = 0; }
+        }
+        __syncwarp();
+        const int gsrc = gw * G;
+        const int n_all = __shfl_sync(FULL, nops, gsrc);
+        const int cpos_all = __shfl_sync(FULL, cpos, gsrc);
+        const unsigned long long off_all = __shfl_sync(FULL, off, gsrc);
+        for (int i = gl; i < n_all; i += G) p.cigar_pool[off_all + i] = cig_g[cpos_all + i];
+        if (valid && gl == 0) {
+            clq_result_t r;
+            r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = (uint32_t)off; r.cigar_len = (uint32_t)nops; r.status = status;
+            p.results[ridx] = r;
+            if (run) atomicAdd(p.cells, (unsigned long long)L1 * (unsigned long long)L2);
+        }
+        __syncwarp();
+    }
+}
+
+// exhaustive_alignment_search's arg-max: ascending reference index, LAST maximum wins
+// (max_by(partial_cmp), alignment_functions.rs:809-813).  One thread per read.
+__global__ void select_best_kernel(const int32_t* scores, uint32_t n_reads, uint32_t n_refs, const uint32_t* cand_mask,
+                                   uint32_t mask_words, int32_t* ref_of_read, const int32_t* single_ref) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_reads) return;
+    if (single_ref && single_ref[i] >= 0) { ref_of_read[i] = single_ref[i]; return; }
+    int best = -1;
+    int32_t bs = INT32_MIN;
+    for (uint32_t r = 0; r < n_refs; r++) {
+        if (cand_mask && !((cand_mask[(size_t)i * mask_words + (r >> 5)] >> (r & 31)) & 1u)) continue;
+        const int32_t v = scores[(size_t)i * n_refs + r];
+        if (v == INT32_MIN) continue;
+        if (best < 0 || v >= bs) { bs = v; best = (int)r; }
+    }
+    ref_of_read[i] = best;
+}
+
+// quick_alignment_search's k-mer vote (alignment_functions.rs:693-767) against the unique-k-mer table built by
+// clq_kmer_index_set (reference/fasta_reference.rs:159-202).  One thread per read:
+//   votes per reference over the read's sampled k-mer runs; best share > threshold -> single_ref[i] = that reference;
+//   otherwise the candidate mask = references with >= 1 vote, or every reference when nothing voted.
+__global__ void kmer_vote_kernel(const uint8_t* read_bytes, const uint64_t* read_off, uint32_t n_reads, const uint8_t* keys,
+                                 const uint32_t* owner, uint32_t n_keys, uint32_t k, uint32_t skip, uint32_t n_refs,
+                                 double threshold, uint32_t* votes_scratch, uint32_t* cand_mask, uint32_t mask_words,
+                                 int32_t* single_ref) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_reads) return;
+    const uint8_t* rd = read_bytes + read_off[i];
+    const uint32_t L2 = (uint32_t)(read_off[i + 1] - read_off[i]);
+    uint32_t* votes = votes_scratch + (size_t)i * n_refs;
+    for (uint32_t r = 0; r < n_refs; r++) votes[r] = 0;
+    uint32_t total = 0;
+    long long prev = -1;  // start of the previous window (consecutive dedup_with_count)
+    for (uint32_t pos = 0; k > 0 && pos + k <= L2; pos += skip) {
+        bool same = prev >= 0;
+        if (same) {
+            for (uint32_t c = 0; c < k; c++) {
+                uint8_t a = rd[prev + c], b = rd[pos + c];
+                a = (a >= 'a' && a <= 'z') ? a - 32 : a;
+                b = (b >= 'a' && b <= 'z') ? b - 32 : b;
+                if (a != b) { same = false; break; }
+            }
+        }
+        prev = pos;
+        if (same) continue;  // same run: one vote per run
+        uint32_t lo = 0, hi = n_keys;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            int cmp = 0;
+            for (uint32_t c = 0; c < k; c++) {
+                uint8_t b = rd[pos + c];
+                b = (b >= 'a' && b <= 'z') ? b - 32 : b;
+                const uint8_t a = keys[(size_t)mid * k + c];
+                if (a != b) { cmp = a < b ? -1 : 1; break; }
+            }
+            if (cmp == 0) { votes[owner[mid]]++; total++; break; }
+            if (cmp < 0) lo = mid + 1; else hi = mid;
+        }
+    }
+    uint32_t* mask = cand_mask + (size_t)i * mask_words;
+    for (uint32_t wd = 0; wd < mask_words; wd++) mask[wd] = 0;
+    int single = -1;
+    if (total == 0) {
+        for (uint32_t r = 0; r < n_refs; r++) mask[r >> 5] |= 1u << (r & 31);
+    } else {
+        const double count = (double)total;
+        double bestp = -1.0;
+        int bi = -1;
+        for (uint32_t r = 0; r < n_refs; r++) {
+            if (!votes[r]) continue;
+            mask[r >> 5] |= 1u << (r & 31);
+            const double pr = (double)votes[r] / count;
+            if (pr >= bestp) { bestp = pr; bi = (int)r; }
+        }
+        if (bestp > threshold) single = bi;
+    }
+    single_ref[i] = single;
+    if (single >= 0) {
+        for (uint32_t wd = 0; wd < mask_words; wd++) mask[wd] = 0;  // no exhaustive fill for this read
+    }
+}
+
+}  // namespace clq

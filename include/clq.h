@@ -1,0 +1,167 @@
+/*
+ * clq.h -- C ABI of libclq: B200-native batched amplicon alignment, a drop-in for the alignment hot
+ * path of mckennalab/clique (global affine-gap Gotoh DP + traceback, best-candidate reference selection).
+ *
+ * The reference has no FFI of its own; the seam is the set of Rust functions its callers use.  Each entry
+ * point below names the reference interface it replaces (file:line relative to rust_cmd/src/ of the
+ * reference).  INTEGRATION.md shows the Rust `extern "C"` block + shim that binds these symbols.
+ *
+ * Conventions: plain C, no exceptions across the boundary, every call returns an int32 status (0 = OK,
+ * negative = call-level error, see clq_strerror), per-read outcomes are reported in clq_result_t.status.
+ * The caller owns all host buffers.  One clq_ctx per GPU; a ctx is not thread-safe, distinct ctxs are fully
+ * independent (read-sharded multi-GPU: one ctx per device, no collectives).
+ * There is no CPU fallback: without a CUDA device every entry point that needs one fails with CLQ_E_CUDA.
+ */
+#ifndef CLQ_H
+#define CLQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLQ_VERSION 100
+
+/* ---- per-read status (clq_result_t.status) ---- */
+#define CLQ_OK 0
+#define CLQ_READ_TOO_LONG 1             /* align_reads drops reads >= max_read_size with warn!; alignment_functions.rs:147,240-247 */
+#define CLQ_SCORING_NOT_REPRESENTABLE 2 /* scores are not dyadic rationals / gap_open >= 0: no exact integer form */
+#define CLQ_TRACEBACK_DIVERGED 3        /* the reference would spin forever on a stale Up(0) cell; alignment/alignment_matrix.rs:977-1051 */
+#define CLQ_CIGAR_POOL_FULL 4
+#define CLQ_NO_CANDIDATE 5              /* no reference to align to: Option::None; alignment_functions.rs:536-543 */
+
+/* ---- call-level errors (negative return values) ---- */
+#define CLQ_E_INVALID (-1)
+#define CLQ_E_CUDA (-2)
+#define CLQ_E_NOMEM (-3)
+#define CLQ_E_LIMIT (-4)
+#define CLQ_E_STATE (-5)
+#define CLQ_E_UNSUPPORTED (-6)
+
+/* ---- flags for clq_submit / clq_launch ---- */
+#define CLQ_BAND_MAXLEN 0u           /* perform_affine_alignment: bandwidth = max(L1,L2); alignment/alignment_matrix.rs:366-372 */
+#define CLQ_BAND_READLEN 1u          /* align_two_strings_passed_matrix(.., &read.len()); alignment_functions.rs:737-746,790-799 */
+#define CLQ_BAND_MASK 3u
+#define CLQ_SEARCH_FIXED (0u << 2)      /* fixed_ref[i] names the reference of read i */
+#define CLQ_SEARCH_EXHAUSTIVE (1u << 2) /* exhaustive_alignment_search; alignment_functions.rs:769-827 */
+#define CLQ_SEARCH_QUICK (2u << 2)      /* quick_alignment_search (fast_lookup = true); alignment_functions.rs:693-767 */
+#define CLQ_SEARCH_MASK (3u << 2)
+#define CLQ_SCORE_ONLY (1u << 4)        /* skip traceback: score + ref_index only */
+#define CLQ_CONVEX (1u << 5)            /* two-piece affine gaps (scoring given as clq_convex_t) */
+
+/* CIGAR op encoding in the pool: len << 4 | code, BAM codes (AlignmentTag -> Op, alignment/alignment_matrix.rs:95-107) */
+#define CLQ_OP_M 0u /* AlignmentTag::MatchMismatch */
+#define CLQ_OP_I 1u /* AlignmentTag::Ins */
+#define CLQ_OP_D 2u /* AlignmentTag::Del */
+
+typedef struct clq_ctx clq_ctx;
+
+/* AffineScoring (alignment/scoring_functions.rs:65-73) in exact scaled-integer form: every field is the
+ * f64 value times `scale`.  Build it with clq_affine_from_f64. */
+typedef struct {
+    int32_t scale;         /* power of two, 1..64 */
+    int32_t match, mismatch, special;
+    int32_t oe_in, e_in;   /* interior cells: gap_open + gap_extend, gap_extend                              */
+    int32_t oe_fin, e_fin; /* x == L1 || y == L2: gap_open + gap_extend*mult, gap_extend*mult (:625-627)      */
+    int32_t b0, b1;        /* boundary g(k) = b0 + k*b1 = (gap_open + k*gap_extend)*mult (:389-405)           */
+    int32_t max_neg;       /* MAX_NEG_SCORE * scale = -100000 * scale (:34)                                   */
+} clq_affine_t;
+
+/* two-piece affine ("convex") scoring; semantics defined by this repo, gap(k) = max(o1+k*e1, o2+k*e2) */
+typedef struct {
+    int32_t match, mismatch, special;
+    int32_t o1, e1, o2, e2;
+    int32_t max_neg;
+} clq_convex_t;
+
+/* capacity of a context; a batch exceeding it is rejected with CLQ_E_LIMIT */
+typedef struct {
+    uint32_t max_reads;       /* reads per batch (per slot)                                            */
+    uint64_t max_read_bytes;  /* total read bytes per batch                                            */
+    uint32_t max_read_len;    /* reads >= this are dropped with CLQ_READ_TOO_LONG (align_reads' rule)   */
+    uint32_t max_refs;
+    uint64_t max_ref_bytes;
+    uint64_t cigar_pool_ops;  /* CIGAR pool capacity per slot, in uint32 ops                            */
+    uint32_t n_slots;         /* independent stream slots for double buffering (1..4)                   */
+} clq_limits_t;
+
+/* one record per read: AlignmentResult.score / cigar_string + AlignmentWithRef.ref_name
+ * (alignment/alignment_matrix.rs:694-706, alignment_functions.rs:451-456) */
+typedef struct {
+    int32_t score_scaled; /* AlignmentResult.score * scale (exact) */
+    uint32_t ref_index;   /* index into the clq_refs_set order     */
+    uint32_t cigar_off;   /* first op in the CIGAR pool            */
+    uint32_t cigar_len;   /* run-length merged ops                 */
+    uint32_t status;
+} clq_result_t;
+
+/* timing / accounting of the last clq_launch on a slot */
+typedef struct {
+    float kernel_ms;       /* CUDA-event time over all kernels of the launch, on the slot's stream */
+    float dp_ms;           /* the dominant DP kernel(s) alone                                       */
+    uint32_t launches;     /* kernels launched                                                      */
+    uint32_t dp_launches;
+    uint64_t cells;        /* sum of L1*L2 over every (read, reference) pair filled                 */
+    uint64_t h2d_bytes;    /* bytes copied host->device by clq_upload                               */
+    uint64_t d2h_bytes;    /* bytes copied device->host by clq_download + clq_wait                  */
+} clq_stats_t;
+
+int32_t clq_version(void);
+const char* clq_strerror(int32_t code);
+int32_t clq_device_count(void);
+
+/* AffineScoring{..} -> exact integer form; CLQ_SCORING_NOT_REPRESENTABLE if no scale <= 64 makes every
+ * derived constant integral, if gap_open >= 0 (the direction encoding needs a real opening penalty) or if a
+ * value leaves the int32 working range. */
+int32_t clq_affine_from_f64(double match_score, double mismatch_score, double special_character_score,
+                            double gap_open, double gap_extend, double final_gap_multiplier, clq_affine_t* out);
+
+/* pinned host memory for the caller's batch buffers (double-buffered H2D/D2H) */
+int32_t clq_host_alloc(size_t bytes, void** out);
+int32_t clq_host_free(void* p);
+
+/* replaces create_scoring_record_3d + the rayon thread-local matrices: alignment/alignment_matrix.rs:226-233,
+ * alignment_functions.rs:115-141 */
+int32_t clq_ctx_create(int32_t device, const clq_limits_t* limits, clq_ctx** out);
+void clq_ctx_destroy(clq_ctx* ctx);
+const char* clq_ctx_last_error(const clq_ctx* ctx);
+
+/* replaces ReferenceManager::from_yaml_input / from_fa_file (the reference set): reference/fasta_reference.rs:90-146.
+ * bytes = raw ASCII, case preserved; off has n_refs + 1 entries. */
+int32_t clq_refs_set(clq_ctx* ctx, uint32_t n_refs, const uint8_t* bytes, const uint64_t* off);
+
+/* replaces ReferenceManager::unique_kmers: reference/fasta_reference.rs:159-202 (k = 8, skip = 4 in the CLI, main.rs:271) */
+int32_t clq_kmer_index_set(clq_ctx* ctx, uint32_t k, uint32_t skip);
+
+/* The batch call: replaces the closure body of align_reads' par_bridge loop up to the alignment result
+ * (alignment_functions.rs:135-162) = align_to_reference_choices (:520-631) -> quick/exhaustive search ->
+ * align_two_strings_passed_matrix (:383-449) -> perform_affine_alignment_bandwidth + perform_3d_global_traceback
+ * (alignment/alignment_matrix.rs:376-425, :941-1086) -> simplify_cigar_string (alignment_manager.rs:386-423).
+ * With CLQ_SEARCH_FIXED | CLQ_BAND_MAXLEN it is align_two_strings (alignment_manager.rs:231-273) per read.
+ * Asynchronous: enqueues H2D copies, kernels and D2H copies on the slot's stream.  read_off has n_reads + 1
+ * entries; fixed_ref may be NULL unless CLQ_SEARCH_FIXED; scoring points at a clq_affine_t (or clq_convex_t with
+ * CLQ_CONVEX).  The host buffers must stay valid until clq_wait returns. */
+int32_t clq_submit(clq_ctx* ctx, int32_t slot, uint32_t n_reads, const uint8_t* read_bytes, const uint64_t* read_off,
+                   const int32_t* fixed_ref, const void* scoring, uint32_t flags, double match_threshold);
+
+/* blocks until the slot's work is done and copies results out; cigar_used receives the ops written */
+int32_t clq_wait(clq_ctx* ctx, int32_t slot, clq_result_t* results, uint32_t* cigar_pool, uint64_t cigar_cap,
+                 uint64_t* cigar_used);
+
+/* the three stages of clq_submit, separately (kernel-only timing with device-resident inputs) */
+int32_t clq_upload(clq_ctx* ctx, int32_t slot, uint32_t n_reads, const uint8_t* read_bytes, const uint64_t* read_off,
+                   const int32_t* fixed_ref);
+int32_t clq_launch(clq_ctx* ctx, int32_t slot, const void* scoring, uint32_t flags, double match_threshold);
+int32_t clq_download(clq_ctx* ctx, int32_t slot);
+int32_t clq_sync(clq_ctx* ctx, int32_t slot);
+int32_t clq_slot_stats(clq_ctx* ctx, int32_t slot, clq_stats_t* out);
+
+/* tuning knob for experiments: 0 = automatic kernel geometry */
+int32_t clq_set_option(clq_ctx* ctx, const char* key, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,318 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+Bar: bit-exact scores, CIGARs, selected references and statuses (tie-breaking included)."""
+import numpy as np
+import pytest
+
+import _oracle as O
+from clique_b200 import (AffineScoring, Aligner, ClqError, Reference, ReferenceManager, TRACEBACK_DIVERGED,
+                         READ_TOO_LONG, NO_CANDIDATE, CIGAR_POOL_FULL)
+from clique_b200 import synth
+from clique_b200.aligner import pack_reads
+
+pytestmark = pytest.mark.gpu
+
+SCORINGS = {
+    "cli": (10.0, -9.0, 9.0, -20.0, -2.0, 1.0),
+    "default_dna": (5.0, -4.0, 4.0, -10.0, -0.5, 0.5),
+    "merger": (10.0, -5.0, 8.0, -15.0, -1.0, 0.25),
+    "test": (6.0, -6.0, 5.0, -10.0, -10.0, 1.0),
+}
+
+
+@pytest.fixture(scope="module")
+def al():
+    a = Aligner(device=0, max_reads=1 << 16, max_read_bytes=1 << 27, max_read_len=1 << 14, cigar_ops_per_read=256, n_slots=2)
+    yield a
+    a.close()
+
+
+def rand_seq(rng, n, alphabet=b"ACGT"):
+    return bytes(rng.choice(list(alphabet), size=n).astype(np.uint8)) if n else b""
+
+
+def mutate(rng, s, p):
+    out = bytearray()
+    for c in s:
+        r = rng.random()
+        if r < p / 3:
+            continue
+        if r < 2 * p / 3:
+            out.append(rng.choice(list(b"ACGT"))); continue
+        if r < p:
+            out += rand_seq(rng, int(rng.integers(1, 4)))
+        out.append(c)
+    return bytes(out)
+
+
+def compare(br, want, n, ctx=""):
+    """br: BatchResult (GPU); want: oracle align_batch dict"""
+    scale = br.scale
+    for i in range(n):
+        assert int(br.status[i]) == int(want["status"][i]), (ctx, i, "status", int(br.status[i]), int(want["status"][i]))
+        if int(want["status"][i]) == NO_CANDIDATE:
+            continue
+        assert int(br.ref_index[i]) == int(want["ref_index"][i]), (ctx, i, "ref")
+        assert int(br.score_scaled[i]) == want["score"][i] * scale, (ctx, i, "score", int(br.score_scaled[i]), want["score"][i])
+        if int(want["status"][i]) == 0:
+            o, l = int(want["cigar_off"][i]), int(want["cigar_len"][i])
+            assert O.cigar_str(br.cigar(i)) == O.cigar_str(want["cigar_pool"][o:o + l]), (ctx, i, "cigar")
+
+
+def run_both(al, refs, reads, sc, search="fixed", band="readlen", fixed_ref=None, kmer=(8, 4)):
+    rm = ReferenceManager([Reference(r, b"r%d" % i) for i, r in enumerate(refs)], kmer[0], kmer[1])
+    al.set_references(rm)
+    qb, qo = pack_reads(reads)
+    br = al.align_batch(qb, qo, AffineScoring(*sc), search, band, fixed_ref=fixed_ref)
+    rb, ro = O.pack_seqs(refs)
+    want = O.align_batch(rb, ro, qb, qo, sc, search=search, fixed_ref=fixed_ref, band_mode=band, kmer=kmer, threads=8)
+    return br, want
+
+
+# ---------------------------------------------------------------- reference goldens through the C ABI
+def test_pair_goldens(al, goldens):
+    for p in goldens["pairs"]:
+        sc = AffineScoring(**p["scoring"])
+        r = al.align_two_strings(p["ref"].encode(), p["read"].encode(), None, sc)
+        e = p["expect"]
+        if "ref_aligned" in e:
+            assert r.reference_aligned.decode() == e["ref_aligned"], p["name"]
+        if "read_aligned" in e:
+            assert r.read_aligned.decode() == e["read_aligned"], p["name"]
+        if "cigar" in e:
+            assert r.cigar() == e["cigar"]
+        if "total_del" in e:
+            assert sum(n for c, n in r.cigar_string if c == "D") == e["total_del"]
+        if "total_ins" in e:
+            assert sum(n for c, n in r.cigar_string if c == "I") == e["total_ins"]
+        o = O.align_pair(p["ref"].encode(), p["read"].encode(), p["scoring"], "maxlen")
+        assert r.score == o["score"] and r.cigar() == O.cigar_str(o["cigar"])
+        assert len(r.path) == o["path_len"]
+    k = goldens["survey_kats"]
+    by = {p["name"]: p for p in goldens["pairs"]}
+    p = by["affine_alignment_test_favor_non_special_characters"]
+    r = al.align_two_strings(p["ref"].encode(), p["read"].encode(), None, AffineScoring(**p["scoring"]))
+    assert r.score == 391.5 and r.cigar() == k[p["name"]]["cigar"]
+
+
+def test_merger_goldens(al, goldens):
+    for m in goldens["mergers"]:
+        r = al.align_two_strings(m["read1"].encode(), m["read2_revcomp"].encode(), None, AffineScoring(**m["scoring"]))
+        o = O.align_pair(m["read1"].encode(), m["read2_revcomp"].encode(), m["scoring"], "maxlen")
+        assert r.reference_aligned == o["ref_aligned"] and r.read_aligned == o["read_aligned"] and r.score == o["score"]
+    assert r.score == o["score"]
+
+
+def test_best_reference_goldens(al, goldens):
+    for t in goldens["best_ref"]:
+        recs = goldens["fastas"][t["fasta"]]
+        rm = ReferenceManager.from_fasta_records([(r["name"], r["seq"]) for r in recs], *t["kmer"])
+        al.set_references(rm)
+        sc = AffineScoring(**t["scoring"])
+        for search in (al.exhaustive_alignment_search, al.quick_alignment_search):
+            w = search("testread", t["read"].encode(), None, sc)
+            assert w.ref_name.decode() == t["expect_ref_name"], (t["name"], search.__name__)
+        w = al.align_to_reference_choices("testread", t["read"].encode(), None, False, sc)
+        want = goldens["survey_kats"][t["name"]]["scores"]
+        assert w.alignment.score == max(want)
+        # per-candidate scores through the score-only path
+        qb, qo = pack_reads([t["read"].encode()] * len(recs))
+        br = al.align_batch(qb, qo, sc, "fixed", "readlen", fixed_ref=np.arange(len(recs)), score_only=True)
+        assert [int(s) for s in br.score_scaled] == want
+
+
+# ---------------------------------------------------------------- randomized parity vs the oracle
+@pytest.mark.parametrize("name", list(SCORINGS))
+@pytest.mark.parametrize("band", ["readlen", "maxlen"])
+def test_random_pairs(al, name, band):
+    rng = np.random.default_rng(abs(hash((name, band))) % 2**32)
+    refs, reads, fixed = [], [], []
+    for it in range(48):
+        l1 = int(rng.integers(0, 120)) if it % 7 else 0
+        alpha = b"ACGTN#acgtRY" if it % 5 == 0 else b"ACGTN"
+        refs.append(rand_seq(rng, l1, alpha))
+    for it in range(1500):
+        r = int(rng.integers(0, len(refs)))
+        kind = it % 4
+        if kind == 0:
+            rd = rand_seq(rng, int(rng.integers(0, 140)), b"ACGTN")
+        elif kind == 1:
+            rd = mutate(rng, refs[r], 0.12)
+        elif kind == 2:
+            rd = mutate(rng, refs[r], 0.02)[: int(rng.integers(1, 60))]
+        else:
+            rd = rand_seq(rng, int(rng.integers(0, 12)), b"ACGTNacgt*")
+        reads.append(rd); fixed.append(r)
+    br, want = run_both(al, refs, reads, SCORINGS[name], "fixed", band, np.array(fixed, np.int32))
+    compare(br, want, len(reads), (name, band))
+    assert (want["status"] == TRACEBACK_DIVERGED).sum() > 0      # the stale-cell path is exercised
+    assert (want["status"] == 0).sum() > 1000
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5])
+def test_every_geometry_and_multi_stripe(al, cfg):
+    """force each (lanes x columns) geometry; reads longer than one stripe exercise the column hand-over"""
+    rng = np.random.default_rng(100 + cfg)
+    W = [128, 192, 320, 384, 512, 1024][cfg]
+    refs = [rand_seq(rng, int(rng.integers(30, 400)), b"ACGTN") for _ in range(6)]
+    reads, fixed = [], []
+    for it in range(120):
+        r = int(rng.integers(0, len(refs)))
+        L = int(rng.choice([W - 1, W, W + 1, 2 * W, 2 * W + 3, int(rng.integers(1, 2 * W + 40))]))
+        rd = mutate(rng, refs[r], 0.08)
+        rd = (rd * (L // max(len(rd), 1) + 1))[:L]
+        reads.append(rd); fixed.append(r)
+    al.set_option("force_cfg", cfg)
+    try:
+        for name in ("cli", "default_dna"):
+            br, want = run_both(al, refs, reads, SCORINGS[name], "fixed", "readlen", np.array(fixed, np.int32))
+            compare(br, want, len(reads), (cfg, name))
+    finally:
+        al.set_option("force_cfg", -1)
+
+
+def test_config_c2_sample(al):
+    c = synth.config_c2(4000)
+    br, want = run_both(al, c["refs"], [bytes(c["read_bytes"][i * 300:(i + 1) * 300]) for i in range(4000)], c["scoring"],
+                        "fixed", "readlen", c["fixed_ref"])
+    compare(br, want, 4000, "C2")
+
+
+def test_config_c3_sample(al):
+    c = synth.config_c3(300)
+    off = c["read_off"]
+    reads = [bytes(c["read_bytes"][int(off[i]):int(off[i + 1])]) for i in range(300)]
+    br, want = run_both(al, c["refs"], reads, c["scoring"], "fixed", "readlen", c["fixed_ref"])
+    compare(br, want, 300, "C3")
+
+
+@pytest.mark.parametrize("search", ["exhaustive", "quick"])
+def test_config_c4_sample(al, search):
+    n = 200 if search == "exhaustive" else 600
+    c = synth.config_c4(n, search=search)
+    off = c["read_off"]
+    reads = [bytes(c["read_bytes"][int(off[i]):int(off[i + 1])]) for i in range(n)]
+    br, want = run_both(al, c["refs"], reads, c["scoring"], search, "readlen")
+    compare(br, want, n, "C4/" + search)
+    assert (br.ref_index == c["truth"][:n]).mean() > 0.9
+
+
+def test_config_c5_sample(al):
+    c = synth.config_c5(160)
+    off = c["read_off"]
+    reads = [bytes(c["read_bytes"][int(off[i]):int(off[i + 1])]) for i in range(160)]
+    br, want = run_both(al, c["refs"], reads, c["scoring"], "fixed", "readlen", c["fixed_ref"])
+    compare(br, want, 160, "C5")
+
+
+def test_quick_search_vote_paths(al):
+    """reads that vote for one reference (> 0.90), for several, and for none (alignment_functions.rs:719-764)"""
+    rng = np.random.default_rng(5)
+    core = rand_seq(rng, 120)
+    refs = [rand_seq(rng, 60) + core + rand_seq(rng, 60) for _ in range(5)] + [rand_seq(rng, 200)]
+    reads = []
+    for i in range(120):
+        k = i % 4
+        if k == 0:
+            reads.append(mutate(rng, refs[i % 6], 0.01))
+        elif k == 1:
+            reads.append(refs[i % 5][:100] + refs[(i + 1) % 5][100:])      # chimeric: votes split
+        elif k == 2:
+            reads.append(rand_seq(rng, int(rng.integers(5, 200))))           # no votes -> exhaustive over all
+        else:
+            reads.append(core)                                               # shared core only: no unique k-mer
+    for kmer in ((8, 4), (15, 5), (8, 8)):
+        br, want = run_both(al, refs, reads, SCORINGS["cli"], "quick", "readlen", kmer=kmer)
+        compare(br, want, len(reads), ("quick", kmer))
+
+
+# ---------------------------------------------------------------- statuses and limits
+def test_statuses(al):
+    rng = np.random.default_rng(9)
+    refs = [rand_seq(rng, 50)]
+    reads = [rand_seq(rng, 40), rand_seq(rng, (1 << 14) + 5), rand_seq(rng, 30)]
+    rm = ReferenceManager([Reference(refs[0], b"a")])
+    al.set_references(rm)
+    qb, qo = pack_reads(reads)
+    br = al.align_batch(qb, qo, AffineScoring(*SCORINGS["cli"]), "fixed", "readlen", fixed_ref=[0, 0, 7])
+    assert list(br.status) == [0, READ_TOO_LONG, NO_CANDIDATE]
+    with pytest.raises(ClqError):
+        al.align_batch(qb, qo, AffineScoring(*SCORINGS["cli"]), "fixed", "readlen")       # fixed_ref missing
+    al.set_references(ReferenceManager([]))
+    assert al.align_to_reference_choices("r", reads[0], None, True, AffineScoring(*SCORINGS["cli"])) is None
+    with pytest.raises(ClqError) as e:
+        al.align_two_strings(b"ACGTACGTACGTACGTACGTACGTAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA", b"ACG", None,
+                             AffineScoring(*SCORINGS["cli"]))
+    assert e.value.code == TRACEBACK_DIVERGED
+
+
+def test_cigar_pool_full():
+    a = Aligner(device=0, max_reads=64, max_read_bytes=1 << 20, cigar_ops_per_read=1, n_slots=1)
+    try:
+        rng = np.random.default_rng(2)
+        ref = rand_seq(rng, 200)
+        a.set_references(ReferenceManager([Reference(ref, b"a")]))
+        a.limits.cigar_pool_ops = 1024
+        reads = [mutate(rng, ref, 0.3) for _ in range(64)]
+        qb, qo = pack_reads(reads)
+        br = a.align_batch(qb, qo, AffineScoring(*SCORINGS["cli"]), "fixed", "readlen", fixed_ref=np.zeros(64, np.int32))
+        st = set(int(s) for s in br.status)
+        assert st <= {0, CIGAR_POOL_FULL} and 0 in st
+    finally:
+        a.close()
+
+
+def test_align_reads_double_buffered(al):
+    c = synth.config_c4(900, search="quick")
+    off = c["read_off"]
+    reads = [bytes(c["read_bytes"][int(off[i]):int(off[i + 1])]) for i in range(900)]
+    rm = ReferenceManager([Reference(r, n) for r, n in zip(c["refs"], c["ref_names"])])
+    al.set_references(rm)
+    got = dict(al.align_reads(reads, AffineScoring(*c["scoring"]), fast_lookup=True, batch_size=128))
+    assert sorted(got) == list(range(900))
+    rb, ro = O.pack_seqs(c["refs"])
+    qb, qo = pack_reads(reads)
+    want = O.align_batch(rb, ro, qb, qo, c["scoring"], search="quick", band_mode="readlen", threads=8)
+    for i in range(900):
+        w = got[i]
+        assert w.ref_name == c["ref_names"][int(want["ref_index"][i])]
+        o, l = int(want["cigar_off"][i]), int(want["cigar_len"][i])
+        assert w.alignment.cigar() == O.cigar_str(want["cigar_pool"][o:o + l]) and w.alignment.score == want["score"][i]
+
+
+# ---------------------------------------------------------------- full-size, size-independent properties
+def test_full_size_properties():
+    """BASELINE config C2 at its full 1M reads: every CIGAR consumes exactly the reference and the read, the score equals
+    the CIGAR re-scored on the host, results are identical across two stream slots, and a 20k sample matches the oracle."""
+    n = 1_000_000
+    c = synth.config_c2(n)
+    a = Aligner(device=0, max_reads=n, max_read_bytes=n * 300 + 64, cigar_ops_per_read=12, n_slots=2)
+    try:
+        a.set_references(ReferenceManager([Reference(c["refs"][0], b"amp")]))
+        sc = AffineScoring(*c["scoring"])
+        a.submit(0, c["read_bytes"], c["read_off"], sc, "fixed", "readlen", fixed_ref=c["fixed_ref"])
+        a.submit(1, c["read_bytes"], c["read_off"], sc, "fixed", "readlen", fixed_ref=c["fixed_ref"])
+        b0, b1 = a.wait(0), a.wait(1)
+        assert (b0.status == 0).all()
+        assert (b0.score_scaled == b1.score_scaled).all() and (b0.cigar_len == b1.cigar_len).all()
+        ops = b0.cigar_pool
+        ln, code = (ops >> 4).astype(np.int64), ops & 0xF
+        owner = np.repeat(np.arange(n), b0.cigar_len)
+        # pool order is arbitrary: address ops through (cigar_off, cigar_len)
+        starts = b0.cigar_off.astype(np.int64)
+        pos = np.repeat(starts, b0.cigar_len) + (np.arange(int(b0.cigar_len.sum())) - np.repeat(np.cumsum(b0.cigar_len) - b0.cigar_len, b0.cigar_len))
+        l_, c_ = ln[pos], code[pos]
+        ref_consumed = np.bincount(owner, weights=l_ * (c_ != 1), minlength=n)
+        read_consumed = np.bincount(owner, weights=l_ * (c_ != 2), minlength=n)
+        assert (ref_consumed == 215).all() and (read_consumed == 300).all()
+        # oracle on a sample
+        sel = np.random.default_rng(1).choice(n, 3000, replace=False)
+        rb, ro = O.pack_seqs(c["refs"])
+        reads = [bytes(c["read_bytes"][i * 300:(i + 1) * 300]) for i in sel]
+        qb, qo = pack_reads(reads)
+        want = O.align_batch(rb, ro, qb, qo, c["scoring"], search="fixed", fixed_ref=np.zeros(len(sel), np.int32), band_mode="readlen", threads=8)
+        for k, i in enumerate(sel):
+            assert int(b0.score_scaled[i]) == want["score"][k]
+            o, l = int(want["cigar_off"][k]), int(want["cigar_len"][k])
+            assert O.cigar_str(b0.cigar(i)) == O.cigar_str(want["cigar_pool"][o:o + l])
+    finally:
+        a.close()
