@@ -212,6 +212,10 @@ def main():
     al.set_references(ReferenceManager([Reference(r, nm) for r, nm in zip(c["refs"], c["ref_names"])]))
     sc = AffineScoring(*c["scoring"])
     sci = sc.to_int()
+    for opt in ("force_cfg", "force_generic", "debug_flags"):     # experiment knobs, e.g. CLQ_FORCE_CFG=3
+        if os.environ.get("CLQ_" + opt.upper()):
+            al.set_option(opt, int(os.environ["CLQ_" + opt.upper()]))
+    score_only = bool(int(os.environ.get("CLQ_SCORE_ONLY", "0")))
 
     # pinned host buffers for the e2e path, split into chunks that alternate over the two stream slots
     h_bytes = al.alloc_pinned(total_bytes, np.uint8)
@@ -238,7 +242,7 @@ def main():
     al.upload(0, h_bytes, c["read_off"], c["fixed_ref"])
     al.sync(0)
     for _ in range(args.warmup):
-        al.launch(0, sci, c["search"], c["band"])
+        al.launch(0, sci, c["search"], c["band"], score_only)
         al.sync(0)
     clocks = ClockSampler(dev)
     clocks.start()
@@ -246,7 +250,7 @@ def main():
     step_ms, dp_ms, launches, cells = [], [], 0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        al.launch(0, sci, c["search"], c["band"])
+        al.launch(0, sci, c["search"], c["band"], score_only)
         st = al.stats(0)       # synchronises the slot's stream; times come from CUDA events on that stream
         step_ms.append(st["kernel_ms"]); dp_ms.append(st["dp_ms"]); launches += st["launches"]; cells = st["cells"]
     barrier()

@@ -28,7 +28,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
     DevBuf read_bytes, read_off, fixed_ref, order, results, scores, cand_mask, single_ref, ref_of_read, votes;
-    DevBuf cigar_pool, bits, cig_scratch, col_scratch;
+    DevBuf cigar_pool, bits, cig_scratch, col_scratch, tb_rec;
     DevBuf counters;                 // [0..3] task counters (u32, padded to 8 B each), [4] cigar cursor, [5] cells
     unsigned long long* h_counters = nullptr;  // pinned mirror
     uint32_t n_reads = 0;
@@ -56,7 +56,12 @@ struct clq_ctx {
     uint32_t kmer_k = 0, kmer_skip = 0, n_keys = 0;
     std::vector<Slot> slots;
     int force_cfg = -1;
-    int64_t max_scratch_bytes = 48ll << 30;
+    int debug_flags = 0;
+    int force_generic = 0;           // option "force_generic": never take the FAST (PRMT/DPX) kernel variant
+    bool fast_ok = false;            // the reference set has <= 6 distinct non-special bytes
+    uint8_t cls[256] = {};           // byte -> class: 0 special, 1 other, 2..7 reference bytes
+    DevBuf cls_lut;
+    int64_t max_scratch_bytes = 24ll << 30;  // per slot: direction bits of one sub-batch
 };
 
 namespace {
@@ -91,9 +96,9 @@ void release(DevBuf& b) {
     b.cap = 0;
 }
 
-template <int G, int C, bool TB, bool FIN>
+template <int G, int C, bool TB, bool FIN, bool FAST>
 cudaError_t launch_one(const KParams& p, int sm_count, size_t smem, cudaStream_t st, int* grid_out, bool query_only) {
-    auto kern = gotoh_kernel<G, C, TB, FIN>;
+    auto kern = gotoh_kernel<G, C, TB, FIN, FAST>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -110,21 +115,41 @@ cudaError_t launch_one(const KParams& p, int sm_count, size_t smem, cudaStream_t
     return cudaGetLastError();
 }
 
-template <bool TB, bool FIN>
+template <bool TB, bool FIN, bool FAST>
 cudaError_t launch_cfg(int cfg, const KParams& p, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
     switch (cfg) {
-        case 0: return launch_one<8, 16, TB, FIN>(p, sm, smem, st, grid, q);
-        case 1: return launch_one<8, 24, TB, FIN>(p, sm, smem, st, grid, q);
-        case 2: return launch_one<8, 40, TB, FIN>(p, sm, smem, st, grid, q);
-        case 3: return launch_one<16, 24, TB, FIN>(p, sm, smem, st, grid, q);
-        case 4: return launch_one<32, 16, TB, FIN>(p, sm, smem, st, grid, q);
-        default: return launch_one<32, 32, TB, FIN>(p, sm, smem, st, grid, q);
+        case 0: return launch_one<8, 16, TB, FIN, FAST>(p, sm, smem, st, grid, q);
+        case 1: return launch_one<8, 24, TB, FIN, FAST>(p, sm, smem, st, grid, q);
+        case 2: return launch_one<8, 40, TB, FIN, FAST>(p, sm, smem, st, grid, q);
+        case 3: return launch_one<16, 24, TB, FIN, FAST>(p, sm, smem, st, grid, q);
+        case 4: return launch_one<32, 16, TB, FIN, FAST>(p, sm, smem, st, grid, q);
+        default: return launch_one<32, 32, TB, FIN, FAST>(p, sm, smem, st, grid, q);
     }
 }
 
-cudaError_t launch_any(int cfg, bool tb, bool fin, const KParams& p, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
-    if (tb) return fin ? launch_cfg<true, true>(cfg, p, sm, smem, st, grid, q) : launch_cfg<true, false>(cfg, p, sm, smem, st, grid, q);
-    return fin ? launch_cfg<false, true>(cfg, p, sm, smem, st, grid, q) : launch_cfg<false, false>(cfg, p, sm, smem, st, grid, q);
+// variant = (traceback?, final-gap multiplier?, fast PRMT/DPX path?)
+cudaError_t launch_any(int cfg, bool tb, bool fin, bool fast, const KParams& p, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
+    if (fast) return tb ? launch_cfg<true, false, true>(cfg, p, sm, smem, st, grid, q) : launch_cfg<false, false, true>(cfg, p, sm, smem, st, grid, q);
+    if (tb) return fin ? launch_cfg<true, true, false>(cfg, p, sm, smem, st, grid, q) : launch_cfg<true, false, false>(cfg, p, sm, smem, st, grid, q);
+    return fin ? launch_cfg<false, true, false>(cfg, p, sm, smem, st, grid, q) : launch_cfg<false, false, false>(cfg, p, sm, smem, st, grid, q);
+}
+
+template <int G, int C>
+cudaError_t launch_walk_one(const KParams& p, uint32_t cnt, cudaStream_t st) {
+    walk_kernel<G, C><<<(cnt + 127) / 128, 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.cig_scratch, p.cig_stride, p.cigar_pool,
+                                                         p.cigar_cap, p.cigar_cursor, p.results);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_walk(int cfg, const KParams& p, uint32_t cnt, cudaStream_t st) {
+    switch (cfg) {
+        case 0: return launch_walk_one<8, 16>(p, cnt, st);
+        case 1: return launch_walk_one<8, 24>(p, cnt, st);
+        case 2: return launch_walk_one<8, 40>(p, cnt, st);
+        case 3: return launch_walk_one<16, 24>(p, cnt, st);
+        case 4: return launch_walk_one<32, 16>(p, cnt, st);
+        default: return launch_walk_one<32, 32>(p, cnt, st);
+    }
 }
 
 int pick_cfg(const clq_ctx* c, uint32_t max_len) {
@@ -241,11 +266,11 @@ void clq_ctx_destroy(clq_ctx* c) {
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
         for (DevBuf* b : {&s.read_bytes, &s.read_off, &s.fixed_ref, &s.order, &s.results, &s.scores, &s.cand_mask, &s.single_ref,
-                          &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.counters})
+                          &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.tb_rec, &s.counters})
             release(*b);
         if (s.h_counters) cudaFreeHost(s.h_counters);
     }
-    release(c->ref_bytes); release(c->ref_off); release(c->kmer_keys); release(c->kmer_owner);
+    release(c->ref_bytes); release(c->ref_off); release(c->kmer_keys); release(c->kmer_owner); release(c->cls_lut);
     delete c;
 }
 
@@ -254,6 +279,8 @@ const char* clq_ctx_last_error(const clq_ctx* c) { return c ? c->err.c_str() : "
 int32_t clq_set_option(clq_ctx* c, const char* key, int64_t value) {
     if (!c || !key) return CLQ_E_INVALID;
     if (!strcmp(key, "force_cfg")) { c->force_cfg = (int)value; return CLQ_OK; }
+    if (!strcmp(key, "force_generic")) { c->force_generic = (int)value; return CLQ_OK; }
+    if (!strcmp(key, "debug_flags")) { c->debug_flags = (int)value; return CLQ_OK; }
     if (!strcmp(key, "max_scratch_bytes")) { c->max_scratch_bytes = value; return CLQ_OK; }
     return fail(c, CLQ_E_INVALID, std::string("unknown option ") + key);
 }
@@ -281,6 +308,20 @@ int32_t clq_refs_set(clq_ctx* c, uint32_t n_refs, const uint8_t* bytes, const ui
     CU(c, cudaMemcpy(c->ref_off.p, c->h_ref_off.data(), (n_refs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
     c->n_keys = 0;
     c->kmer_k = 0;
+    // byte classes for the FAST kernels: every special byte (N or < 58, alignment/scoring_functions.rs:100-102) is class 0,
+    // each distinct non-special reference byte gets its own class 2..7, every other byte can only mismatch: class 1.
+    int next = 2;
+    c->fast_ok = true;
+    for (int b = 0; b < 256; b++) c->cls[b] = (b == 'N' || b < 58) ? 0 : 1;
+    for (uint64_t i = 0; i < total; i++) {
+        const uint8_t b = bytes[i];
+        if (c->cls[b] == 1) {
+            if (next > 7) { c->fast_ok = false; break; }
+            c->cls[b] = (uint8_t)next++;
+        }
+    }
+    if ((rc = ensure(c, c->cls_lut, 256)) != CLQ_OK) return rc;
+    CU(c, cudaMemcpy(c->cls_lut.p, c->cls, 256, cudaMemcpyHostToDevice));
     return CLQ_OK;
 }
 
@@ -429,13 +470,15 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     CU(c, cudaSetDevice(c->device));
     const bool fin = sc.oe_fin != sc.oe_in || sc.e_fin != sc.e_in;
     const bool score_only = (flags & CLQ_SCORE_ONLY) != 0;
+    auto fits8 = [](int v) { return v >= -128 && v <= 127; };
+    const bool fast = c->fast_ok && !c->force_generic && !fin && fits8(sc.match) && fits8(sc.mismatch) && fits8(sc.special);
     const uint32_t n = s->n_reads;
     const int cfg = pick_cfg(c, s->max_len);
     const int G = kCfgs[cfg].G, C = kCfgs[cfg].C, W = G * C, GPW = 32 / G;
     const uint32_t L1max = c->max_ref_len, L2max = s->max_len;
     const uint32_t ns_max = std::max<uint32_t>(1, (L2max + W - 1) / W);
     const uint32_t ref_sm_stride = (L1max + 15) / 16 * 16 + 16;
-    const size_t smem = (size_t)(kThreads / 32) * GPW * ref_sm_stride;
+    const size_t smem = (size_t)(kThreads / 32) * GPW * ref_sm_stride + (fast ? 320 : 0);
     if (smem > 200 * 1024) return fail(c, CLQ_E_LIMIT, "references too long for this geometry's shared-memory staging");
 
     KParams p = {};
@@ -454,32 +497,38 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     unsigned long long* ctr = (unsigned long long*)s->counters.p;
     p.cigar_cursor = ctr + 4;
     p.cells = ctr + 5;
+    p.cls_lut = (const uint8_t*)c->cls_lut.p;
+    p.debug_flags = (uint32_t)c->debug_flags;
+    if (fast) {  // profile table: row = reference class, column = read class
+        int8_t tab[8][8];
+        for (int r = 0; r < 8; r++)
+            for (int q = 0; q < 8; q++)
+                tab[r][q] = (int8_t)((r == 0 || q == 0) ? sc.special : ((r == q && r >= 2) ? sc.match : sc.mismatch));
+        memcpy(p.tab, tab, 64);
+    }
 
     // grid + scratch sizing (per resident group)
     int grid_tb = 0, grid_sc = 0;
     cudaError_t ce;
-    if ((ce = launch_any(cfg, true, fin, p, c->sm_count, smem, s->stream, &grid_tb, true)) != cudaSuccess)
+    if ((ce = launch_any(cfg, true, fin, fast, p, c->sm_count, smem, s->stream, &grid_tb, true)) != cudaSuccess)
         return fail(c, CLQ_E_CUDA, std::string("occupancy(tb): ") + cudaGetErrorString(ce));
-    if ((ce = launch_any(cfg, false, fin, p, c->sm_count, smem, s->stream, &grid_sc, true)) != cudaSuccess)
+    if ((ce = launch_any(cfg, false, fin, fast, p, c->sm_count, smem, s->stream, &grid_sc, true)) != cudaSuccess)
         return fail(c, CLQ_E_CUDA, std::string("occupancy(score): ") + cudaGetErrorString(ce));
     const uint64_t bits_stride = (uint64_t)ns_max * (L1max + G) * G * (C / 8);
     const uint32_t cig_stride = L1max + L2max + 8;
     const uint32_t col_stride = L1max + 8;
-    const uint64_t per_group = bits_stride * 4 + (uint64_t)cig_stride * 4 + (uint64_t)col_stride * 16;
-    if (!score_only) {
-        const uint64_t groups_per_cta = (uint64_t)(kThreads / 32) * GPW;
-        const uint64_t max_ctas = std::max<uint64_t>(1, (uint64_t)c->max_scratch_bytes / (per_group * groups_per_cta));
-        if ((uint64_t)grid_tb > max_ctas) grid_tb = (int)max_ctas;
-    }
-    const uint64_t groups_tb = (uint64_t)grid_tb * (kThreads / 32) * GPW;
-    const uint64_t groups_sc = (uint64_t)grid_sc * (kThreads / 32) * GPW;
+    // traceback scratch is per task of a sub-batch: direction bits + CIGAR scratch + walker record
+    const uint64_t per_task = bits_stride * 4 + (uint64_t)cig_stride * 4 + sizeof(TbRec);
+    uint64_t sub = std::max<uint64_t>(1, std::min<uint64_t>(n, (uint64_t)c->max_scratch_bytes / per_task));
+    const uint64_t groups = (uint64_t)std::max(grid_tb, grid_sc) * (kThreads / 32) * GPW;
     int32_t rc;
-    if (!score_only) {
-        if ((rc = ensure(c, s->bits, groups_tb * bits_stride * 4)) != CLQ_OK) return rc;
-        if ((rc = ensure(c, s->cig_scratch, groups_tb * cig_stride * 4)) != CLQ_OK) return rc;
+    if (!score_only && n) {
+        if ((rc = ensure(c, s->bits, sub * bits_stride * 4)) != CLQ_OK) return rc;
+        if ((rc = ensure(c, s->cig_scratch, sub * cig_stride * 4)) != CLQ_OK) return rc;
+        if ((rc = ensure(c, s->tb_rec, sub * sizeof(TbRec))) != CLQ_OK) return rc;
         if ((rc = ensure(c, s->cigar_pool, (size_t)c->lim.cigar_pool_ops * 4 + 16)) != CLQ_OK) return rc;
     }
-    if ((rc = ensure(c, s->col_scratch, std::max(groups_tb, groups_sc) * col_stride * 16)) != CLQ_OK) return rc;
+    if ((rc = ensure(c, s->col_scratch, groups * col_stride * 16)) != CLQ_OK) return rc;
     p.bits = (uint32_t*)s->bits.p;
     p.bits_stride = bits_stride;
     p.cig_scratch = (uint32_t*)s->cig_scratch.p;
@@ -488,6 +537,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     p.col_stride = col_stride;
     p.cigar_pool = (uint32_t*)s->cigar_pool.p;
     p.cigar_cap = c->lim.cigar_pool_ops;
+    p.tb_rec = (TbRec*)s->tb_rec.p;
 
     s->flags = flags;
     s->stats.launches = 0;
@@ -528,7 +578,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
             q.task_counter = (unsigned int*)(ctr + 0);
             CU(c, cudaEventRecord(s->ev[1], s->stream));
             int g = grid_sc;
-            if ((ce = launch_any(cfg, false, fin, q, c->sm_count, smem, s->stream, &g, false)) != cudaSuccess)
+            if ((ce = launch_any(cfg, false, fin, fast, q, c->sm_count, smem, s->stream, &g, false)) != cudaSuccess)
                 return fail(c, CLQ_E_CUDA, std::string("score kernel: ") + cudaGetErrorString(ce));
             CU(c, cudaEventRecord(s->ev[2], s->stream));
             s->stats.launches++;
@@ -544,16 +594,37 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     if (n) {
         KParams q = p;
         q.all_pairs = 0;
-        q.n_tasks = n;
         q.ref_of_read = ref_of_read;
         q.task_counter = (unsigned int*)(ctr + 1);
         CU(c, cudaEventRecord(s->ev[3], s->stream));
-        int g = score_only ? grid_sc : grid_tb;
-        if ((ce = launch_any(cfg, !score_only, fin, q, c->sm_count, smem, s->stream, &g, false)) != cudaSuccess)
-            return fail(c, CLQ_E_CUDA, std::string("traceback kernel: ") + cudaGetErrorString(ce));
+        if (score_only) {
+            q.n_tasks = n;
+            q.task_base = 0;
+            int g = grid_sc;
+            if ((ce = launch_any(cfg, false, fin, fast, q, c->sm_count, smem, s->stream, &g, false)) != cudaSuccess)
+                return fail(c, CLQ_E_CUDA, std::string("score kernel: ") + cudaGetErrorString(ce));
+            s->stats.launches++;
+            s->stats.dp_launches++;
+        } else {
+            // fill (direction bits into the sub-batch's slots) then walk (one thread per pair), sub-batch by sub-batch
+            for (uint64_t base = 0; base < n; base += sub) {
+                const uint32_t cnt = (uint32_t)std::min<uint64_t>(sub, n - base);
+                q.n_tasks = cnt;
+                q.task_base = (uint32_t)base;
+                if (base) CU(c, cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned long long), s->stream));
+                int g = grid_tb;
+                if ((ce = launch_any(cfg, true, fin, fast, q, c->sm_count, smem, s->stream, &g, false)) != cudaSuccess)
+                    return fail(c, CLQ_E_CUDA, std::string("fill kernel: ") + cudaGetErrorString(ce));
+                s->stats.launches++;
+                s->stats.dp_launches++;
+                if (!(c->debug_flags & 1)) {
+                    if ((ce = launch_walk(cfg, q, cnt, s->stream)) != cudaSuccess)
+                        return fail(c, CLQ_E_CUDA, std::string("walk kernel: ") + cudaGetErrorString(ce));
+                    s->stats.launches++;
+                }
+            }
+        }
         CU(c, cudaEventRecord(s->ev[4], s->stream));
-        s->stats.launches++;
-        s->stats.dp_launches++;
         s->n_dp |= 2;
     }
     CU(c, cudaEventRecord(s->ev[5], s->stream));

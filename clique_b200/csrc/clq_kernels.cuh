@@ -5,7 +5,8 @@
 // memory, lane l works on row x = t - l at step t, and the right-edge values of a lane's stripe travel to the
 // next lane with __shfl_up_sync.  Reads longer than G*C columns are processed in column stripes whose boundary
 // column is parked in a small global scratch.  With TB the kernel also records 4 direction bits per cell
-// (coalesced, one G*C/8-word row per step), walks them back on one lane and emits the run-length CIGAR.
+// (coalesced, one G*C/8-word row per step) into the task's slot of the bits scratch; walk_kernel (one thread per
+// pair) then walks them back and emits the run-length CIGAR.
 //
 // Arithmetic restated from the reference (file:line relative to rust_cmd/src/ of mckennalab/clique):
 //   update_3d_score                alignment/alignment_matrix.rs:618-665
@@ -19,10 +20,16 @@
 //   M = B[x-1,y-1] + m,  E = max(E[x-1,y] + le, B[x-1,y] + x1),  F = max(F[x,y-1] + le, B[x,y-1] + x1),
 //   B = max(M, E, F).
 // Direction bits per cell (x,y), enough to replay all three traceback layers exactly:
-//   A    (2 bits) = argmax(M,E,F) with priority M > F > E  (0=M 1=E 2=F; 3 marks a band-skipped "stale" cell)
-//   ext1 (1 bit)  = E[x,y] extended E[x-1,y] (strictly better than opening)          -> T1 = Up
-//   ext2 (1 bit)  = F[x,y] extended F[x,y-1] (>= the E-open, > the M-open)            -> T2 = Left
+//   ext1 (bit 3) = E[x,y] extended E[x-1,y] (strictly better than opening)          -> T1 = Up
+//   ext2 (bit 2) = F[x,y] extended F[x,y-1] (>= the E-open, > the M-open)            -> T2 = Left
+//   eP   (bit 1) = E > max(M,F),  fM (bit 0) = F > M   =>  A = argmax(M,E,F) with priority M > F > E = eP ? E : (fM ? F : M)
 //   T0[x,y] = A[x-1,y-1];  T1[x,y] = ext1 ? Up : (A[x-1,y]==F ? Left : Diag);  T2[x,y] = ext2 ? Left : (A[x,y-1]==E ? Up : Diag)
+// Band-skipped ("stale") cells are (x <= K, y == L2); the walker recognises them by coordinates.
+//
+// FAST variant (uniform gap constants, <= 8 byte classes, int8 scores): substitution score by one PRMT from an 8-byte
+// profile row, E and F kept shifted by -x1 so that every max-plus step is one DPX instruction
+//   Eh = viaddmax(Eh_up, le, B_up); Fh = viaddmax(Fh_left, le, B_left); P = viaddmax(Fh, x1, M); B = viaddmax(Eh, x1, P)
+// and the four direction bits are the sign bits of four differences, shifted into the row word with SHF.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -34,6 +41,8 @@ namespace clq {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int kThreads = 128;  // 4 warps per CTA
+
+struct TbRec;
 
 struct KParams {
     const uint8_t* ref_bytes;
@@ -65,9 +74,29 @@ struct KParams {
     unsigned long long* cigar_cursor;
     unsigned int* task_counter;
     unsigned long long* cells;
+    const uint8_t* cls_lut;      // FAST: byte -> class (0 special, 1 other, 2..7 reference bytes)
+    uint32_t tab[16];            // FAST: 8 profile rows (reference class) x 8 int8 scores (read class)
+    uint32_t debug_flags;        // experiments only: 1 = skip the traceback walk
+    uint32_t task_base;          // first task of this sub-batch in the processing order
+    struct TbRec* tb_rec;        // TB: one record per task of the sub-batch for walk_kernel
+};
+
+// what the fill kernel leaves for the walker: one record per task of the sub-batch
+struct TbRec {
+    uint32_t ridx;   // read index (results slot)
+    int32_t L1, L2;  // L1 < 0: nothing to walk (dropped read / no candidate)
+    int32_t zK;      // start layer | stale rows K << 2
 };
 
 __device__ __forceinline__ bool is_special(int c) { return c == 'N' || c < 58; }
+
+// prmt.b32 in its default mode: selector nibble bits [2:0] pick a byte of {hi,lo}, bit 3 replicates that byte's sign.
+// (__byte_perm masks bit 3 away, so the raw instruction is needed for the sign-extending byte lookup.)
+__device__ __forceinline__ int prmt_s8(uint32_t lo, uint32_t hi, uint32_t sel) {
+    int d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
+    return d;
+}
 
 // rows 1..K whose band skips the last column (f64 centre, alignment/alignment_matrix.rs:413-417)
 __device__ inline int stale_rows(int L1, int L2, uint32_t band_mode) {
@@ -109,9 +138,8 @@ __device__ __forceinline__ void row_step(int (&E)[C], int (&B)[C], const int (&b
         if (TB) {
             const bool ext1 = Eext > Eopen;
             const bool ext2 = (Fext >= El + x1c) && (Fext > Ml + x1c);
-            const uint32_t a = (Pv >= Ev) ? ((Mv >= Fv) ? 0u : 2u) : 1u;
-            const uint32_t nib = a | (ext1 ? 4u : 0u) | (ext2 ? 8u : 0u);
-            w[j >> 3] |= nib << (4 * (j & 7));
+            const uint32_t nib = (ext1 ? 8u : 0u) | (ext2 ? 4u : 0u) | ((Ev > Pv) ? 2u : 0u) | ((Fv > Mv) ? 1u : 0u);
+            w[j >> 3] |= nib << (28 - 4 * (j & 7));
         }
         diag = B[j];
         E[j] = Ev;
@@ -123,10 +151,55 @@ __device__ __forceinline__ void row_step(int (&E)[C], int (&B)[C], const int (&b
     }
 }
 
-template <int G, int C, bool TB, bool FIN>
+// FAST wavefront step: Eh/Fh are E/F shifted by -x1 (uniform gap constants), m by PRMT, max-plus by DPX, bits by SHF.
+template <int C, bool TB, bool LAST>
+__device__ __forceinline__ void row_step_fast(int (&Eh)[C], int (&B)[C], const int (&sel)[C], uint32_t (&w)[C / 8], int& Fh,
+                                              int& Ehl, int& Ml, int& Bl, int diag, uint32_t tlo, uint32_t thi, int le, int x1,
+                                              bool own_last, int jL, int& capM, int& capE, int& capF) {
+    const int x1m1 = x1 - 1;
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+        const int m = prmt_s8(tlo, thi, (uint32_t)sel[j]);
+        const int Mv = diag + m;
+        const int EhU = Eh[j], BU = B[j];
+        const int Ehn = __viaddmax_s32(EhU, le, BU);
+        int d2 = 0;
+        if (TB) d2 = __viaddmax_s32(Ehl, x1m1, Ml) - Fh - le;  // < 0  <=>  F extends (>= E-open, > M-open)
+        const int Fhn = __viaddmax_s32(Fh, le, Bl);
+        const int Pv = __viaddmax_s32(Fhn, x1, Mv);
+        const int Bn = __viaddmax_s32(Ehn, x1, Pv);
+        if (TB) {
+            uint32_t acc = w[j >> 3];
+            acc = __funnelshift_l((uint32_t)(BU - Ehn), acc, 1);  // ext1: Eh_up + le > B_up
+            acc = __funnelshift_l((uint32_t)d2, acc, 1);          // ext2
+            acc = __funnelshift_l((uint32_t)(Pv - Bn), acc, 1);   // eP: E > max(M,F)
+            acc = __funnelshift_l((uint32_t)(Mv - Pv), acc, 1);   // fM: F > M
+            w[j >> 3] = acc;
+        }
+        diag = BU;
+        Eh[j] = Ehn;
+        B[j] = Bn;
+        Fh = Fhn; Ehl = Ehn; Ml = Mv; Bl = Bn;
+        if (LAST) {
+            if (own_last && j == jL) { capM = Mv; capE = Ehn + x1; capF = Fhn + x1; }
+        }
+    }
+}
+
+template <int G, int C, bool TB, bool FIN, bool FAST>
 __global__ void __launch_bounds__(kThreads) gotoh_kernel(const KParams p) {
     static_assert(C % 8 == 0, "C must be a multiple of 8 (4 direction bits per cell, whole words per lane)");
-    extern __shared__ uint8_t smem[];
+    static_assert(!(FAST && FIN), "the FAST variant needs uniform gap constants");
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    // FAST: [0,256) class LUT, [256,320) profile table, then the per-group reference rows
+    uint8_t* smem = smem_raw + (FAST ? 320 : 0);
+    if (FAST) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) smem_raw[i] = p.cls_lut[i];
+        if (threadIdx.x < 16) ((uint32_t*)(smem_raw + 256))[threadIdx.x] = p.tab[threadIdx.x];
+        __syncthreads();
+    }
+    const uint8_t* lut_sm = smem_raw;
+    const uint8_t* tab_sm = smem_raw + 256;
     constexpr int GPW = 32 / G;
     constexpr int W = G * C;
     constexpr int WPL = C / 8;
@@ -135,8 +208,6 @@ __global__ void __launch_bounds__(kThreads) gotoh_kernel(const KParams p) {
     const int wpb = blockDim.x >> 5;
     const uint32_t ggid = (blockIdx.x * wpb + warp) * GPW + gw;
     uint8_t* ref_sm = smem + (size_t)(warp * GPW + gw) * p.ref_sm_stride;
-    uint32_t* bits_g = TB ? p.bits + (size_t)ggid * p.bits_stride : nullptr;
-    uint32_t* cig_g = TB ? p.cig_scratch + (size_t)ggid * p.cig_stride : nullptr;
     int32_t* col_g = p.col_scratch + (size_t)ggid * 4 * p.col_stride;
     const clq_affine_t sc = p.sc;
     int staged_ref = -1;
@@ -150,6 +221,7 @@ __global__ void __launch_bounds__(kThreads) gotoh_kernel(const KParams p) {
         bool valid = task < p.n_tasks;
         uint32_t ridx = 0;
         int ref = -1;
+        uint32_t* bits_g = TB ? p.bits + (size_t)task * p.bits_stride : nullptr;
         if (valid) {
             if (p.all_pairs) {
                 const uint32_t q = task / p.n_refs;
@@ -157,7 +229,7 @@ __global__ void __launch_bounds__(kThreads) gotoh_kernel(const KParams p) {
                 ridx = p.order ? p.order[q] : q;
                 if (p.cand_mask && !((p.cand_mask[(size_t)ridx * p.mask_words + (ref >> 5)] >> (ref & 31)) & 1u)) valid = false;
             } else {
-                ridx = p.order ? p.order[task] : task;
+                ridx = p.order ? p.order[p.task_base + task] : p.task_base + task;
                 ref = p.ref_of_read[ridx];
             }
         }
@@ -181,7 +253,7 @@ __global__ void __launch_bounds__(kThreads) gotoh_kernel(const KParams p) {
         const bool run = ok && L1 > 0 && L2 > 0;
 
         if (run && ref != staged_ref) {
-            for (int i = gl; i < L1; i += G) ref_sm[i] = refp[i];
+            for (int i = gl; i < L1; i += G) ref_sm[i] = FAST ? lut_sm[refp[i]] : refp[i];
             staged_ref = ref;
         }
         __syncwarp();
@@ -205,13 +277,14 @@ __global__ void __launch_bounds__(kThreads) gotoh_kernel(const KParams p) {
 #pragma unroll
             for (int j = 0; j < C; j++) {
                 const int y = y0 + j + 1;
-                int code = 0x400;  // padding column: never equal, not special
+                int code = FAST ? 1 : 0x400;  // padding column: never equal, not special
                 if (act_s && y <= L2) {
                     const int c = readp[y - 1];
-                    code = is_special(c) ? (c | 0x100) : c;
+                    code = FAST ? (int)lut_sm[c] : (is_special(c) ? (c | 0x100) : c);
                 }
-                bq[j] = code;
-                E[j] = B[j] = sc.b0 + y * sc.b1;  // row 0: S[0,y] = (MAXNEG, g(y), g(y))
+                bq[j] = FAST ? (code * 0x1111 | 0x8880) : code;  // FAST: PRMT selector (byte + sign replication)
+                B[j] = sc.b0 + y * sc.b1;  // row 0: S[0,y] = (MAXNEG, g(y), g(y))
+                E[j] = B[j] - (FAST ? sc.oe_in : 0);
             }
             int prevBl = (y0 == 0) ? 0 : sc.b0 + y0 * sc.b1;  // B[0, y0]
             int oF = 0, oE = 0, oM = 0, oB = 0;
@@ -235,7 +308,8 @@ __global__ void __launch_bounds__(kThreads) gotoh_kernel(const KParams p) {
                 if (act) {
                     if (gl == 0) {
                         if (s == 0) {
-                            Fl = El = Bl = sc.b0 + x * sc.b1;  // S[x,0] = (MAXNEG, g(x), g(x))
+                            Bl = sc.b0 + x * sc.b1;  // S[x,0] = (MAXNEG, g(x), g(x))
+                            Fl = El = Bl - (FAST ? sc.oe_in : 0);
                             Ml = sc.max_neg;
                         } else {
                             Fl = nF; El = nE; Ml = nM; Bl = nB;
@@ -247,28 +321,32 @@ __global__ void __launch_bounds__(kThreads) gotoh_kernel(const KParams p) {
                     }
                     const int r = rnext;
                     if (x < L1) rnext = ref_sm[x];
-                    const bool rsp = is_special(r);
-                    const int rcode = rsp ? 0x200 : r;
-                    const int mt = rsp ? sc.special : sc.match;
-                    const int mm = rsp ? sc.special : sc.mismatch;
                     const int BlIn = Bl;
-                    if (x == L1)
-                        row_step<C, TB, FIN, true>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, rcode, mt, mm, sc, own_last, jL, capM, capE, capF);
-                    else
-                        row_step<C, TB, FIN, false>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, rcode, mt, mm, sc, own_last, jL, capM, capE, capF);
+                    if (FAST) {
+                        const uint2 tr = *(const uint2*)(tab_sm + r * 8);
+                        if (x == L1)
+                            row_step_fast<C, TB, true>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, sc.e_in, sc.oe_in, own_last, jL, capM, capE, capF);
+                        else
+                            row_step_fast<C, TB, false>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, sc.e_in, sc.oe_in, own_last, jL, capM, capE, capF);
+                    } else {
+                        const bool rsp = is_special(r);
+                        const int rcode = rsp ? 0x200 : r;
+                        const int mt = rsp ? sc.special : sc.match;
+                        const int mm = rsp ? sc.special : sc.mismatch;
+                        if (x == L1)
+                            row_step<C, TB, FIN, true>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, rcode, mt, mm, sc, own_last, jL, capM, capE, capF);
+                        else
+                            row_step<C, TB, FIN, false>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, rcode, mt, mm, sc, own_last, jL, capM, capE, capF);
+                    }
                     prevBl = BlIn;
                     oF = Fl; oE = El; oM = Ml; oB = Bl;
                     if (K > 0 && own_last && x <= K) {
                         // band-skipped cell (x, L2): fresh-matrix state (0,0,0) / Up(0)
+                        const int e0 = FAST ? -sc.oe_in : 0;
 #pragma unroll
                         for (int j = 0; j < C; j++)
-                            if (j == jL) { E[j] = 0; B[j] = 0; }
-                        if (TB) {
-#pragma unroll
-                            for (int k = 0; k < WPL; k++)
-                                if (k == (jL >> 3)) w[k] |= 3u << (4 * (jL & 7));
-                        }
-                        if (jL == C - 1) { oF = 0; oE = 0; oM = 0; oB = 0; }
+                            if (j == jL) { E[j] = e0; B[j] = 0; }
+                        if (jL == C - 1) { oF = e0; oE = e0; oM = 0; oB = 0; }
                         if (x == L1) { capM = 0; capE = 0; capF = 0; }
                     }
                     if (TB) {
@@ -312,69 +390,88 @@ __global__ void __launch_bounds__(kThreads) gotoh_kernel(const KParams p) {
             continue;
         }
 
-        // ---- traceback walk on the group's lane 0 ----
-        int nops = 0, cpos = 0;
-        if (ok && gl == 0) {
-            int x = L1, y = L2;
-            cpos = (int)p.cig_stride;
-            uint32_t cur_op = 3, cur_len = 0;
-            auto emit = [&](uint32_t op, uint32_t n) {
-                if (op == cur_op) cur_len += n;
-                else {
-                    if (cur_len) cig_g[--cpos] = (cur_len << 4) | cur_op;
-                    cur_op = op; cur_len = n;
-                }
-            };
-            auto nibble = [&](int xx, int yy) -> uint32_t {
-                int c = yy - 1;
-                const int s = c / W;
-                c -= s * W;
-                const int ln = c / C, j = c - ln * C;
-                const size_t idx = ((size_t)(s * T + (xx + ln - 1)) * G + ln) * WPL + (j >> 3);
-                return (bits_g[idx] >> (4 * (j & 7))) & 15u;
-            };
-            uint32_t nib = (x > 0 && y > 0) ? nibble(x, y) : 0;
-            while (x > 0 && y > 0) {
-                if ((nib & 3u) == 3u) { status = CLQ_TRACEBACK_DIVERGED; break; }
-                const uint32_t old = nib;
-                if (z == 0) { emit(CLQ_OP_M, 1); x--; y--; }
-                else if (z == 1) { emit(CLQ_OP_D, 1); x--; }
-                else { emit(CLQ_OP_I, 1); y--; }
-                if (x == 0 || y == 0) break;
-                nib = nibble(x, y);
-                const uint32_t a = nib & 3u;
-                if (z == 0) z = (a == 1u) ? 1 : (a == 2u ? 2 : 0);
-                else if (z == 1) z = (old & 4u) ? 1 : (a == 2u ? 2 : 0);
-                else z = (old & 8u) ? 2 : (a == 1u ? 1 : 0);
-            }
-            if (status == CLQ_OK) {
-                if (x > 0) emit(CLQ_OP_D, (uint32_t)x);
-                if (y > 0) emit(CLQ_OP_I, (uint32_t)y);
-            }
-            if (cur_len) cig_g[--cpos] = (cur_len << 4) | cur_op;
-            nops = (int)p.cig_stride - cpos;
-            if (status != CLQ_OK) nops = 0;
-        }
-        // ---- copy the CIGAR into the pool (group-cooperative) ----
-        unsigned long long off = 0;
-        if (ok && gl == 0 && nops > 0) {
-            off = atomicAdd(p.cigar_cursor, (unsigned long long)nops);
-            if (off + (unsigned long long)nops > p.cigar_cap) { status = CLQ_CIGAR_POOL_FULL; nops = 0; }
-        }
-        __syncwarp();
-        const int gsrc = gw * G;
-        const int n_all = __shfl_sync(FULL, nops, gsrc);
-        const int cpos_all = __shfl_sync(FULL, cpos, gsrc);
-        const unsigned long long off_all = __shfl_sync(FULL, off, gsrc);
-        for (int i = gl; i < n_all; i += G) p.cigar_pool[off_all + i] = cig_g[cpos_all + i];
+        // ---- leave the start layer for walk_kernel ----
         if (valid && gl == 0) {
             clq_result_t r;
-            r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = (uint32_t)off; r.cigar_len = (uint32_t)nops; r.status = status;
+            r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = 0; r.cigar_len = 0; r.status = status;
             p.results[ridx] = r;
+            TbRec rec;
+            rec.ridx = ridx; rec.L1 = ok ? L1 : -1; rec.L2 = L2; rec.zK = z | (K << 2);
+            p.tb_rec[task] = rec;
             if (run) atomicAdd(p.cells, (unsigned long long)L1 * (unsigned long long)L2);
         }
-        __syncwarp();
     }
+}
+
+// perform_3d_global_traceback (alignment/alignment_matrix.rs:941-1086) + simplify_cigar_string (alignment_manager.rs:386-423)
+// over the direction bits gotoh_kernel<.., TB=true, ..> stored.  One thread per pair: the walk is a chain of dependent
+// loads (one 32-byte sector per step), so it is spread over as many threads as there are pairs in the sub-batch.
+template <int G, int C>
+__global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n_tasks, const uint32_t* bits, uint64_t bits_stride,
+                                                   uint32_t* cig_scratch, uint32_t cig_stride, uint32_t* cigar_pool, uint64_t cigar_cap,
+                                                   unsigned long long* cigar_cursor, clq_result_t* results) {
+    constexpr int W = G * C;
+    constexpr int WPL = C / 8;
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_tasks) return;
+    const TbRec rec = recs[q];
+    if (rec.L1 < 0) return;
+    const int L1 = rec.L1, L2 = rec.L2, K = rec.zK >> 2;
+    int z = rec.zK & 3;
+    const int T = L1 + G - 1;
+    const uint32_t* bits_g = bits + (size_t)q * bits_stride;
+    uint32_t* cig_g = cig_scratch + (size_t)q * cig_stride;
+    uint32_t status = CLQ_OK;
+    int x = L1, y = L2;
+    int cpos = (int)cig_stride;
+    uint32_t cur_op = 3, cur_len = 0;
+    auto emit = [&](uint32_t op, uint32_t n) {
+        if (op == cur_op) cur_len += n;
+        else {
+            if (cur_len) cig_g[--cpos] = (cur_len << 4) | cur_op;
+            cur_op = op; cur_len = n;
+        }
+    };
+    auto nibble = [&](int xx, int yy) -> uint32_t {
+        int c = yy - 1;
+        const int s = c / W;
+        c -= s * W;
+        const int ln = c / C, j = c - ln * C;
+        const size_t idx = ((size_t)(s * T + (xx + ln - 1)) * G + ln) * WPL + (j >> 3);
+        return (__ldg(bits_g + idx) >> (28 - 4 * (j & 7))) & 15u;
+    };
+    auto argmax = [](uint32_t nb) -> int { return (nb & 2u) ? 1 : ((nb & 1u) ? 2 : 0); };
+    uint32_t nib = (x > 0 && y > 0) ? nibble(x, y) : 0;
+    while (x > 0 && y > 0) {
+        if (y == L2 && x <= K) { status = CLQ_TRACEBACK_DIVERGED; break; }  // stale Up(0) cell: the reference spins here
+        const uint32_t old = nib;
+        if (z == 0) { emit(CLQ_OP_M, 1); x--; y--; }
+        else if (z == 1) { emit(CLQ_OP_D, 1); x--; }
+        else { emit(CLQ_OP_I, 1); y--; }
+        if (x == 0 || y == 0) break;
+        nib = nibble(x, y);
+        const int a = (y == L2 && x <= K) ? 0 : argmax(nib);  // a stale source cell holds (0,0,0): Diag
+        if (z == 0) z = a;
+        else if (z == 1) z = (old & 8u) ? 1 : (a == 2 ? 2 : 0);
+        else z = (old & 4u) ? 2 : (a == 1 ? 1 : 0);
+    }
+    if (status == CLQ_OK) {
+        if (x > 0) emit(CLQ_OP_D, (uint32_t)x);
+        if (y > 0) emit(CLQ_OP_I, (uint32_t)y);
+    }
+    if (cur_len) cig_g[--cpos] = (cur_len << 4) | cur_op;
+    int nops = (int)cig_stride - cpos;
+    unsigned long long off = 0;
+    if (status != CLQ_OK) nops = 0;
+    if (nops > 0) {
+        off = atomicAdd(cigar_cursor, (unsigned long long)nops);
+        if (off + (unsigned long long)nops > cigar_cap) { status = CLQ_CIGAR_POOL_FULL; nops = 0; }
+    }
+    for (int i = 0; i < nops; i++) cigar_pool[off + i] = cig_g[cpos + i];
+    clq_result_t* r = results + rec.ridx;
+    r->cigar_off = (uint32_t)off;
+    r->cigar_len = (uint32_t)nops;
+    r->status = status;
 }
 
 // exhaustive_alignment_search's arg-max: ascending reference index, LAST maximum wins
