@@ -514,7 +514,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         return fail(c, CLQ_E_CUDA, std::string("occupancy(tb): ") + cudaGetErrorString(ce));
     if ((ce = launch_any(cfg, false, fin, fast, p, c->sm_count, smem, s->stream, &grid_sc, true)) != cudaSuccess)
         return fail(c, CLQ_E_CUDA, std::string("occupancy(score): ") + cudaGetErrorString(ce));
-    const uint64_t bits_stride = (uint64_t)ns_max * (L1max + G) * G * (C / 8);
+    const uint64_t bits_stride = ((uint64_t)ns_max * (L1max + G) * G * (C / 8) + 3) / 4 * 4;  // 16-byte aligned slots
     const uint32_t cig_stride = L1max + L2max + 8;
     const uint32_t col_stride = L1max + 8;
     // traceback scratch is per task of a sub-batch: direction bits + CIGAR scratch + walker record

@@ -187,7 +187,7 @@ __device__ __forceinline__ void row_step_fast(int (&Eh)[C], int (&B)[C], const i
 }
 
 template <int G, int C, bool TB, bool FIN, bool FAST>
-__global__ void __launch_bounds__(kThreads) gotoh_kernel(const KParams p) {
+__global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 40) ? 3 : 1) gotoh_kernel(const KParams p) {
     static_assert(C % 8 == 0, "C must be a multiple of 8 (4 direction bits per cell, whole words per lane)");
     static_assert(!(FAST && FIN), "the FAST variant needs uniform gap constants");
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -350,9 +350,18 @@ __global__ void __launch_bounds__(kThreads) gotoh_kernel(const KParams p) {
                         if (x == L1) { capM = 0; capE = 0; capF = 0; }
                     }
                     if (TB) {
-                        uint32_t* dst = bits_g + ((size_t)(s * T + (t - 1)) * G + gl) * WPL;
+                        // one row of G*WPL words per (stripe, step): [G x 4 words as 128-bit stores][G x (WPL-4) words]
+                        uint32_t* row = bits_g + (size_t)(s * T + (t - 1)) * (G * WPL);
+                        if constexpr (WPL >= 4) {
+                            *reinterpret_cast<uint4*>(row + gl * 4) = make_uint4(w[0], w[1], w[2], w[3]);
 #pragma unroll
-                        for (int k = 0; k < WPL; k++) dst[k] = w[k];
+                            for (int k = 4; k < WPL; k++) row[G * 4 + gl * (WPL - 4) + (k - 4)] = w[k];
+                        } else if constexpr (WPL == 2) {
+                            *reinterpret_cast<uint2*>(row + gl * 2) = make_uint2(w[0], w[1]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < WPL; k++) row[gl * WPL + k] = w[k];
+                        }
                     }
                     if (gl == G - 1 && s < NS - 1) {
                         col_g[x] = oF; col_g[p.col_stride + x] = oE; col_g[2 * p.col_stride + x] = oM; col_g[3 * p.col_stride + x] = oB;
@@ -437,7 +446,9 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
         const int s = c / W;
         c -= s * W;
         const int ln = c / C, j = c - ln * C;
-        const size_t idx = ((size_t)(s * T + (xx + ln - 1)) * G + ln) * WPL + (j >> 3);
+        const int k = j >> 3;
+        const int in_row = (WPL >= 4) ? (k < 4 ? ln * 4 + k : G * 4 + ln * (WPL - 4) + (k - 4)) : ln * WPL + k;
+        const size_t idx = (size_t)(s * T + (xx + ln - 1)) * (G * WPL) + in_row;
         return (__ldg(bits_g + idx) >> (28 - 4 * (j & 7))) & 15u;
     };
     auto argmax = [](uint32_t nb) -> int { return (nb & 2u) ? 1 : ((nb & 1u) ? 2 : 0); };
