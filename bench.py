@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=4)
     ap.add_argument("--cpu-sample-seconds", type=float, default=12.0)
     ap.add_argument("--ref-step-seconds", type=float, default=4.0)
+    ap.add_argument("--convex", action="store_true", help="two-piece affine gaps o1=-20,e1=-2,o2=-40,e2=-1 (self-pinned semantics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-live-peak", action="store_true", help="use the committed INT32 peak instead of running tools/int_peak")
     args = ap.parse_args()
@@ -185,7 +186,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from clique_b200 import AffineScoring, Aligner, Reference, ReferenceManager
+    from clique_b200 import AffineScoring, Aligner, Reference, ReferenceManager, TwoPieceScoring
 
     if world > 1:
         torch.cuda.set_device(local_rank)
@@ -210,7 +211,7 @@ def main():
     al = Aligner(device=dev, max_reads=n, max_read_bytes=total_bytes + 64, max_read_len=1 << 15, max_refs=max(64, len(c["refs"])),
                  cigar_ops_per_read=ops_per_read, n_slots=2)
     al.set_references(ReferenceManager([Reference(r, nm) for r, nm in zip(c["refs"], c["ref_names"])]))
-    sc = AffineScoring(*c["scoring"])
+    sc = TwoPieceScoring(10, -9, 9, -20, -2, -40, -1) if args.convex else AffineScoring(*c["scoring"])
     sci = sc.to_int()
     for opt in ("force_cfg", "force_generic", "debug_flags"):     # experiment knobs, e.g. CLQ_FORCE_CFG=3
         if os.environ.get("CLQ_" + opt.upper()):
@@ -305,7 +306,7 @@ def main():
     if rank == 0:
         peak, peak_how = int32_peak(not args.no_live_peak)
         dp = float(np.mean(dp_ms))
-        ops = OPS_PER_CELL_TB if args.workload != "C4" else None
+        ops = (30 if args.convex else OPS_PER_CELL_TB) if args.workload != "C4" else None   # two-piece: 20 / 30
         if args.workload == "C4":   # 64 score-only fills + 1 traceback fill per read
             alg_ops = cells * OPS_PER_CELL_SCORE + (cells / 65.0) * (OPS_PER_CELL_TB - OPS_PER_CELL_SCORE)
         else:
@@ -324,7 +325,7 @@ def main():
             "metric": "reads/s", "value": value, "unit": "reads/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "gcups": gcups,
-            "config": {"workload": WORKLOAD_DESC[args.workload], "reads_per_gpu_per_step": n, "cells_per_gpu_per_step": int(cells),
+            "config": {"workload": WORKLOAD_DESC[args.workload] + (" [two-piece affine (convex) gaps, self-pinned]" if args.convex else ""), "reads_per_gpu_per_step": n, "cells_per_gpu_per_step": int(cells),
                        "parallelism": "read-sharded x%d, no collectives" % n_gpus, "status_ok_reads": n_ok,
                        "l2": "inputs larger than L2 (%.0f MB of reads + %.0f MB of direction bits per step)" % (total_bytes / 1e6, 0.5 * cells / 1e6)},
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"], "power_w_max": clk.get("power_w_max"),
@@ -334,11 +335,22 @@ def main():
             "gpu_launches": int(launches),
             "wall_ms_per_step_device_resident": wall_ms / args.steps,
             "roofline": {"bound": "int32-alu", "achieved": achieved, "peak": peak, "unit": "TIOP/s", "frac": achieved / peak,
-                         "traffic": None, "ops_per_cell": OPS_PER_CELL_TB, "kernel_ms": dp, "peak_source": peak_how,
+                         "traffic": None, "ops_per_cell": ops if ops else "12 score-only + 18 traceback", "kernel_ms": dp, "peak_source": peak_how,
                          "hbm": {"achieved": alg_bytes / (dp / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": alg_bytes / (dp / 1e3) / 1e9 / hbm_peak, "of": "measured" if peaks else "fallback"}},
         }
-        if not args.no_cpu_baseline and n_gpus == 1:
+        if args.convex and n_gpus == 1:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import _oracle as O
+            ocv = O.Convex(10, -9, 9, -20, -2, -40, -1, -100000)
+            bad, ns = 0, 64
+            for i in range(ns):
+                rd = bytes(c["read_bytes"][int(c["read_off"][i]):int(c["read_off"][i + 1])])
+                w = O.convex_align_pair(c["refs"][int(c["fixed_ref"][i]) if c["fixed_ref"] is not None else int(res.ref_index[i])], rd, ocv)
+                if w["score"] != int(res.score_scaled[i]) or O.cigar_str(w["cigar"]) != res.cigar_string(i):
+                    bad += 1
+            line["parity"] = {"checked_reads": ns, "mismatches": bad, "oracle": "orc_convex_align_pair (self-pinned)"}
+        elif not args.no_cpu_baseline and n_gpus == 1:
             threads = os.cpu_count() or 1
             probe = min(n, 256 if args.workload == "C2" else 16)
             dt, _ = cpu_reference_run(c, probe, threads)

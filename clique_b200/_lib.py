@@ -29,6 +29,10 @@ class AffineInt(C.Structure):
                                           "b0", "b1", "max_neg")]
 
 
+class ConvexInt(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("match", "mismatch", "special", "o1", "e1", "o2", "e2", "max_neg")]
+
+
 class Limits(C.Structure):
     _fields_ = [("max_reads", C.c_uint32), ("max_read_bytes", C.c_uint64), ("max_read_len", C.c_uint32),
                 ("max_refs", C.c_uint32), ("max_ref_bytes", C.c_uint64), ("cigar_pool_ops", C.c_uint64),

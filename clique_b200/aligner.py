@@ -59,6 +59,39 @@ class AffineScoring:
 
 
 @dataclass
+class ConvexScoring:
+    """ConvexScoring, alignment/scoring_functions.rs:36-53: only a gap *function* in the reference (never called)."""
+    match_score: float
+    mismatch_score: float
+    gap_score: float
+    gap_open: float
+    gap_extend: float
+
+    def match_mismatch(self, a, b):
+        return self.match_score if a == b else self.mismatch_score
+
+    def gap(self, length):  # alignment/scoring_functions.rs:50-52 -- ignores gap_score / gap_extend, gap(0) = -inf
+        import math
+        return self.gap_open + (math.log10(length) if length > 0 else float("-inf"))
+
+
+@dataclass
+class TwoPieceScoring:
+    """Two-piece affine ("convex") gaps as this repository defines them (parity unpinned):
+    a gap of length k costs max(o1 + k*e1, o2 + k*e2); integer scores."""
+    match: int
+    mismatch: int
+    special: int
+    o1: int
+    e1: int
+    o2: int
+    e2: int
+
+    def to_int(self) -> L.ConvexInt:
+        return L.ConvexInt(self.match, self.mismatch, self.special, self.o1, self.e1, self.o2, self.e2, -100000)
+
+
+@dataclass
 class Reference:
     """Reference{sequence, name}, reference/fasta_reference.rs:41-46 (the suffix table is out of scope)."""
     sequence: bytes
@@ -291,9 +324,12 @@ class Aligner:
         self._pending[slot] = [n, None, (rb, ro, fr)]
 
     def launch(self, slot, scoring, search="fixed", band="readlen", score_only=False, threshold=0.90):
-        sci = scoring if isinstance(scoring, L.AffineInt) else scoring.to_int()
-        self._check(self.lib.clq_launch(self.ctx, slot, C.byref(sci), self._flags(search, band, score_only), threshold))
-        self._pending[slot][1] = sci.scale
+        sci = scoring if isinstance(scoring, (L.AffineInt, L.ConvexInt)) else scoring.to_int()
+        flags = self._flags(search, band, score_only)
+        if isinstance(sci, L.ConvexInt):
+            flags |= L.CONVEX
+        self._check(self.lib.clq_launch(self.ctx, slot, C.byref(sci), flags, threshold))
+        self._pending[slot][1] = getattr(sci, "scale", 1)
 
     def sync(self, slot):
         self._check(self.lib.clq_sync(self.ctx, slot))

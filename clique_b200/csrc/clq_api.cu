@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "clq_kernels.cuh"
+#include "clq_convex.cuh"
 
 using namespace clq;
 
@@ -132,6 +133,55 @@ cudaError_t launch_any(int cfg, bool tb, bool fin, bool fast, const KParams& p, 
     if (fast) return tb ? launch_cfg<true, false, true>(cfg, p, sm, smem, st, grid, q) : launch_cfg<false, false, true>(cfg, p, sm, smem, st, grid, q);
     if (tb) return fin ? launch_cfg<true, true, false>(cfg, p, sm, smem, st, grid, q) : launch_cfg<true, false, false>(cfg, p, sm, smem, st, grid, q);
     return fin ? launch_cfg<false, true, false>(cfg, p, sm, smem, st, grid, q) : launch_cfg<false, false, false>(cfg, p, sm, smem, st, grid, q);
+}
+
+// two-piece affine ("convex") geometries: C must be a multiple of 16 (8 direction bits per cell, 128-bit row stores)
+const Cfg kCvxCfgs[] = {{8, 16}, {16, 16}, {16, 32}, {32, 32}};
+constexpr int kNumCvxCfgs = sizeof(kCvxCfgs) / sizeof(kCvxCfgs[0]);
+
+template <int G, int C, bool TB>
+cudaError_t launch_cvx_one(const KParams& p, const ConvexParams& cp, int sm_count, size_t smem, cudaStream_t st, int* grid_out, bool query_only) {
+    auto kern = convex_kernel<G, C, TB>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int nb = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (nb < 1) return cudaErrorLaunchOutOfResources;
+    int grid = nb * sm_count;
+    if (*grid_out > 0) grid = std::min(grid, *grid_out);
+    *grid_out = grid;
+    if (query_only) return cudaSuccess;
+    kern<<<grid, kThreads, smem, st>>>(p, cp);
+    return cudaGetLastError();
+}
+
+template <bool TB>
+cudaError_t launch_cvx(int cfg, const KParams& p, const ConvexParams& cp, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
+    switch (cfg) {
+        case 0: return launch_cvx_one<8, 16, TB>(p, cp, sm, smem, st, grid, q);
+        case 1: return launch_cvx_one<16, 16, TB>(p, cp, sm, smem, st, grid, q);
+        case 2: return launch_cvx_one<16, 32, TB>(p, cp, sm, smem, st, grid, q);
+        default: return launch_cvx_one<32, 32, TB>(p, cp, sm, smem, st, grid, q);
+    }
+}
+
+template <int G, int C>
+cudaError_t launch_cvx_walk_one(const KParams& p, uint32_t cnt, cudaStream_t st) {
+    convex_walk_kernel<G, C><<<(cnt + 127) / 128, 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.cig_scratch, p.cig_stride, p.cigar_pool,
+                                                                p.cigar_cap, p.cigar_cursor, p.results);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cvx_walk(int cfg, const KParams& p, uint32_t cnt, cudaStream_t st) {
+    switch (cfg) {
+        case 0: return launch_cvx_walk_one<8, 16>(p, cnt, st);
+        case 1: return launch_cvx_walk_one<16, 16>(p, cnt, st);
+        case 2: return launch_cvx_walk_one<16, 32>(p, cnt, st);
+        default: return launch_cvx_walk_one<32, 32>(p, cnt, st);
+    }
 }
 
 template <int G, int C>
@@ -458,28 +508,53 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     Slot* s = get_slot(c, slot);
     if (!s || !scoring) return CLQ_E_INVALID;
     if (s->state < 1) return fail(c, CLQ_E_STATE, "clq_launch before clq_upload");
-    if (flags & CLQ_CONVEX) return fail(c, CLQ_E_UNSUPPORTED, "convex (two-piece) mode is not built yet");
+    const bool convex = (flags & CLQ_CONVEX) != 0;
     const uint32_t band = flags & CLQ_BAND_MASK;
     const uint32_t search = flags & CLQ_SEARCH_MASK;
     if (band > CLQ_BAND_READLEN) return fail(c, CLQ_E_UNSUPPORTED, "explicit bandwidth is not supported (the hot path never passes one)");
     if (search == CLQ_SEARCH_FIXED && !s->have_fixed && s->n_reads) return fail(c, CLQ_E_INVALID, "CLQ_SEARCH_FIXED needs fixed_ref");
     if (search == CLQ_SEARCH_QUICK && c->kmer_k == 0) return fail(c, CLQ_E_STATE, "CLQ_SEARCH_QUICK needs clq_kmer_index_set");
     if (search > CLQ_SEARCH_QUICK) return CLQ_E_INVALID;
-    const clq_affine_t sc = *(const clq_affine_t*)scoring;
-    if (!(sc.oe_in - sc.e_in < 0) || sc.scale < 1) return fail(c, CLQ_SCORING_NOT_REPRESENTABLE, "gap_open must be negative");
-    CU(c, cudaSetDevice(c->device));
-    const bool fin = sc.oe_fin != sc.oe_in || sc.e_fin != sc.e_in;
-    const bool score_only = (flags & CLQ_SCORE_ONLY) != 0;
+    clq_affine_t sc = {};
+    ConvexParams cp = {};
     auto fits8 = [](int v) { return v >= -128 && v <= 127; };
-    const bool fast = c->fast_ok && !c->force_generic && !fin && fits8(sc.match) && fits8(sc.mismatch) && fits8(sc.special);
+    bool fin = false, fast = false;
+    if (convex) {
+        cp.cv = *(const clq_convex_t*)scoring;
+        const clq_convex_t& cv = cp.cv;
+        if (!(cv.o1 < 0 && cv.o2 < 0 && cv.e1 <= 0 && cv.e2 <= 0)) return fail(c, CLQ_SCORING_NOT_REPRESENTABLE, "convex: gap opens must be negative");
+        if (!c->fast_ok || !fits8(cv.match) || !fits8(cv.mismatch) || !fits8(cv.special))
+            return fail(c, CLQ_E_UNSUPPORTED, "convex mode needs <= 6 distinct non-special reference bytes and int8 substitution scores");
+        if (band != CLQ_BAND_MAXLEN && band != CLQ_BAND_READLEN) return CLQ_E_INVALID;
+        sc.scale = 1; sc.match = cv.match; sc.mismatch = cv.mismatch; sc.special = cv.special;  // profile table below
+        fast = true;
+    } else {
+        sc = *(const clq_affine_t*)scoring;
+        if (!(sc.oe_in - sc.e_in < 0) || sc.scale < 1) return fail(c, CLQ_SCORING_NOT_REPRESENTABLE, "gap_open must be negative");
+        fin = sc.oe_fin != sc.oe_in || sc.e_fin != sc.e_in;
+        fast = c->fast_ok && !c->force_generic && !fin && fits8(sc.match) && fits8(sc.mismatch) && fits8(sc.special);
+    }
+    CU(c, cudaSetDevice(c->device));
+    const bool score_only = (flags & CLQ_SCORE_ONLY) != 0;
     const uint32_t n = s->n_reads;
-    const int cfg = pick_cfg(c, s->max_len);
-    const int G = kCfgs[cfg].G, C = kCfgs[cfg].C, W = G * C, GPW = 32 / G;
+    int cfg = pick_cfg(c, s->max_len);
+    if (convex) {
+        cfg = kNumCvxCfgs - 1;
+        for (int i = 0; i < kNumCvxCfgs; i++)
+            if ((uint32_t)(kCvxCfgs[i].G * kCvxCfgs[i].C) >= s->max_len) { cfg = i; break; }
+        if (c->force_cfg >= 0 && c->force_cfg < kNumCvxCfgs) cfg = c->force_cfg;
+    }
+    const int G = convex ? kCvxCfgs[cfg].G : kCfgs[cfg].G, C = convex ? kCvxCfgs[cfg].C : kCfgs[cfg].C, W = G * C, GPW = 32 / G;
+    const int bits_per_cell = convex ? 8 : 4;
     const uint32_t L1max = c->max_ref_len, L2max = s->max_len;
     const uint32_t ns_max = std::max<uint32_t>(1, (L2max + W - 1) / W);
     const uint32_t ref_sm_stride = (L1max + 15) / 16 * 16 + 16;
     const size_t smem = (size_t)(kThreads / 32) * GPW * ref_sm_stride + (fast ? 320 : 0);
     if (smem > 200 * 1024) return fail(c, CLQ_E_LIMIT, "references too long for this geometry's shared-memory staging");
+    auto launch_dp = [&](bool tb, const KParams& kp, int* grid, bool query) -> cudaError_t {
+        if (convex) return tb ? launch_cvx<true>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query) : launch_cvx<false>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query);
+        return launch_any(cfg, tb, fin, fast, kp, c->sm_count, smem, s->stream, grid, query);
+    };
 
     KParams p = {};
     p.ref_bytes = (const uint8_t*)c->ref_bytes.p;
@@ -510,11 +585,11 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     // grid + scratch sizing (per resident group)
     int grid_tb = 0, grid_sc = 0;
     cudaError_t ce;
-    if ((ce = launch_any(cfg, true, fin, fast, p, c->sm_count, smem, s->stream, &grid_tb, true)) != cudaSuccess)
+    if ((ce = launch_dp(true, p, &grid_tb, true)) != cudaSuccess)
         return fail(c, CLQ_E_CUDA, std::string("occupancy(tb): ") + cudaGetErrorString(ce));
-    if ((ce = launch_any(cfg, false, fin, fast, p, c->sm_count, smem, s->stream, &grid_sc, true)) != cudaSuccess)
+    if ((ce = launch_dp(false, p, &grid_sc, true)) != cudaSuccess)
         return fail(c, CLQ_E_CUDA, std::string("occupancy(score): ") + cudaGetErrorString(ce));
-    const uint64_t bits_stride = ((uint64_t)ns_max * (L1max + G) * G * (C / 8) + 3) / 4 * 4;  // 16-byte aligned slots
+    const uint64_t bits_stride = ((uint64_t)ns_max * (L1max + G) * G * (C * bits_per_cell / 32) + 3) / 4 * 4;  // 16-byte aligned slots
     const uint32_t cig_stride = L1max + L2max + 8;
     const uint32_t col_stride = L1max + 8;
     // traceback scratch is per task of a sub-batch: direction bits + CIGAR scratch + walker record
@@ -578,7 +653,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
             q.task_counter = (unsigned int*)(ctr + 0);
             CU(c, cudaEventRecord(s->ev[1], s->stream));
             int g = grid_sc;
-            if ((ce = launch_any(cfg, false, fin, fast, q, c->sm_count, smem, s->stream, &g, false)) != cudaSuccess)
+            if ((ce = launch_dp(false, q, &g, false)) != cudaSuccess)
                 return fail(c, CLQ_E_CUDA, std::string("score kernel: ") + cudaGetErrorString(ce));
             CU(c, cudaEventRecord(s->ev[2], s->stream));
             s->stats.launches++;
@@ -601,7 +676,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
             q.n_tasks = n;
             q.task_base = 0;
             int g = grid_sc;
-            if ((ce = launch_any(cfg, false, fin, fast, q, c->sm_count, smem, s->stream, &g, false)) != cudaSuccess)
+            if ((ce = launch_dp(false, q, &g, false)) != cudaSuccess)
                 return fail(c, CLQ_E_CUDA, std::string("score kernel: ") + cudaGetErrorString(ce));
             s->stats.launches++;
             s->stats.dp_launches++;
@@ -613,12 +688,12 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
                 q.task_base = (uint32_t)base;
                 if (base) CU(c, cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned long long), s->stream));
                 int g = grid_tb;
-                if ((ce = launch_any(cfg, true, fin, fast, q, c->sm_count, smem, s->stream, &g, false)) != cudaSuccess)
+                if ((ce = launch_dp(true, q, &g, false)) != cudaSuccess)
                     return fail(c, CLQ_E_CUDA, std::string("fill kernel: ") + cudaGetErrorString(ce));
                 s->stats.launches++;
                 s->stats.dp_launches++;
                 if (!(c->debug_flags & 1)) {
-                    if ((ce = launch_walk(cfg, q, cnt, s->stream)) != cudaSuccess)
+                    if ((ce = convex ? launch_cvx_walk(cfg, q, cnt, s->stream) : launch_walk(cfg, q, cnt, s->stream)) != cudaSuccess)
                         return fail(c, CLQ_E_CUDA, std::string("walk kernel: ") + cudaGetErrorString(ce));
                     s->stats.launches++;
                 }

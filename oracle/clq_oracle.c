@@ -393,31 +393,28 @@ int orci_align_pair(const uint8_t* ref, size_t l1, const uint8_t* read, size_t l
 }
 
 /* ------------------------------------------------------------------------------------------------
- * "convex" = two-piece affine global alignment (definition owned by this repo; PARITY UNPINNED).
+ * "convex" = two-piece affine global alignment (definition owned by this repo; PARITY UNPINNED: the reference has
+ * no convex DP, only the never-called ConvexScoring::gap).
  *
- * A gap of length k costs w(k) = max(o1 + k*e1, o2 + k*e2).  Five states per cell:
- *   M  (layer 0), E1/E2 (gap consuming the reference: Del, pieces 1/2), F1/F2 (gap consuming the read: Ins).
- *   M [x,y] = max5(x-1,y-1) + m(x,y)
- *   Ei[x,y] = max(Ei[x-1,y] + ei, B[x-1,y] + oi + ei)      B = max over all five states
- *   Fi[x,y] = max(Fi[x,y-1] + ei, B[x,y-1] + oi + ei)
- * i.e. the same "any state may open any gap" connectivity as the affine recurrence
- * (alignment/alignment_matrix.rs:618-665), same MAX_NEG sentinel and boundary shape
- * (S[x,0] = w(x) in every gap state, M = MAX_NEG; S[0,0] = (0, MAX_NEG...)), no final-gap multiplier.
- * Tie order (total): on equal values the state with the higher priority wins,
- *   M > F2 > F1 > E2 > E1   for "which state does the max come from" (opening / diagonal),
- *   extension wins over opening only when strictly greater for E-states, and when >= for F-states against
- *   E-sourced openings (the affine rule generalised: Diag > Left > Up).
- * To keep this simple and total the restatement below evaluates candidates in a fixed order and keeps the
- * first strictly greater one, with the order chosen to realise the priorities above.
- * Start state at (L1, L2) = last maximum in the order (M, E1, E2, F1, F2).
+ * A gap of length k costs w(k) = max(o1 + k*e1, o2 + k*e2) (o_i < 0).  Five states per cell:
+ *   M (diagonal), E1/E2 (gap consuming the reference = Del, piece 1/2), F1/F2 (gap consuming the read = Ins).
+ *   A(cell) = argmax over (M, F1, F2, E1, E2) scanned in that order with strict '>', so earlier states win ties;
+ *   B(cell) = that maximum.
+ *   M [x,y] = B(x-1,y-1) + m(x,y)                                   came from A(x-1,y-1)
+ *   Ei[x,y] = max(Ei[x-1,y] + ei, B(x-1,y) + oi + ei)               extends iff strictly greater, else from A(x-1,y)
+ *   Fi[x,y] = max(Fi[x,y-1] + ei, B(x,y-1) + oi + ei)               extends iff strictly greater, else from A(x,y-1)
+ * i.e. the affine recurrence's "any state may open any gap" connectivity (alignment/alignment_matrix.rs:618-665),
+ * the same MAX_NEG sentinel and boundary shape: S[0,0] = (0, NEG, NEG, NEG, NEG); S[k,0] and S[0,k] hold NEG in M and
+ * oi + k*ei in Ei and Fi.  No band, no final-gap multiplier.  Score = B(L1,L2), start state = A(L1,L2); the walk and
+ * the trailing boundary run follow perform_3d_global_traceback (:977-1065).
  * ---------------------------------------------------------------------------------------------- */
 enum { CV_M = 0, CV_E1 = 1, CV_E2 = 2, CV_F1 = 3, CV_F2 = 4 };
 
-/* candidates are listed from highest to lowest priority; first maximum wins */
-static inline int64_t pick(const int64_t* v, const uint8_t* who, int n, uint8_t* src) {
-    int64_t best = v[0];
-    *src = who[0];
-    for (int i = 1; i < n; i++) if (v[i] > best) { best = v[i]; *src = who[i]; }
+static inline int32_t cv_argmax(const int32_t* s5, uint8_t* who) {
+    static const uint8_t order[5] = {CV_M, CV_F1, CV_F2, CV_E1, CV_E2};
+    int32_t best = s5[CV_M];
+    *who = CV_M;
+    for (int i = 1; i < 5; i++) if (s5[order[i]] > best) { best = s5[order[i]]; *who = order[i]; }
     return best;
 }
 
@@ -426,65 +423,51 @@ int orc_convex_align_pair(const uint8_t* ref, size_t l1, const uint8_t* read, si
                           int want_traceback) {
     size_t W = l2 + 1;
     int32_t* S = (int32_t*)malloc((l1 + 1) * W * 5 * sizeof(int32_t));
-    uint8_t* T = (uint8_t*)malloc((l1 + 1) * W * 5);
+    uint8_t* T = (uint8_t*)malloc((l1 + 1) * W * 5); /* source state per layer; 8 | state = "extended" */
     if (!S || !T) { free(S); free(T); return -1; }
 #define SI(x, y, z) S[((x) * W + (y)) * 5 + (z)]
 #define TI(x, y, z) T[((x) * W + (y)) * 5 + (z)]
+    const int32_t o[2] = {sc->o1, sc->o2}, e[2] = {sc->e1, sc->e2};
     for (int z = 0; z < 5; z++) { SI(0, 0, z) = z == CV_M ? 0 : sc->max_neg; TI(0, 0, z) = CV_M; }
     for (size_t x = 1; x <= l1; x++) {
         SI(x, 0, CV_M) = sc->max_neg;
         SI(x, 0, CV_E1) = SI(x, 0, CV_F1) = sc->o1 + (int32_t)x * sc->e1;
         SI(x, 0, CV_E2) = SI(x, 0, CV_F2) = sc->o2 + (int32_t)x * sc->e2;
-        for (int z = 0; z < 5; z++) TI(x, 0, z) = CV_E1;
+        for (int z = 0; z < 5; z++) TI(x, 0, z) = CV_M;
     }
     for (size_t y = 1; y <= l2; y++) {
         SI(0, y, CV_M) = sc->max_neg;
         SI(0, y, CV_E1) = SI(0, y, CV_F1) = sc->o1 + (int32_t)y * sc->e1;
         SI(0, y, CV_E2) = SI(0, y, CV_F2) = sc->o2 + (int32_t)y * sc->e2;
-        for (int z = 0; z < 5; z++) TI(0, y, z) = CV_F1;
+        for (int z = 0; z < 5; z++) TI(0, y, z) = CV_M;
     }
-    static const uint8_t ord_diag[5] = {CV_M, CV_F2, CV_F1, CV_E2, CV_E1};
     for (size_t x = 1; x <= l1; x++) {
         for (size_t y = 1; y <= l2; y++) {
-            uint8_t a = ref[x - 1], b = read[y - 1], src;
-            int64_t ms = (is_special(a) || is_special(b)) ? sc->special : (a == b ? sc->match : sc->mismatch);
-            int64_t v[6];
-            uint8_t who[6];
-            /* M: from any state of the diagonal cell, priority M > F2 > F1 > E2 > E1 */
-            for (int i = 0; i < 5; i++) { v[i] = SI(x - 1, y - 1, ord_diag[i]) + ms; who[i] = ord_diag[i]; }
-            SI(x, y, CV_M) = (int32_t)pick(v, who, 5, &src);
-            TI(x, y, CV_M) = src;
-            /* E pieces (consume reference, move up): opening from (M > F2 > F1 > other E piece) beats extension on ties */
+            uint8_t a = ref[x - 1], b = read[y - 1], who;
+            int32_t ms = (is_special(a) || is_special(b)) ? sc->special : (a == b ? sc->match : sc->mismatch);
+            int32_t bd = cv_argmax(&SI(x - 1, y - 1, 0), &who);
+            SI(x, y, CV_M) = bd + ms;
+            TI(x, y, CV_M) = who;
+            int32_t bu = cv_argmax(&SI(x - 1, y, 0), &who);
             for (int p = 0; p < 2; p++) {
-                int zz = p == 0 ? CV_E1 : CV_E2, other = p == 0 ? CV_E2 : CV_E1;
-                int64_t o = p == 0 ? sc->o1 : sc->o2, e = p == 0 ? sc->e1 : sc->e2;
-                int n = 0;
-                v[n] = SI(x - 1, y, CV_M) + o + e; who[n++] = CV_M;
-                v[n] = SI(x - 1, y, CV_F2) + o + e; who[n++] = CV_F2;
-                v[n] = SI(x - 1, y, CV_F1) + o + e; who[n++] = CV_F1;
-                v[n] = SI(x - 1, y, other) + o + e; who[n++] = (uint8_t)other;
-                v[n] = SI(x - 1, y, zz) + e; who[n++] = (uint8_t)zz;
-                SI(x, y, zz) = (int32_t)pick(v, who, n, &src);
-                TI(x, y, zz) = src;
+                int zz = p == 0 ? CV_E1 : CV_E2;
+                int32_t ext = SI(x - 1, y, zz) + e[p], opn = bu + o[p] + e[p];
+                if (ext > opn) { SI(x, y, zz) = ext; TI(x, y, zz) = 8 | (uint8_t)zz; }
+                else { SI(x, y, zz) = opn; TI(x, y, zz) = who; }
             }
-            /* F pieces (consume read, move left): M-open > extension > other F piece > E2 > E1 on ties */
+            int32_t bl = cv_argmax(&SI(x, y - 1, 0), &who);
             for (int p = 0; p < 2; p++) {
-                int zz = p == 0 ? CV_F1 : CV_F2, other = p == 0 ? CV_F2 : CV_F1;
-                int64_t o = p == 0 ? sc->o1 : sc->o2, e = p == 0 ? sc->e1 : sc->e2;
-                int n = 0;
-                v[n] = SI(x, y - 1, CV_M) + o + e; who[n++] = CV_M;
-                v[n] = SI(x, y - 1, zz) + e; who[n++] = (uint8_t)zz;
-                v[n] = SI(x, y - 1, other) + o + e; who[n++] = (uint8_t)other;
-                v[n] = SI(x, y - 1, CV_E2) + o + e; who[n++] = CV_E2;
-                v[n] = SI(x, y - 1, CV_E1) + o + e; who[n++] = CV_E1;
-                SI(x, y, zz) = (int32_t)pick(v, who, n, &src);
-                TI(x, y, zz) = src;
+                int zz = p == 0 ? CV_F1 : CV_F2;
+                int32_t ext = SI(x, y - 1, zz) + e[p], opn = bl + o[p] + e[p];
+                if (ext > opn) { SI(x, y, zz) = ext; TI(x, y, zz) = 8 | (uint8_t)zz; }
+                else { SI(x, y, zz) = opn; TI(x, y, zz) = who; }
             }
         }
     }
-    size_t x = l1, y = l2, z = 0;
-    int32_t best = SI(x, y, 0);
-    for (size_t k = 1; k < 5; k++) if (SI(x, y, k) >= best) { best = SI(x, y, k); z = k; }
+    size_t x = l1, y = l2;
+    uint8_t zst;
+    int32_t best = cv_argmax(&SI(x, y, 0), &zst);
+    size_t z = zst;
     *score = best;
     *status = ORC_OK;
     *n_cigar = 0;
@@ -493,7 +476,7 @@ int orc_convex_align_pair(const uint8_t* ref, size_t l1, const uint8_t* read, si
         uint32_t* cig = (uint32_t*)malloc((l1 + l2 + 2) * sizeof(uint32_t));
         size_t nc = 0;
         while (x > 0 && y > 0) {
-            size_t nz = TI(x, y, z);
+            size_t nz = TI(x, y, z) & 7;
             if (z == CV_M) { cig[nc++] = (1u << 4) | ORC_OP_M; x--; y--; }
             else if (z == CV_E1 || z == CV_E2) { cig[nc++] = (1u << 4) | ORC_OP_D; x--; }
             else { cig[nc++] = (1u << 4) | ORC_OP_I; y--; }

@@ -326,3 +326,55 @@ def test_full_size_properties():
             assert O.cigar_str(b0.cigar(i)) == O.cigar_str(want["cigar_pool"][o:o + l])
     finally:
         a.close()
+
+
+# ---------------------------------------------------------------- two-piece affine ("convex") mode: self-pinned
+def test_convex_two_piece(al):
+    """CLQ_CONVEX vs this repository's own CPU definition (oracle/clq_oracle.c::orc_convex_align_pair): parity unpinned
+    against the reference, which has no convex DP."""
+    from clique_b200 import TwoPieceScoring
+    rng = np.random.default_rng(77)
+    cv = TwoPieceScoring(10, -9, 9, -20, -2, -40, -1)
+    ocv = O.Convex(10, -9, 9, -20, -2, -40, -1, -100000)
+    refs = [rand_seq(rng, int(rng.integers(0, 300)), b"ACGTN") for _ in range(8)] + [b""]
+    reads, fixed = [], []
+    for it in range(400):
+        r = int(rng.integers(0, len(refs)))
+        kind = it % 4
+        if kind == 0:
+            rd = mutate(rng, refs[r], 0.1)
+        elif kind == 1:      # long deletions / insertions: the second piece wins
+            cut = int(rng.integers(0, max(1, len(refs[r]))))
+            rd = refs[r][:cut] + refs[r][cut + int(rng.integers(10, 60)):]
+        elif kind == 2:
+            cut = int(rng.integers(0, max(1, len(refs[r]))))
+            rd = refs[r][:cut] + rand_seq(rng, int(rng.integers(10, 60))) + refs[r][cut:]
+        else:
+            rd = rand_seq(rng, int(rng.integers(0, 700)), b"ACGTN")
+        reads.append(rd); fixed.append(r)
+    al.set_references(ReferenceManager([Reference(r, b"r%d" % i) for i, r in enumerate(refs)]))
+    qb, qo = pack_reads(reads)
+    for cfg in (-1, 0, 3):
+        al.set_option("force_cfg", cfg)
+        try:
+            br = al.align_batch(qb, qo, cv, "fixed", "readlen", fixed_ref=np.array(fixed, np.int32))
+            so = al.align_batch(qb, qo, cv, "fixed", "readlen", fixed_ref=np.array(fixed, np.int32), score_only=True)
+        finally:
+            al.set_option("force_cfg", -1)
+        for i, rd in enumerate(reads):
+            w = O.convex_align_pair(refs[fixed[i]], rd, ocv)
+            assert int(br.status[i]) == 0
+            assert int(br.score_scaled[i]) == w["score"] == int(so.score_scaled[i]), (cfg, i)
+            assert br.cigar_string(i) == O.cigar_str(w["cigar"]), (cfg, i)
+    # best-candidate selection under the convex score
+    br = al.align_batch(qb[:int(qo[40])], qo[:41], cv, "exhaustive", "readlen")
+    for i in range(40):
+        scores = [O.convex_align_pair(r, reads[i], ocv, traceback=False)["score"] for r in refs]
+        best = max(j for j, sc in enumerate(scores) if sc == max(scores))
+        assert int(br.ref_index[i]) == best and int(br.score_scaled[i]) == scores[best]
+
+
+def test_convex_gap_helper():
+    from clique_b200 import ConvexScoring
+    c = ConvexScoring(5.0, -4.0, -2.0, -10.0, -1.0)      # alignment/scoring_functions.rs:200-213
+    assert c.gap(1) == -10.0 and c.gap(10) == -9.0 and c.match_mismatch(65, 65) == 5.0 and c.match_mismatch(65, 84) == -4.0
