@@ -10,6 +10,7 @@
 
 #include "clq_kernels.cuh"
 #include "clq_convex.cuh"
+#include "clq_pack.cuh"
 
 using namespace clq;
 
@@ -58,6 +59,7 @@ struct clq_ctx {
     std::vector<Slot> slots;
     int force_cfg = -1;
     int debug_flags = 0;
+    int no_pack = 0;                 // option "no_pack": never take the s16x2 PACK kernels
     int force_generic = 0;           // option "force_generic": never take the FAST (PRMT/DPX) kernel variant
     bool fast_ok = false;            // the reference set has <= 6 distinct non-special bytes
     uint8_t cls[256] = {};           // byte -> class: 0 special, 1 other, 2..7 reference bytes
@@ -133,6 +135,37 @@ cudaError_t launch_any(int cfg, bool tb, bool fin, bool fast, const KParams& p, 
     if (fast) return tb ? launch_cfg<true, false, true>(cfg, p, sm, smem, st, grid, q) : launch_cfg<false, false, true>(cfg, p, sm, smem, st, grid, q);
     if (tb) return fin ? launch_cfg<true, true, false>(cfg, p, sm, smem, st, grid, q) : launch_cfg<true, false, false>(cfg, p, sm, smem, st, grid, q);
     return fin ? launch_cfg<false, true, false>(cfg, p, sm, smem, st, grid, q) : launch_cfg<false, false, false>(cfg, p, sm, smem, st, grid, q);
+}
+
+template <int G, int C, bool TB>
+cudaError_t launch_pack_one(const KParams& p, const PackParams& pp, int sm_count, size_t smem, cudaStream_t st, int* grid_out, bool query_only) {
+    auto kern = pack_kernel<G, C, TB>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int nb = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (nb < 1) return cudaErrorLaunchOutOfResources;
+    int grid = nb * sm_count;
+    if (*grid_out > 0) grid = std::min(grid, *grid_out);
+    *grid_out = grid;
+    if (query_only) return cudaSuccess;
+    kern<<<grid, kThreads, smem, st>>>(p, pp);
+    return cudaGetLastError();
+}
+
+template <bool TB>
+cudaError_t launch_pack(int cfg, const KParams& p, const PackParams& pp, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
+    switch (cfg) {
+        case 0: return launch_pack_one<8, 16, TB>(p, pp, sm, smem, st, grid, q);
+        case 1: return launch_pack_one<8, 24, TB>(p, pp, sm, smem, st, grid, q);
+        case 2: return launch_pack_one<8, 40, TB>(p, pp, sm, smem, st, grid, q);
+        case 3: return launch_pack_one<16, 24, TB>(p, pp, sm, smem, st, grid, q);
+        case 4: return launch_pack_one<32, 16, TB>(p, pp, sm, smem, st, grid, q);
+        default: return launch_pack_one<32, 32, TB>(p, pp, sm, smem, st, grid, q);
+    }
 }
 
 // two-piece affine ("convex") geometries: C must be a multiple of 16 (8 direction bits per cell, 128-bit row stores)
@@ -331,6 +364,7 @@ int32_t clq_set_option(clq_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "force_cfg")) { c->force_cfg = (int)value; return CLQ_OK; }
     if (!strcmp(key, "force_generic")) { c->force_generic = (int)value; return CLQ_OK; }
     if (!strcmp(key, "debug_flags")) { c->debug_flags = (int)value; return CLQ_OK; }
+    if (!strcmp(key, "no_pack")) { c->no_pack = (int)value; return CLQ_OK; }
     if (!strcmp(key, "max_scratch_bytes")) { c->max_scratch_bytes = value; return CLQ_OK; }
     return fail(c, CLQ_E_INVALID, std::string("unknown option ") + key);
 }
@@ -551,8 +585,26 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     const uint32_t ref_sm_stride = (L1max + 15) / 16 * 16 + 16;
     const size_t smem = (size_t)(kThreads / 32) * GPW * ref_sm_stride + (fast ? 320 : 0);
     if (smem > 200 * 1024) return fail(c, CLQ_E_LIMIT, "references too long for this geometry's shared-memory staging");
+    // s16x2 PACK kernels: two reads per lane group.  Needs the FAST preconditions plus a proof that every cell value of
+    // this batch fits a 15-bit window: B >= 2*g(0) + (L1+L2)*e (the all-gap corner path), everything else is within a gap
+    // open / one substitution of B, and nothing exceeds max(match, special) * min(L1, L2).
+    PackParams pkp = {};
+    bool pack = false;
+    if (fast && !convex && !c->no_pack && n) {
+        const int64_t smin = std::min<int64_t>(std::min(sc.match, sc.mismatch), std::min(sc.special, 0));
+        const int64_t smax = std::max<int64_t>(std::max(sc.match, sc.special), 0);
+        const int64_t low = 2ll * sc.b0 + (int64_t)(L1max + L2max + W) * sc.b1 + 2ll * sc.oe_in - 1 + smin - 16;
+        const int64_t high = smax * std::min<int64_t>(L1max, L2max) - sc.oe_in + 16;
+        if (sc.b1 <= 0 && high - low + 128 <= 32767) {
+            pack = true;
+            pkp.bias = (int32_t)(64 - low);
+        }
+    }
+    const bool pack_pairs = pack && c->n_refs == 1;  // pair mode needs one reference for both reads of a task
     auto launch_dp = [&](bool tb, const KParams& kp, int* grid, bool query) -> cudaError_t {
         if (convex) return tb ? launch_cvx<true>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query) : launch_cvx<false>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query);
+        if (pack && (kp.all_pairs || pack_pairs))
+            return tb ? launch_pack<true>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query) : launch_pack<false>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query);
         return launch_any(cfg, tb, fin, fast, kp, c->sm_count, smem, s->stream, grid, query);
     };
 
@@ -585,16 +637,18 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     // grid + scratch sizing (per resident group)
     int grid_tb = 0, grid_sc = 0;
     cudaError_t ce;
+    KParams pq = p;
+    pq.all_pairs = (search != CLQ_SEARCH_FIXED) ? 1 : 0;   // which kernel family the score stage will use
     if ((ce = launch_dp(true, p, &grid_tb, true)) != cudaSuccess)
         return fail(c, CLQ_E_CUDA, std::string("occupancy(tb): ") + cudaGetErrorString(ce));
-    if ((ce = launch_dp(false, p, &grid_sc, true)) != cudaSuccess)
+    if ((ce = launch_dp(false, pq, &grid_sc, true)) != cudaSuccess)
         return fail(c, CLQ_E_CUDA, std::string("occupancy(score): ") + cudaGetErrorString(ce));
     const uint64_t bits_stride = ((uint64_t)ns_max * (L1max + G) * G * (C * bits_per_cell / 32) + 3) / 4 * 4;  // 16-byte aligned slots
     const uint32_t cig_stride = L1max + L2max + 8;
     const uint32_t col_stride = L1max + 8;
     // traceback scratch is per task of a sub-batch: direction bits + CIGAR scratch + walker record
     const uint64_t per_task = bits_stride * 4 + (uint64_t)cig_stride * 4 + sizeof(TbRec);
-    uint64_t sub = std::max<uint64_t>(1, std::min<uint64_t>(n, (uint64_t)c->max_scratch_bytes / per_task));
+    uint64_t sub = std::max<uint64_t>(2, std::min<uint64_t>((uint64_t)n + 1, (uint64_t)c->max_scratch_bytes / per_task)) & ~1ull;  // even: PACK tasks are read pairs
     const uint64_t groups = (uint64_t)std::max(grid_tb, grid_sc) * (kThreads / 32) * GPW;
     int32_t rc;
     if (!score_only && n) {
@@ -645,7 +699,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
             if ((rc = ensure(c, s->scores, (size_t)n * nrefs * 4)) != CLQ_OK) return rc;
             KParams q = p;
             q.all_pairs = 1;
-            q.n_tasks = n * nrefs;
+            q.n_tasks = pack ? ((n + 1) / 2) * nrefs : n * nrefs;
             if ((uint64_t)n * nrefs > 0xfffffff0ull) return fail(c, CLQ_E_LIMIT, "reads x references exceeds 2^32 tasks per batch");
             q.cand_mask = cand;
             q.mask_words = mask_words;
@@ -673,8 +727,9 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         q.task_counter = (unsigned int*)(ctr + 1);
         CU(c, cudaEventRecord(s->ev[3], s->stream));
         if (score_only) {
-            q.n_tasks = n;
+            q.n_tasks = pack_pairs ? (n + 1) / 2 : n;
             q.task_base = 0;
+            q.task_end = n;
             int g = grid_sc;
             if ((ce = launch_dp(false, q, &g, false)) != cudaSuccess)
                 return fail(c, CLQ_E_CUDA, std::string("score kernel: ") + cudaGetErrorString(ce));
@@ -684,8 +739,9 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
             // fill (direction bits into the sub-batch's slots) then walk (one thread per pair), sub-batch by sub-batch
             for (uint64_t base = 0; base < n; base += sub) {
                 const uint32_t cnt = (uint32_t)std::min<uint64_t>(sub, n - base);
-                q.n_tasks = cnt;
+                q.n_tasks = pack_pairs ? (cnt + 1) / 2 : cnt;
                 q.task_base = (uint32_t)base;
+                q.task_end = (uint32_t)(base + cnt);
                 if (base) CU(c, cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned long long), s->stream));
                 int g = grid_tb;
                 if ((ce = launch_dp(true, q, &g, false)) != cudaSuccess)
@@ -693,7 +749,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
                 s->stats.launches++;
                 s->stats.dp_launches++;
                 if (!(c->debug_flags & 1)) {
-                    if ((ce = convex ? launch_cvx_walk(cfg, q, cnt, s->stream) : launch_walk(cfg, q, cnt, s->stream)) != cudaSuccess)
+                    if ((ce = convex ? launch_cvx_walk(cfg, q, cnt, s->stream) : launch_walk(cfg, q, pack_pairs ? 2 * q.n_tasks : cnt, s->stream)) != cudaSuccess)
                         return fail(c, CLQ_E_CUDA, std::string("walk kernel: ") + cudaGetErrorString(ce));
                     s->stats.launches++;
                 }

@@ -77,7 +77,8 @@ struct KParams {
     const uint8_t* cls_lut;      // FAST: byte -> class (0 special, 1 other, 2..7 reference bytes)
     uint32_t tab[16];            // FAST: 8 profile rows (reference class) x 8 int8 scores (read class)
     uint32_t debug_flags;        // experiments only: 1 = skip the traceback walk
-    uint32_t task_base;          // first task of this sub-batch in the processing order
+    uint32_t task_base;          // first read (processing position) of this sub-batch
+    uint32_t task_end;           // one past its last read (PACK kernel: two reads per task)
     struct TbRec* tb_rec;        // TB: one record per task of the sub-batch for walk_kernel
 };
 

@@ -1,0 +1,331 @@
+// clq_pack.cuh -- s16x2 ("PACK") variant of the FAST affine kernel: one lane group aligns TWO reads against the same
+// reference at once, read A in the low and read B in the high 16-bit half of every register, so each DPX instruction
+// (VIADDMNMX.S16x2) advances two cells.  Same recurrence, same direction bits, same bit layout and the same walker as
+// gotoh_kernel<.., FAST> (clq_kernels.cuh); only the arithmetic width differs.
+//
+// Exactness: the host proves per batch that every value a cell can take lies in a window narrower than 2^15
+// (clq_api.cu::pack_bias), values are stored with a common positive bias so that both halves are always in [64, 32767]:
+// signed and unsigned order coincide, 32-bit subtractions of a >= b never borrow across halves, and the boundary
+// sentinel MAX_NEG (which only ever loses a max, alignment/alignment_matrix.rs:385-406) is represented by 0.
+// Direction bits: with x >= y per half, "x > y" is min_u16x2(x - y, 1); four such bit pairs per cell pair are shifted
+// into packed accumulators (low half = read A, high half = read B) and unzipped with PRMT into each read's row word.
+#pragma once
+
+#include "clq_kernels.cuh"
+
+namespace clq {
+
+__device__ __forceinline__ uint32_t dup16(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }
+__device__ __forceinline__ uint32_t set_lo(uint32_t w, int v) { return (w & 0xffff0000u) | ((uint32_t)v & 0xffffu); }
+__device__ __forceinline__ uint32_t set_hi(uint32_t w, int v) { return (w & 0x0000ffffu) | ((uint32_t)v << 16); }
+__device__ __forceinline__ int get_lo(uint32_t w) { return (int)(w & 0xffffu); }
+__device__ __forceinline__ int get_hi(uint32_t w) { return (int)(w >> 16); }
+
+struct PackParams {
+    int32_t bias;  // added to every stored score
+};
+
+template <int C, bool TB, bool LAST>
+__device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C], const uint32_t (&sel)[C], uint32_t (&wA)[C / 8],
+                                              uint32_t (&wB)[C / 8], uint32_t& Fh, uint32_t& Ehl, uint32_t& Ml, uint32_t& Bl, uint32_t diag,
+                                              uint32_t tlo, uint32_t thi, uint32_t LE, uint32_t X1, uint32_t X1M1, bool ownA, int jA,
+                                              bool ownB, int jB, uint32_t (&cap)[3]) {
+    const uint32_t ONE = 0x00010001u;
+    uint32_t acc0 = 0, acc1 = 0;
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+        const uint32_t m = (uint32_t)prmt_s8(tlo, thi, sel[j]);  // [mA, mB] as s16x2
+        const uint32_t Mv = __viaddmax_s16x2(diag, m, 0u);       // per-half add (biased values are > 0)
+        const uint32_t EhU = Eh[j], BU = B[j];
+        const uint32_t Ehn = __viaddmax_s16x2(EhU, LE, BU);
+        uint32_t t2 = 0, u2 = 0;
+        if (TB) {
+            t2 = __viaddmax_s16x2(Ehl, X1M1, Ml);
+            u2 = __viaddmax_s16x2(Fh, LE, t2);  // > t2  <=>  F extends (>= E-open, > M-open)
+        }
+        const uint32_t Fhn = __viaddmax_s16x2(Fh, LE, Bl);
+        const uint32_t Pv = __viaddmax_s16x2(Fhn, X1, Mv);
+        const uint32_t Bn = __viaddmax_s16x2(Ehn, X1, Pv);
+        if (TB) {
+            uint32_t a = ((j & 4) ? acc1 : acc0);
+            if ((j & 3) == 0) a = 0;
+            a = a * 2u + __vminu2(Ehn - BU, ONE);  // ext1
+            a = a * 2u + __vminu2(u2 - t2, ONE);   // ext2
+            a = a * 2u + __vminu2(Bn - Pv, ONE);   // eP: E > max(M,F)
+            a = a * 2u + __vminu2(Pv - Mv, ONE);   // fM: F > M
+            if (j & 4) acc1 = a; else acc0 = a;
+            if ((j & 7) == 7) {
+                wA[j >> 3] = __byte_perm(acc1, acc0, 0x5410);  // low halves: read A's 8 nibbles
+                wB[j >> 3] = __byte_perm(acc1, acc0, 0x7632);  // high halves: read B's
+            }
+        }
+        diag = BU;
+        Eh[j] = Ehn;
+        B[j] = Bn;
+        Fh = Fhn; Ehl = Ehn; Ml = Mv; Bl = Bn;
+        if (LAST) {
+            if (ownA && j == jA) { cap[0] = set_lo(cap[0], get_lo(Mv)); cap[1] = set_lo(cap[1], get_lo(Ehn)); cap[2] = set_lo(cap[2], get_lo(Fhn)); }
+            if (ownB && j == jB) { cap[0] = set_hi(cap[0], get_hi(Mv)); cap[1] = set_hi(cap[1], get_hi(Ehn)); cap[2] = set_hi(cap[2], get_hi(Fhn)); }
+        }
+    }
+}
+
+// Tasks are read PAIRS.  Pair mode (all_pairs == 0): pair t = reads at processing positions task_base + 2t, +1, all against
+// reference ref_of_read[.] (the host only takes this kernel when the batch has a single reference).  All-pairs mode: pair
+// t = (read pair t / n_refs, reference t % n_refs).
+template <int G, int C, bool TB>
+__global__ void __launch_bounds__(kThreads, (TB && C >= 40) ? 3 : 1) pack_kernel(const KParams p, const PackParams pp) {
+    static_assert(C % 8 == 0, "C must be a multiple of 8");
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + 320;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) smem_raw[i] = p.cls_lut[i];
+    if (threadIdx.x < 16) ((uint32_t*)(smem_raw + 256))[threadIdx.x] = p.tab[threadIdx.x];
+    __syncthreads();
+    const uint8_t* lut_sm = smem_raw;
+    const uint8_t* tab_sm = smem_raw + 256;
+    constexpr int GPW = 32 / G;
+    constexpr int W = G * C;
+    constexpr int WPL = C / 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gl = lane % G, gw = lane / G;
+    const int wpb = blockDim.x >> 5;
+    const uint32_t ggid = (blockIdx.x * wpb + warp) * GPW + gw;
+    uint8_t* ref_sm = smem + (size_t)(warp * GPW + gw) * p.ref_sm_stride;
+    uint32_t* col_g = (uint32_t*)p.col_scratch + (size_t)ggid * 4 * p.col_stride;
+    const clq_affine_t sc = p.sc;
+    const int bias = pp.bias;
+    const int x1 = sc.oe_in, le = sc.e_in;
+    const uint32_t LE = dup16(le), X1 = dup16(x1), X1M1 = dup16(x1 - 1);
+    int staged_ref = -1;
+
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(p.task_counter, (unsigned)GPW);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= p.n_tasks) break;
+        const uint32_t task = base + gw;
+        const bool tvalid = task < p.n_tasks;
+        // ---- decode the two reads of this task ----
+        uint32_t ridx[2] = {0, 0};
+        bool valid[2] = {false, false};
+        int ref = -1;
+        if (tvalid) {
+            if (p.all_pairs) {
+                const uint32_t q = task / p.n_refs;
+                ref = (int)(task - q * p.n_refs);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t pos = 2 * q + h;
+                    if (pos < p.n_reads) {
+                        ridx[h] = p.order ? p.order[pos] : pos;
+                        valid[h] = !(p.cand_mask && !((p.cand_mask[(size_t)ridx[h] * p.mask_words + (ref >> 5)] >> (ref & 31)) & 1u));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t pos = p.task_base + 2 * task + h;
+                    if (pos < p.task_end) {
+                        ridx[h] = p.order ? p.order[pos] : pos;
+                        valid[h] = true;
+                    }
+                }
+                // the reference of the pair = the first usable per-read reference (the host takes this kernel only for
+                // single-reference batches, so two usable references are always equal)
+                for (int h = 1; h >= 0; h--)
+                    if (valid[h]) {
+                        const int rh = p.ref_of_read[ridx[h]];
+                        if (rh >= 0 && (uint32_t)rh < p.n_refs) ref = rh;
+                    }
+            }
+        }
+        int L1 = 0, L2[2] = {0, 0};
+        const uint8_t* refp = nullptr;
+        const uint8_t* readp[2] = {nullptr, nullptr};
+        uint32_t status[2] = {CLQ_OK, CLQ_OK};
+        bool ok[2], run[2];
+        const bool ref_ok = ref >= 0 && (uint32_t)ref < p.n_refs;
+        if (ref_ok) {
+            const uint64_t f0 = p.ref_off[ref];
+            L1 = (int)(p.ref_off[ref + 1] - f0);
+            refp = p.ref_bytes + f0;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (valid[h]) {
+                const uint64_t r0 = p.read_off[ridx[h]];
+                L2[h] = (int)(p.read_off[ridx[h] + 1] - r0);
+                readp[h] = p.read_bytes + r0;
+                int rh = ref;
+                if (!p.all_pairs) rh = p.ref_of_read[ridx[h]];
+                if ((uint32_t)L2[h] >= p.max_read_len) status[h] = CLQ_READ_TOO_LONG;
+                else if (rh < 0 || (uint32_t)rh >= p.n_refs || rh != ref) status[h] = CLQ_NO_CANDIDATE;
+            }
+            ok[h] = valid[h] && status[h] == CLQ_OK;
+            run[h] = ok[h] && L1 > 0 && L2[h] > 0;
+        }
+        const bool anyrun = run[0] || run[1];
+        if (anyrun && ref != staged_ref) {
+            for (int i = gl; i < L1; i += G) ref_sm[i] = lut_sm[refp[i]];
+            staged_ref = ref;
+        }
+        __syncwarp();
+
+        const int L2m = max(run[0] ? L2[0] : 0, run[1] ? L2[1] : 0);
+        int K[2], NSh[2], lLh[2], jLh[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            K[h] = run[h] ? stale_rows(L1, L2[h], p.band_mode) : 0;
+            NSh[h] = run[h] ? (L2[h] + W - 1) / W : 0;
+            const int cL = run[h] ? (L2[h] - 1) - (NSh[h] - 1) * W : 0;
+            lLh[h] = cL / C;
+            jLh[h] = cL - lLh[h] * C;
+        }
+        const int NS = anyrun ? (L2m + W - 1) / W : 0;
+        const int NSmax = __reduce_max_sync(FULL, NS);
+        const int T = anyrun ? L1 + G - 1 : 0;
+        const int Tmax = __reduce_max_sync(FULL, T);
+        uint32_t cap[3] = {0, 0, 0};
+        uint32_t* bitsA = TB ? p.bits + (size_t)(2 * task) * p.bits_stride : nullptr;
+        uint32_t* bitsB = TB ? p.bits + (size_t)(2 * task + 1) * p.bits_stride : nullptr;
+
+        for (int s = 0; s < NSmax; s++) {
+            const bool act_s = anyrun && s < NS;
+            const bool ownA = run[0] && s == NSh[0] - 1 && gl == lLh[0];
+            const bool ownB = run[1] && s == NSh[1] - 1 && gl == lLh[1];
+            const int y0 = s * W + gl * C;
+            uint32_t Eh[C], B[C], sel[C];
+            uint32_t wA[WPL], wB[WPL];
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                const int y = y0 + j + 1;
+                uint32_t ca = 1, cb = 1;  // padding column: class "other"
+                if (run[0] && y <= L2[0]) ca = lut_sm[readp[0][y - 1]];
+                if (run[1] && y <= L2[1]) cb = lut_sm[readp[1][y - 1]];
+                sel[j] = (ca * 0x11u | 0x80u) | ((cb * 0x11u | 0x80u) << 8);  // bytes [mA, sign(mA), mB, sign(mB)]
+                const int g = sc.b0 + y * sc.b1 + bias;                        // row 0: S[0,y] = (MAXNEG, g(y), g(y))
+                B[j] = dup16(g);
+                Eh[j] = dup16(g - x1);
+            }
+            uint32_t prevBl = dup16(((y0 == 0) ? 0 : sc.b0 + y0 * sc.b1) + bias);
+            uint32_t oF = 0, oE = 0, oM = 0, oB = 0;
+            uint32_t nF = 0, nE = 0, nM = 0, nB = 0;
+            if (s > 0 && gl == 0 && act_s) {
+                nF = col_g[1]; nE = col_g[p.col_stride + 1]; nM = col_g[2 * p.col_stride + 1]; nB = col_g[3 * p.col_stride + 1];
+            }
+            int rnext = act_s ? ref_sm[0] : 0;
+
+            for (int t = 1; t <= Tmax; t++) {
+                const int x = t - gl;
+                uint32_t Fl = __shfl_up_sync(FULL, oF, 1, G);
+                uint32_t Bl = __shfl_up_sync(FULL, oB, 1, G);
+                uint32_t El = 0, Ml = 0;
+                if (TB) {
+                    El = __shfl_up_sync(FULL, oE, 1, G);
+                    Ml = __shfl_up_sync(FULL, oM, 1, G);
+                }
+                const bool act = act_s && x >= 1 && x <= L1;
+                if (act) {
+                    if (gl == 0) {
+                        if (s == 0) {
+                            const int g = sc.b0 + x * sc.b1 + bias;  // S[x,0] = (MAXNEG, g(x), g(x))
+                            Bl = dup16(g);
+                            Fl = El = dup16(g - x1);
+                            Ml = 0;  // the sentinel: below every biased value
+                        } else {
+                            Fl = nF; El = nE; Ml = nM; Bl = nB;
+                            if (x < L1) {
+                                nF = col_g[x + 1]; nE = col_g[p.col_stride + x + 1];
+                                nM = col_g[2 * p.col_stride + x + 1]; nB = col_g[3 * p.col_stride + x + 1];
+                            }
+                        }
+                    }
+                    const int r = rnext;
+                    if (x < L1) rnext = ref_sm[x];
+                    const uint32_t BlIn = Bl;
+                    const uint2 tr = *(const uint2*)(tab_sm + r * 8);
+                    if (x == L1)
+                        pack_row_step<C, TB, true>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap);
+                    else
+                        pack_row_step<C, TB, false>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap);
+                    prevBl = BlIn;
+                    oF = Fl; oE = El; oM = Ml; oB = Bl;
+                    // band-skipped cells (x <= K, y == L2): fresh-matrix state (0,0,0), per read
+                    if ((ownA && x <= K[0]) || (ownB && x <= K[1])) {
+                        const bool sa = ownA && x <= K[0], sb = ownB && x <= K[1];
+                        const int e0 = -x1 + bias, b0v = bias;
+#pragma unroll
+                        for (int j = 0; j < C; j++) {
+                            if (sa && j == jLh[0]) { Eh[j] = set_lo(Eh[j], e0); B[j] = set_lo(B[j], b0v); }
+                            if (sb && j == jLh[1]) { Eh[j] = set_hi(Eh[j], e0); B[j] = set_hi(B[j], b0v); }
+                        }
+                        if (sa && jLh[0] == C - 1) { oF = set_lo(oF, e0); oE = set_lo(oE, e0); oM = set_lo(oM, b0v); oB = set_lo(oB, b0v); }
+                        if (sb && jLh[1] == C - 1) { oF = set_hi(oF, e0); oE = set_hi(oE, e0); oM = set_hi(oM, b0v); oB = set_hi(oB, b0v); }
+                        if (x == L1) {
+                            if (sa) { cap[0] = set_lo(cap[0], bias); cap[1] = set_lo(cap[1], e0); cap[2] = set_lo(cap[2], e0); }
+                            if (sb) { cap[0] = set_hi(cap[0], bias); cap[1] = set_hi(cap[1], e0); cap[2] = set_hi(cap[2], e0); }
+                        }
+                    }
+                    if (TB) {
+                        const size_t roff = (size_t)(s * T + (t - 1)) * (G * WPL);
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            if (!run[h] || s >= NSh[h]) continue;
+                            uint32_t* row = (h ? bitsB : bitsA) + roff;
+                            const uint32_t(&w)[WPL] = h ? wB : wA;
+                            if constexpr (WPL >= 4) {
+                                *reinterpret_cast<uint4*>(row + gl * 4) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+                                for (int k = 4; k < WPL; k++) row[G * 4 + gl * (WPL - 4) + (k - 4)] = w[k];
+                            } else if constexpr (WPL == 2) {
+                                *reinterpret_cast<uint2*>(row + gl * 2) = make_uint2(w[0], w[1]);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < WPL; k++) row[gl * WPL + k] = w[k];
+                            }
+                        }
+                    }
+                    if (gl == G - 1 && s < NS - 1) {
+                        col_g[x] = oF; col_g[p.col_stride + x] = oE; col_g[2 * p.col_stride + x] = oM; col_g[3 * p.col_stride + x] = oB;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- final cells: score + start layer = LAST maximum of (M, E, F) per read ----
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int src = gw * G + lLh[h];
+            const uint32_t c0 = __shfl_sync(FULL, cap[0], src), c1 = __shfl_sync(FULL, cap[1], src), c2 = __shfl_sync(FULL, cap[2], src);
+            int score = 0, z = 0;
+            if (run[h]) {
+                const int cM = (h ? get_hi(c0) : get_lo(c0)) - bias;
+                const int cE = (h ? get_hi(c1) : get_lo(c1)) - bias + x1;
+                const int cF = (h ? get_hi(c2) : get_lo(c2)) - bias + x1;
+                score = cM; z = 0;
+                if (cE >= score) { score = cE; z = 1; }
+                if (cF >= score) { score = cF; z = 2; }
+            } else if (ok[h]) {
+                const int n = L1 > L2[h] ? L1 : L2[h];
+                if (n > 0) { score = sc.b0 + n * sc.b1; z = 2; }
+            }
+            if (valid[h] && gl == 0) {
+                if (!TB && p.all_pairs) p.scores[(size_t)ridx[h] * p.n_refs + ref] = ok[h] ? score : INT32_MIN;
+                else {
+                    clq_result_t r;
+                    r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = 0; r.cigar_len = 0; r.status = status[h];
+                    p.results[ridx[h]] = r;
+                }
+                if (run[h]) atomicAdd(p.cells, (unsigned long long)L1 * (unsigned long long)L2[h]);
+            }
+            if (TB && tvalid && gl == 0) {
+                TbRec rec;
+                rec.ridx = ridx[h]; rec.L1 = ok[h] ? L1 : -1; rec.L2 = L2[h]; rec.zK = z | (K[h] << 2);
+                p.tb_rec[2 * task + h] = rec;
+            }
+        }
+    }
+}
+
+}  // namespace clq
