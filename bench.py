@@ -248,12 +248,12 @@ def main():
     clocks = ClockSampler(dev)
     clocks.start()
     barrier()
-    step_ms, dp_ms, launches, cells = [], [], 0, 0
+    step_ms, dp_ms, launches, cells, variant = [], [], 0, 0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         al.launch(0, sci, c["search"], c["band"], score_only)
         st = al.stats(0)       # synchronises the slot's stream; times come from CUDA events on that stream
-        step_ms.append(st["kernel_ms"]); dp_ms.append(st["dp_ms"]); launches += st["launches"]; cells = st["cells"]
+        step_ms.append(st["kernel_ms"]); dp_ms.append(st["dp_ms"]); launches += st["launches"]; cells = st["cells"]; variant = st["variant"]
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     clk = clocks.stop()
@@ -312,6 +312,9 @@ def main():
         else:
             alg_ops = cells * ops
         achieved = alg_ops / (dp / 1e3) / 1e12
+        pack = 2 if (variant & 2) else 1     # s16x2 kernels advance two cells per instruction (peak x pack)
+        kernel = {0: "generic int32", 1: "FAST int32 (PRMT profile + DPX)", 3: "PACK s16x2 (two reads per lane group, DPX)",
+                  5: "CONVEX int32 (two-piece affine, DPX)"}.get(variant & 7, "variant %d" % (variant & 15))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -321,6 +324,13 @@ def main():
         lens = (c["read_off"][1:] - c["read_off"][:-1]).astype(np.int64)
         # algorithmic HBM bytes per launch: raw reads in + results/CIGAR out + 0.5 B/cell of direction bits written once
         alg_bytes = float(total_bytes + n * 20 + 4 * int(res.cigar_len.sum()) + 0.5 * (cells if args.workload != "C4" else cells / 65.0))
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+            if tr["workload"] == args.workload and (variant & 2):
+                traffic = tr["dram_bytes_per_launch"] / tr["reads_per_launch"] * n   # bytes per step, scaled from the ncu capture
+        except Exception:
+            pass
         line = {
             "metric": "reads/s", "value": value, "unit": "reads/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
@@ -334,8 +344,9 @@ def main():
                     "ms_per_step": e2e_ms, "how": "clq_submit/clq_wait on pinned host buffers, %d chunks over 2 stream slots" % nch},
             "gpu_launches": int(launches),
             "wall_ms_per_step_device_resident": wall_ms / args.steps,
-            "roofline": {"bound": "int32-alu", "achieved": achieved, "peak": peak, "unit": "TIOP/s", "frac": achieved / peak,
-                         "traffic": None, "ops_per_cell": ops if ops else "12 score-only + 18 traceback", "kernel_ms": dp, "peak_source": peak_how,
+            "roofline": {"bound": "int32-alu", "achieved": achieved, "peak": peak * pack, "unit": "TIOP/s", "frac": achieved / (peak * pack),
+                         "pack": pack, "peak_int32_alu_pipe": peak, "frac_of_unpacked_int32_peak": achieved / peak, "kernel": kernel,
+                         "traffic": traffic, "ops_per_cell": ops if ops else "12 score-only + 18 traceback", "kernel_ms": dp, "peak_source": peak_how,
                          "hbm": {"achieved": alg_bytes / (dp / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": alg_bytes / (dp / 1e3) / 1e9 / hbm_peak, "of": "measured" if peaks else "fallback"}},
         }

@@ -669,6 +669,8 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     p.tb_rec = (TbRec*)s->tb_rec.p;
 
     s->flags = flags;
+    s->stats.variant = (fast ? 1u : 0u) | ((pack && (pack_pairs || search != CLQ_SEARCH_FIXED)) ? 2u : 0u) | (convex ? 4u : 0u) | (fin ? 8u : 0u) | ((uint32_t)cfg << 8);
+    s->stats.sub_batches = 0;
     s->stats.launches = 0;
     s->stats.dp_launches = 0;
     s->n_dp = 0;
@@ -748,6 +750,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
                     return fail(c, CLQ_E_CUDA, std::string("fill kernel: ") + cudaGetErrorString(ce));
                 s->stats.launches++;
                 s->stats.dp_launches++;
+                s->stats.sub_batches++;
                 if (!(c->debug_flags & 1)) {
                     if ((ce = convex ? launch_cvx_walk(cfg, q, cnt, s->stream) : launch_walk(cfg, q, pack_pairs ? 2 * q.n_tasks : cnt, s->stream)) != cudaSuccess)
                         return fail(c, CLQ_E_CUDA, std::string("walk kernel: ") + cudaGetErrorString(ce));

@@ -47,12 +47,13 @@ __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C
         const uint32_t Pv = __viaddmax_s16x2(Fhn, X1, Mv);
         const uint32_t Bn = __viaddmax_s16x2(Ehn, X1, Pv);
         if (TB) {
+            // nibble pair [ext1 ext2 eP fM] of this cell pair, then 4 cells per 16-bit half
+            uint32_t nib = __vminu2(Ehn - BU, ONE);                 // ext1
+            nib = nib * 2u + __vminu2(u2 - t2, ONE);                // ext2
+            nib = nib * 2u + __vminu2(Bn - Pv, ONE);                // eP: E > max(M,F)
+            nib = nib * 2u + __vminu2(Pv - Mv, ONE);                // fM: F > M
             uint32_t a = ((j & 4) ? acc1 : acc0);
-            if ((j & 3) == 0) a = 0;
-            a = a * 2u + __vminu2(Ehn - BU, ONE);  // ext1
-            a = a * 2u + __vminu2(u2 - t2, ONE);   // ext2
-            a = a * 2u + __vminu2(Bn - Pv, ONE);   // eP: E > max(M,F)
-            a = a * 2u + __vminu2(Pv - Mv, ONE);   // fM: F > M
+            a = ((j & 3) == 0) ? nib : a * 16u + nib;
             if (j & 4) acc1 = a; else acc0 = a;
             if ((j & 7) == 7) {
                 wA[j >> 3] = __byte_perm(acc1, acc0, 0x5410);  // low halves: read A's 8 nibbles
