@@ -41,7 +41,7 @@ class Limits(C.Structure):
 
 class Result(C.Structure):
     _fields_ = [("score_scaled", C.c_int32), ("ref_index", C.c_uint32), ("cigar_off", C.c_uint32),
-                ("cigar_len", C.c_uint32), ("status", C.c_uint32)]
+                ("cigar_len", C.c_uint32), ("status", C.c_uint32), ("matches", C.c_uint32), ("mismatches", C.c_uint32)]
 
 
 class Stats(C.Structure):

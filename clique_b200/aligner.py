@@ -201,6 +201,13 @@ class BatchResult:
     status: np.ndarray
     cigar_pool: np.ndarray
     stats: dict = field(default_factory=dict)
+    matches: Optional[np.ndarray] = None      # get_reference_alignment_rate's counters, fused into the traceback walk
+    mismatches: Optional[np.ndarray] = None
+
+    def alignment_rate(self, i):
+        """get_reference_alignment_rate (consensus/consensus_builders.rs:288-307): the `rm` tag of read i (NaN when 0/0)."""
+        m, mm = float(self.matches[i]), float(self.mismatches[i])
+        return m / (m + mm) if m + mm > 0 else float("nan")
 
     @property
     def score(self):
@@ -212,6 +219,19 @@ class BatchResult:
 
     def cigar_string(self, i):
         return cigar_to_string(self.cigar(i))
+
+
+def get_reference_alignment_rate(reference_aligned, read_aligned):
+    """Host mirror of get_reference_alignment_rate (consensus/consensus_builders.rs:288-307) over gapped strings; the batch
+    path gets the same counters from the GPU walk (BatchResult.matches / .mismatches)."""
+    m = mm = 0
+    for a, b in zip(_b(reference_aligned), _b(read_aligned)):
+        if a > 64 and a != 78 and b > 64:
+            if a == b:
+                m += 1
+            else:
+                mm += 1
+    return m / (m + mm) if m + mm else float("nan")
 
 
 def _b(x):
@@ -229,7 +249,7 @@ def pack_reads(reads):
 
 
 _RESULT_DT = np.dtype([("score_scaled", "<i4"), ("ref_index", "<u4"), ("cigar_off", "<u4"), ("cigar_len", "<u4"),
-                       ("status", "<u4")])
+                       ("status", "<u4"), ("matches", "<u4"), ("mismatches", "<u4")])
 
 
 class Aligner:
@@ -354,7 +374,7 @@ class Aligner:
         r = res[:n]
         cp = (lambda a: a.copy()) if copy else (lambda a: a)
         out = BatchResult(scale, cp(r["score_scaled"]), cp(r["ref_index"]), cp(r["cigar_off"]), cp(r["cigar_len"]),
-                          cp(r["status"]), cp(pool[:used.value]))
+                          cp(r["status"]), cp(pool[:used.value]), matches=cp(r["matches"]), mismatches=cp(r["mismatches"]))
         if with_stats:
             out.stats = self.stats(slot)
         return out
@@ -530,5 +550,7 @@ def concat_results(outs: Sequence[BatchResult]) -> BatchResult:
         offs.append(o.cigar_off.astype(np.uint32) + np.uint32(base))
         base += len(o.cigar_pool)
     cat = lambda f: np.concatenate([getattr(o, f) for o in outs]) if outs else np.zeros(0)
+    have_rate = all(o.matches is not None for o in outs)
     return BatchResult(outs[0].scale, cat("score_scaled"), cat("ref_index"), np.concatenate(offs), cat("cigar_len"),
-                       cat("status"), cat("cigar_pool"))
+                       cat("status"), cat("cigar_pool"), matches=cat("matches") if have_rate else None,
+                       mismatches=cat("mismatches") if have_rate else None)

@@ -204,7 +204,7 @@ cudaError_t launch_cvx(int cfg, const KParams& p, const ConvexParams& cp, int sm
 template <int G, int C>
 cudaError_t launch_cvx_walk_one(const KParams& p, uint32_t cnt, cudaStream_t st) {
     convex_walk_kernel<G, C><<<(cnt + 127) / 128, 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.cig_scratch, p.cig_stride, p.cigar_pool,
-                                                                p.cigar_cap, p.cigar_cursor, p.results);
+                                                                p.cigar_cap, p.cigar_cursor, p.results, p.ref_bytes, p.ref_off, p.read_bytes, p.read_off);
     return cudaGetLastError();
 }
 
@@ -220,7 +220,7 @@ cudaError_t launch_cvx_walk(int cfg, const KParams& p, uint32_t cnt, cudaStream_
 template <int G, int C>
 cudaError_t launch_walk_one(const KParams& p, uint32_t cnt, cudaStream_t st) {
     walk_kernel<G, C><<<(cnt + 127) / 128, 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.cig_scratch, p.cig_stride, p.cigar_pool,
-                                                         p.cigar_cap, p.cigar_cursor, p.results);
+                                                         p.cigar_cap, p.cigar_cursor, p.results, p.ref_bytes, p.ref_off, p.read_bytes, p.read_off);
     return cudaGetLastError();
 }
 

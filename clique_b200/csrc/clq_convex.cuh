@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kThreads) convex_kernel(const KParams p, const
             if (!TB && p.all_pairs) p.scores[(size_t)ridx * p.n_refs + ref] = ok ? score : INT32_MIN;
             else {
                 clq_result_t r;
-                r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = 0; r.cigar_len = 0; r.status = status;
+                r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = 0; r.cigar_len = 0; r.status = status; r.matches = 0; r.mismatches = 0;
                 p.results[ridx] = r;
                 if (TB) {
                     TbRec rec;
@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(kThreads) convex_kernel(const KParams p, const
 template <int G, int C>
 __global__ void __launch_bounds__(128) convex_walk_kernel(const TbRec* recs, uint32_t n_tasks, const uint32_t* bits, uint64_t bits_stride,
                                                           uint32_t* cig_scratch, uint32_t cig_stride, uint32_t* cigar_pool, uint64_t cigar_cap,
-                                                          unsigned long long* cigar_cursor, clq_result_t* results) {
+                                                          unsigned long long* cigar_cursor, clq_result_t* results, const uint8_t* ref_bytes,
+        const uint64_t* ref_off, const uint8_t* read_bytes, const uint64_t* read_off) {
     constexpr int W = G * C;
     constexpr int WPL = C / 4;
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -247,6 +248,14 @@ __global__ void __launch_bounds__(128) convex_walk_kernel(const TbRec* recs, uin
     uint32_t* cig_g = cig_scratch + (size_t)q * cig_stride;
     uint32_t status = CLQ_OK;
     int x = L1, y = L2;
+    // get_reference_alignment_rate (consensus/consensus_builders.rs:288-307) fused into the walk: only M columns can count
+    const uint8_t* refp = ref_bytes + ref_off[results[rec.ridx].ref_index];
+    const uint8_t* readp = read_bytes + read_off[rec.ridx];
+    uint32_t n_match = 0, n_mismatch = 0;
+    auto count = [&](int xx, int yy) {
+        const uint8_t rb = __ldg(refp + xx - 1), qb = __ldg(readp + yy - 1);
+        if (rb > 64 && rb != 'N' && qb > 64) { if (rb == qb) n_match++; else n_mismatch++; }
+    };
     int cpos = (int)cig_stride;
     uint32_t cur_op = 3, cur_len = 0;
     auto emit = [&](uint32_t op, uint32_t n) {
@@ -270,7 +279,7 @@ __global__ void __launch_bounds__(128) convex_walk_kernel(const TbRec* recs, uin
     while (x > 0 && y > 0) {
         const uint32_t old = cur;
         bool ext;
-        if (z == 0) { emit(CLQ_OP_M, 1); x--; y--; ext = false; }
+        if (z == 0) { emit(CLQ_OP_M, 1); count(x, y); x--; y--; ext = false; }
         else if (z <= 2) { emit(CLQ_OP_D, 1); x--; ext = (old >> (z == 1 ? 7 : 6)) & 1u; }
         else { emit(CLQ_OP_I, 1); y--; ext = (old >> (z == 3 ? 5 : 4)) & 1u; }
         if (x == 0 || y == 0) break;
@@ -291,6 +300,8 @@ __global__ void __launch_bounds__(128) convex_walk_kernel(const TbRec* recs, uin
     r->cigar_off = (uint32_t)off;
     r->cigar_len = (uint32_t)nops;
     r->status = status;
+    r->matches = n_match;
+    r->mismatches = n_mismatch;
 }
 
 }  // namespace clq

@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 40) ? 3 : 1) got
                 if (p.all_pairs) p.scores[(size_t)ridx * p.n_refs + ref] = ok ? score : INT32_MIN;
                 else {
                     clq_result_t r;
-                    r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = 0; r.cigar_len = 0; r.status = status;
+                    r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = 0; r.cigar_len = 0; r.status = status; r.matches = 0; r.mismatches = 0;
                     p.results[ridx] = r;
                 }
                 if (run) atomicAdd(p.cells, (unsigned long long)L1 * (unsigned long long)L2);
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 40) ? 3 : 1) got
         // ---- leave the start layer for walk_kernel ----
         if (valid && gl == 0) {
             clq_result_t r;
-            r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = 0; r.cigar_len = 0; r.status = status;
+            r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = 0; r.cigar_len = 0; r.status = status; r.matches = 0; r.mismatches = 0;
             p.results[ridx] = r;
             TbRec rec;
             rec.ridx = ridx; rec.L1 = ok ? L1 : -1; rec.L2 = L2; rec.zK = z | (K << 2);
@@ -419,7 +419,8 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 40) ? 3 : 1) got
 template <int G, int C>
 __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n_tasks, const uint32_t* bits, uint64_t bits_stride,
                                                    uint32_t* cig_scratch, uint32_t cig_stride, uint32_t* cigar_pool, uint64_t cigar_cap,
-                                                   unsigned long long* cigar_cursor, clq_result_t* results) {
+                                                   unsigned long long* cigar_cursor, clq_result_t* results, const uint8_t* ref_bytes,
+        const uint64_t* ref_off, const uint8_t* read_bytes, const uint64_t* read_off) {
     constexpr int W = G * C;
     constexpr int WPL = C / 8;
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -433,6 +434,14 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
     uint32_t* cig_g = cig_scratch + (size_t)q * cig_stride;
     uint32_t status = CLQ_OK;
     int x = L1, y = L2;
+    // get_reference_alignment_rate (consensus/consensus_builders.rs:288-307) fused into the walk: only M columns can count
+    const uint8_t* refp = ref_bytes + ref_off[results[rec.ridx].ref_index];
+    const uint8_t* readp = read_bytes + read_off[rec.ridx];
+    uint32_t n_match = 0, n_mismatch = 0;
+    auto count = [&](int xx, int yy) {
+        const uint8_t rb = __ldg(refp + xx - 1), qb = __ldg(readp + yy - 1);
+        if (rb > 64 && rb != 'N' && qb > 64) { if (rb == qb) n_match++; else n_mismatch++; }
+    };
     int cpos = (int)cig_stride;
     uint32_t cur_op = 3, cur_len = 0;
     auto emit = [&](uint32_t op, uint32_t n) {
@@ -457,7 +466,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
     while (x > 0 && y > 0) {
         if (y == L2 && x <= K) { status = CLQ_TRACEBACK_DIVERGED; break; }  // stale Up(0) cell: the reference spins here
         const uint32_t old = nib;
-        if (z == 0) { emit(CLQ_OP_M, 1); x--; y--; }
+        if (z == 0) { emit(CLQ_OP_M, 1); count(x, y); x--; y--; }
         else if (z == 1) { emit(CLQ_OP_D, 1); x--; }
         else { emit(CLQ_OP_I, 1); y--; }
         if (x == 0 || y == 0) break;
@@ -484,6 +493,8 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
     r->cigar_off = (uint32_t)off;
     r->cigar_len = (uint32_t)nops;
     r->status = status;
+    r->matches = n_match;
+    r->mismatches = n_mismatch;
 }
 
 // exhaustive_alignment_search's arg-max: ascending reference index, LAST maximum wins

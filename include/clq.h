@@ -95,6 +95,8 @@ typedef struct {
     uint32_t cigar_off;   /* first op in the CIGAR pool            */
     uint32_t cigar_len;   /* run-length merged ops                 */
     uint32_t status;
+    uint32_t matches;     /* get_reference_alignment_rate's counters (consensus/consensus_builders.rs:288-307): aligned   */
+    uint32_t mismatches;  /* columns with ref > 64, ref != 'N', read > 64; the `rm` tag = matches / (matches + mismatches) */
 } clq_result_t;
 
 /* timing / accounting of the last clq_launch on a slot */

@@ -177,6 +177,19 @@ size_t orc_simplify_cigar(const uint32_t* in, size_t n, uint32_t* out) {
     return k;
 }
 
+/* get_reference_alignment_rate, consensus/consensus_builders.rs:288-307 */
+double orc_alignment_rate(const uint8_t* ref_aligned, const uint8_t* read_aligned, size_t n, uint32_t* matches, uint32_t* mismatches) {
+    uint32_t m = 0, mm = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (ref_aligned[i] > 64 && ref_aligned[i] != FASTA_N && read_aligned[i] > 64) {
+            if (ref_aligned[i] == read_aligned[i]) m++; else mm++;
+        }
+    }
+    if (matches) *matches = m;
+    if (mismatches) *mismatches = mm;
+    return (double)m / (double)(m + mm);
+}
+
 /* perform_3d_global_traceback (global), alignment/alignment_matrix.rs:941-1086 */
 int orc_traceback(orc_matrix_t* m, const uint8_t* s1, size_t l1, const uint8_t* s2, size_t l2, orc_result_t* res,
                   uint32_t* cigar, size_t cigar_cap, uint8_t* ref_aligned, uint8_t* read_aligned, size_t aligned_cap) {
@@ -234,6 +247,7 @@ int orc_traceback(orc_matrix_t* m, const uint8_t* s1, size_t l1, const uint8_t* 
     uint32_t* merged = (uint32_t*)malloc((nc + 1) * sizeof(uint32_t));
     size_t nm = orc_simplify_cigar(cig, nc, merged);
 
+    orc_alignment_rate(a1, a2, na, &res->matches, &res->mismatches); /* order-independent: the strings are still reversed */
     res->score = score;
     res->n_cigar = (uint32_t)nm;
     res->aligned_len = (uint32_t)na;
@@ -736,6 +750,8 @@ static void* worker_main(void* arg) {
         out->ref_index[i] = best_ref;
         out->status[i] = (uint32_t)best.status;
         out->cigar_len[i] = best.n_cigar;
+        if (out->matches) out->matches[i] = best.matches;
+        if (out->mismatches) out->mismatches[i] = best.mismatches;
         if (w->cig.n + best.n_cigar > w->cig.cap) {
             w->cig.cap = (w->cig.n + best.n_cigar) * 2 + 1024;
             w->cig.v = (uint32_t*)realloc(w->cig.v, w->cig.cap * sizeof(uint32_t));

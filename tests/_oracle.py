@@ -34,7 +34,7 @@ class Convex(C.Structure):
 
 class Result(C.Structure):
     _fields_ = [("score", C.c_double), ("status", C.c_int32), ("n_cigar", C.c_uint32), ("aligned_len", C.c_uint32),
-                ("path_len", C.c_uint32)]
+                ("path_len", C.c_uint32), ("matches", C.c_uint32), ("mismatches", C.c_uint32)]
 
 
 class Batch(C.Structure):
@@ -48,7 +48,7 @@ class Batch(C.Structure):
 class BatchOut(C.Structure):
     _fields_ = [("score", C.c_void_p), ("ref_index", C.c_void_p), ("status", C.c_void_p), ("cigar_off", C.c_void_p),
                 ("cigar_len", C.c_void_p), ("cigar_pool", C.c_void_p), ("cigar_cap", C.c_uint64),
-                ("cigar_used", C.c_uint64), ("cells", C.c_uint64)]
+                ("cigar_used", C.c_uint64), ("cells", C.c_uint64), ("matches", C.c_void_p), ("mismatches", C.c_void_p)]
 
 
 def build(force=False):
@@ -80,6 +80,8 @@ def lib():
         L.orc_fill.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(Affine), C.c_size_t]
         L.orc_traceback.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(Result),
                                     C.c_void_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_size_t]
+        L.orc_alignment_rate.restype = C.c_double
+        L.orc_alignment_rate.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.orc_simplify_cigar.restype = C.c_size_t
         L.orc_simplify_cigar.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.orc_affine_to_int.argtypes = [C.POINTER(Affine), C.POINTER(AffineInt)]
@@ -149,7 +151,7 @@ def align_pair(ref, read, sc, band_mode="maxlen", band_k=0, dim=None):
         L.orc_traceback(m, ref, l1, read, l2, C.byref(res), cig.ctypes.data, len(cig), a1, a2, l1 + l2 + 2)
         return {"score": res.score, "status": res.status, "cigar": cig[:res.n_cigar].copy(),
                 "ref_aligned": a1.raw[:res.aligned_len], "read_aligned": a2.raw[:res.aligned_len],
-                "path_len": res.path_len}
+                "path_len": res.path_len, "matches": res.matches, "mismatches": res.mismatches}
     finally:
         L.orc_matrix_free(m)
 
@@ -200,7 +202,8 @@ def align_batch(ref_bytes, ref_off, read_bytes, read_off, sc, search="fixed", fi
         cigar_cap = int(n_reads) * 64 + int(read_off[-1]) + 1024
     out = {"score": np.zeros(n_reads, np.float64), "ref_index": np.zeros(n_reads, np.uint32),
            "status": np.zeros(n_reads, np.uint32), "cigar_off": np.zeros(n_reads, np.uint64),
-           "cigar_len": np.zeros(n_reads, np.uint32), "cigar_pool": np.zeros(cigar_cap, np.uint32)}
+           "cigar_len": np.zeros(n_reads, np.uint32), "cigar_pool": np.zeros(cigar_cap, np.uint32),
+           "matches": np.zeros(n_reads, np.uint32), "mismatches": np.zeros(n_reads, np.uint32)}
     fr = None
     if fixed_ref is not None:
         fr = np.ascontiguousarray(fixed_ref, dtype=np.int32)
@@ -208,7 +211,8 @@ def align_batch(ref_bytes, ref_off, read_bytes, read_off, sc, search="fixed", fi
               fr.ctypes.data if fr is not None else None, SEARCH[search], BAND[band_mode], band_k, kmer[0], kmer[1],
               threshold, threads, 1 if traceback_all else 0)
     o = BatchOut(out["score"].ctypes.data, out["ref_index"].ctypes.data, out["status"].ctypes.data,
-                 out["cigar_off"].ctypes.data, out["cigar_len"].ctypes.data, out["cigar_pool"].ctypes.data, cigar_cap, 0, 0)
+                 out["cigar_off"].ctypes.data, out["cigar_len"].ctypes.data, out["cigar_pool"].ctypes.data, cigar_cap, 0, 0,
+                 out["matches"].ctypes.data, out["mismatches"].ctypes.data)
     s = affine(sc)
     rc = L.orc_align_batch(C.byref(b), C.byref(s), C.byref(o))
     out["rc"] = rc
@@ -216,6 +220,12 @@ def align_batch(ref_bytes, ref_off, read_bytes, read_off, sc, search="fixed", fi
     out["cells"] = o.cells
     out["cigar_pool"] = out["cigar_pool"][:o.cigar_used]
     return out
+
+
+def alignment_rate(ref_aligned, read_aligned):
+    m, mm = C.c_uint32(), C.c_uint32()
+    r = lib().orc_alignment_rate(bytes(ref_aligned), bytes(read_aligned), len(ref_aligned), C.byref(m), C.byref(mm))
+    return r, m.value, mm.value
 
 
 def apply_cigar(ref, read, cigar):

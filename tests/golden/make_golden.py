@@ -228,6 +228,22 @@ kmers = [
      "not_contains": [["cas_tag", "TCACCTATTAGCGGCTAA"], ["v10", "TCACCTATTAGCGGCTAA"]]},
 ]
 
+# --- get_reference_alignment_rate, consensus/consensus_builders.rs:771-795, :1059-1080 (the `rm` tag) ---
+CB = "consensus/consensus_builders.rs"
+alignment_rate = []
+for lo, hi in ((771, 796), (1059, 1080)):
+    block_all = "\n".join(lines(CB, lo, hi))
+    for block in re.split(r"fn test_", block_all)[1:]:      # one scope per #[test] function
+        strs = {}
+        for m in re.finditer(r"let (\w+) = b\"([^\"]*)\";", block):
+            strs[m.group(1)] = m.group(2)
+        for m in re.finditer(r"get_reference_alignment_rate\((\w+), (\w+)\)", block):
+            ref_v, read_v = m.group(1), m.group(2)
+            tail = block[m.end():m.end() + 200]
+            val = re.search(r"(?:assert_eq!\(\w+, |^, )([0-9.]+)\)", tail, flags=re.M) or re.search(r", ([0-9.]+)\)", tail)
+            alignment_rate.append({"ref": strs[ref_v], "read": strs[read_v], "rate": float(val.group(1)), "cite": "%s:%d-%d" % (CB, lo, hi)})
+assert len(alignment_rate) == 8, alignment_rate
+
 # --- ConvexScoring::gap KATs, alignment/scoring_functions.rs:200-213 ---
 convex_gap = [{"gap_open": -10.0, "len": 1, "gap": -10.0}, {"gap_open": -10.0, "len": 10, "gap": -9.0}]
 
@@ -253,7 +269,7 @@ out = {
     "scorings": {"default_dna": DEFAULT_DNA, "merger": MERGER,
                  "cli": scoring_at(AF, 104, 111)},
     "pairs": pairs, "mergers": mergers, "best_ref": best_ref, "fastas": fastas, "tie_table": tie_table,
-    "match_mismatch_default_dna": mm_table, "simplify_cigar": simplify, "kmers": kmers, "convex_gap": convex_gap,
+    "match_mismatch_default_dna": mm_table, "simplify_cigar": simplify, "kmers": kmers, "convex_gap": convex_gap, "alignment_rate": alignment_rate,
     "amplicon_c2": amplicon_c2, "amplicon_c3": amplicon_c3, "survey_kats": survey_kats,
 }
 with open(OUT, "w") as f:

@@ -56,6 +56,7 @@ def compare(br, want, n, ctx=""):
         if int(want["status"][i]) == 0:
             o, l = int(want["cigar_off"][i]), int(want["cigar_len"][i])
             assert O.cigar_str(br.cigar(i)) == O.cigar_str(want["cigar_pool"][o:o + l]), (ctx, i, "cigar")
+            assert (int(br.matches[i]), int(br.mismatches[i])) == (int(want["matches"][i]), int(want["mismatches"][i])), (ctx, i, "rm")
 
 
 def run_both(al, refs, reads, sc, search="fixed", band="readlen", fixed_ref=None, kmer=(8, 4)):
@@ -378,3 +379,16 @@ def test_convex_gap_helper():
     from clique_b200 import ConvexScoring
     c = ConvexScoring(5.0, -4.0, -2.0, -10.0, -1.0)      # alignment/scoring_functions.rs:200-213
     assert c.gap(1) == -10.0 and c.gap(10) == -9.0 and c.match_mismatch(65, 65) == 5.0 and c.match_mismatch(65, 84) == -4.0
+
+
+def test_alignment_rate_tag(al, goldens):
+    """the `rm` tag (get_reference_alignment_rate) from the counters the GPU walk produces vs the host mirror on the gapped strings"""
+    from clique_b200.aligner import get_reference_alignment_rate
+    for t in goldens["alignment_rate"]:
+        assert get_reference_alignment_rate(t["ref"], t["read"]) == t["rate"]
+    p = goldens["pairs"][3]
+    r = al.align_two_strings(p["ref"].encode(), p["read"].encode(), None, AffineScoring(**p["scoring"]))
+    al.set_references(ReferenceManager([Reference(p["ref"].encode(), b"r")]))
+    qb, qo = pack_reads([p["read"].encode()])
+    br = al.align_batch(qb, qo, AffineScoring(**p["scoring"]), "fixed", "maxlen", fixed_ref=[0])
+    assert br.alignment_rate(0) == get_reference_alignment_rate(r.reference_aligned, r.read_aligned)

@@ -169,3 +169,15 @@ def test_panel_fixture(goldens):
     recs = goldens["fastas"]["18guide1_pcr_sequence.first64"]
     assert len(recs) == 64 and all(len(r["seq"]) == 302 for r in recs)
     assert len(goldens["amplicon_c2"]) == 215 and len(goldens["amplicon_c3"]) == 1000
+
+
+def test_alignment_rate_goldens(goldens):
+    # get_reference_alignment_rate, consensus/consensus_builders.rs:771-795, :1059-1080
+    for t in goldens["alignment_rate"]:
+        r, m, mm = O.alignment_rate(t["ref"].encode(), t["read"].encode())
+        assert r == t["rate"], t
+    # the traceback reports the same counters as the function applied to its gapped strings
+    for p in goldens["pairs"]:
+        a = O.align_pair(p["ref"].encode(), p["read"].encode(), p["scoring"], "maxlen")
+        r, m, mm = O.alignment_rate(a["ref_aligned"], a["read_aligned"])
+        assert (a["matches"], a["mismatches"]) == (m, mm)
