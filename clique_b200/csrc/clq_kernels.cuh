@@ -112,6 +112,33 @@ __device__ inline int stale_rows(int L1, int L2, uint32_t band_mode) {
     return K;
 }
 
+// Time-transposed direction-bit store.  The walker follows a path that moves up one row per step, so it wants the
+// words of consecutive steps side by side; the fill produces one row per step.  Each lane therefore parks its WPL words of
+// the last 8 steps in shared memory ([word][step & 7][lane], conflict-free, private to the lane so no barrier) and
+// writes them out as full 32-byte sectors: bits[block of 8 steps][lane][word][step & 7].
+template <int G, int WPL>
+__device__ __forceinline__ void tt_store(uint32_t* tt, uint32_t* bits_g, const uint32_t (&w)[WPL], int s, int Tb, int t, int lane,
+                                         int gl, bool last_row) {
+    const int ph = (t - 1) & 7;
+#pragma unroll
+    for (int k = 0; k < WPL; k++) tt[(k * 8 + ph) * 32 + lane] = w[k];
+    if (ph == 7 || last_row) {
+        uint32_t* dst = bits_g + ((size_t)(s * Tb + ((t - 1) >> 3)) * (G * WPL) + gl * WPL) * 8;
+#pragma unroll
+        for (int k = 0; k < WPL; k++) {
+            const uint32_t* src = tt + (k * 8) * 32 + lane;
+            *reinterpret_cast<uint4*>(dst + k * 8) = make_uint4(src[0], src[32], src[64], src[96]);
+            *reinterpret_cast<uint4*>(dst + k * 8 + 4) = make_uint4(src[128], src[160], src[192], src[224]);
+        }
+    }
+}
+
+// word index of cell (x, y)'s nibble in the layout tt_store writes (lane ln owns column y, word k of its row)
+template <int G, int WPL>
+__device__ __forceinline__ size_t tt_index(int s, int Tb, int t, int ln, int k) {
+    return ((size_t)(s * Tb + ((t - 1) >> 3)) * (G * WPL) + ln * WPL + k) * 8 + ((t - 1) & 7);
+}
+
 // One wavefront step of one lane: C cells of row x.
 template <int C, bool TB, bool FIN, bool LAST>
 __device__ __forceinline__ void row_step(int (&E)[C], int (&B)[C], const int (&bq)[C], uint32_t (&w)[C / 8],
@@ -209,6 +236,8 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 40) ? 3 : 1) got
     const int wpb = blockDim.x >> 5;
     const uint32_t ggid = (blockIdx.x * wpb + warp) * GPW + gw;
     uint8_t* ref_sm = smem + (size_t)(warp * GPW + gw) * p.ref_sm_stride;
+    // TB: per-warp transposition buffer for the direction bits, after the reference rows
+    uint32_t* tt_sm = reinterpret_cast<uint32_t*>(smem + (size_t)wpb * GPW * p.ref_sm_stride) + (size_t)warp * (WPL * 256);
     int32_t* col_g = p.col_scratch + (size_t)ggid * 4 * p.col_stride;
     const clq_affine_t sc = p.sc;
     int staged_ref = -1;
@@ -350,20 +379,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 40) ? 3 : 1) got
                         if (jL == C - 1) { oF = e0; oE = e0; oM = 0; oB = 0; }
                         if (x == L1) { capM = 0; capE = 0; capF = 0; }
                     }
-                    if (TB) {
-                        // one row of G*WPL words per (stripe, step): [G x 4 words as 128-bit stores][G x (WPL-4) words]
-                        uint32_t* row = bits_g + (size_t)(s * T + (t - 1)) * (G * WPL);
-                        if constexpr (WPL >= 4) {
-                            *reinterpret_cast<uint4*>(row + gl * 4) = make_uint4(w[0], w[1], w[2], w[3]);
-#pragma unroll
-                            for (int k = 4; k < WPL; k++) row[G * 4 + gl * (WPL - 4) + (k - 4)] = w[k];
-                        } else if constexpr (WPL == 2) {
-                            *reinterpret_cast<uint2*>(row + gl * 2) = make_uint2(w[0], w[1]);
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < WPL; k++) row[gl * WPL + k] = w[k];
-                        }
-                    }
+                    if (TB) tt_store<G, WPL>(tt_sm, bits_g, w, s, (T + 7) >> 3, t, lane, gl, x == L1);
                     if (gl == G - 1 && s < NS - 1) {
                         col_g[x] = oF; col_g[p.col_stride + x] = oE; col_g[2 * p.col_stride + x] = oM; col_g[3 * p.col_stride + x] = oB;
                     }
@@ -456,9 +472,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
         const int s = c / W;
         c -= s * W;
         const int ln = c / C, j = c - ln * C;
-        const int k = j >> 3;
-        const int in_row = (WPL >= 4) ? (k < 4 ? ln * 4 + k : G * 4 + ln * (WPL - 4) + (k - 4)) : ln * WPL + k;
-        const size_t idx = (size_t)(s * T + (xx + ln - 1)) * (G * WPL) + in_row;
+        const size_t idx = tt_index<G, WPL>(s, (T + 7) >> 3, xx + ln, ln, j >> 3);
         return (__ldg(bits_g + idx) >> (28 - 4 * (j & 7))) & 15u;
     };
     auto argmax = [](uint32_t nb) -> int { return (nb & 2u) ? 1 : ((nb & 1u) ? 2 : 0); };

@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 40) ? 3 : 1) pack_kernel
     const int wpb = blockDim.x >> 5;
     const uint32_t ggid = (blockIdx.x * wpb + warp) * GPW + gw;
     uint8_t* ref_sm = smem + (size_t)(warp * GPW + gw) * p.ref_sm_stride;
+    // TB: per-warp transposition buffers (read A, read B) for the direction bits, after the reference rows
+    uint32_t* tt_sm = reinterpret_cast<uint32_t*>(smem + (size_t)wpb * GPW * p.ref_sm_stride) + (size_t)warp * (2 * WPL * 256);
     uint32_t* col_g = (uint32_t*)p.col_scratch + (size_t)ggid * 4 * p.col_stride;
     const clq_affine_t sc = p.sc;
     const int bias = pp.bias;
@@ -268,23 +270,8 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 40) ? 3 : 1) pack_kernel
                         }
                     }
                     if (TB) {
-                        const size_t roff = (size_t)(s * T + (t - 1)) * (G * WPL);
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            if (!run[h] || s >= NSh[h]) continue;
-                            uint32_t* row = (h ? bitsB : bitsA) + roff;
-                            const uint32_t(&w)[WPL] = h ? wB : wA;
-                            if constexpr (WPL >= 4) {
-                                *reinterpret_cast<uint4*>(row + gl * 4) = make_uint4(w[0], w[1], w[2], w[3]);
-#pragma unroll
-                                for (int k = 4; k < WPL; k++) row[G * 4 + gl * (WPL - 4) + (k - 4)] = w[k];
-                            } else if constexpr (WPL == 2) {
-                                *reinterpret_cast<uint2*>(row + gl * 2) = make_uint2(w[0], w[1]);
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < WPL; k++) row[gl * WPL + k] = w[k];
-                            }
-                        }
+                        if (run[0] && s < NSh[0]) tt_store<G, WPL>(tt_sm, bitsA, wA, s, (T + 7) >> 3, t, lane, gl, x == L1);
+                        if (run[1] && s < NSh[1]) tt_store<G, WPL>(tt_sm + WPL * 256, bitsB, wB, s, (T + 7) >> 3, t, lane, gl, x == L1);
                     }
                     if (gl == G - 1 && s < NS - 1) {
                         col_g[x] = oF; col_g[p.col_stride + x] = oE; col_g[2 * p.col_stride + x] = oM; col_g[3 * p.col_stride + x] = oB;
