@@ -585,7 +585,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     const uint32_t ref_sm_stride = (L1max + 15) / 16 * 16 + 16;
     // + per-warp transposition buffers of the direction bits (C/8 KiB per warp, twice for the PACK kernels); the
     // convex kernels keep the plain row layout
-    const size_t smem = (size_t)(kThreads / 32) * GPW * ref_sm_stride + (fast ? 320 : 0) + (convex ? 0 : (size_t)(kThreads / 32) * (C / 8) * 1024 * 2);
+    const size_t smem = (size_t)(kThreads / 32) * GPW * ref_sm_stride + (fast ? 320 : 0) + ((!convex && G <= 8) ? (size_t)(kThreads / 32) * (C / 8) * 1024 * 2 : 0);
     if (smem > 200 * 1024) return fail(c, CLQ_E_LIMIT, "references too long for this geometry's shared-memory staging");
     // s16x2 PACK kernels: two reads per lane group.  Needs the FAST preconditions plus a proof that every cell value of
     // this batch fits a 15-bit window: B >= 2*g(0) + (L1+L2)*e (the all-gap corner path), everything else is within a gap
@@ -645,9 +645,11 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         return fail(c, CLQ_E_CUDA, std::string("occupancy(tb): ") + cudaGetErrorString(ce));
     if ((ce = launch_dp(false, pq, &grid_sc, true)) != cudaSuccess)
         return fail(c, CLQ_E_CUDA, std::string("occupancy(score): ") + cudaGetErrorString(ce));
-    // affine kernels: blocks of 8 steps x G lanes x WPL words x 8 (time-transposed); convex: one row per step
-    const uint64_t bits_stride = convex ? ((uint64_t)ns_max * (L1max + G) * G * (C * bits_per_cell / 32) + 3) / 4 * 4
-                                        : (uint64_t)ns_max * ((L1max + G + 7) / 8) * G * (C / 8) * 8;
+    // direction bits per pair: G <= 8 geometries store blocks of 8 steps x G lanes x WPL words x 8 (time-transposed,
+    // BitsLayout in clq_kernels.cuh), the others and the convex kernels one row per step
+    const bool transposed = !convex && G <= 8;
+    const uint64_t bits_stride = transposed ? (uint64_t)ns_max * ((L1max + G + 7) / 8) * G * (C / 8) * 8
+                                            : ((uint64_t)ns_max * (L1max + G) * G * (C * bits_per_cell / 32) + 7) / 8 * 8;
     const uint32_t cig_stride = L1max + L2max + 8;
     const uint32_t col_stride = L1max + 8;
     // traceback scratch is per task of a sub-batch: direction bits + CIGAR scratch + walker record

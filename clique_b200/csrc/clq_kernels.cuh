@@ -139,6 +139,47 @@ __device__ __forceinline__ size_t tt_index(int s, int Tb, int t, int ln, int k) 
     return ((size_t)(s * Tb + ((t - 1) >> 3)) * (G * WPL) + ln * WPL + k) * 8 + ((t - 1) & 7);
 }
 
+// Row-per-step layout (long-read geometries, G >= 16): one row of G*WPL words per (stripe, step), 128-bit stores of whole
+// sectors [G x 4 words][G x (WPL-4) words].  The transposed layout only pays off when the walk is a visible share of the
+// step (short reads); for long reads the extra shared-memory traffic costs more than the walk gains.
+template <int G, int WPL>
+__device__ __forceinline__ void row_store(uint32_t* bits_g, const uint32_t (&w)[WPL], int s, int T, int t, int gl) {
+    uint32_t* row = bits_g + (size_t)(s * T + (t - 1)) * (G * WPL);
+    if constexpr (WPL >= 4) {
+        *reinterpret_cast<uint4*>(row + gl * 4) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+        for (int k = 4; k < WPL; k++) row[G * 4 + gl * (WPL - 4) + (k - 4)] = w[k];
+    } else if constexpr (WPL == 2) {
+        *reinterpret_cast<uint2*>(row + gl * 2) = make_uint2(w[0], w[1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < WPL; k++) row[gl * WPL + k] = w[k];
+    }
+}
+
+template <int G, int WPL>
+__device__ __forceinline__ size_t row_index(int s, int T, int t, int ln, int k) {
+    const int in_row = (WPL >= 4) ? (k < 4 ? ln * 4 + k : G * 4 + ln * (WPL - 4) + (k - 4)) : ln * WPL + k;
+    return (size_t)(s * T + (t - 1)) * (G * WPL) + in_row;
+}
+
+// which layout a geometry uses (host: clq_api.cu::bits_words_per_pair must agree)
+template <int G>
+struct BitsLayout { static constexpr bool transposed = (G <= 8); };
+
+template <int G, int WPL>
+__device__ __forceinline__ void bits_store(uint32_t* tt, uint32_t* bits_g, const uint32_t (&w)[WPL], int s, int T, int t, int lane, int gl,
+                                           bool last_row) {
+    if constexpr (BitsLayout<G>::transposed) tt_store<G, WPL>(tt, bits_g, w, s, (T + 7) >> 3, t, lane, gl, last_row);
+    else row_store<G, WPL>(bits_g, w, s, T, t, gl);
+}
+
+template <int G, int WPL>
+__device__ __forceinline__ size_t bits_index(int s, int T, int t, int ln, int k) {
+    if constexpr (BitsLayout<G>::transposed) return tt_index<G, WPL>(s, (T + 7) >> 3, t, ln, k);
+    else return row_index<G, WPL>(s, T, t, ln, k);
+}
+
 // One wavefront step of one lane: C cells of row x.
 template <int C, bool TB, bool FIN, bool LAST>
 __device__ __forceinline__ void row_step(int (&E)[C], int (&B)[C], const int (&bq)[C], uint32_t (&w)[C / 8],
@@ -379,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 40) ? 3 : 1) got
                         if (jL == C - 1) { oF = e0; oE = e0; oM = 0; oB = 0; }
                         if (x == L1) { capM = 0; capE = 0; capF = 0; }
                     }
-                    if (TB) tt_store<G, WPL>(tt_sm, bits_g, w, s, (T + 7) >> 3, t, lane, gl, x == L1);
+                    if (TB) bits_store<G, WPL>(tt_sm, bits_g, w, s, T, t, lane, gl, x == L1);
                     if (gl == G - 1 && s < NS - 1) {
                         col_g[x] = oF; col_g[p.col_stride + x] = oE; col_g[2 * p.col_stride + x] = oM; col_g[3 * p.col_stride + x] = oB;
                     }
@@ -472,7 +513,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
         const int s = c / W;
         c -= s * W;
         const int ln = c / C, j = c - ln * C;
-        const size_t idx = tt_index<G, WPL>(s, (T + 7) >> 3, xx + ln, ln, j >> 3);
+        const size_t idx = bits_index<G, WPL>(s, T, xx + ln, ln, j >> 3);
         return (__ldg(bits_g + idx) >> (28 - 4 * (j & 7))) & 15u;
     };
     auto argmax = [](uint32_t nb) -> int { return (nb & 2u) ? 1 : ((nb & 1u) ? 2 : 0); };

@@ -270,8 +270,8 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 40) ? 3 : 1) pack_kernel
                         }
                     }
                     if (TB) {
-                        if (run[0] && s < NSh[0]) tt_store<G, WPL>(tt_sm, bitsA, wA, s, (T + 7) >> 3, t, lane, gl, x == L1);
-                        if (run[1] && s < NSh[1]) tt_store<G, WPL>(tt_sm + WPL * 256, bitsB, wB, s, (T + 7) >> 3, t, lane, gl, x == L1);
+                        if (run[0] && s < NSh[0]) bits_store<G, WPL>(tt_sm, bitsA, wA, s, T, t, lane, gl, x == L1);
+                        if (run[1] && s < NSh[1]) bits_store<G, WPL>(tt_sm + WPL * 256, bitsB, wB, s, T, t, lane, gl, x == L1);
                     }
                     if (gl == G - 1 && s < NS - 1) {
                         col_g[x] = oF; col_g[p.col_stride + x] = oE; col_g[2 * p.col_stride + x] = oM; col_g[3 * p.col_stride + x] = oB;
