@@ -107,19 +107,19 @@ def int32_peak(live=True):
     return max(alu), how
 
 
-def make_workload(name, n_reads):
+def make_workload(name, n_reads, search=""):
     from clique_b200 import synth
     if name == "C2":
         return synth.config_c2(n_reads)
     if name == "C3":
         return synth.config_c3(n_reads, unique=min(n_reads, 65536))
     if name == "C4":
-        return synth.config_c4(n_reads, search="exhaustive", unique=min(n_reads, 262144))
+        return synth.config_c4(n_reads, search=search or "exhaustive", unique=min(n_reads, 262144))
     return synth.config_c5(n_reads)
 
 
 def default_reads(name):
-    return {"C2": 1_000_000, "C3": 100_000, "C4": 100_000, "C5": 20_000}[name]
+    return {"C2": 1_000_000, "C3": 100_000, "C4": 100_000, "C5": 60_000}[name]
 
 
 def cpu_reference_run(c, n_sample, threads):
@@ -141,7 +141,7 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    c = make_workload(args.workload, 20000 if args.workload == "C2" else 2000)
+    c = make_workload(args.workload, 20000 if args.workload == "C2" else 2000, args.search)
     n_have = len(c["read_off"]) - 1
     probe = min(n_have, 256 if args.workload == "C2" else 16)
     dt, out = cpu_reference_run(c, probe, threads)
@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=4)
     ap.add_argument("--cpu-sample-seconds", type=float, default=12.0)
     ap.add_argument("--ref-step-seconds", type=float, default=4.0)
+    ap.add_argument("--search", default="", choices=["", "exhaustive", "quick"], help="C4 only: candidate search (default exhaustive)")
     ap.add_argument("--convex", action="store_true", help="two-piece affine gaps o1=-20,e1=-2,o2=-40,e2=-1 (self-pinned semantics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-live-peak", action="store_true", help="use the committed INT32 peak instead of running tools/int_peak")
@@ -194,7 +195,7 @@ def main():
     n_gpus = world
     dev = local_rank if world > 1 else 0
     n = args.reads or default_reads(args.workload)
-    c = make_workload(args.workload, n)
+    c = make_workload(args.workload, n, args.search)
     # weak scaling: every rank aligns its own n reads per step (same generator, rank-specific rotation of the batch)
     if rank:
         k = (rank * 7919) % n
@@ -307,8 +308,9 @@ def main():
         peak, peak_how = int32_peak(not args.no_live_peak)
         dp = float(np.mean(dp_ms))
         ops = (30 if args.convex else OPS_PER_CELL_TB) if args.workload != "C4" else None   # two-piece: 20 / 30
-        if args.workload == "C4":   # 64 score-only fills + 1 traceback fill per read
-            alg_ops = cells * OPS_PER_CELL_SCORE + (cells / 65.0) * (OPS_PER_CELL_TB - OPS_PER_CELL_SCORE)
+        if args.workload == "C4":   # n score-only fills + 1 traceback fill per read (cells counts both)
+            tb_cells = float(sum(len(r) for r in c["refs"])) / len(c["refs"]) * float(total_bytes)
+            alg_ops = cells * OPS_PER_CELL_SCORE + min(tb_cells, cells) * (OPS_PER_CELL_TB - OPS_PER_CELL_SCORE)
         else:
             alg_ops = cells * ops
         achieved = alg_ops / (dp / 1e3) / 1e12
@@ -323,7 +325,8 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         lens = (c["read_off"][1:] - c["read_off"][:-1]).astype(np.int64)
         # algorithmic HBM bytes per launch: raw reads in + results/CIGAR out + 0.5 B/cell of direction bits written once
-        alg_bytes = float(total_bytes + n * 20 + 4 * int(res.cigar_len.sum()) + 0.5 * (cells if args.workload != "C4" else cells / 65.0))
+        tb_cells_hbm = cells if args.workload != "C4" else min(float(sum(len(r) for r in c["refs"])) / len(c["refs"]) * float(total_bytes), cells)
+        alg_bytes = float(total_bytes + n * 28 + 4 * int(res.cigar_len.sum()) + (1.0 if args.convex else 0.5) * tb_cells_hbm)
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
@@ -335,7 +338,7 @@ def main():
             "metric": "reads/s", "value": value, "unit": "reads/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "gcups": gcups,
-            "config": {"workload": WORKLOAD_DESC[args.workload] + (" [two-piece affine (convex) gaps, self-pinned]" if args.convex else ""), "reads_per_gpu_per_step": n, "cells_per_gpu_per_step": int(cells),
+            "config": {"workload": WORKLOAD_DESC[args.workload].replace("(exhaustive)", "(%s)" % c["search"]) + (" [two-piece affine (convex) gaps, self-pinned]" if args.convex else ""), "reads_per_gpu_per_step": n, "cells_per_gpu_per_step": int(cells),
                        "parallelism": "read-sharded x%d, no collectives" % n_gpus, "status_ok_reads": n_ok,
                        "l2": "inputs larger than L2 (%.0f MB of reads + %.0f MB of direction bits per step)" % (total_bytes / 1e6, 0.5 * cells / 1e6)},
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"], "power_w_max": clk.get("power_w_max"),

@@ -30,7 +30,9 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
     DevBuf read_bytes, read_off, fixed_ref, order, results, scores, cand_mask, single_ref, ref_of_read, votes;
-    DevBuf cigar_pool, bits, cig_scratch, col_scratch, tb_rec;
+    DevBuf cigar_pool, bits, cig_scratch, col_scratch, tb_rec, bits_off;
+    std::vector<uint32_t> h_len;     // read lengths in processing order (only when lengths vary: have_order)
+    std::vector<int32_t> h_ref;      // fixed_ref in processing order (same condition, when given)
     DevBuf counters;                 // [0..3] task counters (u32, padded to 8 B each), [4] cigar cursor, [5] cells
     unsigned long long* h_counters = nullptr;  // pinned mirror
     uint32_t n_reads = 0;
@@ -64,7 +66,7 @@ struct clq_ctx {
     bool fast_ok = false;            // the reference set has <= 6 distinct non-special bytes
     uint8_t cls[256] = {};           // byte -> class: 0 special, 1 other, 2..7 reference bytes
     DevBuf cls_lut;
-    int64_t max_scratch_bytes = 24ll << 30;  // per slot: direction bits of one sub-batch
+    int64_t max_scratch_bytes = 40ll << 30;  // per slot: direction bits of one sub-batch
 };
 
 namespace {
@@ -203,7 +205,7 @@ cudaError_t launch_cvx(int cfg, const KParams& p, const ConvexParams& cp, int sm
 
 template <int G, int C>
 cudaError_t launch_cvx_walk_one(const KParams& p, uint32_t cnt, cudaStream_t st) {
-    convex_walk_kernel<G, C><<<(cnt + 127) / 128, 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.cig_scratch, p.cig_stride, p.cigar_pool,
+    convex_walk_kernel<G, C><<<(cnt + 127) / 128, 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.bits_off, p.task_base, p.cig_scratch, p.cig_stride, p.cigar_pool,
                                                                 p.cigar_cap, p.cigar_cursor, p.results, p.ref_bytes, p.ref_off, p.read_bytes, p.read_off);
     return cudaGetLastError();
 }
@@ -219,7 +221,7 @@ cudaError_t launch_cvx_walk(int cfg, const KParams& p, uint32_t cnt, cudaStream_
 
 template <int G, int C>
 cudaError_t launch_walk_one(const KParams& p, uint32_t cnt, cudaStream_t st) {
-    walk_kernel<G, C><<<(cnt + 127) / 128, 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.cig_scratch, p.cig_stride, p.cigar_pool,
+    walk_kernel<G, C><<<(cnt + 127) / 128, 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.bits_off, p.task_base, p.cig_scratch, p.cig_stride, p.cigar_pool,
                                                          p.cigar_cap, p.cigar_cursor, p.results, p.ref_bytes, p.ref_off, p.read_bytes, p.read_off);
     return cudaGetLastError();
 }
@@ -349,7 +351,7 @@ void clq_ctx_destroy(clq_ctx* c) {
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
         for (DevBuf* b : {&s.read_bytes, &s.read_off, &s.fixed_ref, &s.order, &s.results, &s.scores, &s.cand_mask, &s.single_ref,
-                          &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.tb_rec, &s.counters})
+                          &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.tb_rec, &s.bits_off, &s.counters})
             release(*b);
         if (s.h_counters) cudaFreeHost(s.h_counters);
     }
@@ -511,6 +513,14 @@ int32_t clq_upload(clq_ctx* c, int32_t slot, uint32_t n_reads, const uint8_t* re
         CU(c, cudaMemcpyAsync(s->order.p, order.data(), (size_t)n_reads * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
         CU(c, cudaStreamSynchronize(s->stream));  // `order` is a reused host vector
         s->have_order = true;
+        s->h_len.resize(n_reads);
+        s->h_ref.clear();
+        if (fixed_ref) s->h_ref.resize(n_reads);
+        for (uint32_t i = 0; i < n_reads; i++) {
+            const uint32_t r = order[i];
+            s->h_len[i] = (uint32_t)(read_off[r + 1] - read_off[r]);
+            if (fixed_ref) s->h_ref[i] = fixed_ref[r];
+        }
     }
     uint64_t h2d = 0;
     if (total) {
@@ -652,20 +662,70 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
                                             : ((uint64_t)ns_max * (L1max + G) * G * (C * bits_per_cell / 32) + 7) / 8 * 8;
     const uint32_t cig_stride = L1max + L2max + 8;
     const uint32_t col_stride = L1max + 8;
-    // traceback scratch is per task of a sub-batch: direction bits + CIGAR scratch + walker record
+    // traceback scratch is per task of a sub-batch: direction bits + CIGAR scratch + walker record.  When the read lengths
+    // vary (processing order = longest first) every position gets a slot of its own size and sub-batches are cut by bytes,
+    // so a batch of mixed 300 bp - 5 kb reads is not split into tiny sub-batches sized for its longest pair.
+    auto bits_words = [&](uint64_t l1, uint64_t l2) -> uint64_t {
+        const uint64_t ns = std::max<uint64_t>(1, (l2 + W - 1) / W), T = l1 + G - 1;
+        const uint64_t wds = transposed ? ns * ((T + 7) / 8) * G * (C / 8) * 8 : ns * T * G * (C * bits_per_cell / 32);
+        return (wds + 7) / 8 * 8;
+    };
+    int32_t rc;
     const uint64_t per_task = bits_stride * 4 + (uint64_t)cig_stride * 4 + sizeof(TbRec);
     uint64_t sub = std::max<uint64_t>(2, std::min<uint64_t>((uint64_t)n + 1, (uint64_t)c->max_scratch_bytes / per_task)) & ~1ull;  // even: PACK tasks are read pairs
+    std::vector<uint64_t> cuts;          // sub-batch boundaries in processing positions
+    const bool var_slots = !score_only && n && s->have_order && s->h_len.size() == n;
+    uint64_t max_sub_words = sub * bits_stride, max_sub_tasks = sub;
+    if (var_slots) {
+        static thread_local std::vector<uint64_t> off;
+        off.resize((size_t)n + 1);
+        off[0] = 0;
+        const bool fixed_known = search == CLQ_SEARCH_FIXED && s->h_ref.size() == n;
+        for (uint32_t i = 0; i < n; i++) {
+            uint64_t l1 = L1max;
+            if (fixed_known && s->h_ref[i] >= 0 && (uint32_t)s->h_ref[i] < c->n_refs)
+                l1 = c->h_ref_off[s->h_ref[i] + 1] - c->h_ref_off[s->h_ref[i]];
+            const uint64_t l2 = s->h_len[i] >= c->lim.max_read_len ? 0 : s->h_len[i];
+            off[i + 1] = off[i] + bits_words(l1, l2);
+        }
+        const uint64_t budget_words = (uint64_t)c->max_scratch_bytes / 4;
+        cuts.push_back(0);
+        max_sub_words = 0; max_sub_tasks = 0;
+        uint64_t start = 0;
+        for (uint64_t i = 0; i < n;) {
+            // grow [start, i) while it fits; always an even number of positions except for the last sub-batch
+            uint64_t j = i + 2 <= n ? i + 2 : n;
+            if (off[j] - off[start] + (j - start) * (cig_stride + 4) > budget_words && i > start) {
+                cuts.push_back(i);
+                max_sub_words = std::max(max_sub_words, off[i] - off[start]);
+                max_sub_tasks = std::max(max_sub_tasks, i - start);
+                start = i;
+                continue;
+            }
+            i = j;
+        }
+        cuts.push_back(n);
+        max_sub_words = std::max(max_sub_words, off[n] - off[start]);
+        max_sub_tasks = std::max<uint64_t>(max_sub_tasks, n - start);
+        max_sub_tasks = (max_sub_tasks + 1) & ~1ull;
+        if ((rc = ensure(c, s->bits_off, ((size_t)n + 1) * sizeof(uint64_t))) != CLQ_OK) return rc;
+        CU(c, cudaMemcpyAsync(s->bits_off.p, off.data(), ((size_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+        CU(c, cudaStreamSynchronize(s->stream));  // `off` is a reused host vector
+    } else {
+        for (uint64_t b = 0; b < n; b += sub) cuts.push_back(b);
+        cuts.push_back(n);
+    }
     const uint64_t groups = (uint64_t)std::max(grid_tb, grid_sc) * (kThreads / 32) * GPW;
-    int32_t rc;
     if (!score_only && n) {
-        if ((rc = ensure(c, s->bits, sub * bits_stride * 4)) != CLQ_OK) return rc;
-        if ((rc = ensure(c, s->cig_scratch, sub * cig_stride * 4)) != CLQ_OK) return rc;
-        if ((rc = ensure(c, s->tb_rec, sub * sizeof(TbRec))) != CLQ_OK) return rc;
+        if ((rc = ensure(c, s->bits, max_sub_words * 4 + 64)) != CLQ_OK) return rc;
+        if ((rc = ensure(c, s->cig_scratch, max_sub_tasks * cig_stride * 4)) != CLQ_OK) return rc;
+        if ((rc = ensure(c, s->tb_rec, max_sub_tasks * sizeof(TbRec))) != CLQ_OK) return rc;
         if ((rc = ensure(c, s->cigar_pool, (size_t)c->lim.cigar_pool_ops * 4 + 16)) != CLQ_OK) return rc;
     }
     if ((rc = ensure(c, s->col_scratch, groups * col_stride * 16)) != CLQ_OK) return rc;
     p.bits = (uint32_t*)s->bits.p;
     p.bits_stride = bits_stride;
+    p.bits_off = var_slots ? (const uint64_t*)s->bits_off.p : nullptr;
     p.cig_scratch = (uint32_t*)s->cig_scratch.p;
     p.cig_stride = cig_stride;
     p.col_scratch = (int32_t*)s->col_scratch.p;
@@ -745,8 +805,10 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
             s->stats.dp_launches++;
         } else {
             // fill (direction bits into the sub-batch's slots) then walk (one thread per pair), sub-batch by sub-batch
-            for (uint64_t base = 0; base < n; base += sub) {
-                const uint32_t cnt = (uint32_t)std::min<uint64_t>(sub, n - base);
+            for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
+                const uint64_t base = cuts[ci];
+                const uint32_t cnt = (uint32_t)(cuts[ci + 1] - base);
+                if (!cnt) continue;
                 q.n_tasks = pack_pairs ? (cnt + 1) / 2 : cnt;
                 q.task_base = (uint32_t)base;
                 q.task_end = (uint32_t)(base + cnt);

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kThreads) convex_kernel(const KParams p, const
         bool valid = task < p.n_tasks;
         uint32_t ridx = 0;
         int ref = -1;
-        uint32_t* bits_g = TB ? p.bits + (size_t)task * p.bits_stride : nullptr;
+        uint32_t* bits_g = TB ? p.bits + bits_slot(p.bits_off, p.bits_stride, p.task_base, task) : nullptr;
         if (valid) {
             if (p.all_pairs) {
                 const uint32_t q = task / p.n_refs;
@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(kThreads) convex_kernel(const KParams p, const
 // traceback over the 8-bit direction records of convex_kernel; states: 0 M, 1 E1, 2 E2, 3 F1, 4 F2
 template <int G, int C>
 __global__ void __launch_bounds__(128) convex_walk_kernel(const TbRec* recs, uint32_t n_tasks, const uint32_t* bits, uint64_t bits_stride,
+                                                          const uint64_t* bits_off, uint32_t task_base,
                                                           uint32_t* cig_scratch, uint32_t cig_stride, uint32_t* cigar_pool, uint64_t cigar_cap,
                                                           unsigned long long* cigar_cursor, clq_result_t* results, const uint8_t* ref_bytes,
         const uint64_t* ref_off, const uint8_t* read_bytes, const uint64_t* read_off) {
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(128) convex_walk_kernel(const TbRec* recs, uin
     const int L1 = rec.L1, L2 = rec.L2;
     int z = rec.zK;
     const int T = L1 + G - 1;
-    const uint32_t* bits_g = bits + (size_t)q * bits_stride;
+    const uint32_t* bits_g = bits + bits_slot(bits_off, bits_stride, task_base, q);
     uint32_t* cig_g = cig_scratch + (size_t)q * cig_stride;
     uint32_t status = CLQ_OK;
     int x = L1, y = L2;

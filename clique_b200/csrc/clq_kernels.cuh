@@ -64,7 +64,8 @@ struct KParams {
     uint32_t max_read_len;
     uint32_t ref_sm_stride;      // bytes of shared memory per group
     uint32_t* bits;              // traceback bits scratch
-    uint64_t bits_stride;        // words per group
+    uint64_t bits_stride;        // words per task slot (uniform slots)
+    const uint64_t* bits_off;    // or: word offset of every processing position's slot (variable-size slots), nullptr = uniform
     uint32_t* cig_scratch;
     uint32_t cig_stride;         // ops per group
     int32_t* col_scratch;        // stripe boundary column: 4 arrays of col_stride per group
@@ -90,6 +91,11 @@ struct TbRec {
 };
 
 __device__ __forceinline__ bool is_special(int c) { return c == 'N' || c < 58; }
+
+// direction-bit slot of the read at slot index `slot` of the current sub-batch (processing position task_base + slot)
+__device__ __forceinline__ size_t bits_slot(const uint64_t* bits_off, uint64_t bits_stride, uint32_t task_base, uint32_t slot) {
+    return bits_off ? (size_t)(bits_off[task_base + slot] - bits_off[task_base]) : (size_t)slot * bits_stride;
+}
 
 // prmt.b32 in its default mode: selector nibble bits [2:0] pick a byte of {hi,lo}, bit 3 replicates that byte's sign.
 // (__byte_perm masks bit 3 away, so the raw instruction is needed for the sign-extending byte lookup.)
@@ -256,7 +262,7 @@ __device__ __forceinline__ void row_step_fast(int (&Eh)[C], int (&B)[C], const i
 }
 
 template <int G, int C, bool TB, bool FIN, bool FAST>
-__global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 40) ? 3 : 1) gotoh_kernel(const KParams p) {
+__global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) gotoh_kernel(const KParams p) {
     static_assert(C % 8 == 0, "C must be a multiple of 8 (4 direction bits per cell, whole words per lane)");
     static_assert(!(FAST && FIN), "the FAST variant needs uniform gap constants");
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 40) ? 3 : 1) got
         bool valid = task < p.n_tasks;
         uint32_t ridx = 0;
         int ref = -1;
-        uint32_t* bits_g = TB ? p.bits + (size_t)task * p.bits_stride : nullptr;
+        uint32_t* bits_g = TB ? p.bits + bits_slot(p.bits_off, p.bits_stride, p.task_base, task) : nullptr;
         if (valid) {
             if (p.all_pairs) {
                 const uint32_t q = task / p.n_refs;
@@ -475,6 +481,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 40) ? 3 : 1) got
 // loads (one 32-byte sector per step), so it is spread over as many threads as there are pairs in the sub-batch.
 template <int G, int C>
 __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n_tasks, const uint32_t* bits, uint64_t bits_stride,
+                                                   const uint64_t* bits_off, uint32_t task_base,
                                                    uint32_t* cig_scratch, uint32_t cig_stride, uint32_t* cigar_pool, uint64_t cigar_cap,
                                                    unsigned long long* cigar_cursor, clq_result_t* results, const uint8_t* ref_bytes,
         const uint64_t* ref_off, const uint8_t* read_bytes, const uint64_t* read_off) {
@@ -487,7 +494,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
     const int L1 = rec.L1, L2 = rec.L2, K = rec.zK >> 2;
     int z = rec.zK & 3;
     const int T = L1 + G - 1;
-    const uint32_t* bits_g = bits + (size_t)q * bits_stride;
+    const uint32_t* bits_g = bits + bits_slot(bits_off, bits_stride, task_base, q);
     uint32_t* cig_g = cig_scratch + (size_t)q * cig_stride;
     uint32_t status = CLQ_OK;
     int x = L1, y = L2;

@@ -75,7 +75,7 @@ __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C
 // reference ref_of_read[.] (the host only takes this kernel when the batch has a single reference).  All-pairs mode: pair
 // t = (read pair t / n_refs, reference t % n_refs).
 template <int G, int C, bool TB>
-__global__ void __launch_bounds__(kThreads, (TB && C >= 40) ? 3 : 1) pack_kernel(const KParams p, const PackParams pp) {
+__global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel(const KParams p, const PackParams pp) {
     static_assert(C % 8 == 0, "C must be a multiple of 8");
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + 320;
@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 40) ? 3 : 1) pack_kernel
         const int T = anyrun ? L1 + G - 1 : 0;
         const int Tmax = __reduce_max_sync(FULL, T);
         uint32_t cap[3] = {0, 0, 0};
-        uint32_t* bitsA = TB ? p.bits + (size_t)(2 * task) * p.bits_stride : nullptr;
-        uint32_t* bitsB = TB ? p.bits + (size_t)(2 * task + 1) * p.bits_stride : nullptr;
+        uint32_t* bitsA = TB ? p.bits + bits_slot(p.bits_off, p.bits_stride, p.task_base, 2 * task) : nullptr;
+        uint32_t* bitsB = (TB && valid[1]) ? p.bits + bits_slot(p.bits_off, p.bits_stride, p.task_base, 2 * task + 1) : nullptr;
 
         for (int s = 0; s < NSmax; s++) {
             const bool act_s = anyrun && s < NS;
