@@ -203,6 +203,15 @@ class BatchResult:
     stats: dict = field(default_factory=dict)
     matches: Optional[np.ndarray] = None      # get_reference_alignment_rate's counters, fused into the traceback walk
     mismatches: Optional[np.ndarray] = None
+    tags: Optional[np.ndarray] = None         # [n_reads, tag_stride] read bytes aligned to the tag columns (CLQ_EXTRACT_TAGS)
+
+    def tag_strings(self, i, reference):
+        """extract_tagged_sequences' digit keys for read i (extractor.rs:271-332): {symbol byte: read bytes aligned to the
+        reference columns holding that symbol}, rebuilt from the GPU's per-column bytes."""
+        ref = np.frombuffer(_b(reference), dtype=np.uint8)
+        cols = ref[(ref >= 48) & (ref <= 57)]
+        row = self.tags[i, :len(cols)]
+        return {int(d): bytes(row[cols == d]) for d in np.unique(cols)}
 
     def alignment_rate(self, i):
         """get_reference_alignment_rate (consensus/consensus_builders.rs:288-307): the `rm` tag of read i (NaN when 0/0)."""
@@ -343,13 +352,16 @@ class Aligner:
         self._check(self.lib.clq_upload(self.ctx, slot, n, rb.ctypes.data, ro.ctypes.data, fr.ctypes.data if fr is not None else None))
         self._pending[slot] = [n, None, (rb, ro, fr)]
 
-    def launch(self, slot, scoring, search="fixed", band="readlen", score_only=False, threshold=0.90):
+    def launch(self, slot, scoring, search="fixed", band="readlen", score_only=False, threshold=0.90, extract_tags=False):
         sci = scoring if isinstance(scoring, (L.AffineInt, L.ConvexInt)) else scoring.to_int()
         flags = self._flags(search, band, score_only)
         if isinstance(sci, L.ConvexInt):
             flags |= L.CONVEX
+        if extract_tags:
+            flags |= L.EXTRACT_TAGS
         self._check(self.lib.clq_launch(self.ctx, slot, C.byref(sci), flags, threshold))
         self._pending[slot][1] = getattr(sci, "scale", 1)
+        self._pending[slot].append(bool(extract_tags))
 
     def sync(self, slot):
         self._check(self.lib.clq_sync(self.ctx, slot))
@@ -360,14 +372,16 @@ class Aligner:
         return {k: getattr(st, k) for k, _ in L.Stats._fields_}
 
     def submit(self, slot, read_bytes, read_off, scoring, search="fixed", band="readlen", fixed_ref=None, score_only=False,
-               threshold=0.90):
+               threshold=0.90, extract_tags=False):
         """clq_submit: asynchronous H2D + kernels + D2H on the slot's stream."""
         self.upload(slot, read_bytes, read_off, fixed_ref)
-        self.launch(slot, scoring, search, band, score_only, threshold)
+        self.launch(slot, scoring, search, band, score_only, threshold, extract_tags)
         self._check(self.lib.clq_download(self.ctx, slot))
 
     def wait(self, slot, copy=True, with_stats=False) -> BatchResult:
-        n, scale, _keep = self._pending[slot]
+        n, scale, _keep = self._pending[slot][:3]
+        want_tags = len(self._pending[slot]) > 3 and self._pending[slot][-1]
+        del self._pending[slot][3:]
         used = C.c_uint64()
         res, pool = self._res[slot], self._pool[slot]
         self._check(self.lib.clq_wait(self.ctx, slot, res.ctypes.data, pool.ctypes.data, len(pool), C.byref(used)))
@@ -375,13 +389,20 @@ class Aligner:
         cp = (lambda a: a.copy()) if copy else (lambda a: a)
         out = BatchResult(scale, cp(r["score_scaled"]), cp(r["ref_index"]), cp(r["cigar_off"]), cp(r["cigar_len"]),
                           cp(r["status"]), cp(pool[:used.value]), matches=cp(r["matches"]), mismatches=cp(r["mismatches"]))
+        if want_tags:
+            stride = C.c_uint32()
+            self._check(self.lib.clq_tags_download(self.ctx, slot, None, 0, C.byref(stride)))
+            buf = np.zeros((n, stride.value), np.uint8)
+            if buf.size:
+                self._check(self.lib.clq_tags_download(self.ctx, slot, buf.ctypes.data, buf.size, C.byref(stride)))
+            out.tags = buf
         if with_stats:
             out.stats = self.stats(slot)
         return out
 
     def align_batch(self, read_bytes, read_off, scoring, search="fixed", band="readlen", fixed_ref=None, score_only=False,
-                    threshold=0.90, with_stats=False) -> BatchResult:
-        self.submit(0, read_bytes, read_off, scoring, search, band, fixed_ref, score_only, threshold)
+                    threshold=0.90, with_stats=False, extract_tags=False) -> BatchResult:
+        self.submit(0, read_bytes, read_off, scoring, search, band, fixed_ref, score_only, threshold, extract_tags)
         return self.wait(0, with_stats=with_stats)
 
     # ---- the reference's call surface ----

@@ -30,7 +30,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
     DevBuf read_bytes, read_off, fixed_ref, order, results, scores, cand_mask, single_ref, ref_of_read, votes;
-    DevBuf cigar_pool, bits, cig_scratch, col_scratch, tb_rec, bits_off;
+    DevBuf cigar_pool, bits, cig_scratch, col_scratch, tb_rec, bits_off, tags;
     std::vector<uint32_t> h_len;     // read lengths in processing order (only when lengths vary: have_order)
     std::vector<int32_t> h_ref;      // fixed_ref in processing order (same condition, when given)
     DevBuf counters;                 // [0..3] task counters (u32, padded to 8 B each), [4] cigar cursor, [5] cells
@@ -53,7 +53,8 @@ struct clq_ctx {
     int sm_count = 0;
     clq_limits_t lim = {};
     std::string err;
-    DevBuf ref_bytes, ref_off, kmer_keys, kmer_owner;
+    DevBuf ref_bytes, ref_off, kmer_keys, kmer_owner, tag_slot;
+    uint32_t tag_stride = 0;         // most tag columns ('0'..'9') of any reference, rounded up to 4
     std::vector<uint8_t> h_ref_bytes;
     std::vector<uint64_t> h_ref_off;
     uint32_t n_refs = 0, max_ref_len = 0;
@@ -222,7 +223,8 @@ cudaError_t launch_cvx_walk(int cfg, const KParams& p, uint32_t cnt, cudaStream_
 template <int G, int C>
 cudaError_t launch_walk_one(const KParams& p, uint32_t cnt, cudaStream_t st) {
     walk_kernel<G, C><<<(cnt + 127) / 128, 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.bits_off, p.task_base, p.cig_scratch, p.cig_stride, p.cigar_pool,
-                                                         p.cigar_cap, p.cigar_cursor, p.results, p.ref_bytes, p.ref_off, p.read_bytes, p.read_off);
+                                                         p.cigar_cap, p.cigar_cursor, p.results, p.ref_bytes, p.ref_off, p.read_bytes, p.read_off,
+                                                         p.tag_slot, p.tags, p.tag_stride);
     return cudaGetLastError();
 }
 
@@ -351,11 +353,11 @@ void clq_ctx_destroy(clq_ctx* c) {
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
         for (DevBuf* b : {&s.read_bytes, &s.read_off, &s.fixed_ref, &s.order, &s.results, &s.scores, &s.cand_mask, &s.single_ref,
-                          &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.tb_rec, &s.bits_off, &s.counters})
+                          &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.tb_rec, &s.bits_off, &s.tags, &s.counters})
             release(*b);
         if (s.h_counters) cudaFreeHost(s.h_counters);
     }
-    release(c->ref_bytes); release(c->ref_off); release(c->kmer_keys); release(c->kmer_owner); release(c->cls_lut);
+    release(c->ref_bytes); release(c->ref_off); release(c->kmer_keys); release(c->kmer_owner); release(c->cls_lut); release(c->tag_slot);
     delete c;
 }
 
@@ -408,6 +410,18 @@ int32_t clq_refs_set(clq_ctx* c, uint32_t n_refs, const uint8_t* bytes, const ui
     }
     if ((rc = ensure(c, c->cls_lut, 256)) != CLQ_OK) return rc;
     CU(c, cudaMemcpy(c->cls_lut.p, c->cls, 256, cudaMemcpyHostToDevice));
+    // tag columns: reference bytes '0'..'9' (SPECIAL_CHARACTERS, extractor.rs:19-34); slot = rank within its reference
+    std::vector<uint16_t> slot(total + 1, 0xffffu);
+    uint32_t most = 0;
+    for (uint32_t r = 0; r < n_refs; r++) {
+        uint32_t k = 0;
+        for (uint64_t i = off[r]; i < off[r + 1]; i++)
+            if (bytes[i] >= '0' && bytes[i] <= '9' && k < 0xffffu) slot[i] = (uint16_t)k++;
+        most = std::max(most, k);
+    }
+    c->tag_stride = (most + 3) / 4 * 4;
+    if ((rc = ensure(c, c->tag_slot, (total + 1) * sizeof(uint16_t))) != CLQ_OK) return rc;
+    CU(c, cudaMemcpy(c->tag_slot.p, slot.data(), (total + 1) * sizeof(uint16_t), cudaMemcpyHostToDevice));
     return CLQ_OK;
 }
 
@@ -580,6 +594,8 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     }
     CU(c, cudaSetDevice(c->device));
     const bool score_only = (flags & CLQ_SCORE_ONLY) != 0;
+    const bool want_tags = (flags & CLQ_EXTRACT_TAGS) != 0 && c->tag_stride > 0;
+    if ((flags & CLQ_EXTRACT_TAGS) && (convex || score_only)) return fail(c, CLQ_E_UNSUPPORTED, "CLQ_EXTRACT_TAGS needs the affine traceback");
     const uint32_t n = s->n_reads;
     int cfg = pick_cfg(c, s->max_len);
     if (convex) {
@@ -733,6 +749,12 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     p.cigar_pool = (uint32_t*)s->cigar_pool.p;
     p.cigar_cap = c->lim.cigar_pool_ops;
     p.tb_rec = (TbRec*)s->tb_rec.p;
+    if (want_tags && n) {
+        if ((rc = ensure(c, s->tags, (size_t)n * c->tag_stride)) != CLQ_OK) return rc;
+        p.tag_slot = (const uint16_t*)c->tag_slot.p;
+        p.tags = (uint8_t*)s->tags.p;
+        p.tag_stride = c->tag_stride;
+    }
 
     s->flags = flags;
     s->stats.variant = (fast ? 1u : 0u) | ((pack && (pack_pairs || search != CLQ_SEARCH_FIXED)) ? 2u : 0u) | (convex ? 4u : 0u) | (fin ? 8u : 0u) | ((uint32_t)cfg << 8);
@@ -902,6 +924,23 @@ int32_t clq_wait(clq_ctx* c, int32_t slot, clq_result_t* results, uint32_t* ciga
     CU(c, cudaStreamSynchronize(s->stream));
     s->stats.d2h_bytes = d2h;
     s->state = 1;  // inputs stay resident: the slot can be launched again
+    return CLQ_OK;
+}
+
+int32_t clq_tags_download(clq_ctx* c, int32_t slot, uint8_t* tags, uint64_t cap, uint32_t* tag_stride) {
+    Slot* s = get_slot(c, slot);
+    if (!s || !tag_stride) return CLQ_E_INVALID;
+    if (!s->launched) return fail(c, CLQ_E_STATE, "clq_tags_download before clq_launch");
+    *tag_stride = 0;
+    if (!(s->flags & CLQ_EXTRACT_TAGS)) return fail(c, CLQ_E_STATE, "the last launch on this slot did not ask for CLQ_EXTRACT_TAGS");
+    *tag_stride = c->tag_stride;
+    const uint64_t bytes = (uint64_t)s->n_reads * c->tag_stride;
+    if (!bytes || !tags) return CLQ_OK;  // tags == NULL: only report the stride
+    if (cap < bytes) return fail(c, CLQ_E_LIMIT, "caller's tag buffer is smaller than n_reads * tag_stride");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpyAsync(tags, s->tags.p, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(c, cudaStreamSynchronize(s->stream));
+    s->stats.d2h_bytes += bytes;
     return CLQ_OK;
 }
 

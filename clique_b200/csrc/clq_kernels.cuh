@@ -81,6 +81,9 @@ struct KParams {
     uint32_t task_base;          // first read (processing position) of this sub-batch
     uint32_t task_end;           // one past its last read (PACK kernel: two reads per task)
     struct TbRec* tb_rec;        // TB: one record per task of the sub-batch for walk_kernel
+    const uint16_t* tag_slot;    // CLQ_EXTRACT_TAGS: per reference byte, rank among the reference's tag columns (0xffff = none)
+    uint8_t* tags;               // [n_reads * tag_stride] read bytes aligned to the tag columns ('-' = deleted)
+    uint32_t tag_stride;
 };
 
 // what the fill kernel leaves for the walker: one record per task of the sub-batch
@@ -484,7 +487,8 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
                                                    const uint64_t* bits_off, uint32_t task_base,
                                                    uint32_t* cig_scratch, uint32_t cig_stride, uint32_t* cigar_pool, uint64_t cigar_cap,
                                                    unsigned long long* cigar_cursor, clq_result_t* results, const uint8_t* ref_bytes,
-        const uint64_t* ref_off, const uint8_t* read_bytes, const uint64_t* read_off) {
+                                                   const uint64_t* ref_off, const uint8_t* read_bytes, const uint64_t* read_off,
+                                                   const uint16_t* tag_slot, uint8_t* tags, uint32_t tag_stride) {
     constexpr int W = G * C;
     constexpr int WPL = C / 8;
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -499,12 +503,24 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
     uint32_t status = CLQ_OK;
     int x = L1, y = L2;
     // get_reference_alignment_rate (consensus/consensus_builders.rs:288-307) fused into the walk: only M columns can count
-    const uint8_t* refp = ref_bytes + ref_off[results[rec.ridx].ref_index];
+    const uint64_t ref0 = ref_off[results[rec.ridx].ref_index];
+    const uint8_t* refp = ref_bytes + ref0;
     const uint8_t* readp = read_bytes + read_off[rec.ridx];
     uint32_t n_match = 0, n_mismatch = 0;
+    // extract_tagged_sequences' digit tags (extractor.rs:271-332, the (false,_,false) arm) fused into the walk: the read byte
+    // (or '-') aligned to every reference column that holds a tag symbol '0'..'9', at that column's rank
+    const uint16_t* slotp = tag_slot ? tag_slot + ref0 : nullptr;
+    uint8_t* tagp = tags ? tags + (size_t)rec.ridx * tag_stride : nullptr;
+    auto tag = [&](int xx, uint8_t b) {
+        if (slotp) {
+            const uint16_t sl = __ldg(slotp + xx - 1);
+            if (sl != 0xffffu) tagp[sl] = b;
+        }
+    };
     auto count = [&](int xx, int yy) {
         const uint8_t rb = __ldg(refp + xx - 1), qb = __ldg(readp + yy - 1);
         if (rb > 64 && rb != 'N' && qb > 64) { if (rb == qb) n_match++; else n_mismatch++; }
+        if (rb < 58) tag(xx, qb);
     };
     int cpos = (int)cig_stride;
     uint32_t cur_op = 3, cur_len = 0;
@@ -529,7 +545,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
         if (y == L2 && x <= K) { status = CLQ_TRACEBACK_DIVERGED; break; }  // stale Up(0) cell: the reference spins here
         const uint32_t old = nib;
         if (z == 0) { emit(CLQ_OP_M, 1); count(x, y); x--; y--; }
-        else if (z == 1) { emit(CLQ_OP_D, 1); x--; }
+        else if (z == 1) { emit(CLQ_OP_D, 1); tag(x, '-'); x--; }
         else { emit(CLQ_OP_I, 1); y--; }
         if (x == 0 || y == 0) break;
         nib = nibble(x, y);
@@ -539,7 +555,10 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
         else z = (old & 4u) ? 2 : (a == 1 ? 1 : 0);
     }
     if (status == CLQ_OK) {
-        if (x > 0) emit(CLQ_OP_D, (uint32_t)x);
+        if (x > 0) {
+            emit(CLQ_OP_D, (uint32_t)x);
+            if (slotp) for (int xx = x; xx >= 1; xx--) tag(xx, '-');
+        }
         if (y > 0) emit(CLQ_OP_I, (uint32_t)y);
     }
     if (cur_len) cig_g[--cpos] = (cur_len << 4) | cur_op;

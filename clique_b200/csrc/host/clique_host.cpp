@@ -1,0 +1,694 @@
+// clique_host.cpp -- implementation of include/clique_host.hpp over the libclq C ABI.  No alignment arithmetic here.
+#include "../../../include/clique_host.hpp"
+
+#include <algorithm>
+#include <charconv>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <thread>
+
+namespace clique {
+
+namespace {
+[[noreturn]] void fail(int32_t code, const std::string& msg) { throw ClqError(code, "libclq error " + std::to_string(code) + ": " + msg); }
+
+template <class T>
+T* pinned(size_t n) {
+    void* p = nullptr;
+    const int32_t rc = clq_host_alloc(std::max<size_t>(n, 1) * sizeof(T), &p);
+    if (rc != CLQ_OK) fail(rc, "clq_host_alloc(" + std::to_string(n * sizeof(T)) + " bytes): no CUDA device? libclq has no CPU fallback");
+    return static_cast<T*>(p);
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ scoring
+double AffineScoring::match_mismatch(uint8_t a, uint8_t b) const {
+    // alignment/scoring_functions.rs:100-102: N or any byte below ':' on either side is "special"
+    if (a == 'N' || b == 'N' || a < 58 || b < 58) return special_character_score;
+    return a == b ? match_score : mismatch_score;
+}
+
+clq_affine_t AffineScoring::to_int() const {
+    clq_affine_t out;
+    const int32_t rc = clq_affine_from_f64(match_score, mismatch_score, special_character_score, gap_open, gap_extend, final_gap_multiplier, &out);
+    if (rc != CLQ_OK) fail(rc, "scoring has no exact scaled-integer form (or gap_open >= 0)");
+    return out;
+}
+
+double ConvexScoring::gap(size_t length) const {
+    return gap_open + (length > 0 ? std::log10((double)length) : -std::numeric_limits<double>::infinity());
+}
+
+// ------------------------------------------------------------------------------------------------ cigar
+char AlignmentTag::op_char() const {
+    switch (kind) {
+        case MatchMismatch: return 'M';
+        case Ins: return 'I';
+        case Del: return 'D';
+        case SoftClip: return 'S';
+        case HardClip: return 'H';
+        case InversionOpen: return '<';
+        default: return '>';
+    }
+}
+
+std::string cigar_to_string(const std::vector<AlignmentTag>& cigar) {
+    std::string s;
+    for (const auto& t : cigar) {
+        if (t.kind != AlignmentTag::InversionOpen && t.kind != AlignmentTag::InversionClose) s += std::to_string(t.len);
+        s += t.op_char();
+    }
+    return s;
+}
+
+std::vector<AlignmentTag> simplify_cigar_string(const std::vector<AlignmentTag>& cigar_tokens) {
+    std::vector<AlignmentTag> out;
+    std::optional<AlignmentTag> last;
+    for (const auto& tok : cigar_tokens) {
+        if (!last) { last = tok; continue; }
+        if (last->kind == tok.kind && tok.kind == AlignmentTag::InversionOpen) throw std::logic_error("Cannot have two inversion open tags in a row");
+        if (last->kind == tok.kind && tok.kind == AlignmentTag::InversionClose) throw std::logic_error("Cannot have two inversion closed tags in a row");
+        const bool mergeable = tok.kind == AlignmentTag::MatchMismatch || tok.kind == AlignmentTag::Del || tok.kind == AlignmentTag::Ins;
+        if (mergeable && last->kind == tok.kind) last->len += tok.len;
+        else { out.push_back(*last); last = tok; }
+    }
+    if (last) out.push_back(*last);
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------ AlignmentResult
+AlignmentResult AlignmentResult::from_cigar(const std::string& reference_name, const std::string& read_name, const uint8_t* reference,
+                                            size_t l1, const uint8_t* read, size_t l2, std::optional<Bytes> quals, const uint32_t* ops,
+                                            size_t n_ops, double score) {
+    AlignmentResult r;
+    r.reference_name = reference_name;
+    r.read_name = read_name;
+    r.read_quals = std::move(quals);
+    r.score = score;
+    r.reference_aligned.reserve(l1 + l2);
+    r.read_aligned.reserve(l1 + l2);
+    size_t x = 0, y = 0;
+    for (size_t k = 0; k < n_ops; k++) {
+        const size_t n = ops[k] >> 4;
+        const uint32_t c = ops[k] & 15u;
+        r.cigar_string.push_back({(AlignmentTag::Kind)c, n});
+        // the leading boundary run (emitted after the main loop of the traceback) has no `path` entries
+        const bool boundary = k == 0 && c != CLQ_OP_M;
+        if (c == CLQ_OP_M) {
+            if (x + n > l1 || y + n > l2) fail(CLQ_E_INVALID, "CIGAR overruns the sequences");
+            r.reference_aligned.insert(r.reference_aligned.end(), reference + x, reference + x + n);
+            r.read_aligned.insert(r.read_aligned.end(), read + y, read + y + n);
+            for (size_t i = 0; i < n; i++) r.path.push_back({x + i + 1, y + i + 1});
+            x += n; y += n;
+        } else if (c == CLQ_OP_D) {
+            if (x + n > l1) fail(CLQ_E_INVALID, "CIGAR overruns the reference");
+            r.reference_aligned.insert(r.reference_aligned.end(), reference + x, reference + x + n);
+            r.read_aligned.insert(r.read_aligned.end(), n, (uint8_t)'-');
+            if (!boundary) for (size_t i = 0; i < n; i++) r.path.push_back({x + i + 1, y});
+            x += n;
+        } else {
+            if (y + n > l2) fail(CLQ_E_INVALID, "CIGAR overruns the read");
+            r.reference_aligned.insert(r.reference_aligned.end(), n, (uint8_t)'-');
+            r.read_aligned.insert(r.read_aligned.end(), read + y, read + y + n);
+            if (!boundary) for (size_t i = 0; i < n; i++) r.path.push_back({x, y + i + 1});
+            y += n;
+        }
+    }
+    return r;
+}
+
+AlignmentResult AlignmentResult::from_match_segment(const Bytes& str1, const Bytes& str2, const std::string& reference_name,
+                                                    const std::string& read_name, size_t start_x, size_t start_y, const AffineScoring& af) {
+    AlignmentResult r;
+    r.reference_name = reference_name;
+    r.read_name = read_name;
+    r.reference_aligned = str1;
+    r.read_aligned = str2;
+    r.cigar_string = {{AlignmentTag::MatchMismatch, str1.size()}};
+    for (size_t i = 0; i < str1.size(); i++) r.path.push_back({start_x + i, start_y + i});
+    r.score = 0.0;
+    for (size_t i = 0; i < std::min(str1.size(), str2.size()); i++) r.score += af.match_mismatch(str1[i], str2[i]);
+    r.reference_start = start_x;
+    r.read_start = start_y;
+    return r;
+}
+
+std::string f64_to_string(double v) {
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
+    char buf[400];
+    const auto res = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::fixed);
+    return std::string(buf, res.ptr);
+}
+
+SamRecord AlignmentResult::to_sam_record(int32_t reference_id, const TagMap& extra_tags, const std::optional<std::vector<std::string>>& read_names) const {
+    SamRecord rec;
+    rec.name = read_name;
+    rec.reference_sequence_id = reference_id;
+    rec.alignment_start = reference_start + 1;
+    rec.cigar = cigar_string;
+    for (uint8_t b : read_aligned) if (b != '-') rec.sequence.push_back(b);
+    rec.quality_scores.assign(rec.sequence.size(), (uint8_t)'H');
+    // Data::insert replaces the value of an existing tag in place and appends new ones (extra tags first; the reference
+    // iterates a HashMap there, this build takes key order)
+    auto put = [&](TagKey k, std::string v) {
+        for (auto& kv : rec.data) if (kv.first == k) { kv.second = std::move(v); return; }
+        rec.data.emplace_back(k, std::move(v));
+    };
+    for (const auto& kv : extra_tags) put(kv.first, kv.second);
+    put({'r', 'm'}, f64_to_string(get_reference_alignment_rate(reference_aligned, read_aligned)));
+    put({'r', 's'}, f64_to_string(score));
+    if (read_names) {
+        std::string joined;
+        for (size_t i = 0; i < read_names->size(); i++) joined += (i ? "," : "") + (*read_names)[i];
+        put({'a', 'r'}, joined);
+    }
+    put({'a', 's'}, f64_to_string(score));
+    return rec;
+}
+
+std::string SamRecord::to_sam_line(const std::vector<std::string>& reference_names) const {
+    std::string s = name.empty() ? "*" : name;
+    s += '\t' + std::to_string(flags) + '\t';
+    s += (reference_sequence_id >= 0 && (size_t)reference_sequence_id < reference_names.size()) ? reference_names[reference_sequence_id] : "*";
+    s += '\t' + std::to_string(alignment_start) + "\t255\t";
+    s += cigar.empty() ? "*" : cigar_to_string(cigar);
+    s += "\t*\t0\t0\t";
+    s += sequence.empty() ? "*" : std::string(sequence.begin(), sequence.end());
+    s += '\t';
+    if (quality_scores.empty()) s += '*';
+    else for (uint8_t q : quality_scores) s += (char)(q + 33);
+    for (const auto& kv : data) {
+        s += '\t';
+        s += kv.first[0]; s += kv.first[1];
+        s += ":Z:" + kv.second;
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------ strings
+double get_reference_alignment_rate(const Bytes& reference, const Bytes& read) {
+    uint64_t m = 0, mm = 0;
+    for (size_t i = 0; i < reference.size(); i++) {
+        const uint8_t a = reference[i], b = read.at(i);  // the reference unwraps read.get(index): shorter read panics
+        if (a > 64 && a != 'N' && b > 64) { if (a == b) m++; else mm++; }
+    }
+    return (double)m / (double)(m + mm);
+}
+
+bool is_valid_fasta_base(uint8_t b) {
+    if (b >= 'a' && b <= 'z') b -= 32;
+    switch (b) {
+        case 'A': case 'C': case 'G': case 'T': case 'U': case 'R': case 'Y': case 'S': case 'W': case 'K': case 'M':
+        case 'B': case 'D': case 'H': case 'V': case 'N': return true;
+        default: return false;
+    }
+}
+
+std::map<uint8_t, std::string> extract_tagged_sequences(const Bytes& aligned_read, const Bytes& aligned_ref) {
+    std::map<uint8_t, std::string> out;
+    bool in_extractor = false;
+    uint8_t next_read = 'a', next_ref = 'A';
+    const size_t n = std::min(aligned_read.size(), aligned_ref.size());
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t rb = aligned_ref[i], qb = aligned_read[i];
+        const bool valid = is_valid_fasta_base(rb);
+        const bool upper = (rb >= 'A' && rb <= 'Z') || (rb == '-' && in_extractor);
+        const bool special = rb >= '0' && rb <= '9';
+        if (upper) {
+            in_extractor = true;
+            out[next_ref] += (char)rb;
+            out[next_read] += (char)qb;
+        } else if (!valid && !in_extractor && special) {
+            out[rb] += (char)qb;
+        } else if (!valid && in_extractor && special) {
+            out[next_ref] += (char)rb;
+            out[next_read] += (char)qb;
+            out[rb] += (char)qb;
+        } else {
+            if (in_extractor) { next_read++; next_ref++; }
+            in_extractor = false;
+        }
+    }
+    return out;
+}
+
+Bytes reverse_complement(const uint8_t* dna, size_t n) {
+    Bytes out(n);
+    for (size_t i = 0; i < n; i++) {
+        uint8_t b = dna[n - 1 - i];
+        if (b >= 'a' && b <= 'z') b -= 32;
+        switch (b) {
+            case 'A': b = 'T'; break; case 'T': b = 'A'; break; case 'G': b = 'C'; break; case 'C': b = 'G'; break;
+            case 'R': b = 'Y'; break; case 'Y': b = 'R'; break; case 'K': b = 'M'; break; case 'M': b = 'K'; break;
+            case 'B': b = 'V'; break; case 'V': b = 'B'; break; case 'D': b = 'H'; break; case 'H': b = 'D'; break;
+            default: break;
+        }
+        out[i] = b;
+    }
+    return out;
+}
+
+Bytes orient_sequence(const uint8_t* sequence, size_t n, AlignedReadOrientation o) {
+    switch (o) {
+        case AlignedReadOrientation::Forward: return Bytes(sequence, sequence + n);
+        case AlignedReadOrientation::Reverse: { Bytes b(sequence, sequence + n); std::reverse(b.begin(), b.end()); return b; }
+        case AlignedReadOrientation::ReverseComplement: return reverse_complement(sequence, n);
+        default: throw std::logic_error("We can't merge reads when the orientation is marked 'Unknown' in the yaml specification file");
+    }
+}
+
+MergedSequence merge_reads_by_concatenation(const ReadSetContainer& reads, const std::vector<ReadPosition>& layout) {
+    MergedSequence m;
+    auto add = [&](const FastqRecord& r, AlignedReadOrientation o) {
+        const Bytes s = orient_sequence(r.seq.data(), r.seq.size(), o);
+        m.read_bases.insert(m.read_bases.end(), s.begin(), s.end());
+        m.read_quals.insert(m.read_quals.end(), r.qual.begin(), r.qual.end());  // qualities are appended as they are (merger.rs:55)
+    };
+    auto need = [](const std::optional<FastqRecord>& r, const char* what) -> const FastqRecord& {
+        if (!r) throw std::logic_error(std::string("read layout names ") + what + " but the read set has none");
+        return *r;
+    };
+    for (const auto& pos : layout) {
+        switch (pos.kind) {
+            case ReadPosition::Read1: add(reads.read_one, pos.orientation); break;
+            case ReadPosition::Read2: add(need(reads.read_two, "read2"), pos.orientation); break;
+            case ReadPosition::Index1: add(need(reads.index_one, "index1"), pos.orientation); break;
+            case ReadPosition::Index2: add(need(reads.index_two, "index2"), pos.orientation); break;
+            case ReadPosition::Spacer:
+                m.read_bases.insert(m.read_bases.end(), pos.spacer_sequence.begin(), pos.spacer_sequence.end());
+                m.read_quals.insert(m.read_quals.end(), pos.spacer_sequence.size(), (uint8_t)'H');
+                break;
+        }
+    }
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------ references
+ReferenceManager::ReferenceManager(std::vector<Reference> refs, size_t ks, size_t kskip) : references(std::move(refs)), kmer_size(ks), kmer_skip(kskip) {
+    for (size_t i = 0; i < references.size(); i++) {
+        reference_name_to_ref[references[i].name] = i;
+        longest_ref = std::max(longest_ref, references[i].sequence.size());
+    }
+}
+
+ReferenceManager ReferenceManager::from_fa_file(const std::string& path, size_t ks, size_t kskip) {
+    std::ifstream f(path);
+    if (!f) throw std::runtime_error("Unable to open reference file " + path);
+    std::vector<Reference> refs;
+    std::string line;
+    while (std::getline(f, line)) {
+        while (!line.empty() && (line.back() == '\r' || line.back() == '\n' || line.back() == ' ')) line.pop_back();
+        if (line.empty()) continue;
+        if (line[0] == '>') {
+            const size_t e = line.find_first_of(" \t", 1);
+            refs.push_back({Bytes(), to_bytes(line.substr(1, e == std::string::npos ? std::string::npos : e - 1))});
+        } else if (!refs.empty()) {
+            refs.back().sequence.insert(refs.back().sequence.end(), line.begin(), line.end());
+        }
+    }
+    return ReferenceManager(std::move(refs), ks, kskip);
+}
+
+std::vector<std::string> ReferenceManager::names() const {
+    std::vector<std::string> n;
+    for (const auto& r : references) n.push_back(to_string(r.name));
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------ ReadBatch
+ReadBatch::ReadBatch(uint32_t max_reads, uint64_t max_bytes) : max_reads_(max_reads), max_bytes_(max_bytes) {
+    bytes_ = pinned<uint8_t>(max_bytes + 16);
+    off_ = pinned<uint64_t>((size_t)max_reads + 1);
+    fixed_ = pinned<int32_t>(max_reads);
+    names_.reserve(max_reads);
+    off_[0] = 0;
+}
+
+ReadBatch::~ReadBatch() {
+    clq_host_free(bytes_);
+    clq_host_free(off_);
+    clq_host_free(fixed_);
+}
+
+void ReadBatch::clear() {
+    n_ = 0;
+    off_[0] = 0;
+    names_.clear();
+    quals_.clear();
+    have_quals_ = false;
+}
+
+bool ReadBatch::push(const std::string& name, const uint8_t* seq, size_t n, const uint8_t* qual, int32_t fixed_ref) {
+    if (n_ >= max_reads_ || off_[n_] + n > max_bytes_) return false;
+    if (n) std::memcpy(bytes_ + off_[n_], seq, n);
+    if (qual) {
+        if (!have_quals_) { quals_.assign((size_t)off_[n_], (uint8_t)'H'); have_quals_ = true; }
+        quals_.insert(quals_.end(), qual, qual + n);
+    } else if (have_quals_) {
+        quals_.insert(quals_.end(), n, (uint8_t)'H');
+    }
+    fixed_[n_] = fixed_ref;
+    off_[n_ + 1] = off_[n_] + n;
+    names_.push_back(name);
+    n_++;
+    return true;
+}
+
+std::optional<Bytes> ReadBatch::quals(uint32_t i) const {
+    if (!have_quals_) return std::nullopt;
+    return Bytes(quals_.begin() + (size_t)off_[i], quals_.begin() + (size_t)off_[i + 1]);
+}
+
+// ------------------------------------------------------------------------------------------------ BatchView
+std::string BatchView::cigar_string(uint32_t i) const {
+    std::string s;
+    const uint32_t* c = cigar(i);
+    for (uint32_t k = 0; k < cigar_len(i); k++) {
+        s += std::to_string(c[k] >> 4);
+        s += "MID"[c[k] & 3u];
+    }
+    return s;
+}
+
+double BatchView::alignment_rate(uint32_t i) const {
+    const double m = results[i].matches, mm = results[i].mismatches;
+    return m / (m + mm);
+}
+
+std::map<uint8_t, std::string> BatchView::digit_tags(uint32_t i) const {
+    std::map<uint8_t, std::string> out;
+    if (!tags || status(i) != CLQ_OK) return out;
+    const Bytes& ref = rm->references[ref_index(i)].sequence;
+    const uint8_t* row = tags + (size_t)i * tag_stride;
+    uint32_t k = 0;
+    for (uint8_t b : ref)
+        if (b >= '0' && b <= '9' && k < tag_stride) out[b] += (char)row[k++];
+    return out;
+}
+
+std::optional<AlignmentWithRef> BatchView::alignment(uint32_t i) const {
+    if (status(i) != CLQ_OK) return std::nullopt;  // the reference warns / logs and moves on (alignment_functions.rs:165-176, :240-247)
+    const Reference& r = rm->references[ref_index(i)];
+    AlignmentWithRef a;
+    a.alignment = AlignmentResult::from_cigar(to_string(r.name), batch->name(i), r.sequence.data(), r.sequence.size(), batch->read(i),
+                                              batch->read_len(i), batch->quals(i), cigar(i), cigar_len(i), score(i));
+    a.ref_name = r.name;
+    a.ref_sequence = r.sequence;
+    return a;
+}
+
+TagMap BatchView::align_reads_tags(uint32_t i, const std::string& umi_symbols) const {
+    TagMap t;
+    const auto dt = digit_tags(i);
+    for (char sym : umi_symbols) {
+        const auto it = dt.find((uint8_t)sym);
+        if (it != dt.end()) t[{'e', sym}] = it->second;
+    }
+    t[{'r', 'c'}] = "1";
+    t[{'a', 'r'}] = batch->name(i);
+    t[{'r', 'm'}] = f64_to_string(alignment_rate(i));
+    t[{'a', 's'}] = f64_to_string(score(i));
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------ Aligner
+Aligner::Aligner(const AlignerOptions& opt) : opt_(opt) {
+    if (clq_device_count() <= opt.device) fail(CLQ_E_CUDA, "CUDA device " + std::to_string(opt.device) + " not available; libclq has no CPU fallback");
+    if (!opt_.max_read_bytes) opt_.max_read_bytes = (uint64_t)opt_.max_reads * 512;
+    clq_limits_t lim = {};
+    lim.max_reads = opt_.max_reads;
+    lim.max_read_bytes = opt_.max_read_bytes;
+    lim.max_read_len = opt_.max_read_len;
+    lim.max_refs = opt_.max_refs;
+    lim.max_ref_bytes = opt_.max_ref_bytes;
+    pool_ops_ = std::max<uint64_t>(1024, (uint64_t)opt_.max_reads * opt_.cigar_ops_per_read);
+    lim.cigar_pool_ops = pool_ops_;
+    lim.n_slots = std::max<uint32_t>(1, std::min<uint32_t>(4, opt_.n_slots));
+    opt_.n_slots = lim.n_slots;
+    const int32_t rc = clq_ctx_create(opt_.device, &lim, &ctx_);
+    if (rc != CLQ_OK) fail(rc, clq_strerror(rc));
+    for (uint32_t s = 0; s < opt_.n_slots; s++) {
+        res_.push_back(pinned<clq_result_t>(opt_.max_reads));
+        pool_.push_back(pinned<uint32_t>(pool_ops_));
+        tags_.push_back(nullptr);
+    }
+    flags_.assign(opt_.n_slots, 0);
+    scale_.assign(opt_.n_slots, 1);
+}
+
+Aligner::~Aligner() {
+    if (ctx_) clq_ctx_destroy(ctx_);
+    for (auto* p : res_) clq_host_free(p);
+    for (auto* p : pool_) clq_host_free(p);
+    for (auto* p : tags_) if (p) clq_host_free(p);
+}
+
+void Aligner::check(int32_t rc, const char* what) const {
+    if (rc != CLQ_OK) fail(rc, std::string(what) + ": " + clq_strerror(rc) + ": " + clq_ctx_last_error(ctx_));
+}
+
+void Aligner::set_references(const ReferenceManager& rm, bool build_kmer_index) {
+    Bytes flat;
+    std::vector<uint64_t> off(1, 0);
+    for (const auto& r : rm.references) {
+        flat.insert(flat.end(), r.sequence.begin(), r.sequence.end());
+        off.push_back(flat.size());
+    }
+    if (flat.empty()) flat.push_back(0);
+    check(clq_refs_set(ctx_, (uint32_t)rm.references.size(), flat.data(), off.data()), "clq_refs_set");
+    if (build_kmer_index && !rm.references.empty())
+        check(clq_kmer_index_set(ctx_, (uint32_t)rm.kmer_size, (uint32_t)rm.kmer_skip), "clq_kmer_index_set");
+    rm_ = rm;
+}
+
+uint32_t Aligner::search_flags(bool fast_lookup) const {
+    if (rm_.references.size() == 1) return CLQ_SEARCH_FIXED | CLQ_BAND_READLEN;
+    return (fast_lookup ? CLQ_SEARCH_QUICK : CLQ_SEARCH_EXHAUSTIVE) | CLQ_BAND_READLEN;
+}
+
+void Aligner::submit(int slot, const ReadBatch& b, const clq_affine_t& sc, uint32_t flags, double threshold) {
+    const bool fixed = (flags & CLQ_SEARCH_MASK) == CLQ_SEARCH_FIXED;
+    check(clq_submit(ctx_, slot, b.size(), b.bytes(), b.offsets(), fixed ? b.fixed_ref() : nullptr, &sc, flags, threshold), "clq_submit");
+    flags_[slot] = flags;
+    scale_[slot] = sc.scale;
+}
+
+BatchView Aligner::wait(int slot, const ReadBatch& b) {
+    uint64_t used = 0;
+    check(clq_wait(ctx_, slot, res_[slot], pool_[slot], pool_ops_, &used), "clq_wait");
+    BatchView v;
+    v.batch = &b;
+    v.rm = &rm_;
+    v.results = res_[slot];
+    v.cigar_pool = pool_[slot];
+    v.scale = scale_[slot];
+    v.device = opt_.device;
+    if (flags_[slot] & CLQ_EXTRACT_TAGS) {
+        uint32_t stride = 0;
+        check(clq_tags_download(ctx_, slot, nullptr, 0, &stride), "clq_tags_download");
+        const uint64_t need = (uint64_t)opt_.max_reads * stride;
+        if (need > tags_cap_) {
+            for (auto*& p : tags_) { if (p) clq_host_free(p); p = pinned<uint8_t>(need); }
+            tags_cap_ = need;
+        }
+        if (stride && b.size()) check(clq_tags_download(ctx_, slot, tags_[slot], tags_cap_, &stride), "clq_tags_download");
+        v.tags = stride ? tags_[slot] : nullptr;
+        v.tag_stride = stride;
+    }
+    return v;
+}
+
+clq_stats_t Aligner::stats(int slot) {
+    clq_stats_t st;
+    check(clq_slot_stats(ctx_, slot, &st), "clq_slot_stats");
+    return st;
+}
+
+AlignmentResult Aligner::single(const Bytes& reference, const Bytes& read, std::optional<Bytes> qual, const AffineScoring& sc, uint32_t band,
+                                const std::string& ref_name, const std::string& read_name) {
+    // a private one-reference set for this call; the caller's set is restored afterwards
+    const ReferenceManager saved = rm_;
+    set_references(ReferenceManager({Reference{reference, to_bytes(ref_name)}}), false);
+    if (!one_ || one_->capacity() < 1) one_ = std::make_unique<ReadBatch>(1, opt_.max_read_bytes);
+    one_->clear();
+    if (!one_->push(read_name, read.data(), read.size(), qual ? qual->data() : nullptr, 0)) fail(CLQ_E_LIMIT, "read exceeds max_read_bytes");
+    std::optional<AlignmentWithRef> out;
+    uint32_t st = CLQ_OK;
+    try {
+        submit(0, *one_, sc.to_int(), CLQ_SEARCH_FIXED | band);
+        const BatchView v = wait(0, *one_);
+        st = v.status(0);
+        out = v.alignment(0);
+    } catch (...) {
+        if (!saved.references.empty()) set_references(saved);
+        throw;
+    }
+    if (!saved.references.empty()) set_references(saved);
+    if (st == CLQ_TRACEBACK_DIVERGED) fail((int32_t)st, "the reference's traceback does not terminate for this pair (stale band cell)");
+    if (st != CLQ_OK || !out) fail((int32_t)st, clq_strerror((int32_t)st));
+    return std::move(*out->alignment);
+}
+
+AlignmentResult Aligner::align_two_strings(const Bytes& reference_sequence, const Bytes& read_sequence, std::optional<Bytes> read_qual,
+                                           const AffineScoring& scoring_function, bool local, const std::string& ref_name,
+                                           const std::string& read_name) {
+    if (local) fail(CLQ_E_UNSUPPORTED, "local alignment is outside the hot path (SURVEY.md section 2)");
+    return single(reference_sequence, read_sequence, std::move(read_qual), scoring_function, CLQ_BAND_MAXLEN, ref_name, read_name);
+}
+
+AlignmentResult Aligner::align_two_strings_passed_matrix(const std::string& ref_name, const std::string& read_name, const Bytes& reference,
+                                                         const Bytes& read, std::optional<Bytes> qual, const AffineScoring& scoring,
+                                                         size_t max_indel) {
+    uint32_t band;
+    if (max_indel == read.size()) band = CLQ_BAND_READLEN;
+    else if (max_indel >= std::max(reference.size(), read.size())) band = CLQ_BAND_MAXLEN;  // the band covers the whole matrix
+    else fail(CLQ_E_UNSUPPORTED, "explicit small bandwidths are not supported (no caller of the hot path passes one)");
+    return single(reference, read, std::move(qual), scoring, band, ref_name, read_name);
+}
+
+std::optional<AlignmentWithRef> Aligner::search(const std::string& read_name, const Bytes& read, std::optional<Bytes> qual,
+                                                const AffineScoring& sc, uint32_t mode, double threshold) {
+    if (rm_.references.empty()) return std::nullopt;
+    if (!one_) one_ = std::make_unique<ReadBatch>(1, opt_.max_read_bytes);
+    one_->clear();
+    if (!one_->push(read_name, read.data(), read.size(), qual ? qual->data() : nullptr, 0)) fail(CLQ_E_LIMIT, "read exceeds max_read_bytes");
+    submit(0, *one_, sc.to_int(), mode | CLQ_BAND_READLEN, threshold);
+    const BatchView v = wait(0, *one_);
+    const uint32_t st = v.status(0);
+    if (st == CLQ_NO_CANDIDATE) return std::nullopt;
+    if (st == CLQ_TRACEBACK_DIVERGED) fail((int32_t)st, "the reference's traceback does not terminate for this pair (stale band cell)");
+    if (st != CLQ_OK) fail((int32_t)st, clq_strerror((int32_t)st));
+    return v.alignment(0);
+}
+
+std::optional<AlignmentWithRef> Aligner::exhaustive_alignment_search(const std::string& read_name, const Bytes& read, std::optional<Bytes> qual,
+                                                                     const AffineScoring& scoring) {
+    return search(read_name, read, std::move(qual), scoring, CLQ_SEARCH_EXHAUSTIVE, 0.90);
+}
+
+std::optional<AlignmentWithRef> Aligner::quick_alignment_search(const std::string& read_name, const Bytes& read, std::optional<Bytes> qual,
+                                                                const AffineScoring& scoring, double match_threshold) {
+    return search(read_name, read, std::move(qual), scoring, CLQ_SEARCH_QUICK, match_threshold);
+}
+
+std::optional<AlignmentWithRef> Aligner::align_to_reference_choices(const std::string& read_name, const Bytes& read, std::optional<Bytes> qual,
+                                                                    bool fast_lookup, const AffineScoring& scoring) {
+    if (rm_.references.empty()) return std::nullopt;
+    if (rm_.references.size() == 1) return search(read_name, read, std::move(qual), scoring, CLQ_SEARCH_FIXED, 0.90);
+    return search(read_name, read, std::move(qual), scoring, fast_lookup ? CLQ_SEARCH_QUICK : CLQ_SEARCH_EXHAUSTIVE, 0.90);
+}
+
+namespace {
+void account(AlignReadsStats& st, const BatchView& v) {
+    st.batches++;
+    st.reads += v.size();
+    for (uint32_t i = 0; i < v.size(); i++) (v.status(i) == CLQ_OK ? st.aligned : st.dropped)++;
+}
+
+void prepare_fixed(ReadBatch& b, uint32_t flags) {
+    // single-reference panels: every read aligns to reference 0 (alignment_functions.rs:544-548)
+    if ((flags & CLQ_SEARCH_MASK) == CLQ_SEARCH_FIXED)
+        for (uint32_t i = 0; i < b.size(); i++) if (b.fixed_ref()[i] < 0) b.fixed_ref_mut()[i] = 0;
+}
+}  // namespace
+
+AlignReadsStats Aligner::align_reads(const ReadSource& source, const AffineScoring& scoring, bool fast_lookup, const ResultSink& sink,
+                                     bool extract_tags) {
+    const auto t0 = std::chrono::steady_clock::now();
+    AlignReadsStats st;
+    if (rm_.references.empty()) return st;
+    const clq_affine_t sc = scoring.to_int();
+    const uint32_t flags = search_flags(fast_lookup) | (extract_tags ? CLQ_EXTRACT_TAGS : 0u);
+    const uint32_t ns = opt_.n_slots;
+    std::vector<std::unique_ptr<ReadBatch>> bufs;
+    for (uint32_t s = 0; s < ns; s++) bufs.push_back(std::make_unique<ReadBatch>(opt_.max_reads, opt_.max_read_bytes));
+    std::vector<bool> busy(ns, false);
+    uint64_t next_index = 0;
+    bool more = true;
+    uint32_t slot = 0;
+    auto drain = [&](uint32_t s) {
+        const BatchView v = wait((int)s, *bufs[s]);
+        st.cells += stats((int)s).cells;
+        account(st, v);
+        sink(v);
+        busy[s] = false;
+    };
+    while (more) {
+        if (busy[slot]) drain(slot);
+        ReadBatch& b = *bufs[slot];
+        b.clear();
+        b.first_index = next_index;  // a sharded source overrides this with the batch's place in the whole input
+        more = source(b);
+        if (b.size()) {
+            prepare_fixed(b, flags);
+            submit((int)slot, b, sc, flags);
+            busy[slot] = true;
+            next_index += b.size();
+            slot = (slot + 1) % ns;
+        }
+    }
+    for (uint32_t k = 0; k < ns; k++) {
+        const uint32_t s = (slot + k) % ns;
+        if (busy[s]) drain(s);
+    }
+    st.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------------ ShardedAligner
+ShardedAligner::ShardedAligner(const std::vector<int>& devices, AlignerOptions opt) {
+    for (int d : devices) {
+        opt.device = d;
+        aligners_.push_back(std::make_unique<Aligner>(opt));
+    }
+}
+
+void ShardedAligner::set_references(const ReferenceManager& rm, bool build_kmer_index) {
+    for (auto& a : aligners_) a->set_references(rm, build_kmer_index);
+}
+
+AlignReadsStats ShardedAligner::align_reads(const ReadSource& source, const AffineScoring& scoring, bool fast_lookup, const ResultSink& sink,
+                                            bool extract_tags) {
+    const auto t0 = std::chrono::steady_clock::now();
+    AlignReadsStats total;
+    std::mutex src_mu, sink_mu;
+    bool more = true;
+    uint64_t next_index = 0;
+    std::exception_ptr err;
+    // every device thread runs the single-GPU loop over a shared, mutex-guarded source: batches go to whichever GPU is
+    // free next (dynamic read sharding, no collective)
+    const ReadSource shared_source = [&](ReadBatch& b) -> bool {
+        std::lock_guard<std::mutex> g(src_mu);
+        if (!more) return false;
+        b.first_index = next_index;
+        more = source(b);
+        next_index += b.size();
+        return more;
+    };
+    const ResultSink locked_sink = [&](const BatchView& v) {
+        std::lock_guard<std::mutex> g(sink_mu);
+        sink(v);
+    };
+    auto work = [&](Aligner* a) {
+        try {
+            const AlignReadsStats st = a->align_reads(shared_source, scoring, fast_lookup, locked_sink, extract_tags);
+            std::lock_guard<std::mutex> g(sink_mu);
+            total.reads += st.reads; total.aligned += st.aligned; total.dropped += st.dropped; total.batches += st.batches; total.cells += st.cells;
+        } catch (...) {
+            std::lock_guard<std::mutex> g(sink_mu);
+            if (!err) err = std::current_exception();
+        }
+    };
+    std::vector<std::thread> th;
+    for (auto& a : aligners_) th.emplace_back(work, a.get());
+    for (auto& t : th) t.join();
+    if (err) std::rethrow_exception(err);
+    total.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return total;
+}
+
+}  // namespace clique

@@ -1,0 +1,135 @@
+// clqh_c.cpp -- a thin extern "C" view of the pure host functions of include/clique_host.hpp, so that the CPU test suite
+// (ctypes) can check them against the oracle and the reference's golden vectors without a GPU.  Not part of the drop-in
+// boundary (that is include/clq.h); declared in include/clqh.h.
+#include <cstring>
+
+#include "../../../include/clique_host.hpp"
+#include "../../../include/clqh.h"
+
+using namespace clique;
+
+namespace {
+size_t put_records(const std::map<uint8_t, std::string>& m, uint8_t* out, size_t cap) {
+    size_t w = 0;
+    for (const auto& kv : m) {
+        if (w + 5 + kv.second.size() > cap) return 0;
+        out[w] = kv.first;
+        const uint32_t len = (uint32_t)kv.second.size();
+        std::memcpy(out + w + 1, &len, 4);
+        std::memcpy(out + w + 5, kv.second.data(), len);
+        w += 5 + len;
+    }
+    return w;
+}
+
+size_t put_string(const std::string& s, char* out, size_t cap) {
+    if (s.size() + 1 > cap) return 0;
+    std::memcpy(out, s.c_str(), s.size() + 1);
+    return s.size();
+}
+
+std::vector<AlignmentTag> decode(const uint32_t* ops, size_t n) {
+    std::vector<AlignmentTag> v;
+    for (size_t i = 0; i < n; i++) v.push_back({(AlignmentTag::Kind)(ops[i] & 15u), ops[i] >> 4});
+    return v;
+}
+}  // namespace
+
+extern "C" {
+
+size_t clqh_extract_tagged_sequences(const uint8_t* aligned_read, size_t n_read, const uint8_t* aligned_ref, size_t n_ref, uint8_t* out,
+                                     size_t cap) {
+    return put_records(extract_tagged_sequences(Bytes(aligned_read, aligned_read + n_read), Bytes(aligned_ref, aligned_ref + n_ref)), out, cap);
+}
+
+void clqh_reverse_complement(const uint8_t* dna, size_t n, uint8_t* out) {
+    const Bytes r = reverse_complement(dna, n);
+    if (n) std::memcpy(out, r.data(), n);
+}
+
+size_t clqh_f64_to_string(double v, char* out, size_t cap) { return put_string(f64_to_string(v), out, cap); }
+
+double clqh_get_reference_alignment_rate(const uint8_t* ref_aligned, const uint8_t* read_aligned, size_t n) {
+    return get_reference_alignment_rate(Bytes(ref_aligned, ref_aligned + n), Bytes(read_aligned, read_aligned + n));
+}
+
+size_t clqh_simplify_cigar(const uint32_t* ops, size_t n, uint32_t* out) {
+    const auto v = simplify_cigar_string(decode(ops, n));
+    for (size_t i = 0; i < v.size(); i++) out[i] = (uint32_t)(v[i].len << 4) | (uint32_t)v[i].kind;
+    return v.size();
+}
+
+int32_t clqh_from_cigar(const uint8_t* ref, size_t l1, const uint8_t* read, size_t l2, const uint32_t* ops, size_t n_ops,
+                        uint8_t* ref_aligned, uint8_t* read_aligned, size_t aligned_cap, size_t* aligned_len, uint32_t* path_xy,
+                        size_t path_cap, size_t* path_len) {
+    try {
+        const AlignmentResult r = AlignmentResult::from_cigar("ref", "read", ref, l1, read, l2, std::nullopt, ops, n_ops, 0.0);
+        if (r.reference_aligned.size() > aligned_cap || r.path.size() > path_cap) return CLQ_E_LIMIT;
+        std::memcpy(ref_aligned, r.reference_aligned.data(), r.reference_aligned.size());
+        std::memcpy(read_aligned, r.read_aligned.data(), r.read_aligned.size());
+        *aligned_len = r.reference_aligned.size();
+        for (size_t i = 0; i < r.path.size(); i++) { path_xy[2 * i] = (uint32_t)r.path[i].x; path_xy[2 * i + 1] = (uint32_t)r.path[i].y; }
+        *path_len = r.path.size();
+        return CLQ_OK;
+    } catch (const ClqError& e) {
+        return e.code;
+    }
+}
+
+size_t clqh_sam_line(const char* ref_name, const char* read_name, const uint8_t* ref, size_t l1, const uint8_t* read, size_t l2,
+                     const uint32_t* ops, size_t n_ops, double score, int32_t reference_id, const char* extra_tags, char* out, size_t cap) {
+    try {
+        const AlignmentResult r = AlignmentResult::from_cigar(ref_name, read_name, ref, l1, read, l2, std::nullopt, ops, n_ops, score);
+        TagMap extra;  // "k1=value;k2=value"
+        std::string s = extra_tags ? extra_tags : "";
+        size_t pos = 0;
+        while (pos < s.size()) {
+            const size_t e = s.find(';', pos);
+            const std::string item = s.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
+            if (item.size() >= 3 && item[2] == '=') extra[{item[0], item[1]}] = item.substr(3);
+            if (e == std::string::npos) break;
+            pos = e + 1;
+        }
+        std::vector<std::string> names((size_t)std::max(reference_id, 0) + 1, "*");
+        if (reference_id >= 0) names[reference_id] = ref_name;
+        return put_string(r.to_sam_record(reference_id, extra, std::nullopt).to_sam_line(names), out, cap);
+    } catch (const std::exception&) {
+        return 0;
+    }
+}
+
+size_t clqh_merge_reads_by_concatenation(const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const char* layout, uint8_t* out,
+                                         size_t cap) {
+    // layout: comma-separated items "1F" / "2R" / "2C" (read number + Forward / Reverse / reverse-Complement) or "S:ACGT" (spacer)
+    try {
+        ReadSetContainer rs;
+        rs.read_one = {"r", Bytes(r1, r1 + n1), Bytes(n1, (uint8_t)'I')};
+        if (r2) rs.read_two = FastqRecord{"r", Bytes(r2, r2 + n2), Bytes(n2, (uint8_t)'I')};
+        std::vector<ReadPosition> lay;
+        std::string s = layout ? layout : "";
+        size_t pos = 0;
+        while (pos < s.size()) {
+            const size_t e = s.find(',', pos);
+            const std::string item = s.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
+            ReadPosition p;
+            if (item.rfind("S:", 0) == 0) { p.kind = ReadPosition::Spacer; p.spacer_sequence = item.substr(2); }
+            else if (item.size() == 2) {
+                p.kind = item[0] == '1' ? ReadPosition::Read1 : ReadPosition::Read2;
+                p.orientation = item[1] == 'F' ? AlignedReadOrientation::Forward
+                              : item[1] == 'R' ? AlignedReadOrientation::Reverse
+                              : item[1] == 'C' ? AlignedReadOrientation::ReverseComplement : AlignedReadOrientation::Unknown;
+            } else return 0;
+            lay.push_back(p);
+            if (e == std::string::npos) break;
+            pos = e + 1;
+        }
+        const MergedSequence m = merge_reads_by_concatenation(rs, lay);
+        if (m.read_bases.size() > cap) return 0;
+        if (!m.read_bases.empty()) std::memcpy(out, m.read_bases.data(), m.read_bases.size());
+        return m.read_bases.size();
+    } catch (const std::exception&) {
+        return (size_t)-1;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,348 @@
+// clique_host.hpp -- C++17 host layer above the libclq C ABI (include/clq.h).
+//
+// The reference (mckennalab/clique) is compiled Rust and no Rust toolchain exists in this image, so the host side of the
+// drop-in is C++.  Every type and function here mirrors one of the reference's (same name, argument meaning and error
+// behaviour; file:line relative to rust_cmd/src/ of the reference); a Rust maintainer binds the C ABI directly
+// (INTEGRATION.md), this layer is what a C++ caller -- and tools/clq_align -- use.  It does no alignment arithmetic:
+// scores, CIGARs, selected references, the `rm` counters and the digit tags all come from the CUDA kernels.  There is no
+// CPU fallback: constructing an Aligner without a CUDA device throws.
+#pragma once
+
+#include <array>
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "clq.h"
+
+namespace clique {
+
+using Bytes = std::vector<uint8_t>;
+
+inline Bytes to_bytes(const std::string& s) { return Bytes(s.begin(), s.end()); }
+inline std::string to_string(const Bytes& b) { return std::string(b.begin(), b.end()); }
+
+/// panics / call-level errors of the reference surface become exceptions carrying the libclq status code
+class ClqError : public std::runtime_error {
+public:
+    ClqError(int32_t code, const std::string& what) : std::runtime_error(what), code(code) {}
+    int32_t code;
+};
+
+// ------------------------------------------------------------------------------------------------ scoring
+/// AffineScoring, alignment/scoring_functions.rs:65-113
+struct AffineScoring {
+    double match_score, mismatch_score, special_character_score, gap_open, gap_extend, final_gap_multiplier;
+    static AffineScoring default_dna() { return {5.0, -4.0, 4.0, -10.0, -0.5, 0.5}; }            // :77-86
+    static AffineScoring align_reads_default() { return {10.0, -9.0, 9.0, -20.0, -2.0, 1.0}; }   // alignment_functions.rs:104-111
+    static AffineScoring merger_default() { return {10.0, -5.0, 8.0, -15.0, -1.0, 0.25}; }       // merger.rs:130-139
+    /// match_mismatch, :100-102 (host mirror, used by from_match_segment only; the DP runs on the GPU)
+    double match_mismatch(uint8_t a, uint8_t b) const;
+    /// exact scaled-integer form for the kernels; throws CLQ_SCORING_NOT_REPRESENTABLE (no CPU fallback exists)
+    clq_affine_t to_int() const;
+};
+
+/// ConvexScoring, alignment/scoring_functions.rs:36-53 -- only a gap *function* in the reference (nothing calls it)
+struct ConvexScoring {
+    double match_score, mismatch_score, gap_score, gap_open, gap_extend;
+    double match_mismatch(uint8_t a, uint8_t b) const { return a == b ? match_score : mismatch_score; }
+    double gap(size_t length) const;  // gap_open + log10(length); gap(0) = -inf
+};
+
+// ------------------------------------------------------------------------------------------------ results
+/// AlignmentTag, alignment/alignment_matrix.rs:58-120 (the op codes are the BAM codes the C ABI uses)
+struct AlignmentTag {
+    enum Kind : uint8_t { MatchMismatch = CLQ_OP_M, Ins = CLQ_OP_I, Del = CLQ_OP_D, SoftClip = 4, HardClip = 5, InversionOpen = 14, InversionClose = 15 };
+    Kind kind;
+    size_t len;
+    bool operator==(const AlignmentTag& o) const { return kind == o.kind && len == o.len; }
+    char op_char() const;
+};
+
+std::string cigar_to_string(const std::vector<AlignmentTag>& cigar);
+/// simplify_cigar_string, alignment_manager.rs:386-423 (twin: alignment_functions.rs:874-911): merges adjacent M / D / I
+/// runs, never soft clips; inversion tags throw when doubled as the reference panics.
+std::vector<AlignmentTag> simplify_cigar_string(const std::vector<AlignmentTag>& cigar_tokens);
+
+/// AlignmentLocation, alignment/alignment_matrix.rs:687-690
+struct AlignmentLocation {
+    size_t x, y;
+    bool operator==(const AlignmentLocation& o) const { return x == o.x && y == o.y; }
+};
+
+using TagKey = std::array<char, 2>;
+using TagMap = std::map<TagKey, std::string>;
+
+/// what AlignmentResult::to_sam_record builds (a noodles RecordBuf in the reference), alignment/alignment_matrix.rs:741-771
+struct SamRecord {
+    std::string name;
+    uint16_t flags = 0;                 // Flags::empty()
+    int32_t reference_sequence_id = 0;
+    size_t alignment_start = 1;         // reference_start + 1
+    std::vector<AlignmentTag> cigar;
+    Bytes sequence;                     // read_aligned without '-'
+    Bytes quality_scores;               // raw scores: b'H' (72) per base, whatever the input qualities were (:760-763)
+    std::vector<std::pair<TagKey, std::string>> data;  // all Z-typed; extra tags in key order, then rm, rs, [ar], as
+    /// one SAM text line (no newline); RNAME from `reference_names`, MAPQ 255, RNEXT *, PNEXT 0, TLEN 0, QUAL = score + 33
+    std::string to_sam_line(const std::vector<std::string>& reference_names) const;
+};
+
+/// AlignmentResult, alignment/alignment_matrix.rs:694-706
+struct AlignmentResult {
+    std::string reference_name, read_name;
+    Bytes reference_aligned, read_aligned;  // gapped, '-' = FASTA_UNSET
+    std::optional<Bytes> read_quals;        // passed through
+    std::vector<AlignmentTag> cigar_string;
+    std::vector<AlignmentLocation> path;
+    double score = 0.0;
+    size_t reference_start = 0, read_start = 0;
+    std::optional<std::pair<AlignmentLocation, AlignmentLocation>> bounding_box;
+
+    /// Rebuilds the record perform_3d_global_traceback returns (alignment/alignment_matrix.rs:941-1086) from the kernels'
+    /// output: gapped strings and `path` are pure functions of CIGAR + sequences (one path entry per unit op executed inside
+    /// the main loop, i.e. excluding the leading boundary run emitted after it, :1054-1065).
+    static AlignmentResult from_cigar(const std::string& reference_name, const std::string& read_name, const uint8_t* reference,
+                                      size_t l1, const uint8_t* read, size_t l2, std::optional<Bytes> quals, const uint32_t* cigar_ops,
+                                      size_t n_ops, double score);
+    /// from_match_segment, :710-733
+    static AlignmentResult from_match_segment(const Bytes& str1, const Bytes& str2, const std::string& reference_name,
+                                              const std::string& read_name, size_t start_x, size_t start_y, const AffineScoring& af_score);
+    /// to_sam_record, :741-771
+    SamRecord to_sam_record(int32_t reference_id, const TagMap& extra_tags, const std::optional<std::vector<std::string>>& read_names) const;
+};
+
+/// f64 `Display` of Rust (what `score.to_string()` writes into the rm / rs / as tags): shortest round-trip digits, never
+/// scientific notation, integral values without ".0", "NaN", "inf"
+std::string f64_to_string(double v);
+
+// ------------------------------------------------------------------------------------------------ post-alignment strings
+/// get_reference_alignment_rate, consensus/consensus_builders.rs:288-307 (the `rm` tag; NaN when nothing is comparable)
+double get_reference_alignment_rate(const Bytes& reference_aligned, const Bytes& read_aligned);
+/// is_valid_fasta_base, utils/base_utils.rs:17-23
+bool is_valid_fasta_base(uint8_t b);
+/// extract_tagged_sequences, extractor.rs:271-332: digit keys '0'..'9' collect the read bytes aligned to tag columns,
+/// 'A','B',.. / 'a','b',.. the reference / read bytes of each upper-case extractor region.  Zips the inputs.
+std::map<uint8_t, std::string> extract_tagged_sequences(const Bytes& aligned_read, const Bytes& aligned_ref);
+/// reverse_complement, utils/read_utils.rs:50-72 (upper-cases, IUPAC aware, unknown bytes unchanged)
+Bytes reverse_complement(const uint8_t* dna, size_t n);
+inline Bytes reverse_complement(const Bytes& dna) { return reverse_complement(dna.data(), dna.size()); }
+
+// ------------------------------------------------------------------------------------------------ input side
+/// AlignedReadOrientation / ReadPosition, read_strategies/sequence_layout.rs (the parts merge_reads_by_concatenation uses)
+enum class AlignedReadOrientation { Forward, Reverse, ReverseComplement, Unknown };
+struct ReadPosition {
+    enum Kind { Read1, Read2, Index1, Index2, Spacer } kind;
+    AlignedReadOrientation orientation = AlignedReadOrientation::Forward;
+    std::string spacer_sequence;
+};
+struct FastqRecord { std::string id; Bytes seq, qual; };
+/// ReadSetContainer, read_strategies/read_set.rs:9-14
+struct ReadSetContainer {
+    FastqRecord read_one;
+    std::optional<FastqRecord> read_two, index_one, index_two;
+};
+struct MergedSequence { Bytes read_bases, read_quals; };
+/// orient_sequence, merger.rs:107-126 (Unknown throws as the reference panics)
+Bytes orient_sequence(const uint8_t* sequence, size_t n, AlignedReadOrientation orientation);
+/// merge_reads_by_concatenation, merger.rs:40-105
+MergedSequence merge_reads_by_concatenation(const ReadSetContainer& reads, const std::vector<ReadPosition>& layout);
+
+// ------------------------------------------------------------------------------------------------ references
+/// Reference, reference/fasta_reference.rs:41-46 (the suffix table is outside the path)
+struct Reference { Bytes sequence; Bytes name; };
+
+/// ReferenceManager, reference/fasta_reference.rs:64-146.  `references` keeps insertion order = ascending index, the
+/// canonical iteration order of this build (the reference's HashMap order is random per process).
+class ReferenceManager {
+public:
+    ReferenceManager() = default;
+    ReferenceManager(std::vector<Reference> refs, size_t kmer_size = 8, size_t kmer_skip = 4);
+    static ReferenceManager from_fa_file(const std::string& path, size_t kmer_size = 8, size_t kmer_skip = 4);  // :127-130
+    std::vector<Reference> references;
+    std::map<Bytes, size_t> reference_name_to_ref;
+    size_t kmer_size = 8, kmer_skip = 4, longest_ref = 0;
+    std::vector<std::string> names() const;
+};
+
+/// AlignmentWithRef, alignment_functions.rs:451-456
+struct AlignmentWithRef {
+    std::optional<AlignmentResult> alignment;
+    Bytes ref_name, ref_sequence;
+};
+
+// ------------------------------------------------------------------------------------------------ batches
+/// Page-locked staging buffer for one batch of reads (clq_host_alloc): the batch loop fills it in place, the H2D copy is a
+/// true asynchronous DMA from it.  read i = bytes[off[i] .. off[i+1]).
+class ReadBatch {
+public:
+    ReadBatch(uint32_t max_reads, uint64_t max_bytes);
+    ~ReadBatch();
+    ReadBatch(const ReadBatch&) = delete;
+    ReadBatch& operator=(const ReadBatch&) = delete;
+    void clear();
+    /// false when the read does not fit any more (the caller keeps it for the next batch)
+    bool push(const std::string& name, const uint8_t* seq, size_t n, const uint8_t* qual = nullptr, int32_t fixed_ref = -1);
+    uint32_t size() const { return n_; }
+    uint32_t capacity() const { return max_reads_; }
+    const uint8_t* read(uint32_t i) const { return bytes_ + off_[i]; }
+    size_t read_len(uint32_t i) const { return (size_t)(off_[i + 1] - off_[i]); }
+    const std::string& name(uint32_t i) const { return names_[i]; }
+    std::optional<Bytes> quals(uint32_t i) const;
+    const uint8_t* bytes() const { return bytes_; }
+    const uint64_t* offsets() const { return off_; }
+    const int32_t* fixed_ref() const { return fixed_; }
+    int32_t* fixed_ref_mut() { return fixed_; }
+    uint64_t first_index = 0;  // index of read 0 in the whole input
+
+private:
+    uint32_t max_reads_, n_ = 0;
+    uint64_t max_bytes_;
+    uint8_t* bytes_ = nullptr;
+    uint64_t* off_ = nullptr;
+    int32_t* fixed_ = nullptr;
+    std::vector<std::string> names_;
+    Bytes quals_;
+    bool have_quals_ = false;
+};
+
+class Aligner;
+
+/// Results of one batch, valid during the sink callback (views over the aligner's pinned result buffers)
+class BatchView {
+public:
+    uint32_t size() const { return batch->size(); }
+    const ReadBatch* batch = nullptr;
+    const ReferenceManager* rm = nullptr;
+    const clq_result_t* results = nullptr;
+    const uint32_t* cigar_pool = nullptr;
+    const uint8_t* tags = nullptr;  // CLQ_EXTRACT_TAGS output, tag_stride bytes per read (nullptr when not requested)
+    uint32_t tag_stride = 0;
+    int32_t scale = 1;
+    int device = 0;
+
+    uint32_t status(uint32_t i) const { return results[i].status; }
+    double score(uint32_t i) const { return (double)results[i].score_scaled / (double)scale; }
+    uint32_t ref_index(uint32_t i) const { return results[i].ref_index; }
+    const uint32_t* cigar(uint32_t i) const { return cigar_pool + results[i].cigar_off; }
+    uint32_t cigar_len(uint32_t i) const { return results[i].cigar_len; }
+    std::string cigar_string(uint32_t i) const;
+    /// the `rm` tag from the counters the traceback walk kept (get_reference_alignment_rate fused on the GPU)
+    double alignment_rate(uint32_t i) const;
+    /// extract_tagged_sequences' digit keys, rebuilt from the per-column bytes the walk recorded
+    std::map<uint8_t, std::string> digit_tags(uint32_t i) const;
+    /// the owned record of the reference surface; nullopt for dropped reads (too long / no candidate / diverged traceback)
+    std::optional<AlignmentWithRef> alignment(uint32_t i) const;
+    /// the tag set align_reads writes (alignment_functions.rs:193-226): e<symbol> for the symbols in `umi_symbols`,
+    /// rc = "1", ar = read name, rm, as
+    TagMap align_reads_tags(uint32_t i, const std::string& umi_symbols) const;
+};
+
+struct AlignerOptions {
+    int device = 0;
+    uint32_t max_reads = 1u << 18;      // per batch / stream slot
+    uint64_t max_read_bytes = 0;        // 0: max_reads * 512
+    uint32_t max_read_len = 1u << 16;   // align_reads' drop rule: reads >= this are dropped (alignment_functions.rs:147)
+    uint32_t max_refs = 4096;
+    uint64_t max_ref_bytes = 1u << 26;
+    uint32_t cigar_ops_per_read = 32;
+    uint32_t n_slots = 2;               // stream slots: batch k+1 uploads while batch k computes
+};
+
+/// the source side of the batch loop: fill `batch` (already cleared), return false once the input is exhausted
+using ReadSource = std::function<bool(ReadBatch& batch)>;
+using ResultSink = std::function<void(const BatchView& view)>;
+
+struct AlignReadsStats {
+    uint64_t reads = 0, aligned = 0, dropped = 0, batches = 0, cells = 0;
+    double seconds = 0.0;
+};
+
+/// One clq_ctx on one GPU (reference set, stream slots, pinned result buffers).  Not thread-safe; one per device / thread.
+class Aligner {
+public:
+    explicit Aligner(const AlignerOptions& opt = AlignerOptions());
+    ~Aligner();
+    Aligner(const Aligner&) = delete;
+    Aligner& operator=(const Aligner&) = delete;
+
+    void set_references(const ReferenceManager& rm, bool build_kmer_index = true);
+    const ReferenceManager& references() const { return rm_; }
+    const AlignerOptions& options() const { return opt_; }
+
+    // ---- the reference's call surface (single pair / single read) ----
+    /// align_two_strings, alignment_manager.rs:231-273: fresh matrix, bandwidth = max(L1, L2).  `local` throws (outside the path).
+    AlignmentResult align_two_strings(const Bytes& reference_sequence, const Bytes& read_sequence, std::optional<Bytes> read_qual,
+                                      const AffineScoring& scoring_function, bool local, const std::string& ref_name,
+                                      const std::string& read_name);
+    /// align_two_strings_passed_matrix, alignment_functions.rs:383-449; the caller-owned matrix is gone (scores live in
+    /// registers), `max_indel` must be the read length or cover both sequences -- the only values the reference passes.
+    AlignmentResult align_two_strings_passed_matrix(const std::string& ref_name, const std::string& read_name, const Bytes& reference,
+                                                    const Bytes& read, std::optional<Bytes> qual, const AffineScoring& scoring,
+                                                    size_t max_indel);
+    /// exhaustive_alignment_search, alignment_functions.rs:769-827 (ascending index, last maximum wins)
+    std::optional<AlignmentWithRef> exhaustive_alignment_search(const std::string& read_name, const Bytes& read, std::optional<Bytes> qual,
+                                                                const AffineScoring& scoring);
+    /// quick_alignment_search, alignment_functions.rs:693-767
+    std::optional<AlignmentWithRef> quick_alignment_search(const std::string& read_name, const Bytes& read, std::optional<Bytes> qual,
+                                                           const AffineScoring& scoring, double match_threshold = 0.90);
+    /// align_to_reference_choices, alignment_functions.rs:520-631: 0 references -> nullopt; 1 -> clique's own Gotoh with
+    /// bandwidth = read.len() (the commented-out intent of :586-597; the rust-bio detour is parity-unpinned);
+    /// > 1 -> quick (fast_lookup) or exhaustive search.
+    std::optional<AlignmentWithRef> align_to_reference_choices(const std::string& read_name, const Bytes& read, std::optional<Bytes> qual,
+                                                               bool fast_lookup, const AffineScoring& scoring);
+
+    // ---- the batch loop ----
+    /// align_reads' par_bridge loop (alignment_functions.rs:135-249) up to the writer: drains `source` into pinned batches,
+    /// keeps every stream slot busy, hands each finished batch to `sink`.
+    AlignReadsStats align_reads(const ReadSource& source, const AffineScoring& scoring, bool fast_lookup, const ResultSink& sink,
+                                bool extract_tags = true);
+
+    // ---- raw slot interface (used by ShardedAligner and the bench driver) ----
+    uint32_t search_flags(bool fast_lookup) const;
+    void submit(int slot, const ReadBatch& batch, const clq_affine_t& scoring, uint32_t flags, double threshold = 0.90);
+    BatchView wait(int slot, const ReadBatch& batch);
+    clq_stats_t stats(int slot);
+    clq_ctx* ctx() { return ctx_; }
+
+private:
+    void check(int32_t rc, const char* what) const;
+    AlignmentResult single(const Bytes& reference, const Bytes& read, std::optional<Bytes> qual, const AffineScoring& sc, uint32_t band,
+                           const std::string& ref_name, const std::string& read_name);
+    std::optional<AlignmentWithRef> search(const std::string& read_name, const Bytes& read, std::optional<Bytes> qual,
+                                           const AffineScoring& sc, uint32_t search_mode, double threshold);
+    AlignerOptions opt_;
+    clq_ctx* ctx_ = nullptr;
+    ReferenceManager rm_;
+    std::vector<clq_result_t*> res_;
+    std::vector<uint32_t*> pool_;
+    std::vector<uint8_t*> tags_;
+    std::vector<uint32_t> flags_;
+    std::vector<int32_t> scale_;
+    uint64_t pool_ops_ = 0, tags_cap_ = 0;
+    std::unique_ptr<ReadBatch> one_;  // staging for the single-read calls
+};
+
+/// Read-sharded dispatcher over the GPUs of one box: one Aligner + one host thread per device pull
+/// batches from the shared source; no collective, no peer traffic.  The sink is called under a mutex (the reference's
+/// writer is behind Arc<Mutex<..>> too) in completion order; BatchView::batch->first_index places a batch in the input.
+class ShardedAligner {
+public:
+    ShardedAligner(const std::vector<int>& devices, AlignerOptions opt = AlignerOptions());
+    void set_references(const ReferenceManager& rm, bool build_kmer_index = true);
+    AlignReadsStats align_reads(const ReadSource& source, const AffineScoring& scoring, bool fast_lookup, const ResultSink& sink,
+                                bool extract_tags = true);
+    size_t n_devices() const { return aligners_.size(); }
+    Aligner& aligner(size_t k) { return *aligners_[k]; }
+
+private:
+    std::vector<std::unique_ptr<Aligner>> aligners_;
+};
+
+}  // namespace clique

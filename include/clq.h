@@ -50,6 +50,8 @@ extern "C" {
 #define CLQ_SEARCH_MASK (3u << 2)
 #define CLQ_SCORE_ONLY (1u << 4)        /* skip traceback: score + ref_index only */
 #define CLQ_CONVEX (1u << 5)            /* two-piece affine gaps (scoring given as clq_convex_t) */
+#define CLQ_EXTRACT_TAGS (1u << 6)      /* also record the read bytes aligned to the reference's tag columns '0'..'9':
+                                           extract_tagged_sequences' digit keys, extractor.rs:271-332 (see clq_tags_download) */
 
 /* CIGAR op encoding in the pool: len << 4 | code, BAM codes (AlignmentTag -> Op, alignment/alignment_matrix.rs:95-107) */
 #define CLQ_OP_M 0u /* AlignmentTag::MatchMismatch */
@@ -154,6 +156,13 @@ int32_t clq_submit(clq_ctx* ctx, int32_t slot, uint32_t n_reads, const uint8_t* 
 /* blocks until the slot's work is done and copies results out; cigar_used receives the ops written */
 int32_t clq_wait(clq_ctx* ctx, int32_t slot, clq_result_t* results, uint32_t* cigar_pool, uint64_t cigar_cap,
                  uint64_t* cigar_used);
+
+/* After clq_wait on a batch launched with CLQ_EXTRACT_TAGS: tags[i * tag_stride + k] = the read byte (or '-') aligned to
+ * the k-th tag column (reference byte '0'..'9', in reference order) of read i's reference; bytes past that reference's
+ * column count are undefined.  The tag string of symbol d is the concatenation of the bytes whose column holds d
+ * (extract_tagged_sequences, extractor.rs:271-332; align_reads writes them as the e0..e9 BAM tags,
+ * alignment_functions.rs:193-212).  Only defined for reads with status CLQ_OK.  tags == NULL only reports tag_stride. */
+int32_t clq_tags_download(clq_ctx* ctx, int32_t slot, uint8_t* tags, uint64_t cap, uint32_t* tag_stride);
 
 /* the three stages of clq_submit, separately (kernel-only timing with device-resident inputs) */
 int32_t clq_upload(clq_ctx* ctx, int32_t slot, uint32_t n_reads, const uint8_t* read_bytes, const uint64_t* read_off,

@@ -1,0 +1,43 @@
+/*
+ * clqh.h -- extern "C" view of the pure host-side functions of the C++ host layer (include/clique_host.hpp), exported by
+ * libclq_host.so for the ctypes test-suite.  These are string functions of the path's *output* (SURVEY.md section 8f):
+ * they need no GPU.  The drop-in boundary of the alignment path itself is include/clq.h.
+ * Citations: file:line relative to rust_cmd/src/ of the reference.
+ */
+#ifndef CLQH_H
+#define CLQH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* extract_tagged_sequences, extractor.rs:271-332.  The BTreeMap is returned as records [key u8][len u32 LE][bytes] in key
+ * order; returns bytes written (0 if cap is too small). */
+size_t clqh_extract_tagged_sequences(const uint8_t* aligned_read, size_t n_read, const uint8_t* aligned_ref, size_t n_ref, uint8_t* out,
+                                     size_t cap);
+/* reverse_complement, utils/read_utils.rs:50-72 */
+void clqh_reverse_complement(const uint8_t* dna, size_t n, uint8_t* out);
+/* f64 Display (score.to_string() in the rm / rs / as tags, alignment/alignment_matrix.rs:747-757) */
+size_t clqh_f64_to_string(double v, char* out, size_t cap);
+/* get_reference_alignment_rate, consensus/consensus_builders.rs:288-307 */
+double clqh_get_reference_alignment_rate(const uint8_t* ref_aligned, const uint8_t* read_aligned, size_t n);
+/* simplify_cigar_string, alignment_manager.rs:386-423, on ops encoded len << 4 | code */
+size_t clqh_simplify_cigar(const uint32_t* ops, size_t n, uint32_t* out);
+/* AlignmentResult rebuilt from CIGAR + sequences (gapped strings + path), alignment/alignment_matrix.rs:1019-1086 */
+int32_t clqh_from_cigar(const uint8_t* ref, size_t l1, const uint8_t* read, size_t l2, const uint32_t* ops, size_t n_ops,
+                        uint8_t* ref_aligned, uint8_t* read_aligned, size_t aligned_cap, size_t* aligned_len, uint32_t* path_xy,
+                        size_t path_cap, size_t* path_len);
+/* AlignmentResult::to_sam_record as one SAM text line, alignment/alignment_matrix.rs:741-771; extra_tags = "k1=v;k2=v" */
+size_t clqh_sam_line(const char* ref_name, const char* read_name, const uint8_t* ref, size_t l1, const uint8_t* read, size_t l2,
+                     const uint32_t* ops, size_t n_ops, double score, int32_t reference_id, const char* extra_tags, char* out, size_t cap);
+/* merge_reads_by_concatenation + orient_sequence, merger.rs:40-126; layout items "1F" "2R" "2C" "S:ACGT"; (size_t)-1 = panic */
+size_t clqh_merge_reads_by_concatenation(const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const char* layout, uint8_t* out,
+                                         size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

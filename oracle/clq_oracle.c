@@ -801,3 +801,87 @@ int orc_align_batch(const orc_batch_t* in, const orc_affine_t* sc, orc_batch_out
     orc_kmer_index_free(kix);
     return rc;
 }
+
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Post-alignment string functions on the path's output.
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* is_valid_fasta_base, utils/base_utils.rs:17-23 */
+static int orc_is_valid_fasta_base(uint8_t b) {
+    if (b >= 'a' && b <= 'z') b = (uint8_t)(b - 32);
+    switch (b) {
+        case 'A': case 'C': case 'G': case 'T': case 'U': case 'R': case 'Y': case 'S': case 'W': case 'K': case 'M':
+        case 'B': case 'D': case 'H': case 'V': case 'N': return 1;
+        default: return 0;
+    }
+}
+
+typedef struct { uint8_t* p; size_t n, cap; } orc_bytes_t;
+
+static void orc_push(orc_bytes_t* v, uint8_t b) {
+    if (v->n == v->cap) {
+        v->cap = v->cap ? v->cap * 2 : 64;
+        v->p = (uint8_t*)realloc(v->p, v->cap);
+    }
+    v->p[v->n++] = b;
+}
+
+/* extract_tagged_sequences, extractor.rs:271-332: the match arms in their source order */
+size_t orc_extract_tagged_sequences(const uint8_t* aligned_read, const uint8_t* aligned_ref, size_t n, uint8_t* out, size_t cap) {
+    orc_bytes_t vals[256];
+    memset(vals, 0, sizeof(vals));
+    int in_extractor = 0;
+    unsigned next_read = 'a', next_ref = 'A';
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t rb = aligned_ref[i], qb = aligned_read[i];
+        const int valid = orc_is_valid_fasta_base(rb);
+        const int upper = (rb >= 'A' && rb <= 'Z') || (rb == '-' && in_extractor);
+        const int special = rb >= '0' && rb <= '9'; /* SPECIAL_CHARACTERS, :19-34 */
+        if (upper) {                                 /* (_x, true, _z) */
+            in_extractor = 1;
+            orc_push(&vals[next_ref & 255], rb);
+            orc_push(&vals[next_read & 255], qb);
+        } else if (!valid && !in_extractor && special) { /* (false, _y, false) if special */
+            orc_push(&vals[rb], qb);
+        } else if (!valid && in_extractor && special) {  /* (false, _y, true) if special */
+            orc_push(&vals[next_ref & 255], rb);
+            orc_push(&vals[next_read & 255], qb);
+            orc_push(&vals[rb], qb);
+        } else {                                     /* (_x, false, _z) */
+            if (in_extractor) { next_read++; next_ref++; }
+            in_extractor = 0;
+        }
+    }
+    size_t w = 0;
+    int overflow = 0;
+    for (int k = 0; k < 256; k++) {
+        if (!vals[k].n) { free(vals[k].p); continue; }
+        if (w + 5 + vals[k].n > cap) overflow = 1;
+        if (!overflow) {
+            out[w] = (uint8_t)k;
+            const uint32_t len = (uint32_t)vals[k].n;
+            memcpy(out + w + 1, &len, 4);
+            memcpy(out + w + 5, vals[k].p, vals[k].n);
+            w += 5 + vals[k].n;
+        }
+        free(vals[k].p);
+    }
+    return overflow ? 0 : w;
+}
+
+/* reverse_complement, utils/read_utils.rs:50-72 */
+void orc_reverse_complement(const uint8_t* dna, size_t n, uint8_t* out) {
+    for (size_t i = 0; i < n; i++) {
+        uint8_t b = dna[n - 1 - i];
+        if (b >= 'a' && b <= 'z') b = (uint8_t)(b - 32);
+        uint8_t c = b;
+        switch (b) {
+            case 'A': c = 'T'; break; case 'T': c = 'A'; break; case 'G': c = 'C'; break; case 'C': c = 'G'; break;
+            case 'R': c = 'Y'; break; case 'Y': c = 'R'; break; case 'K': c = 'M'; break; case 'M': c = 'K'; break;
+            case 'B': c = 'V'; break; case 'V': c = 'B'; break; case 'D': c = 'H'; break; case 'H': c = 'D'; break;
+            default: break; /* S, W, N and unknown bytes map to themselves */
+        }
+        out[i] = c;
+    }
+}

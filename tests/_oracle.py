@@ -100,6 +100,10 @@ def lib():
         L.orc_kmer_votes.restype = C.c_uint32
         L.orc_kmer_votes.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p]
         L.orc_align_batch.argtypes = [C.POINTER(Batch), C.POINTER(Affine), C.POINTER(BatchOut)]
+        L.orc_extract_tagged_sequences.restype = C.c_size_t
+        L.orc_extract_tagged_sequences.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.orc_reverse_complement.restype = None
+        L.orc_reverse_complement.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
         _lib = L
     return _lib
 
@@ -240,3 +244,28 @@ def apply_cigar(ref, read, cigar):
         else:
             r += b"-" * n; q += read[y:y + n]; y += n
     return bytes(r), bytes(q)
+
+
+def parse_tag_records(buf):
+    """[key u8][len u32 LE][bytes] records -> {key: bytes}"""
+    out, i = {}, 0
+    while i < len(buf):
+        k, n = buf[i], int.from_bytes(buf[i + 1:i + 5], "little")
+        out[k] = bytes(buf[i + 5:i + 5 + n])
+        i += 5 + n
+    return out
+
+
+def extract_tagged_sequences(aligned_read, aligned_ref):
+    """extractor.rs:271-332 (zips the two strings: stops at the shorter) -> {key byte: bytes}"""
+    n = min(len(aligned_read), len(aligned_ref))
+    cap = 16 * 256 + 3 * n + 64
+    buf = C.create_string_buffer(cap)
+    w = lib().orc_extract_tagged_sequences(bytes(aligned_read), bytes(aligned_ref), n, buf, cap)
+    return parse_tag_records(buf.raw[:w])
+
+
+def reverse_complement(dna):
+    buf = C.create_string_buffer(max(1, len(dna)))
+    lib().orc_reverse_complement(bytes(dna), len(dna), buf)
+    return buf.raw[:len(dna)]

@@ -244,6 +244,35 @@ for lo, hi in ((771, 796), (1059, 1080)):
             alignment_rate.append({"ref": strs[ref_v], "read": strs[read_v], "rate": float(val.group(1)), "cite": "%s:%d-%d" % (CB, lo, hi)})
 assert len(alignment_rate) == 8, alignment_rate
 
+
+# --- extract_tagged_sequences, extractor.rs:491-546 and :642-667 (the e0..e9 BAM tags of align_reads) ---
+EX = "extractor.rs"
+tagged = []
+L = lits(EX, 492, 507)
+tagged.append({"name": "tagged_sequence_test_space", "cite": EX + ":492-507", "ref": L[0], "read": L[1], "expect": {"1": L[2]}})
+L = lits(EX, 510, 518)
+tagged.append({"name": "test_real_example", "cite": EX + ":510-518", "ref": L[0], "read": L[1], "expect": {"1": L[3]}})
+L = lits(EX, 521, 547)
+tagged.append({"name": "lower_and_uppercase_test", "cite": EX + ":521-547", "ref": L[0], "read": L[1], "expect": {"A": L[3], "a": L[4]}})
+L = lits(EX, 643, 648)
+tagged.append({"name": "test_extract_tagged_sequences_basic", "cite": EX + ":643-648", "ref": L[0], "read": L[1], "expect": {"0": L[2]}})
+L = lits(EX, 651, 657)
+tagged.append({"name": "test_extract_tagged_sequences_multiple_tags", "cite": EX + ":651-657", "ref": L[0], "read": L[1],
+               "expect": {"0": L[2], "1": L[3]}})
+L = lits(EX, 660, 667)
+tagged.append({"name": "test_extract_tagged_sequences_uppercase_tracking", "cite": EX + ":660-667", "ref": L[0], "read": L[1],
+               "expect_keys": ["A", "a"]})
+# (test_real_example's strings differ in length: the function zips them and stops at the shorter)
+
+# --- reverse_complement, utils/read_utils.rs:141-198 ---
+RU = "utils/read_utils.rs"
+revcomp_kats = []
+for ln in lines(RU, 141, 190):
+    m = re.search(r'reverse_complement\(b"([^"]*)"\), b"([^"]*)"\)', ln)
+    if m:
+        revcomp_kats.append({"in": m.group(1), "out": m.group(2)})
+assert len(revcomp_kats) == 24, len(revcomp_kats)
+
 # --- ConvexScoring::gap KATs, alignment/scoring_functions.rs:200-213 ---
 convex_gap = [{"gap_open": -10.0, "len": 1, "gap": -10.0}, {"gap_open": -10.0, "len": 10, "gap": -9.0}]
 
@@ -271,6 +300,7 @@ out = {
     "pairs": pairs, "mergers": mergers, "best_ref": best_ref, "fastas": fastas, "tie_table": tie_table,
     "match_mismatch_default_dna": mm_table, "simplify_cigar": simplify, "kmers": kmers, "convex_gap": convex_gap, "alignment_rate": alignment_rate,
     "amplicon_c2": amplicon_c2, "amplicon_c3": amplicon_c3, "survey_kats": survey_kats,
+    "tagged_sequences": tagged, "reverse_complement": revcomp_kats,
 }
 with open(OUT, "w") as f:
     json.dump(out, f, indent=1)

@@ -392,3 +392,64 @@ def test_alignment_rate_tag(al, goldens):
     qb, qo = pack_reads([p["read"].encode()])
     br = al.align_batch(qb, qo, AffineScoring(**p["scoring"]), "fixed", "maxlen", fixed_ref=[0])
     assert br.alignment_rate(0) == get_reference_alignment_rate(r.reference_aligned, r.read_aligned)
+
+
+# ---------------------------------------------------------------- extract_tagged_sequences' digit tags
+def _digit_tags_oracle(ref, read, cigar):
+    ra, qa = O.apply_cigar(ref, read, cigar)
+    return {k: v for k, v in O.extract_tagged_sequences(qa, ra).items() if 48 <= k <= 57}
+
+
+def test_extract_tags_fused_into_walk(al, goldens):
+    """CLQ_EXTRACT_TAGS: the read bytes aligned to the reference's tag columns ('0'..'9'), recorded by the traceback walk,
+    equal extract_tagged_sequences (extractor.rs:271-332) applied to the oracle's gapped strings."""
+    rng = np.random.default_rng(99)
+    # the C2 lineage amplicon (16 + 12 + 12 tag columns) with deletions that eat into the tag runs
+    c = synth.config_c2(700)
+    off = c["read_off"]
+    reads = [bytes(c["read_bytes"][int(off[i]):int(off[i + 1])]) for i in range(700)]
+    ref = c["refs"][0]
+    for i in range(0, 700, 7):  # heavy indels, short and empty reads
+        reads[i] = mutate(rng, reads[i], 0.25)
+    reads[3] = b""
+    reads[5] = reads[5][:30]
+    # a second reference: tags at both ends, mixed case, the extractor-region example of the reference's unit test
+    t = goldens["tagged_sequences"][2]
+    ref2 = t["ref"].replace("-", "").encode()
+    ref3 = b"0000" + rand_seq(rng, 60) + b"11223" + rand_seq(rng, 40) + b"9999999"
+    refs = [ref, ref2, ref3]
+    reads += [mutate(rng, ref2.replace(b"1", b"T"), 0.1) for _ in range(40)]
+    reads += [mutate(rng, ref3.replace(b"0", b"A").replace(b"1", b"C").replace(b"2", b"G").replace(b"9", b"T"), 0.15) for _ in range(60)]
+    fixed = np.array([0] * 700 + [1] * 40 + [2] * 60, np.int32)
+    for name in ("cli", "default_dna"):
+        sc = SCORINGS[name]
+        al.set_references(ReferenceManager([Reference(r, b"r%d" % i) for i, r in enumerate(refs)]))
+        qb, qo = pack_reads(reads)
+        br = al.align_batch(qb, qo, AffineScoring(*sc), "fixed", "readlen", fixed_ref=fixed, extract_tags=True)
+        rb, ro = O.pack_seqs(refs)
+        want = O.align_batch(rb, ro, qb, qo, sc, search="fixed", fixed_ref=fixed, band_mode="readlen", threads=8)
+        compare(br, want, len(reads), name)
+        n_ok = 0
+        for i, rd in enumerate(reads):
+            if int(want["status"][i]) != 0:
+                continue
+            o, l = int(want["cigar_off"][i]), int(want["cigar_len"][i])
+            exp = _digit_tags_oracle(refs[fixed[i]], rd, want["cigar_pool"][o:o + l])
+            assert br.tag_strings(i, refs[fixed[i]]) == exp, (name, i)
+            n_ok += 1
+        assert n_ok > 700
+    # the search modes carry the tags of the selected reference
+    c4 = synth.config_c4(200)
+    off = c4["read_off"]
+    reads = [bytes(c4["read_bytes"][int(off[i]):int(off[i + 1])]) for i in range(200)]
+    refs = [r[:100] + b"0123" + r[104:] for r in c4["refs"][:8]]
+    al.set_references(ReferenceManager([Reference(r, b"r%d" % i) for i, r in enumerate(refs)]))
+    qb, qo = pack_reads(reads)
+    br = al.align_batch(qb, qo, AffineScoring(*c4["scoring"]), "exhaustive", "readlen", extract_tags=True)
+    rb, ro = O.pack_seqs(refs)
+    want = O.align_batch(rb, ro, qb, qo, c4["scoring"], search="exhaustive", band_mode="readlen", threads=8)
+    compare(br, want, 200, "c4-tags")
+    for i, rd in enumerate(reads):
+        o, l = int(want["cigar_off"][i]), int(want["cigar_len"][i])
+        ri = int(want["ref_index"][i])
+        assert br.tag_strings(i, refs[ri]) == _digit_tags_oracle(refs[ri], rd, want["cigar_pool"][o:o + l]), i

@@ -1,0 +1,285 @@
+"""The C++ host layer (include/clique_host.hpp, libclq_host.so): its pure string functions against the oracle and the
+reference's golden vectors (CPU, through the extern "C" view include/clqh.h), and -- on the GPU -- the batch loop
+ShardedAligner::align_reads through the clq_align driver against the oracle + the Python host layer."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import _oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST_LIB = os.path.join(ROOT, "clique_b200", "libclq_host.so")
+CLQ_ALIGN = os.path.join(ROOT, "clique_b200", "clq_align")
+
+SYMBOLS = ["clqh_extract_tagged_sequences", "clqh_reverse_complement", "clqh_f64_to_string", "clqh_get_reference_alignment_rate",
+           "clqh_simplify_cigar", "clqh_from_cigar", "clqh_sam_line", "clqh_merge_reads_by_concatenation"]
+
+
+@pytest.fixture(scope="module")
+def H():
+    assert os.path.exists(HOST_LIB), "build with `make -C clique_b200/csrc` (python __graft_entry__.py)"
+    L = C.CDLL(HOST_LIB)
+    L.clqh_extract_tagged_sequences.restype = C.c_size_t
+    L.clqh_extract_tagged_sequences.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    L.clqh_reverse_complement.restype = None
+    L.clqh_reverse_complement.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
+    L.clqh_f64_to_string.restype = C.c_size_t
+    L.clqh_f64_to_string.argtypes = [C.c_double, C.c_void_p, C.c_size_t]
+    L.clqh_get_reference_alignment_rate.restype = C.c_double
+    L.clqh_get_reference_alignment_rate.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+    L.clqh_simplify_cigar.restype = C.c_size_t
+    L.clqh_simplify_cigar.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    L.clqh_from_cigar.restype = C.c_int32
+    L.clqh_from_cigar.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                  C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.clqh_sam_line.restype = C.c_size_t
+    L.clqh_sam_line.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                C.c_double, C.c_int32, C.c_char_p, C.c_void_p, C.c_size_t]
+    L.clqh_merge_reads_by_concatenation.restype = C.c_size_t
+    L.clqh_merge_reads_by_concatenation.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_void_p, C.c_size_t]
+    return L
+
+
+def h_extract(H, read, ref):
+    cap = 16 * 256 + 3 * max(len(read), len(ref)) + 64
+    buf = C.create_string_buffer(cap)
+    w = H.clqh_extract_tagged_sequences(read, len(read), ref, len(ref), buf, cap)
+    return O.parse_tag_records(buf.raw[:w])
+
+
+def h_f64(H, v):
+    buf = C.create_string_buffer(512)
+    n = H.clqh_f64_to_string(v, buf, 512)
+    return buf.raw[:n].decode()
+
+
+def h_from_cigar(H, ref, read, ops):
+    ops = np.ascontiguousarray(ops, dtype=np.uint32)
+    cap = len(ref) + len(read) + 8
+    ra, qa = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    path = np.zeros(2 * cap, np.uint32)
+    al, pl = C.c_size_t(), C.c_size_t()
+    rc = H.clqh_from_cigar(ref, len(ref), read, len(read), ops.ctypes.data, len(ops), ra, qa, cap, C.byref(al), path.ctypes.data, cap,
+                           C.byref(pl))
+    assert rc == 0, rc
+    return ra.raw[:al.value], qa.raw[:al.value], path[:2 * pl.value].reshape(-1, 2)
+
+
+# ------------------------------------------------------------------------------------------------ CPU: pure host functions
+def test_host_library_exports(H):
+    out = subprocess.run(["nm", "-D", "--defined-only", HOST_LIB], capture_output=True, text=True, check=True).stdout
+    names = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    for s in SYMBOLS:
+        assert s in names, s
+    # every symbol include/clqh.h declares is exported
+    decl = set(re.findall(r"\b(clqh_\w+)\s*\(", open(os.path.join(ROOT, "include", "clqh.h")).read()))
+    assert decl == set(SYMBOLS)
+
+
+def test_extract_tagged_sequences_goldens_cpp(H, goldens):
+    for t in goldens["tagged_sequences"]:
+        got = h_extract(H, t["read"].encode(), t["ref"].encode())
+        for k, v in t.get("expect", {}).items():
+            assert got[ord(k)].decode() == v, (t["name"], k)
+        for k in t.get("expect_keys", []):
+            assert ord(k) in got
+        assert got == O.extract_tagged_sequences(t["read"].encode(), t["ref"].encode()), t["name"]
+
+
+def test_extract_tagged_sequences_random_vs_oracle(H):
+    rng = np.random.default_rng(7)
+    alpha = np.frombuffer(b"ACGTacgtNn-0123456789#", dtype=np.uint8)
+    for _ in range(300):
+        n = int(rng.integers(0, 120))
+        # runs, so that extractor regions and tag runs of realistic shape appear
+        ref = np.repeat(alpha[rng.integers(0, len(alpha), size=n)], rng.integers(1, 5, size=n))[:n].tobytes()
+        read = alpha[rng.integers(0, 9, size=len(ref))].tobytes()
+        assert h_extract(H, read, ref) == O.extract_tagged_sequences(read, ref)
+
+
+def test_reverse_complement_cpp(H, goldens):
+    for t in goldens["reverse_complement"]:
+        buf = C.create_string_buffer(max(1, len(t["in"])))
+        H.clqh_reverse_complement(t["in"].encode(), len(t["in"]), buf)
+        assert buf.raw[:len(t["in"])].decode() == t["out"], t
+    rng = np.random.default_rng(3)
+    for _ in range(100):
+        s = rng.integers(33, 127, size=int(rng.integers(0, 80))).astype(np.uint8).tobytes()
+        buf = C.create_string_buffer(max(1, len(s)))
+        H.clqh_reverse_complement(s, len(s), buf)
+        assert buf.raw[:len(s)] == O.reverse_complement(s)
+
+
+def test_alignment_rate_cpp(H, goldens):
+    for t in goldens["alignment_rate"]:
+        assert H.clqh_get_reference_alignment_rate(t["ref"].encode(), t["read"].encode(), len(t["ref"])) == t["rate"]
+    assert np.isnan(H.clqh_get_reference_alignment_rate(b"NNNN", b"ACGT", 4))
+
+
+def test_simplify_cigar_cpp(H, goldens):
+    for t in goldens["simplify_cigar"]:
+        ops = np.array(O.cigar_parse(t["in"]), dtype=np.uint32)
+        out = np.zeros(max(1, len(ops)), np.uint32)
+        n = H.clqh_simplify_cigar(ops.ctypes.data if len(ops) else None, len(ops), out.ctypes.data)
+        assert O.cigar_str(out[:n]) == t["out"], t
+
+
+def test_f64_display(H):
+    # Rust `Display` for f64 (score.to_string() / rate.to_string() in the BAM tags)
+    for v, s in [(979.0, "979"), (391.5, "391.5"), (13.75, "13.75"), (-40.0, "-40"), (0.0, "0"), (1.0, "1"), (0.5, "0.5"),
+                 (0.9866666666666667, "0.9866666666666667"), (1e-5, "0.00001"), (2.5e-7, "0.00000025"), (1e21, "1000000000000000000000"),
+                 (float("nan"), "NaN"), (float("inf"), "inf"), (float("-inf"), "-inf"), (1 / 3, "0.3333333333333333")]:
+        assert h_f64(H, v) == s, (v, h_f64(H, v))
+    rng = np.random.default_rng(11)
+    for _ in range(500):
+        m, mm = int(rng.integers(0, 400)), int(rng.integers(1, 50))
+        v = m / (m + mm)
+        s = h_f64(H, v)
+        assert float(s) == v and "e" not in s and (repr(v) == s or repr(v) == s + ".0" or "e" in repr(v))
+
+
+def test_from_cigar_matches_oracle_traceback(H, goldens):
+    # gapped strings and path rebuilt from (CIGAR, sequences) == what the traceback itself produced
+    for p in goldens["pairs"]:
+        ref, read = p["ref"].encode(), p["read"].encode()
+        a = O.align_pair(ref, read, p["scoring"], p["band_mode"])
+        ra, qa, path = h_from_cigar(H, ref, read, a["cigar"])
+        assert ra == a["ref_aligned"] and qa == a["read_aligned"], p["name"]
+        assert len(path) == a["path_len"], p["name"]  # one entry per unit op of the main loop (leading boundary run excluded)
+        assert all(0 <= x <= len(ref) and 0 <= y <= len(read) for x, y in path.tolist())
+        e = p["expect"]
+        if "ref_aligned" in e:
+            assert ra.decode() == e["ref_aligned"] and qa.decode() == e["read_aligned"], p["name"]
+
+
+def test_sam_line(H, goldens):
+    p = goldens["pairs"][2]  # affine_alignment_test: AAAA vs AATAA -> 2M1I2M, score 4
+    ref, read = p["ref"].encode(), p["read"].encode()
+    a = O.align_pair(ref, read, p["scoring"], "maxlen")
+    ops = np.ascontiguousarray(a["cigar"], dtype=np.uint32)
+    buf = C.create_string_buffer(4096)
+    n = H.clqh_sam_line(b"amp", b"r1", ref, len(ref), read, len(read), ops.ctypes.data, len(ops), a["score"], 0, b"e1=ACGT;rc=1;ar=r1", buf, 4096)
+    f = buf.raw[:n].decode().split("\t")
+    # to_sam_record, alignment/alignment_matrix.rs:741-771: empty flags, POS = reference_start + 1, SEQ = read without gaps,
+    # every quality forced to raw 'H' (72 -> 'i' in SAM text), tags rm / rs / as appended after the extra tags
+    assert f[:11] == ["r1", "0", "amp", "1", "255", O.cigar_str(ops), "*", "0", "0", p["read"], "i" * len(read)]
+    tags = dict(x.split(":Z:") for x in f[11:])
+    rate, m, mm = O.alignment_rate(a["ref_aligned"], a["read_aligned"])
+    assert tags == {"ar": "r1", "e1": "ACGT", "rc": "1", "rm": h_f64(H, rate), "rs": h_f64(H, a["score"]), "as": h_f64(H, a["score"])}
+    assert [x[:2] for x in f[11:]] == ["ar", "e1", "rc", "rm", "rs", "as"]
+    assert tags["as"] == "4"
+
+
+def test_merge_reads_by_concatenation(H):
+    # merge_reads_by_concatenation + orient_sequence, merger.rs:40-126
+    def merge(r1, r2, layout):
+        buf = C.create_string_buffer(1024)
+        n = H.clqh_merge_reads_by_concatenation(r1, len(r1), r2, len(r2) if r2 is not None else 0, layout.encode(), buf, 1024)
+        return None if n == 2 ** 64 - 1 else buf.raw[:n]
+
+    assert merge(b"AACC", b"GGTA", "1F,2F") == b"AACCGGTA"                     # ConcatenateBothForward
+    assert merge(b"AACC", b"GGTA", "1F,2C") == b"AACC" + O.reverse_complement(b"GGTA")
+    assert merge(b"AACC", b"GGTA", "1F,S:NNNN,2R") == b"AACCNNNNATGG"
+    assert merge(b"aacc", b"GGTA", "2F,1C") == b"GGTAGGTT"                     # reverse_complement upper-cases
+    assert merge(b"AACC", None, "1F") == b"AACC"
+    assert merge(b"AACC", None, "1F,2F") is None                               # assert!(reads.read_two.is_some()) panics
+    assert merge(b"AACC", b"GG", "1U") is None                                 # Unknown orientation panics
+
+
+# ------------------------------------------------------------------------------------------------ GPU: the batch loop in C++
+def _write_inputs(tmp, refs, names, reads, fastq=True):
+    fa = os.path.join(tmp, "refs.fa")
+    with open(fa, "wb") as f:
+        for n, r in zip(names, refs):
+            f.write(b">" + n + b"\n" + r + b"\n")
+    rp = os.path.join(tmp, "reads.fastq" if fastq else "reads.txt")
+    with open(rp, "wb") as f:
+        for i, r in enumerate(reads):
+            if fastq:
+                f.write(b"@q%d some comment\n" % i + r + b"\n+\n" + b"F" * len(r) + b"\n")
+            else:
+                f.write(r + b"\n")
+    return fa, rp
+
+
+def _run_clq_align(tmp, fa, rp, extra=()):
+    out = os.path.join(tmp, "out.sam")
+    st = os.path.join(tmp, "stats.json")
+    cmd = [CLQ_ALIGN, "--refs", fa, "--reads", rp, "--out", out, "--stats-json", st, "--batch", "257", "--cigar-ops-per-read", "256"] + list(extra)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = [ln.rstrip("\n").split("\t") for ln in open(out) if not ln.startswith("@")]
+    head = [ln.rstrip("\n") for ln in open(out) if ln.startswith("@")]
+    return head, lines, json.load(open(st))
+
+
+def _expect_lines(H, want, refs, names, reads, qnames, umi="0123456789"):
+    """SAM fields the reference's align_reads + to_sam_record would produce, from the oracle's alignment"""
+    exp = []
+    for i, rd in enumerate(reads):
+        if int(want["status"][i]) != 0:
+            continue
+        ri = int(want["ref_index"][i])
+        o, l = int(want["cigar_off"][i]), int(want["cigar_len"][i])
+        cig = want["cigar_pool"][o:o + l]
+        ra, qa = O.apply_cigar(refs[ri], rd, cig)
+        tags = {"rc": "1", "ar": qnames[i], "rm": h_f64(H, O.alignment_rate(ra, qa)[0]), "as": h_f64(H, float(want["score"][i]))}
+        tags["rs"] = tags["as"]
+        for k, v in O.extract_tagged_sequences(qa, ra).items():
+            if chr(k) in umi:
+                tags["e" + chr(k)] = v.decode()
+        exp.append(([qnames[i], "0", names[ri].decode(), "1", "255", O.cigar_str(cig), "*", "0", "0", rd.decode(), "i" * len(rd)], tags))
+    return exp
+
+
+def _check(lines, exp):
+    assert len(lines) == len(exp)
+    for got, (fields, tags) in zip(lines, exp):
+        assert got[:11] == fields, (got[0], got[:6], fields[:6])
+        assert dict(x.split(":Z:") for x in got[11:]) == tags, got[0]
+
+
+@pytest.mark.gpu
+def test_clq_align_single_amplicon(H, tmp_path):
+    from clique_b200 import synth
+    c = synth.config_c2(1500)
+    off = c["read_off"]
+    reads = [bytes(c["read_bytes"][int(off[i]):int(off[i + 1])]) for i in range(1500)]
+    reads[7] = reads[7][:40]                       # ragged
+    reads[11] = reads[11] + reads[12]              # 600 bp >= 2 * 216: dropped with a warning by align_reads
+    refs, names = c["refs"], c["ref_names"]
+    fa, rp = _write_inputs(str(tmp_path), refs, names, reads)
+    head, lines, st = _run_clq_align(str(tmp_path), fa, rp)
+    assert head[1] == "@SQ\tSN:lineage_amplicon\tLN:215" and head[-1] == "@CO\tClique processed"
+    keep = [i for i, r in enumerate(reads) if len(r) < 2 * 216]
+    rb, ro = O.pack_seqs(refs)
+    qb, qo = O.pack_seqs([reads[i] for i in keep])
+    want = O.align_batch(rb, ro, qb, qo, c["scoring"], search="fixed", fixed_ref=np.zeros(len(keep), np.int32), band_mode="readlen", threads=8)
+    exp = _expect_lines(H, want, refs, names, [reads[i] for i in keep], ["q%d" % i for i in keep])
+    _check(lines, exp)
+    assert st["reads"] == 1500 and st["dropped"] == 1500 - len(exp) and st["batches"] == 6
+    # the lineage amplicon has three tag runs (16 + 12 + 12 columns): e0 / e1 / e2 present on every record
+    assert all({"e0", "e1", "e2"} <= {x[:2] for x in ln[11:]} for ln in lines)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["quick", "exhaustive"])
+def test_clq_align_panel(H, tmp_path, mode):
+    from clique_b200 import synth
+    c = synth.config_c4(600, search=mode)
+    off = c["read_off"]
+    reads = [bytes(c["read_bytes"][int(off[i]):int(off[i + 1])]) for i in range(600)]
+    refs, names = c["refs"][:16], c["ref_names"][:16]
+    fa, rp = _write_inputs(str(tmp_path), refs, names, reads, fastq=False)
+    head, lines, st = _run_clq_align(str(tmp_path), fa, rp, ["--exhaustive"] if mode == "exhaustive" else [])
+    rb, ro = O.pack_seqs(refs)
+    qb, qo = O.pack_seqs(reads)
+    want = O.align_batch(rb, ro, qb, qo, c["scoring"], search=mode, band_mode="readlen", kmer=(8, 4), threads=8)
+    exp = _expect_lines(H, want, refs, names, reads, ["read%d" % i for i in range(600)])
+    _check(lines, exp)
+    assert st["reads"] == 600

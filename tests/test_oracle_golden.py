@@ -181,3 +181,21 @@ def test_alignment_rate_goldens(goldens):
         a = O.align_pair(p["ref"].encode(), p["read"].encode(), p["scoring"], "maxlen")
         r, m, mm = O.alignment_rate(a["ref_aligned"], a["read_aligned"])
         assert (a["matches"], a["mismatches"]) == (m, mm)
+
+
+def test_extract_tagged_sequences_goldens(goldens):
+    # extractor.rs:491-546, :642-667
+    for t in goldens["tagged_sequences"]:
+        got = O.extract_tagged_sequences(t["read"].encode(), t["ref"].encode())
+        for k, v in t.get("expect", {}).items():
+            assert got[ord(k)].decode() == v, (t["name"], k)
+        for k in t.get("expect_keys", []):
+            assert ord(k) in got, (t["name"], k)
+
+
+def test_reverse_complement_goldens(goldens):
+    # utils/read_utils.rs:141-198
+    for t in goldens["reverse_complement"]:
+        assert O.reverse_complement(t["in"].encode()).decode() == t["out"], t
+    seq = b"ACGTRYSWKMBDHVN"
+    assert O.reverse_complement(O.reverse_complement(seq)) == seq
