@@ -90,8 +90,19 @@ struct KParams {
 struct TbRec {
     uint32_t ridx;   // read index (results slot)
     int32_t L1, L2;  // L1 < 0: nothing to walk (dropped read / no candidate)
-    int32_t zK;      // start layer | stale rows K << 2
+    int32_t zK;      // start layer | stale rows K << 2 | (columns per lane of the narrow last stripe) / 8 << 20 | its index << 24
 };
+
+// Narrow last stripe (G >= 16 geometries of the FAST / PACK kernels): the last column stripe of a task holds
+// R = L2 - (NS-1)*W <= W columns; instead of C columns per lane (most of them padding) every lane takes
+// Cs = ceil(R / (8 G)) * 8 columns, so a 1100-column read on the (32,32) geometry costs 1024 + 256 columns, not 2048.
+// The walker gets (Cs / 8, stripe index) in TbRec.zK.
+template <int G>
+__host__ __device__ __forceinline__ int narrow_cols(int R, int C) {
+    const int cs = (R + G * 8 - 1) / (G * 8) * 8;
+    return cs < C ? cs : C;
+}
+constexpr int kMaxNarrowStripe = 255;
 
 __device__ __forceinline__ bool is_special(int c) { return c == 'N' || c < 58; }
 
@@ -152,12 +163,13 @@ __device__ __forceinline__ size_t tt_index(int s, int Tb, int t, int ln, int k) 
 // sectors [G x 4 words][G x (WPL-4) words].  The transposed layout only pays off when the walk is a visible share of the
 // step (short reads); for long reads the extra shared-memory traffic costs more than the walk gains.
 template <int G, int WPL>
-__device__ __forceinline__ void row_store(uint32_t* bits_g, const uint32_t (&w)[WPL], int s, int T, int t, int gl) {
+__device__ __forceinline__ void row_store(uint32_t* bits_g, const uint32_t (&w)[WPL], int s, int T, int t, int gl, int nb) {
     uint32_t* row = bits_g + (size_t)(s * T + (t - 1)) * (G * WPL);
     if constexpr (WPL >= 4) {
         *reinterpret_cast<uint4*>(row + gl * 4) = make_uint4(w[0], w[1], w[2], w[3]);
 #pragma unroll
-        for (int k = 4; k < WPL; k++) row[G * 4 + gl * (WPL - 4) + (k - 4)] = w[k];
+        for (int k = 4; k < WPL; k++)
+            if (k < nb) row[G * 4 + gl * (WPL - 4) + (k - 4)] = w[k];
     } else if constexpr (WPL == 2) {
         *reinterpret_cast<uint2*>(row + gl * 2) = make_uint2(w[0], w[1]);
     } else {
@@ -178,9 +190,9 @@ struct BitsLayout { static constexpr bool transposed = (G <= 8); };
 
 template <int G, int WPL>
 __device__ __forceinline__ void bits_store(uint32_t* tt, uint32_t* bits_g, const uint32_t (&w)[WPL], int s, int T, int t, int lane, int gl,
-                                           bool last_row) {
+                                           bool last_row, int nb = WPL) {
     if constexpr (BitsLayout<G>::transposed) tt_store<G, WPL>(tt, bits_g, w, s, (T + 7) >> 3, t, lane, gl, last_row);
-    else row_store<G, WPL>(bits_g, w, s, T, t, gl);
+    else row_store<G, WPL>(bits_g, w, s, T, t, gl, nb);
 }
 
 template <int G, int WPL>
@@ -233,33 +245,39 @@ __device__ __forceinline__ void row_step(int (&E)[C], int (&B)[C], const int (&b
 template <int C, bool TB, bool LAST>
 __device__ __forceinline__ void row_step_fast(int (&Eh)[C], int (&B)[C], const int (&sel)[C], uint32_t (&w)[C / 8], int& Fh,
                                               int& Ehl, int& Ml, int& Bl, int diag, uint32_t tlo, uint32_t thi, int le, int x1,
-                                              bool own_last, int jL, int& capM, int& capE, int& capF) {
+                                              bool own_last, int jL, int& capM, int& capE, int& capF, int nb) {
     const int x1m1 = x1 - 1;
 #pragma unroll
-    for (int j = 0; j < C; j++) {
-        const int m = prmt_s8(tlo, thi, (uint32_t)sel[j]);
-        const int Mv = diag + m;
-        const int EhU = Eh[j], BU = B[j];
-        const int Ehn = __viaddmax_s32(EhU, le, BU);
-        int d2 = 0;
-        if (TB) d2 = __viaddmax_s32(Ehl, x1m1, Ml) - Fh - le;  // < 0  <=>  F extends (>= E-open, > M-open)
-        const int Fhn = __viaddmax_s32(Fh, le, Bl);
-        const int Pv = __viaddmax_s32(Fhn, x1, Mv);
-        const int Bn = __viaddmax_s32(Ehn, x1, Pv);
-        if (TB) {
-            uint32_t acc = w[j >> 3];
-            acc = __funnelshift_l((uint32_t)(BU - Ehn), acc, 1);  // ext1: Eh_up + le > B_up
-            acc = __funnelshift_l((uint32_t)d2, acc, 1);          // ext2
-            acc = __funnelshift_l((uint32_t)(Pv - Bn), acc, 1);   // eP: E > max(M,F)
-            acc = __funnelshift_l((uint32_t)(Mv - Pv), acc, 1);   // fM: F > M
-            w[j >> 3] = acc;
-        }
-        diag = BU;
-        Eh[j] = Ehn;
-        B[j] = Bn;
-        Fh = Fhn; Ehl = Ehn; Ml = Mv; Bl = Bn;
-        if (LAST) {
-            if (own_last && j == jL) { capM = Mv; capE = Ehn + x1; capF = Fhn + x1; }
+    for (int jb = 0; jb < C / 8; jb++) {
+        if (jb < nb) {  // narrow last stripe: only nb blocks of 8 columns per lane are real
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                const int j = jb * 8 + jj;
+                const int m = prmt_s8(tlo, thi, (uint32_t)sel[j]);
+                const int Mv = diag + m;
+                const int EhU = Eh[j], BU = B[j];
+                const int Ehn = __viaddmax_s32(EhU, le, BU);
+                int d2 = 0;
+                if (TB) d2 = __viaddmax_s32(Ehl, x1m1, Ml) - Fh - le;  // < 0  <=>  F extends (>= E-open, > M-open)
+                const int Fhn = __viaddmax_s32(Fh, le, Bl);
+                const int Pv = __viaddmax_s32(Fhn, x1, Mv);
+                const int Bn = __viaddmax_s32(Ehn, x1, Pv);
+                if (TB) {
+                    uint32_t acc = w[jb];
+                    acc = __funnelshift_l((uint32_t)(BU - Ehn), acc, 1);  // ext1: Eh_up + le > B_up
+                    acc = __funnelshift_l((uint32_t)d2, acc, 1);          // ext2
+                    acc = __funnelshift_l((uint32_t)(Pv - Bn), acc, 1);   // eP: E > max(M,F)
+                    acc = __funnelshift_l((uint32_t)(Mv - Pv), acc, 1);   // fM: F > M
+                    w[jb] = acc;
+                }
+                diag = BU;
+                Eh[j] = Ehn;
+                B[j] = Bn;
+                Fh = Fhn; Ehl = Ehn; Ml = Mv; Bl = Bn;
+                if (LAST) {
+                    if (own_last && j == jL) { capM = Mv; capE = Ehn + x1; capF = Fhn + x1; }
+                }
+            }
         }
     }
 }
@@ -343,22 +361,26 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
         const int NSmax = __reduce_max_sync(FULL, NS);
         const int T = run ? L1 + G - 1 : 0;
         const int Tmax = __reduce_max_sync(FULL, T);
-        // the lane / register that own column L2 in the last stripe
+        // the lane / register that own column L2 in the last stripe (narrow: CsL <= C columns per lane there)
         const int cL = run ? (L2 - 1) - (NS - 1) * W : 0;
-        const int lL = cL / C, jL = cL - lL * C;
+        const bool narrow = FAST && G >= 16 && NS - 1 <= kMaxNarrowStripe;
+        const int CsL = (run && narrow) ? narrow_cols<G>(cL + 1, C) : C;
+        const int lL = cL / CsL, jL = cL - lL * CsL;
         int capM = 0, capE = 0, capF = 0;
 
         for (int s = 0; s < NSmax; s++) {
             const bool act_s = run && s < NS;
             const bool own_last = act_s && s == NS - 1 && gl == lL;
-            const int y0 = s * W + gl * C;  // columns y0+1 .. y0+C
+            const int Cs = (G >= 16 && s == NS - 1) ? CsL : C;  // compile-time C for the short-read geometries
+            const int nb = Cs >> 3;
+            const int y0 = s * W + gl * Cs;  // columns y0+1 .. y0+Cs
             int E[C], B[C], bq[C];
             uint32_t w[WPL];
 #pragma unroll
             for (int j = 0; j < C; j++) {
                 const int y = y0 + j + 1;
                 int code = FAST ? 1 : 0x400;  // padding column: never equal, not special
-                if (act_s && y <= L2) {
+                if (act_s && y <= L2 && j < Cs) {
                     const int c = readp[y - 1];
                     code = FAST ? (int)lut_sm[c] : (is_special(c) ? (c | 0x100) : c);
                 }
@@ -405,9 +427,9 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
                     if (FAST) {
                         const uint2 tr = *(const uint2*)(tab_sm + r * 8);
                         if (x == L1)
-                            row_step_fast<C, TB, true>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, sc.e_in, sc.oe_in, own_last, jL, capM, capE, capF);
+                            row_step_fast<C, TB, true>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, sc.e_in, sc.oe_in, own_last, jL, capM, capE, capF, nb);
                         else
-                            row_step_fast<C, TB, false>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, sc.e_in, sc.oe_in, own_last, jL, capM, capE, capF);
+                            row_step_fast<C, TB, false>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, sc.e_in, sc.oe_in, own_last, jL, capM, capE, capF, nb);
                     } else {
                         const bool rsp = is_special(r);
                         const int rcode = rsp ? 0x200 : r;
@@ -426,10 +448,10 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
 #pragma unroll
                         for (int j = 0; j < C; j++)
                             if (j == jL) { E[j] = e0; B[j] = 0; }
-                        if (jL == C - 1) { oF = e0; oE = e0; oM = 0; oB = 0; }
+                        if (jL == Cs - 1) { oF = e0; oE = e0; oM = 0; oB = 0; }
                         if (x == L1) { capM = 0; capE = 0; capF = 0; }
                     }
-                    if (TB) bits_store<G, WPL>(tt_sm, bits_g, w, s, T, t, lane, gl, x == L1);
+                    if (TB) bits_store<G, WPL>(tt_sm, bits_g, w, s, T, t, lane, gl, x == L1, nb);
                     if (gl == G - 1 && s < NS - 1) {
                         col_g[x] = oF; col_g[p.col_stride + x] = oE; col_g[2 * p.col_stride + x] = oM; col_g[3 * p.col_stride + x] = oB;
                     }
@@ -472,7 +494,8 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
             r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = 0; r.cigar_len = 0; r.status = status; r.matches = 0; r.mismatches = 0;
             p.results[ridx] = r;
             TbRec rec;
-            rec.ridx = ridx; rec.L1 = ok ? L1 : -1; rec.L2 = L2; rec.zK = z | (K << 2);
+            rec.ridx = ridx; rec.L1 = ok ? L1 : -1; rec.L2 = L2;
+            rec.zK = z | (K << 2) | ((CsL >> 3) << 20) | ((narrow && run ? NS - 1 : 0) << 24);
             p.tb_rec[task] = rec;
             if (run) atomicAdd(p.cells, (unsigned long long)L1 * (unsigned long long)L2);
         }
@@ -495,7 +518,8 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
     if (q >= n_tasks) return;
     const TbRec rec = recs[q];
     if (rec.L1 < 0) return;
-    const int L1 = rec.L1, L2 = rec.L2, K = rec.zK >> 2;
+    const int L1 = rec.L1, L2 = rec.L2, K = (rec.zK >> 2) & 0x3ffff;
+    const int CsL = ((rec.zK >> 20) & 15) * 8, sL = (rec.zK >> 24) & 255;  // the task's narrow last stripe (G >= 16 only)
     int z = rec.zK & 3;
     const int T = L1 + G - 1;
     const uint32_t* bits_g = bits + bits_slot(bits_off, bits_stride, task_base, q);
@@ -535,7 +559,8 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
         int c = yy - 1;
         const int s = c / W;
         c -= s * W;
-        const int ln = c / C, j = c - ln * C;
+        const int cs = (G >= 16 && s == sL && CsL > 0) ? CsL : C;
+        const int ln = c / cs, j = c - ln * cs;
         const size_t idx = bits_index<G, WPL>(s, T, xx + ln, ln, j >> 3);
         return (__ldg(bits_g + idx) >> (28 - 4 * (j & 7))) & 15u;
     };

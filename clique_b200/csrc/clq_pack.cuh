@@ -29,44 +29,50 @@ template <int C, bool TB, bool LAST>
 __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C], const uint32_t (&sel)[C], uint32_t (&wA)[C / 8],
                                               uint32_t (&wB)[C / 8], uint32_t& Fh, uint32_t& Ehl, uint32_t& Ml, uint32_t& Bl, uint32_t diag,
                                               uint32_t tlo, uint32_t thi, uint32_t LE, uint32_t X1, uint32_t X1M1, bool ownA, int jA,
-                                              bool ownB, int jB, uint32_t (&cap)[3]) {
+                                              bool ownB, int jB, uint32_t (&cap)[3], int nb) {
     const uint32_t ONE = 0x00010001u;
-    uint32_t acc0 = 0, acc1 = 0;
 #pragma unroll
-    for (int j = 0; j < C; j++) {
-        const uint32_t m = (uint32_t)prmt_s8(tlo, thi, sel[j]);  // [mA, mB] as s16x2
-        const uint32_t Mv = __viaddmax_s16x2(diag, m, 0u);       // per-half add (biased values are > 0)
-        const uint32_t EhU = Eh[j], BU = B[j];
-        const uint32_t Ehn = __viaddmax_s16x2(EhU, LE, BU);
-        uint32_t t2 = 0, u2 = 0;
-        if (TB) {
-            t2 = __viaddmax_s16x2(Ehl, X1M1, Ml);
-            u2 = __viaddmax_s16x2(Fh, LE, t2);  // > t2  <=>  F extends (>= E-open, > M-open)
-        }
-        const uint32_t Fhn = __viaddmax_s16x2(Fh, LE, Bl);
-        const uint32_t Pv = __viaddmax_s16x2(Fhn, X1, Mv);
-        const uint32_t Bn = __viaddmax_s16x2(Ehn, X1, Pv);
-        if (TB) {
-            // nibble pair [ext1 ext2 eP fM] of this cell pair, then 4 cells per 16-bit half
-            uint32_t nib = __vminu2(Ehn - BU, ONE);                 // ext1
-            nib = nib * 2u + __vminu2(u2 - t2, ONE);                // ext2
-            nib = nib * 2u + __vminu2(Bn - Pv, ONE);                // eP: E > max(M,F)
-            nib = nib * 2u + __vminu2(Pv - Mv, ONE);                // fM: F > M
-            uint32_t a = ((j & 4) ? acc1 : acc0);
-            a = ((j & 3) == 0) ? nib : a * 16u + nib;
-            if (j & 4) acc1 = a; else acc0 = a;
-            if ((j & 7) == 7) {
-                wA[j >> 3] = __byte_perm(acc1, acc0, 0x5410);  // low halves: read A's 8 nibbles
-                wB[j >> 3] = __byte_perm(acc1, acc0, 0x7632);  // high halves: read B's
+    for (int jb = 0; jb < C / 8; jb++) {
+        if (jb < nb) {  // narrow last stripe: only nb blocks of 8 columns per lane are real
+            uint32_t acc0 = 0, acc1 = 0;
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                const int j = jb * 8 + jj;
+                const uint32_t m = (uint32_t)prmt_s8(tlo, thi, sel[j]);  // [mA, mB] as s16x2
+                const uint32_t Mv = __viaddmax_s16x2(diag, m, 0u);       // per-half add (biased values are > 0)
+                const uint32_t EhU = Eh[j], BU = B[j];
+                const uint32_t Ehn = __viaddmax_s16x2(EhU, LE, BU);
+                uint32_t t2 = 0, u2 = 0;
+                if (TB) {
+                    t2 = __viaddmax_s16x2(Ehl, X1M1, Ml);
+                    u2 = __viaddmax_s16x2(Fh, LE, t2);  // > t2  <=>  F extends (>= E-open, > M-open)
+                }
+                const uint32_t Fhn = __viaddmax_s16x2(Fh, LE, Bl);
+                const uint32_t Pv = __viaddmax_s16x2(Fhn, X1, Mv);
+                const uint32_t Bn = __viaddmax_s16x2(Ehn, X1, Pv);
+                if (TB) {
+                    // nibble pair [ext1 ext2 eP fM] of this cell pair, then 4 cells per 16-bit half
+                    uint32_t nib = __vminu2(Ehn - BU, ONE);                 // ext1
+                    nib = nib * 2u + __vminu2(u2 - t2, ONE);                // ext2
+                    nib = nib * 2u + __vminu2(Bn - Pv, ONE);                // eP: E > max(M,F)
+                    nib = nib * 2u + __vminu2(Pv - Mv, ONE);                // fM: F > M
+                    uint32_t a = ((jj & 4) ? acc1 : acc0);
+                    a = ((jj & 3) == 0) ? nib : a * 16u + nib;
+                    if (jj & 4) acc1 = a; else acc0 = a;
+                    if (jj == 7) {
+                        wA[jb] = __byte_perm(acc1, acc0, 0x5410);  // low halves: read A's 8 nibbles
+                        wB[jb] = __byte_perm(acc1, acc0, 0x7632);  // high halves: read B's
+                    }
+                }
+                diag = BU;
+                Eh[j] = Ehn;
+                B[j] = Bn;
+                Fh = Fhn; Ehl = Ehn; Ml = Mv; Bl = Bn;
+                if (LAST) {
+                    if (ownA && j == jA) { cap[0] = set_lo(cap[0], get_lo(Mv)); cap[1] = set_lo(cap[1], get_lo(Ehn)); cap[2] = set_lo(cap[2], get_lo(Fhn)); }
+                    if (ownB && j == jB) { cap[0] = set_hi(cap[0], get_hi(Mv)); cap[1] = set_hi(cap[1], get_hi(Ehn)); cap[2] = set_hi(cap[2], get_hi(Fhn)); }
+                }
             }
-        }
-        diag = BU;
-        Eh[j] = Ehn;
-        B[j] = Bn;
-        Fh = Fhn; Ehl = Ehn; Ml = Mv; Bl = Bn;
-        if (LAST) {
-            if (ownA && j == jA) { cap[0] = set_lo(cap[0], get_lo(Mv)); cap[1] = set_lo(cap[1], get_lo(Ehn)); cap[2] = set_lo(cap[2], get_lo(Fhn)); }
-            if (ownB && j == jB) { cap[0] = set_hi(cap[0], get_hi(Mv)); cap[1] = set_hi(cap[1], get_hi(Ehn)); cap[2] = set_hi(cap[2], get_hi(Fhn)); }
         }
     }
 }
@@ -175,16 +181,20 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel
         __syncwarp();
 
         const int L2m = max(run[0] ? L2[0] : 0, run[1] ? L2[1] : 0);
+        const int NS = anyrun ? (L2m + W - 1) / W : 0;
+        // narrow last stripe of the PAIR: both reads share the lane mapping, so the longer one sets the width
+        const bool narrow = G >= 16 && NS - 1 <= kMaxNarrowStripe;
+        const int CsL = (anyrun && narrow) ? narrow_cols<G>(L2m - (NS - 1) * W, C) : C;
         int K[2], NSh[2], lLh[2], jLh[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             K[h] = run[h] ? stale_rows(L1, L2[h], p.band_mode) : 0;
             NSh[h] = run[h] ? (L2[h] + W - 1) / W : 0;
             const int cL = run[h] ? (L2[h] - 1) - (NSh[h] - 1) * W : 0;
-            lLh[h] = cL / C;
-            jLh[h] = cL - lLh[h] * C;
+            const int csh = (NSh[h] == NS) ? CsL : C;  // its last column lies in the pair's last stripe?
+            lLh[h] = cL / csh;
+            jLh[h] = cL - lLh[h] * csh;
         }
-        const int NS = anyrun ? (L2m + W - 1) / W : 0;
         const int NSmax = __reduce_max_sync(FULL, NS);
         const int T = anyrun ? L1 + G - 1 : 0;
         const int Tmax = __reduce_max_sync(FULL, T);
@@ -196,15 +206,17 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel
             const bool act_s = anyrun && s < NS;
             const bool ownA = run[0] && s == NSh[0] - 1 && gl == lLh[0];
             const bool ownB = run[1] && s == NSh[1] - 1 && gl == lLh[1];
-            const int y0 = s * W + gl * C;
+            const int Cs = (G >= 16 && s == NS - 1) ? CsL : C;  // compile-time C for the short-read geometries
+            const int nb = Cs >> 3;
+            const int y0 = s * W + gl * Cs;
             uint32_t Eh[C], B[C], sel[C];
             uint32_t wA[WPL], wB[WPL];
 #pragma unroll
             for (int j = 0; j < C; j++) {
                 const int y = y0 + j + 1;
                 uint32_t ca = 1, cb = 1;  // padding column: class "other"
-                if (run[0] && y <= L2[0]) ca = lut_sm[readp[0][y - 1]];
-                if (run[1] && y <= L2[1]) cb = lut_sm[readp[1][y - 1]];
+                if (run[0] && y <= L2[0] && j < Cs) ca = lut_sm[readp[0][y - 1]];
+                if (run[1] && y <= L2[1] && j < Cs) cb = lut_sm[readp[1][y - 1]];
                 sel[j] = (ca * 0x11u | 0x80u) | ((cb * 0x11u | 0x80u) << 8);  // bytes [mA, sign(mA), mB, sign(mB)]
                 const int g = sc.b0 + y * sc.b1 + bias;                        // row 0: S[0,y] = (MAXNEG, g(y), g(y))
                 B[j] = dup16(g);
@@ -248,9 +260,9 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel
                     const uint32_t BlIn = Bl;
                     const uint2 tr = *(const uint2*)(tab_sm + r * 8);
                     if (x == L1)
-                        pack_row_step<C, TB, true>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap);
+                        pack_row_step<C, TB, true>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap, nb);
                     else
-                        pack_row_step<C, TB, false>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap);
+                        pack_row_step<C, TB, false>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap, nb);
                     prevBl = BlIn;
                     oF = Fl; oE = El; oM = Ml; oB = Bl;
                     // band-skipped cells (x <= K, y == L2): fresh-matrix state (0,0,0), per read
@@ -262,16 +274,16 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel
                             if (sa && j == jLh[0]) { Eh[j] = set_lo(Eh[j], e0); B[j] = set_lo(B[j], b0v); }
                             if (sb && j == jLh[1]) { Eh[j] = set_hi(Eh[j], e0); B[j] = set_hi(B[j], b0v); }
                         }
-                        if (sa && jLh[0] == C - 1) { oF = set_lo(oF, e0); oE = set_lo(oE, e0); oM = set_lo(oM, b0v); oB = set_lo(oB, b0v); }
-                        if (sb && jLh[1] == C - 1) { oF = set_hi(oF, e0); oE = set_hi(oE, e0); oM = set_hi(oM, b0v); oB = set_hi(oB, b0v); }
+                        if (sa && jLh[0] == Cs - 1) { oF = set_lo(oF, e0); oE = set_lo(oE, e0); oM = set_lo(oM, b0v); oB = set_lo(oB, b0v); }
+                        if (sb && jLh[1] == Cs - 1) { oF = set_hi(oF, e0); oE = set_hi(oE, e0); oM = set_hi(oM, b0v); oB = set_hi(oB, b0v); }
                         if (x == L1) {
                             if (sa) { cap[0] = set_lo(cap[0], bias); cap[1] = set_lo(cap[1], e0); cap[2] = set_lo(cap[2], e0); }
                             if (sb) { cap[0] = set_hi(cap[0], bias); cap[1] = set_hi(cap[1], e0); cap[2] = set_hi(cap[2], e0); }
                         }
                     }
                     if (TB) {
-                        if (run[0] && s < NSh[0]) bits_store<G, WPL>(tt_sm, bitsA, wA, s, T, t, lane, gl, x == L1);
-                        if (run[1] && s < NSh[1]) bits_store<G, WPL>(tt_sm + WPL * 256, bitsB, wB, s, T, t, lane, gl, x == L1);
+                        if (run[0] && s < NSh[0]) bits_store<G, WPL>(tt_sm, bitsA, wA, s, T, t, lane, gl, x == L1, nb);
+                        if (run[1] && s < NSh[1]) bits_store<G, WPL>(tt_sm + WPL * 256, bitsB, wB, s, T, t, lane, gl, x == L1, nb);
                     }
                     if (gl == G - 1 && s < NS - 1) {
                         col_g[x] = oF; col_g[p.col_stride + x] = oE; col_g[2 * p.col_stride + x] = oM; col_g[3 * p.col_stride + x] = oB;
@@ -309,7 +321,8 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel
             }
             if (TB && tvalid && gl == 0) {
                 TbRec rec;
-                rec.ridx = ridx[h]; rec.L1 = ok[h] ? L1 : -1; rec.L2 = L2[h]; rec.zK = z | (K[h] << 2);
+                rec.ridx = ridx[h]; rec.L1 = ok[h] ? L1 : -1; rec.L2 = L2[h];
+                rec.zK = z | (K[h] << 2) | ((CsL >> 3) << 20) | ((narrow && anyrun ? NS - 1 : 0) << 24);
                 p.tb_rec[2 * task + h] = rec;
             }
         }
