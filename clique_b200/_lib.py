@@ -10,13 +10,13 @@ E_INVALID, E_CUDA, E_NOMEM, E_LIMIT, E_STATE, E_UNSUPPORTED = -1, -2, -3, -4, -5
 
 BAND_MAXLEN, BAND_READLEN = 0, 1
 SEARCH_FIXED, SEARCH_EXHAUSTIVE, SEARCH_QUICK = 0 << 2, 1 << 2, 2 << 2
-SCORE_ONLY, CONVEX, EXTRACT_TAGS = 1 << 4, 1 << 5, 1 << 6
+SCORE_ONLY, CONVEX, EXTRACT_TAGS, RUSTBIO = 1 << 4, 1 << 5, 1 << 6, 1 << 7
 
 # every symbol include/clq.h declares (tests/test_abi.py checks the built library exports each one)
 SYMBOLS = ["clq_version", "clq_strerror", "clq_device_count", "clq_affine_from_f64", "clq_host_alloc", "clq_host_free",
            "clq_ctx_create", "clq_ctx_destroy", "clq_ctx_last_error", "clq_refs_set", "clq_kmer_index_set", "clq_submit",
            "clq_wait", "clq_upload", "clq_launch", "clq_download", "clq_sync", "clq_slot_stats", "clq_set_option",
-           "clq_tags_download"]
+           "clq_tags_download", "clq_rustbio_scoring"]
 
 
 class ClqError(RuntimeError):
@@ -92,6 +92,7 @@ def load_library():
     L.clq_sync.argtypes = [C.c_void_p, C.c_int32]
     L.clq_slot_stats.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Stats)]
     L.clq_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    L.clq_rustbio_scoring.argtypes = [C.c_int32] * 4 + [C.POINTER(AffineInt)]
     L.clq_tags_download.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
     for name in SYMBOLS:
         f = getattr(L, name)

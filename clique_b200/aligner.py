@@ -76,6 +76,24 @@ class ConvexScoring:
 
 
 @dataclass
+class RustBioScoring:
+    """rust_bio_alignment's scoring (alignment_functions.rs:48-61): the closure 1 / -1 with a read 'N' matching anything and
+    gap open -5 / extend -1 are hard-coded there (the function ignores its own parameters).  Selects CLQ_RUSTBIO: rust-bio
+    `Aligner::global` semantics, PARITY UNPINNED (un-vendored `bio = "*"`, DESIGN.md section 2)."""
+    match_score: int = 1
+    mismatch_score: int = -1
+    gap_open: int = -5
+    gap_extend: int = -1
+
+    def to_int(self) -> L.AffineInt:
+        out = L.AffineInt()
+        rc = L.load_library().clq_rustbio_scoring(self.match_score, self.mismatch_score, self.gap_open, self.gap_extend, C.byref(out))
+        if rc != L.CLQ_OK:
+            raise ClqError(rc, "rust-bio scoring %r not representable" % (self,))
+        return out
+
+
+@dataclass
 class TwoPieceScoring:
     """Two-piece affine ("convex") gaps as this repository defines them (parity unpinned):
     a gap of length k costs max(o1 + k*e1, o2 + k*e2); integer scores."""
@@ -357,6 +375,8 @@ class Aligner:
         flags = self._flags(search, band, score_only)
         if isinstance(sci, L.ConvexInt):
             flags |= L.CONVEX
+        if isinstance(scoring, RustBioScoring):
+            flags |= L.RUSTBIO
         if extract_tags:
             flags |= L.EXTRACT_TAGS
         self._check(self.lib.clq_launch(self.ctx, slot, C.byref(sci), flags, threshold))
@@ -451,18 +471,24 @@ class Aligner:
         """quick_alignment_search, alignment_functions.rs:693-767."""
         return self._search(read_name, read, qual_sequence, scoring, "quick", match_threshold)
 
-    def align_to_reference_choices(self, read_name, read, qual_sequence, fast_lookup, scoring: AffineScoring):
-        """align_to_reference_choices, alignment_functions.rs:520-631.  0 references -> None; 1 reference -> clique's own
-        Gotoh with bandwidth = read.len() (the rust-bio detour of :544-603 is out of scope, SURVEY.md fact 5);
-        > 1 -> quick (fast_lookup) or exhaustive search."""
+    def align_to_reference_choices(self, read_name, read, qual_sequence, fast_lookup, scoring: AffineScoring, rust_bio=False):
+        """align_to_reference_choices, alignment_functions.rs:520-631.  0 references -> None; > 1 -> quick (fast_lookup) or
+        exhaustive search; 1 reference -> with rust_bio=True what the reference does today (:544-603: rust-bio global with the
+        hard-coded 1/-1/-5/-1, score reported as 0.0, empty path; PARITY UNPINNED), otherwise clique's own Gotoh with
+        bandwidth = read.len() (the call the reference has commented out at :586-597; pinned)."""
         rm = self.rm
         if rm is None or not rm.references:
             return None
         if len(rm.references) == 1:
             read = _b(read)
             rb, ro = pack_reads([read])
-            br = self.align_batch(rb, ro, scoring, "fixed", "readlen", fixed_ref=[0])
             r = rm.references[0]
+            if rust_bio:
+                br = self.align_batch(rb, ro, RustBioScoring(), "fixed", "maxlen", fixed_ref=[0])
+                al = self._result(br, 0, r.sequence, read, qual_sequence, r.name.decode(), read_name)
+                al.score, al.path = 0.0, []
+                return AlignmentWithRef(al, r.name, r.sequence)
+            br = self.align_batch(rb, ro, scoring, "fixed", "readlen", fixed_ref=[0])
             return AlignmentWithRef(self._result(br, 0, r.sequence, read, qual_sequence, r.name.decode(), read_name), r.name, r.sequence)
         return self._search(read_name, read, qual_sequence, scoring, "quick" if fast_lookup else "exhaustive")
 

@@ -65,8 +65,11 @@ struct clq_ctx {
     int no_pack = 0;                 // option "no_pack": never take the s16x2 PACK kernels
     int force_generic = 0;           // option "force_generic": never take the FAST (PRMT/DPX) kernel variant
     bool fast_ok = false;            // the reference set has <= 6 distinct non-special bytes
-    uint8_t cls[256] = {};           // byte -> class: 0 special, 1 other, 2..7 reference bytes
+    uint8_t cls[256] = {};           // byte -> class: 0 special, 1 other, 2..7 reference bytes (| row << 3, clq_kernels.cuh)
     DevBuf cls_lut;
+    bool rb_ok = false;              // rust-bio mode: the reference set fits the 16-row / 8-column profile
+    uint8_t cls_rb[256] = {};        // rust-bio classes: 0 = 'N', 1 other, 2..7 reference bytes; row << 3; bit 7 = unscorable in a read
+    DevBuf cls_lut_rb;
     int64_t max_scratch_bytes = 40ll << 30;  // per slot: direction bits of one sub-batch
 };
 
@@ -102,9 +105,9 @@ void release(DevBuf& b) {
     b.cap = 0;
 }
 
-template <int G, int C, bool TB, bool FIN, bool FAST>
+template <int G, int C, bool TB, bool FIN, bool FAST, bool RB = false>
 cudaError_t launch_one(const KParams& p, int sm_count, size_t smem, cudaStream_t st, int* grid_out, bool query_only) {
-    auto kern = gotoh_kernel<G, C, TB, FIN, FAST>;
+    auto kern = gotoh_kernel<G, C, TB, FIN, FAST, RB>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -121,28 +124,29 @@ cudaError_t launch_one(const KParams& p, int sm_count, size_t smem, cudaStream_t
     return cudaGetLastError();
 }
 
-template <bool TB, bool FIN, bool FAST>
+template <bool TB, bool FIN, bool FAST, bool RB = false>
 cudaError_t launch_cfg(int cfg, const KParams& p, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
     switch (cfg) {
-        case 0: return launch_one<8, 16, TB, FIN, FAST>(p, sm, smem, st, grid, q);
-        case 1: return launch_one<8, 24, TB, FIN, FAST>(p, sm, smem, st, grid, q);
-        case 2: return launch_one<8, 40, TB, FIN, FAST>(p, sm, smem, st, grid, q);
-        case 3: return launch_one<16, 24, TB, FIN, FAST>(p, sm, smem, st, grid, q);
-        case 4: return launch_one<32, 16, TB, FIN, FAST>(p, sm, smem, st, grid, q);
-        default: return launch_one<32, 32, TB, FIN, FAST>(p, sm, smem, st, grid, q);
+        case 0: return launch_one<8, 16, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q);
+        case 1: return launch_one<8, 24, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q);
+        case 2: return launch_one<8, 40, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q);
+        case 3: return launch_one<16, 24, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q);
+        case 4: return launch_one<32, 16, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q);
+        default: return launch_one<32, 32, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q);
     }
 }
 
-// variant = (traceback?, final-gap multiplier?, fast PRMT/DPX path?)
-cudaError_t launch_any(int cfg, bool tb, bool fin, bool fast, const KParams& p, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
+// variant = (traceback?, final-gap multiplier?, fast PRMT/DPX path?, rust-bio semantics?)
+cudaError_t launch_any(int cfg, bool tb, bool fin, bool fast, bool rb, const KParams& p, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
+    if (rb) return launch_cfg<true, false, true, true>(cfg, p, sm, smem, st, grid, q);
     if (fast) return tb ? launch_cfg<true, false, true>(cfg, p, sm, smem, st, grid, q) : launch_cfg<false, false, true>(cfg, p, sm, smem, st, grid, q);
     if (tb) return fin ? launch_cfg<true, true, false>(cfg, p, sm, smem, st, grid, q) : launch_cfg<true, false, false>(cfg, p, sm, smem, st, grid, q);
     return fin ? launch_cfg<false, true, false>(cfg, p, sm, smem, st, grid, q) : launch_cfg<false, false, false>(cfg, p, sm, smem, st, grid, q);
 }
 
-template <int G, int C, bool TB>
+template <int G, int C, bool TB, bool RB = false>
 cudaError_t launch_pack_one(const KParams& p, const PackParams& pp, int sm_count, size_t smem, cudaStream_t st, int* grid_out, bool query_only) {
-    auto kern = pack_kernel<G, C, TB>;
+    auto kern = pack_kernel<G, C, TB, RB>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -159,15 +163,15 @@ cudaError_t launch_pack_one(const KParams& p, const PackParams& pp, int sm_count
     return cudaGetLastError();
 }
 
-template <bool TB>
+template <bool TB, bool RB = false>
 cudaError_t launch_pack(int cfg, const KParams& p, const PackParams& pp, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
     switch (cfg) {
-        case 0: return launch_pack_one<8, 16, TB>(p, pp, sm, smem, st, grid, q);
-        case 1: return launch_pack_one<8, 24, TB>(p, pp, sm, smem, st, grid, q);
-        case 2: return launch_pack_one<8, 40, TB>(p, pp, sm, smem, st, grid, q);
-        case 3: return launch_pack_one<16, 24, TB>(p, pp, sm, smem, st, grid, q);
-        case 4: return launch_pack_one<32, 16, TB>(p, pp, sm, smem, st, grid, q);
-        default: return launch_pack_one<32, 32, TB>(p, pp, sm, smem, st, grid, q);
+        case 0: return launch_pack_one<8, 16, TB, RB>(p, pp, sm, smem, st, grid, q);
+        case 1: return launch_pack_one<8, 24, TB, RB>(p, pp, sm, smem, st, grid, q);
+        case 2: return launch_pack_one<8, 40, TB, RB>(p, pp, sm, smem, st, grid, q);
+        case 3: return launch_pack_one<16, 24, TB, RB>(p, pp, sm, smem, st, grid, q);
+        case 4: return launch_pack_one<32, 16, TB, RB>(p, pp, sm, smem, st, grid, q);
+        default: return launch_pack_one<32, 32, TB, RB>(p, pp, sm, smem, st, grid, q);
     }
 }
 
@@ -224,7 +228,7 @@ template <int G, int C>
 cudaError_t launch_walk_one(const KParams& p, uint32_t cnt, cudaStream_t st) {
     walk_kernel<G, C><<<(cnt + 127) / 128, 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.bits_off, p.task_base, p.cig_scratch, p.cig_stride, p.cigar_pool,
                                                          p.cigar_cap, p.cigar_cursor, p.results, p.ref_bytes, p.ref_off, p.read_bytes, p.read_off,
-                                                         p.tag_slot, p.tags, p.tag_stride);
+                                                         p.tag_slot, p.tags, p.tag_stride, p.rustbio);
     return cudaGetLastError();
 }
 
@@ -313,6 +317,18 @@ int32_t clq_affine_from_f64(double match_score, double mismatch_score, double sp
     return CLQ_SCORING_NOT_REPRESENTABLE;
 }
 
+int32_t clq_rustbio_scoring(int32_t match_score, int32_t mismatch_score, int32_t gap_open, int32_t gap_extend, clq_affine_t* out) {
+    if (!out) return CLQ_E_INVALID;
+    if (!(gap_open < 0) || gap_extend > 0) return CLQ_SCORING_NOT_REPRESENTABLE;
+    out->scale = 1;
+    out->match = match_score; out->mismatch = mismatch_score; out->special = match_score;
+    out->oe_in = out->oe_fin = gap_open + gap_extend;
+    out->e_in = out->e_fin = gap_extend;
+    out->b0 = gap_open; out->b1 = gap_extend;
+    out->max_neg = -858993459;  // rust-bio's MIN_SCORE
+    return CLQ_OK;
+}
+
 int32_t clq_host_alloc(size_t bytes, void** out) {
     if (!out) return CLQ_E_INVALID;
     cudaError_t e = cudaHostAlloc(out, std::max<size_t>(bytes, 64), cudaHostAllocDefault);
@@ -357,7 +373,7 @@ void clq_ctx_destroy(clq_ctx* c) {
             release(*b);
         if (s.h_counters) cudaFreeHost(s.h_counters);
     }
-    release(c->ref_bytes); release(c->ref_off); release(c->kmer_keys); release(c->kmer_owner); release(c->cls_lut); release(c->tag_slot);
+    release(c->ref_bytes); release(c->ref_off); release(c->kmer_keys); release(c->kmer_owner); release(c->cls_lut); release(c->cls_lut_rb); release(c->tag_slot);
     delete c;
 }
 
@@ -408,8 +424,30 @@ int32_t clq_refs_set(clq_ctx* c, uint32_t n_refs, const uint8_t* bytes, const ui
             c->cls[b] = (uint8_t)next++;
         }
     }
+    for (int b = 0; b < 256; b++) c->cls[b] = (uint8_t)(c->cls[b] | (c->cls[b] << 3));  // row = class in clique's own scoring
     if ((rc = ensure(c, c->cls_lut, 256)) != CLQ_OK) return rc;
     CU(c, cudaMemcpy(c->cls_lut.p, c->cls, 256, cudaMemcpyHostToDevice));
+    // rust-bio mode (alignment_functions.rs:55: a == b || a == b'N', a = read byte): column 0 = read 'N' (wildcard), column 1 =
+    // a byte no reference holds, columns 2..7 = the first six distinct reference bytes (letters before tag symbols); further
+    // reference bytes get rows 8..15 of their own but no column: a read that holds one is reported CLQ_SCORING_NOT_REPRESENTABLE.
+    {
+        for (int b = 0; b < 256; b++) c->cls_rb[b] = 1 | (1 << 3);
+        c->cls_rb['N'] = 0;
+        bool seen[256] = {};
+        std::vector<uint8_t> distinct;
+        for (int pass = 0; pass < 2; pass++)
+            for (uint64_t i = 0; i < total; i++) {
+                const uint8_t b = bytes[i];
+                if (b == 'N' || seen[b] || ((b >= 'A') != (pass == 0))) continue;
+                seen[b] = true;
+                distinct.push_back(b);
+            }
+        c->rb_ok = distinct.size() <= 6 + 8;
+        for (size_t k = 0; k < distinct.size() && c->rb_ok; k++)
+            c->cls_rb[distinct[k]] = k < 6 ? (uint8_t)((2 + k) | ((2 + k) << 3)) : (uint8_t)(1 | ((8 + (k - 6)) << 3) | 0x80);
+        if ((rc = ensure(c, c->cls_lut_rb, 256)) != CLQ_OK) return rc;
+        CU(c, cudaMemcpy(c->cls_lut_rb.p, c->cls_rb, 256, cudaMemcpyHostToDevice));
+    }
     // tag columns: reference bytes '0'..'9' (SPECIAL_CHARACTERS, extractor.rs:19-34); slot = rank within its reference
     std::vector<uint16_t> slot(total + 1, 0xffffu);
     uint32_t most = 0;
@@ -577,6 +615,12 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     ConvexParams cp = {};
     auto fits8 = [](int v) { return v >= -128 && v <= 127; };
     bool fin = false, fast = false;
+    const bool rb = (flags & CLQ_RUSTBIO) != 0;
+    if (rb) {
+        if (convex || search != CLQ_SEARCH_FIXED || (flags & CLQ_SCORE_ONLY))
+            return fail(c, CLQ_E_UNSUPPORTED, "CLQ_RUSTBIO is the single-reference branch: CLQ_SEARCH_FIXED with traceback, affine scoring");
+        if (!c->rb_ok) return fail(c, CLQ_E_UNSUPPORTED, "CLQ_RUSTBIO: the reference set has more than 14 distinct bytes");
+    }
     if (convex) {
         cp.cv = *(const clq_convex_t*)scoring;
         const clq_convex_t& cv = cp.cv;
@@ -591,6 +635,10 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         if (!(sc.oe_in - sc.e_in < 0) || sc.scale < 1) return fail(c, CLQ_SCORING_NOT_REPRESENTABLE, "gap_open must be negative");
         fin = sc.oe_fin != sc.oe_in || sc.e_fin != sc.e_in;
         fast = c->fast_ok && !c->force_generic && !fin && fits8(sc.match) && fits8(sc.mismatch) && fits8(sc.special);
+        if (rb) {
+            if (fin || !fits8(sc.match) || !fits8(sc.mismatch)) return fail(c, CLQ_E_UNSUPPORTED, "CLQ_RUSTBIO needs int8 substitution scores and no final-gap multiplier");
+            fast = true;
+        }
     }
     CU(c, cudaSetDevice(c->device));
     const bool score_only = (flags & CLQ_SCORE_ONLY) != 0;
@@ -611,7 +659,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     const uint32_t ref_sm_stride = (L1max + 15) / 16 * 16 + 16;
     // + per-warp transposition buffers of the direction bits (C/8 KiB per warp, twice for the PACK kernels); the
     // convex kernels keep the plain row layout
-    const size_t smem = (size_t)(kThreads / 32) * GPW * ref_sm_stride + (fast ? 320 : 0) + ((!convex && G <= 8) ? (size_t)(kThreads / 32) * (C / 8) * 1024 * 2 : 0);
+    const size_t smem = (size_t)(kThreads / 32) * GPW * ref_sm_stride + (fast ? kLutBytes + kTabBytes : 0) + ((!convex && G <= 8) ? (size_t)(kThreads / 32) * (C / 8) * 1024 * 2 : 0);
     if (smem > 200 * 1024) return fail(c, CLQ_E_LIMIT, "references too long for this geometry's shared-memory staging");
     // s16x2 PACK kernels: two reads per lane group.  Needs the FAST preconditions plus a proof that every cell value of
     // this batch fits a 15-bit window: B >= 2*g(0) + (L1+L2)*e (the all-gap corner path), everything else is within a gap
@@ -631,9 +679,11 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     const bool pack_pairs = pack && c->n_refs == 1;  // pair mode needs one reference for both reads of a task
     auto launch_dp = [&](bool tb, const KParams& kp, int* grid, bool query) -> cudaError_t {
         if (convex) return tb ? launch_cvx<true>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query) : launch_cvx<false>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query);
-        if (pack && (kp.all_pairs || pack_pairs))
+        if (pack && (kp.all_pairs || pack_pairs)) {
+            if (rb) return launch_pack<true, true>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query);
             return tb ? launch_pack<true>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query) : launch_pack<false>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query);
-        return launch_any(cfg, tb, fin, fast, kp, c->sm_count, smem, s->stream, grid, query);
+        }
+        return launch_any(cfg, tb, fin, fast, rb && tb, kp, c->sm_count, smem, s->stream, grid, query);
     };
 
     KParams p = {};
@@ -645,21 +695,24 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     p.n_reads = n;
     p.order = s->have_order ? (const uint32_t*)s->order.p : nullptr;
     p.sc = sc;
-    p.band_mode = band;
+    p.band_mode = rb ? 0xffu : band;  // rust-bio's global alignment is unbanded
+    p.rustbio = rb ? 1u : 0u;
     p.max_read_len = c->lim.max_read_len;
     p.ref_sm_stride = ref_sm_stride;
     p.results = (clq_result_t*)s->results.p;
     unsigned long long* ctr = (unsigned long long*)s->counters.p;
     p.cigar_cursor = ctr + 4;
     p.cells = ctr + 5;
-    p.cls_lut = (const uint8_t*)c->cls_lut.p;
+    p.cls_lut = (const uint8_t*)(rb ? c->cls_lut_rb.p : c->cls_lut.p);
     p.debug_flags = (uint32_t)c->debug_flags;
     if (fast) {  // profile table: row = reference class, column = read class
-        int8_t tab[8][8];
-        for (int r = 0; r < 8; r++)
-            for (int q = 0; q < 8; q++)
-                tab[r][q] = (int8_t)((r == 0 || q == 0) ? sc.special : ((r == q && r >= 2) ? sc.match : sc.mismatch));
-        memcpy(p.tab, tab, 64);
+        int8_t tab[16][8];
+        for (int r = 0; r < 16; r++)
+            for (int q = 0; q < 8; q++) {
+                if (rb) tab[r][q] = (int8_t)((q == 0 || (r == q && r >= 2 && r < 8)) ? sc.match : sc.mismatch);  // read 'N' matches anything
+                else tab[r][q] = (int8_t)((r == 0 || q == 0) ? sc.special : ((r == q && r >= 2) ? sc.match : sc.mismatch));
+            }
+        memcpy(p.tab, tab, 128);
     }
 
     // grid + scratch sizing (per resident group)
@@ -757,7 +810,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     }
 
     s->flags = flags;
-    s->stats.variant = (fast ? 1u : 0u) | ((pack && (pack_pairs || search != CLQ_SEARCH_FIXED)) ? 2u : 0u) | (convex ? 4u : 0u) | (fin ? 8u : 0u) | ((uint32_t)cfg << 8);
+    s->stats.variant = (rb ? 16u : 0u) | (fast ? 1u : 0u) | ((pack && (pack_pairs || search != CLQ_SEARCH_FIXED)) ? 2u : 0u) | (convex ? 4u : 0u) | (fin ? 8u : 0u) | ((uint32_t)cfg << 8);
     s->stats.sub_batches = 0;
     s->stats.launches = 0;
     s->stats.dp_launches = 0;

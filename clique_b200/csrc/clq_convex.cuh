@@ -67,12 +67,12 @@ template <int G, int C, bool TB>
 __global__ void __launch_bounds__(kThreads) convex_kernel(const KParams p, const ConvexParams cp) {
     static_assert(C % 8 == 0, "C must be a multiple of 8");
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + 320;
+    uint8_t* smem = smem_raw + kLutBytes + kTabBytes;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) smem_raw[i] = p.cls_lut[i];
-    if (threadIdx.x < 16) ((uint32_t*)(smem_raw + 256))[threadIdx.x] = p.tab[threadIdx.x];
+    if (threadIdx.x < 32) ((uint32_t*)(smem_raw + kLutBytes))[threadIdx.x] = p.tab[threadIdx.x];
     __syncthreads();
     const uint8_t* lut_sm = smem_raw;
-    const uint8_t* tab_sm = smem_raw + 256;
+    const uint8_t* tab_sm = smem_raw + kLutBytes;
     constexpr int GPW = 32 / G;
     constexpr int W = G * C;
     constexpr int WPL = C / 4;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kThreads) convex_kernel(const KParams p, const
         const bool ok = valid && status == CLQ_OK;
         const bool run = ok && L1 > 0 && L2 > 0;
         if (run && ref != staged_ref) {
-            for (int i = gl; i < L1; i += G) ref_sm[i] = lut_sm[refp[i]];
+            for (int i = gl; i < L1; i += G) ref_sm[i] = (lut_sm[refp[i]] >> 3) & 15;
             staged_ref = ref;
         }
         __syncwarp();
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kThreads) convex_kernel(const KParams p, const
             for (int j = 0; j < C; j++) {
                 const int y = y0 + j + 1;
                 int code = 1;
-                if (act_s && y <= L2) code = (int)lut_sm[readp[y - 1]];
+                if (act_s && y <= L2) code = (int)lut_sm[readp[y - 1]] & 7;
                 sel[j] = code * 0x1111 | 0x8880;
                 const int g1 = cv.o1 + y * cv.e1, g2 = cv.o2 + y * cv.e2;  // row 0: E_i = F_i = o_i + y*e_i, M = NEG
                 B[j] = max(g1, g2);

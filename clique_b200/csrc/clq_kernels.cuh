@@ -75,8 +75,10 @@ struct KParams {
     unsigned long long* cigar_cursor;
     unsigned int* task_counter;
     unsigned long long* cells;
-    const uint8_t* cls_lut;      // FAST: byte -> class (0 special, 1 other, 2..7 reference bytes)
-    uint32_t tab[16];            // FAST: 8 profile rows (reference class) x 8 int8 scores (read class)
+    const uint8_t* cls_lut;      // FAST: byte -> bits 0..2 read class (column of the profile), bits 3..6 reference class (row),
+                                 //       bit 7 = a READ holding this byte cannot be scored exactly (rust-bio mode only)
+    uint32_t tab[32];            // FAST: 16 profile rows (reference class) x 8 int8 scores (read class)
+    uint32_t rustbio;            // CLQ_RUSTBIO: rust-bio global semantics (boundary init, tie order), see gotoh_kernel<.., RB>
     uint32_t debug_flags;        // experiments only: 1 = skip the traceback walk
     uint32_t task_base;          // first read (processing position) of this sub-batch
     uint32_t task_end;           // one past its last read (PACK kernel: two reads per task)
@@ -121,6 +123,7 @@ __device__ __forceinline__ int prmt_s8(uint32_t lo, uint32_t hi, uint32_t sel) {
 
 // rows 1..K whose band skips the last column (f64 centre, alignment/alignment_matrix.rs:413-417)
 __device__ inline int stale_rows(int L1, int L2, uint32_t band_mode) {
+    if (band_mode > CLQ_BAND_READLEN) return 0;  // unbanded (rust-bio mode)
     long long bw = band_mode == CLQ_BAND_READLEN ? L2 : (L1 > L2 ? L1 : L2);
     long long lim = (long long)L2 - bw;
     if (lim < 0) return 0;
@@ -241,8 +244,12 @@ __device__ __forceinline__ void row_step(int (&E)[C], int (&B)[C], const int (&b
     }
 }
 
+constexpr int kLutBytes = 256, kTabBytes = 128;  // FAST kernels: class LUT + 16-row profile table at the start of smem
+
 // FAST wavefront step: Eh/Fh are E/F shifted by -x1 (uniform gap constants), m by PRMT, max-plus by DPX, bits by SHF.
-template <int C, bool TB, bool LAST>
+// RB (rust-bio global, oracle/clq_oracle.h::orc_rustbio_global): same values, but a gap extends only when strictly better
+// than opening from the best state S = max(M, I, D) of the neighbour: ext2 <=> F_left + e > B_left + o + e.
+template <int C, bool TB, bool LAST, bool RB = false>
 __device__ __forceinline__ void row_step_fast(int (&Eh)[C], int (&B)[C], const int (&sel)[C], uint32_t (&w)[C / 8], int& Fh,
                                               int& Ehl, int& Ml, int& Bl, int diag, uint32_t tlo, uint32_t thi, int le, int x1,
                                               bool own_last, int jL, int& capM, int& capE, int& capF, int nb) {
@@ -258,7 +265,7 @@ __device__ __forceinline__ void row_step_fast(int (&Eh)[C], int (&B)[C], const i
                 const int EhU = Eh[j], BU = B[j];
                 const int Ehn = __viaddmax_s32(EhU, le, BU);
                 int d2 = 0;
-                if (TB) d2 = __viaddmax_s32(Ehl, x1m1, Ml) - Fh - le;  // < 0  <=>  F extends (>= E-open, > M-open)
+                if (TB) d2 = RB ? (Bl - Fh - le) : (__viaddmax_s32(Ehl, x1m1, Ml) - Fh - le);  // < 0  <=>  F extends (>= E-open, > M-open)
                 const int Fhn = __viaddmax_s32(Fh, le, Bl);
                 const int Pv = __viaddmax_s32(Fhn, x1, Mv);
                 const int Bn = __viaddmax_s32(Ehn, x1, Pv);
@@ -282,20 +289,21 @@ __device__ __forceinline__ void row_step_fast(int (&Eh)[C], int (&B)[C], const i
     }
 }
 
-template <int G, int C, bool TB, bool FIN, bool FAST>
+template <int G, int C, bool TB, bool FIN, bool FAST, bool RB = false>
 __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) gotoh_kernel(const KParams p) {
     static_assert(C % 8 == 0, "C must be a multiple of 8 (4 direction bits per cell, whole words per lane)");
     static_assert(!(FAST && FIN), "the FAST variant needs uniform gap constants");
+    static_assert(!RB || FAST, "rust-bio mode runs on the FAST kernels");
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    // FAST: [0,256) class LUT, [256,320) profile table, then the per-group reference rows
-    uint8_t* smem = smem_raw + (FAST ? 320 : 0);
+    // FAST: [0,256) class LUT, [256,384) profile table, then the per-group reference rows
+    uint8_t* smem = smem_raw + (FAST ? kLutBytes + kTabBytes : 0);
     if (FAST) {
         for (int i = threadIdx.x; i < 256; i += blockDim.x) smem_raw[i] = p.cls_lut[i];
-        if (threadIdx.x < 16) ((uint32_t*)(smem_raw + 256))[threadIdx.x] = p.tab[threadIdx.x];
+        if (threadIdx.x < 32) ((uint32_t*)(smem_raw + kLutBytes))[threadIdx.x] = p.tab[threadIdx.x];
         __syncthreads();
     }
     const uint8_t* lut_sm = smem_raw;
-    const uint8_t* tab_sm = smem_raw + 256;
+    const uint8_t* tab_sm = smem_raw + kLutBytes;
     constexpr int GPW = 32 / G;
     constexpr int W = G * C;
     constexpr int WPL = C / 8;
@@ -351,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
         const bool run = ok && L1 > 0 && L2 > 0;
 
         if (run && ref != staged_ref) {
-            for (int i = gl; i < L1; i += G) ref_sm[i] = FAST ? lut_sm[refp[i]] : refp[i];
+            for (int i = gl; i < L1; i += G) ref_sm[i] = FAST ? ((lut_sm[refp[i]] >> 3) & 15) : refp[i];
             staged_ref = ref;
         }
         __syncwarp();
@@ -367,6 +375,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
         const int CsL = (run && narrow) ? narrow_cols<G>(cL + 1, C) : C;
         const int lL = cL / CsL, jL = cL - lL * CsL;
         int capM = 0, capE = 0, capF = 0;
+        int bad = 0;  // RB: the read holds a byte the class table cannot score exactly
 
         for (int s = 0; s < NSmax; s++) {
             const bool act_s = run && s < NS;
@@ -383,10 +392,11 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
                 if (act_s && y <= L2 && j < Cs) {
                     const int c = readp[y - 1];
                     code = FAST ? (int)lut_sm[c] : (is_special(c) ? (c | 0x100) : c);
+                    if (FAST) { bad |= code >> 7; code &= 7; }
                 }
                 bq[j] = FAST ? (code * 0x1111 | 0x8880) : code;  // FAST: PRMT selector (byte + sign replication)
                 B[j] = sc.b0 + y * sc.b1;  // row 0: S[0,y] = (MAXNEG, g(y), g(y))
-                E[j] = B[j] - (FAST ? sc.oe_in : 0);
+                E[j] = RB ? sc.max_neg : B[j] - (FAST ? sc.oe_in : 0);  // rust-bio: D[0][j] = MIN_SCORE
             }
             int prevBl = (y0 == 0) ? 0 : sc.b0 + y0 * sc.b1;  // B[0, y0]
             int oF = 0, oE = 0, oM = 0, oB = 0;
@@ -402,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
                 int Fl = __shfl_up_sync(FULL, oF, 1, G);
                 int Bl = __shfl_up_sync(FULL, oB, 1, G);
                 int El = 0, Ml = 0;
-                if (TB) {
+                if (TB && !RB) {
                     El = __shfl_up_sync(FULL, oE, 1, G);
                     Ml = __shfl_up_sync(FULL, oM, 1, G);
                 }
@@ -413,6 +423,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
                             Bl = sc.b0 + x * sc.b1;  // S[x,0] = (MAXNEG, g(x), g(x))
                             Fl = El = Bl - (FAST ? sc.oe_in : 0);
                             Ml = sc.max_neg;
+                            if (RB) Fl = sc.max_neg;  // rust-bio: I[i][0] = MIN_SCORE on the empty-read boundary
                         } else {
                             Fl = nF; El = nE; Ml = nM; Bl = nB;
                             if (x < L1) {
@@ -427,9 +438,9 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
                     if (FAST) {
                         const uint2 tr = *(const uint2*)(tab_sm + r * 8);
                         if (x == L1)
-                            row_step_fast<C, TB, true>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, sc.e_in, sc.oe_in, own_last, jL, capM, capE, capF, nb);
+                            row_step_fast<C, TB, true, RB>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, sc.e_in, sc.oe_in, own_last, jL, capM, capE, capF, nb);
                         else
-                            row_step_fast<C, TB, false>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, sc.e_in, sc.oe_in, own_last, jL, capM, capE, capF, nb);
+                            row_step_fast<C, TB, false, RB>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, sc.e_in, sc.oe_in, own_last, jL, capM, capE, capF, nb);
                     } else {
                         const bool rsp = is_special(r);
                         const int rcode = rsp ? 0x200 : r;
@@ -468,11 +479,21 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
         int score = 0, z = 0;
         if (run) {
             score = capM; z = 0;
-            if (capE >= score) { score = capE; z = 1; }
-            if (capF >= score) { score = capF; z = 2; }
+            if (RB) {  // rust-bio: S takes the match first, then the insertion, then the deletion, each only when strictly better
+                if (capF > score) { score = capF; z = 2; }
+                if (capE > score) { score = capE; z = 1; }
+            } else {
+                if (capE >= score) { score = capE; z = 1; }
+                if (capF >= score) { score = capF; z = 2; }
+            }
         } else if (ok) {
             const int n = L1 > L2 ? L1 : L2;
             if (n > 0) { score = sc.b0 + n * sc.b1; z = 2; }
+        }
+        if (RB) {
+            const unsigned bm = __ballot_sync(FULL, bad != 0);
+            const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (gw * G));
+            if (ok && (bm & gm)) status = CLQ_SCORING_NOT_REPRESENTABLE;
         }
 
         if (!TB) {
@@ -494,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
             r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = 0; r.cigar_len = 0; r.status = status; r.matches = 0; r.mismatches = 0;
             p.results[ridx] = r;
             TbRec rec;
-            rec.ridx = ridx; rec.L1 = ok ? L1 : -1; rec.L2 = L2;
+            rec.ridx = ridx; rec.L1 = (ok && status == CLQ_OK) ? L1 : -1; rec.L2 = L2;
             rec.zK = z | (K << 2) | ((CsL >> 3) << 20) | ((narrow && run ? NS - 1 : 0) << 24);
             p.tb_rec[task] = rec;
             if (run) atomicAdd(p.cells, (unsigned long long)L1 * (unsigned long long)L2);
@@ -511,7 +532,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
                                                    uint32_t* cig_scratch, uint32_t cig_stride, uint32_t* cigar_pool, uint64_t cigar_cap,
                                                    unsigned long long* cigar_cursor, clq_result_t* results, const uint8_t* ref_bytes,
                                                    const uint64_t* ref_off, const uint8_t* read_bytes, const uint64_t* read_off,
-                                                   const uint16_t* tag_slot, uint8_t* tags, uint32_t tag_stride) {
+                                                   const uint16_t* tag_slot, uint8_t* tags, uint32_t tag_stride, uint32_t rb) {
     constexpr int W = G * C;
     constexpr int WPL = C / 8;
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -576,6 +597,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
         nib = nibble(x, y);
         const int a = (y == L2 && x <= K) ? 0 : argmax(nib);  // a stale source cell holds (0,0,0): Diag
         if (z == 0) z = a;
+        else if (rb) z = (z == 1) ? ((old & 8u) ? 1 : a) : ((old & 4u) ? 2 : a);  // rust-bio: an opened gap resumes in S = argmax
         else if (z == 1) z = (old & 8u) ? 1 : (a == 2 ? 2 : 0);
         else z = (old & 4u) ? 2 : (a == 1 ? 1 : 0);
     }

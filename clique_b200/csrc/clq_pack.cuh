@@ -25,7 +25,7 @@ struct PackParams {
     int32_t bias;  // added to every stored score
 };
 
-template <int C, bool TB, bool LAST>
+template <int C, bool TB, bool LAST, bool RB = false>
 __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C], const uint32_t (&sel)[C], uint32_t (&wA)[C / 8],
                                               uint32_t (&wB)[C / 8], uint32_t& Fh, uint32_t& Ehl, uint32_t& Ml, uint32_t& Bl, uint32_t diag,
                                               uint32_t tlo, uint32_t thi, uint32_t LE, uint32_t X1, uint32_t X1M1, bool ownA, int jA,
@@ -43,11 +43,12 @@ __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C
                 const uint32_t EhU = Eh[j], BU = B[j];
                 const uint32_t Ehn = __viaddmax_s16x2(EhU, LE, BU);
                 uint32_t t2 = 0, u2 = 0;
-                if (TB) {
+                if (TB && !RB) {
                     t2 = __viaddmax_s16x2(Ehl, X1M1, Ml);
                     u2 = __viaddmax_s16x2(Fh, LE, t2);  // > t2  <=>  F extends (>= E-open, > M-open)
                 }
                 const uint32_t Fhn = __viaddmax_s16x2(Fh, LE, Bl);
+                if (TB && RB) { u2 = Fhn; t2 = Bl; }  // rust-bio: F extends <=> F_left + e > B_left + o + e
                 const uint32_t Pv = __viaddmax_s16x2(Fhn, X1, Mv);
                 const uint32_t Bn = __viaddmax_s16x2(Ehn, X1, Pv);
                 if (TB) {
@@ -80,16 +81,16 @@ __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C
 // Tasks are read PAIRS.  Pair mode (all_pairs == 0): pair t = reads at processing positions task_base + 2t, +1, all against
 // reference ref_of_read[.] (the host only takes this kernel when the batch has a single reference).  All-pairs mode: pair
 // t = (read pair t / n_refs, reference t % n_refs).
-template <int G, int C, bool TB>
+template <int G, int C, bool TB, bool RB = false>
 __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel(const KParams p, const PackParams pp) {
     static_assert(C % 8 == 0, "C must be a multiple of 8");
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + 320;
+    uint8_t* smem = smem_raw + kLutBytes + kTabBytes;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) smem_raw[i] = p.cls_lut[i];
-    if (threadIdx.x < 16) ((uint32_t*)(smem_raw + 256))[threadIdx.x] = p.tab[threadIdx.x];
+    if (threadIdx.x < 32) ((uint32_t*)(smem_raw + kLutBytes))[threadIdx.x] = p.tab[threadIdx.x];
     __syncthreads();
     const uint8_t* lut_sm = smem_raw;
-    const uint8_t* tab_sm = smem_raw + 256;
+    const uint8_t* tab_sm = smem_raw + kLutBytes;
     constexpr int GPW = 32 / G;
     constexpr int W = G * C;
     constexpr int WPL = C / 8;
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel
         }
         const bool anyrun = run[0] || run[1];
         if (anyrun && ref != staged_ref) {
-            for (int i = gl; i < L1; i += G) ref_sm[i] = lut_sm[refp[i]];
+            for (int i = gl; i < L1; i += G) ref_sm[i] = (lut_sm[refp[i]] >> 3) & 15;
             staged_ref = ref;
         }
         __syncwarp();
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel
         const int T = anyrun ? L1 + G - 1 : 0;
         const int Tmax = __reduce_max_sync(FULL, T);
         uint32_t cap[3] = {0, 0, 0};
+        uint32_t bad = 0;  // RB: bit h = read h holds a byte the class table cannot score exactly
         uint32_t* bitsA = TB ? p.bits + bits_slot(p.bits_off, p.bits_stride, p.task_base, 2 * task) : nullptr;
         uint32_t* bitsB = (TB && valid[1]) ? p.bits + bits_slot(p.bits_off, p.bits_stride, p.task_base, 2 * task + 1) : nullptr;
 
@@ -217,10 +219,12 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel
                 uint32_t ca = 1, cb = 1;  // padding column: class "other"
                 if (run[0] && y <= L2[0] && j < Cs) ca = lut_sm[readp[0][y - 1]];
                 if (run[1] && y <= L2[1] && j < Cs) cb = lut_sm[readp[1][y - 1]];
+                bad |= (ca >> 7) | ((cb >> 7) << 1);
+                ca &= 7; cb &= 7;
                 sel[j] = (ca * 0x11u | 0x80u) | ((cb * 0x11u | 0x80u) << 8);  // bytes [mA, sign(mA), mB, sign(mB)]
                 const int g = sc.b0 + y * sc.b1 + bias;                        // row 0: S[0,y] = (MAXNEG, g(y), g(y))
                 B[j] = dup16(g);
-                Eh[j] = dup16(g - x1);
+                Eh[j] = RB ? 0u : dup16(g - x1);                               // rust-bio: D[0][j] = MIN_SCORE (the sentinel 0)
             }
             uint32_t prevBl = dup16(((y0 == 0) ? 0 : sc.b0 + y0 * sc.b1) + bias);
             uint32_t oF = 0, oE = 0, oM = 0, oB = 0;
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel
                 uint32_t Fl = __shfl_up_sync(FULL, oF, 1, G);
                 uint32_t Bl = __shfl_up_sync(FULL, oB, 1, G);
                 uint32_t El = 0, Ml = 0;
-                if (TB) {
+                if (TB && !RB) {
                     El = __shfl_up_sync(FULL, oE, 1, G);
                     Ml = __shfl_up_sync(FULL, oM, 1, G);
                 }
@@ -247,6 +251,7 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel
                             Bl = dup16(g);
                             Fl = El = dup16(g - x1);
                             Ml = 0;  // the sentinel: below every biased value
+                            if (RB) Fl = 0;  // rust-bio: I[i][0] = MIN_SCORE on the empty-read boundary
                         } else {
                             Fl = nF; El = nE; Ml = nM; Bl = nB;
                             if (x < L1) {
@@ -260,9 +265,9 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel
                     const uint32_t BlIn = Bl;
                     const uint2 tr = *(const uint2*)(tab_sm + r * 8);
                     if (x == L1)
-                        pack_row_step<C, TB, true>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap, nb);
+                        pack_row_step<C, TB, true, RB>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap, nb);
                     else
-                        pack_row_step<C, TB, false>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap, nb);
+                        pack_row_step<C, TB, false, RB>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap, nb);
                     prevBl = BlIn;
                     oF = Fl; oE = El; oM = Ml; oB = Bl;
                     // band-skipped cells (x <= K, y == L2): fresh-matrix state (0,0,0), per read
@@ -294,6 +299,12 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel
         }
 
         // ---- final cells: score + start layer = LAST maximum of (M, E, F) per read ----
+        if (RB) {
+            const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (gw * G));
+            const unsigned b0 = __ballot_sync(FULL, (bad & 1u) != 0), b1 = __ballot_sync(FULL, (bad & 2u) != 0);
+            if (ok[0] && (b0 & gm)) { status[0] = CLQ_SCORING_NOT_REPRESENTABLE; }
+            if (ok[1] && (b1 & gm)) { status[1] = CLQ_SCORING_NOT_REPRESENTABLE; }
+        }
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int src = gw * G + lLh[h];
@@ -304,8 +315,13 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel
                 const int cE = (h ? get_hi(c1) : get_lo(c1)) - bias + x1;
                 const int cF = (h ? get_hi(c2) : get_lo(c2)) - bias + x1;
                 score = cM; z = 0;
-                if (cE >= score) { score = cE; z = 1; }
-                if (cF >= score) { score = cF; z = 2; }
+                if (RB) {  // rust-bio: match first, then insertion, then deletion, each only when strictly better
+                    if (cF > score) { score = cF; z = 2; }
+                    if (cE > score) { score = cE; z = 1; }
+                } else {
+                    if (cE >= score) { score = cE; z = 1; }
+                    if (cF >= score) { score = cF; z = 2; }
+                }
             } else if (ok[h]) {
                 const int n = L1 > L2[h] ? L1 : L2[h];
                 if (n > 0) { score = sc.b0 + n * sc.b1; z = 2; }
@@ -321,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel
             }
             if (TB && tvalid && gl == 0) {
                 TbRec rec;
-                rec.ridx = ridx[h]; rec.L1 = ok[h] ? L1 : -1; rec.L2 = L2[h];
+                rec.ridx = ridx[h]; rec.L1 = (ok[h] && status[h] == CLQ_OK) ? L1 : -1; rec.L2 = L2[h];
                 rec.zK = z | (K[h] << 2) | ((CsL >> 3) << 20) | ((narrow && anyrun ? NS - 1 : 0) << 24);
                 p.tb_rec[2 * task + h] = rec;
             }

@@ -53,6 +53,14 @@ extern "C" {
 #define CLQ_EXTRACT_TAGS (1u << 6)      /* also record the read bytes aligned to the reference's tag columns '0'..'9':
                                            extract_tagged_sequences' digit keys, extractor.rs:271-332 (see clq_tags_download) */
 
+#define CLQ_RUSTBIO (1u << 7)           /* the single-reference branch of align_to_reference_choices (alignment_functions.rs:544-603):
+                                           rust-bio `pairwise::Aligner::global(read, reference)` semantics -- unbanded, gap(k) =
+                                           open + k*extend on the boundaries without clique's corner rule, a read 'N' matches any
+                                           byte, ties: match > insertion > deletion, extension only when strictly better than
+                                           opening.  PARITY UNPINNED (un-vendored `bio = "*"`); needs CLQ_SEARCH_FIXED,
+                                           scoring from clq_rustbio_scoring.  A read holding a byte the 16 x 8 class table cannot
+                                           score exactly gets CLQ_SCORING_NOT_REPRESENTABLE. */
+
 /* CIGAR op encoding in the pool: len << 4 | code, BAM codes (AlignmentTag -> Op, alignment/alignment_matrix.rs:95-107) */
 #define CLQ_OP_M 0u /* AlignmentTag::MatchMismatch */
 #define CLQ_OP_I 1u /* AlignmentTag::Ins */
@@ -124,6 +132,9 @@ int32_t clq_device_count(void);
  * value leaves the int32 working range. */
 int32_t clq_affine_from_f64(double match_score, double mismatch_score, double special_character_score,
                             double gap_open, double gap_extend, double final_gap_multiplier, clq_affine_t* out);
+
+/* rust_bio_alignment's scoring (alignment_functions.rs:48-61: 1 / -1, gap open -5, gap extend -1 hard-coded) for CLQ_RUSTBIO */
+int32_t clq_rustbio_scoring(int32_t match_score, int32_t mismatch_score, int32_t gap_open, int32_t gap_extend, clq_affine_t* out);
 
 /* pinned host memory for the caller's batch buffers (double-buffered H2D/D2H) */
 int32_t clq_host_alloc(size_t bytes, void** out);

@@ -885,3 +885,165 @@ void orc_reverse_complement(const uint8_t* dna, size_t n, uint8_t* out) {
         out[i] = c;
     }
 }
+
+
+/* ---------------------------------------------------------------------------------------------------------
+ * rust-bio `pairwise::Aligner::global` (PARITY UNPINNED, see clq_oracle.h): a restatement of `custom` with the
+ * clip penalties `global` installs.  Variable names follow the crate's (S, I, D, Sn, Lx, Ly, traceback cells).
+ * --------------------------------------------------------------------------------------------------------- */
+enum { RB_START = 0, RB_INS = 1, RB_DEL = 2, RB_SUBST = 3, RB_MATCH = 4, RB_XCLIP_PREFIX = 5, RB_XCLIP_SUFFIX = 6,
+       RB_YCLIP_PREFIX = 7, RB_YCLIP_SUFFIX = 8 };
+typedef struct { uint8_t s, i, d; } rb_cell_t;
+
+static int32_t rb_max(int32_t a, int32_t b) { return a > b ? a : b; }
+
+int orc_rustbio_global(const uint8_t* ref, size_t l1, const uint8_t* read, size_t l2, int32_t match_score,
+                       int32_t mismatch_score, int32_t gap_open, int32_t gap_extend, int32_t* score, uint32_t* n_cigar,
+                       uint32_t* cigar, size_t cigar_cap) {
+    const uint8_t* x = read; /* global(reference = forward_oriented_seq, read = ref_base.sequence): x is the READ */
+    const uint8_t* y = ref;
+    const size_t m = l2, n = l1;
+    const int32_t MIN = ORC_RUSTBIO_MIN_SCORE;
+    const int32_t xclip_prefix = MIN, xclip_suffix = MIN, yclip_prefix = MIN, yclip_suffix = MIN;
+    int32_t* Sv[2]; int32_t* Iv[2]; int32_t* Dv[2];
+    for (int k = 0; k < 2; k++) {
+        Sv[k] = (int32_t*)malloc((m + 1) * sizeof(int32_t));
+        Iv[k] = (int32_t*)malloc((m + 1) * sizeof(int32_t));
+        Dv[k] = (int32_t*)malloc((m + 1) * sizeof(int32_t));
+    }
+    int32_t* Sn = (int32_t*)malloc((m + 1) * sizeof(int32_t));
+    size_t* Lx = (size_t*)calloc(n + 1, sizeof(size_t));
+    size_t* Ly = (size_t*)calloc(m + 1, sizeof(size_t));
+    rb_cell_t* tb = (rb_cell_t*)calloc((m + 1) * (n + 1), sizeof(rb_cell_t));
+#define TB(i_, j_) tb[(size_t)(i_) * (n + 1) + (j_)]
+    /* initial conditions (both rolling columns) */
+    for (int k = 0; k < 2; k++) {
+        for (size_t i = 0; i <= m; i++) { Dv[k][i] = MIN; Iv[k][i] = MIN; Sv[k][i] = MIN; }
+        Sv[k][0] = 0;
+        if (k == 0) {
+            rb_cell_t c = {RB_START, RB_START, RB_START};
+            TB(0, 0) = c;
+            for (size_t i = 0; i <= m; i++) Sn[i] = MIN;
+            Sn[0] = yclip_suffix;
+            Ly[0] = n;
+        }
+        for (size_t i = 1; i <= m; i++) {
+            rb_cell_t c = {RB_START, RB_START, RB_START};
+            if (i == 1) {
+                Iv[k][i] = gap_open + gap_extend;
+                c.i = RB_START;
+            } else {
+                const int32_t i_score = gap_open + gap_extend * (int32_t)i;
+                const int32_t c_score = xclip_prefix + gap_open + gap_extend;
+                if (i_score > c_score) { Iv[k][i] = i_score; c.i = RB_INS; }
+                else { Iv[k][i] = c_score; c.i = RB_XCLIP_PREFIX; }
+            }
+            if (i == m) c.s = RB_XCLIP_SUFFIX; else Sv[k][i] = MIN;
+            if (Iv[k][i] > Sv[k][i]) { Sv[k][i] = Iv[k][i]; c.s = RB_INS; }
+            if (xclip_prefix > Sv[k][i]) { Sv[k][i] = xclip_prefix; c.s = RB_XCLIP_PREFIX; }
+            if (i != m && Sv[k][i] + xclip_suffix > Sv[k][m]) { Sv[k][m] = Sv[k][i] + xclip_suffix; Lx[0] = m - i; }
+            if (k == 0) TB(i, 0) = c;
+            if (Sv[k][i] + yclip_suffix > Sn[i]) { Sn[i] = Sv[k][i] + yclip_suffix; Ly[i] = n; }
+        }
+    }
+    for (size_t j = 1; j <= n; j++) {
+        const int curr = (int)(j % 2), prev = 1 - curr;
+        {   /* i = 0 */
+            rb_cell_t c = {RB_START, RB_START, RB_START};
+            Iv[curr][0] = MIN;
+            if (j == 1) { Dv[curr][0] = gap_open + gap_extend; c.d = RB_START; }
+            else {
+                const int32_t d_score = gap_open + gap_extend * (int32_t)j;
+                const int32_t c_score = yclip_prefix + gap_open + gap_extend;
+                if (d_score > c_score) { Dv[curr][0] = d_score; c.d = RB_DEL; }
+                else { Dv[curr][0] = c_score; c.d = RB_YCLIP_PREFIX; }
+            }
+            if (Dv[curr][0] > yclip_prefix) { Sv[curr][0] = Dv[curr][0]; c.s = RB_DEL; }
+            else { Sv[curr][0] = yclip_prefix; c.s = RB_YCLIP_PREFIX; }
+            if (j == n && Sn[0] > Sv[curr][0]) { Sv[curr][0] = Sn[0]; c.s = RB_YCLIP_SUFFIX; }
+            else if (Sv[curr][0] + yclip_suffix > Sn[0]) { Sn[0] = Sv[curr][0] + yclip_suffix; Ly[0] = n - j; }
+            TB(0, j) = c;
+        }
+        for (size_t i = 1; i <= m; i++) Sv[curr][i] = MIN;
+        const uint8_t q = y[j - 1];
+        const int32_t xclip_score = xclip_prefix + rb_max(yclip_prefix, gap_open + gap_extend * (int32_t)j);
+        for (size_t i = 1; i <= m; i++) {
+            const uint8_t p = x[i - 1];
+            rb_cell_t c = {RB_START, RB_START, RB_START};
+            /* the reference's closure (alignment_functions.rs:55): a = x byte (the read), N in the read matches anything */
+            const int32_t sub = (p == q || p == 'N') ? match_score : mismatch_score;
+            const int32_t m_score = Sv[prev][i - 1] + sub;
+            const int32_t i_score = Iv[curr][i - 1] + gap_extend;
+            int32_t s_score = Sv[curr][i - 1] + gap_open + gap_extend;
+            int32_t best_i_score;
+            if (i_score > s_score) { best_i_score = i_score; c.i = RB_INS; }
+            else { best_i_score = s_score; c.i = TB(i - 1, j).s; }
+            const int32_t d_score = Dv[prev][i] + gap_extend;
+            s_score = Sv[prev][i] + gap_open + gap_extend;
+            int32_t best_d_score;
+            if (d_score > s_score) { best_d_score = d_score; c.d = RB_DEL; }
+            else { best_d_score = s_score; c.d = TB(i, j - 1).s; }
+            c.s = RB_XCLIP_SUFFIX;
+            int32_t best_s_score = Sv[curr][i];
+            if (m_score > best_s_score) { best_s_score = m_score; c.s = (p == q) ? RB_MATCH : RB_SUBST; }
+            if (best_i_score > best_s_score) { best_s_score = best_i_score; c.s = RB_INS; }
+            if (best_d_score > best_s_score) { best_s_score = best_d_score; c.s = RB_DEL; }
+            if (xclip_score > best_s_score) { best_s_score = xclip_score; c.s = RB_XCLIP_PREFIX; }
+            const int32_t yclip_score = yclip_prefix + gap_open + gap_extend * (int32_t)i;
+            if (yclip_score > best_s_score) { best_s_score = yclip_score; c.s = RB_YCLIP_PREFIX; }
+            Sv[curr][i] = best_s_score;
+            Iv[curr][i] = best_i_score;
+            Dv[curr][i] = best_d_score;
+            if (Sv[curr][i] + xclip_suffix > Sv[curr][m]) { Sv[curr][m] = Sv[curr][i] + xclip_suffix; Lx[j] = m - i; }
+            if (Sv[curr][i] + yclip_suffix > Sn[i]) { Sn[i] = Sv[curr][i] + yclip_suffix; Ly[i] = n - j; }
+            TB(i, j) = c;
+        }
+    }
+    {   /* suffix clipping in the j = n column, then the recomputation of its I values */
+        const size_t j = n;
+        const int curr = (int)(j % 2);
+        for (size_t i = 0; i <= m; i++) {
+            if (Sn[i] > Sv[curr][i]) { Sv[curr][i] = Sn[i]; TB(i, j).s = RB_YCLIP_SUFFIX; }
+            if (Sv[curr][i] + xclip_suffix > Sv[curr][m]) { Sv[curr][m] = Sv[curr][i] + xclip_suffix; Lx[j] = m - i; TB(m, j).s = RB_XCLIP_SUFFIX; }
+        }
+        for (size_t i = 1; i <= m; i++) {
+            const int32_t s_score = Sv[curr][i - 1] + gap_open + gap_extend;
+            if (s_score > Iv[curr][i]) { Iv[curr][i] = s_score; TB(i, j).i = TB(i - 1, j).s; }
+            if (s_score > Sv[curr][i]) {
+                Sv[curr][i] = s_score;
+                TB(i, j).s = RB_INS;
+                if (Sv[curr][i] + xclip_suffix > Sv[curr][m]) { Sv[curr][m] = Sv[curr][i] + xclip_suffix; Lx[j] = m - i; TB(m, j).s = RB_XCLIP_SUFFIX; }
+            }
+        }
+    }
+    *score = Sv[n % 2][m];
+    /* traceback: unit ops pushed back to front, then cigar_to_alignment's simplify_cigar_string (Match and Subst -> M) */
+    size_t i = m, j = n, cap = m + n + 2, nu = 0;
+    uint8_t* unit = (uint8_t*)malloc(cap);
+    int rc = ORC_OK;
+    uint8_t last_layer = TB(i, j).s;
+    for (;;) {
+        uint8_t next_layer;
+        if (last_layer == RB_START) break;
+        else if (last_layer == RB_INS) { unit[nu++] = ORC_OP_I; next_layer = TB(i, j).i; i -= 1; }
+        else if (last_layer == RB_DEL) { unit[nu++] = ORC_OP_D; next_layer = TB(i, j).d; j -= 1; }
+        else if (last_layer == RB_MATCH || last_layer == RB_SUBST) { unit[nu++] = ORC_OP_M; next_layer = TB(i - 1, j - 1).s; i -= 1; j -= 1; }
+        else { rc = ORC_TRACEBACK_DIVERGED; break; } /* clip operations cannot win with MIN_SCORE penalties */
+        last_layer = next_layer;
+        if (nu >= cap) { rc = ORC_TRACEBACK_DIVERGED; break; }
+    }
+    uint32_t nc = 0;
+    if (rc == ORC_OK) {
+        for (size_t k = nu; k-- > 0;) {
+            const uint32_t op = unit[k];
+            if (nc && (cigar[nc - 1] & 15u) == op) cigar[nc - 1] += 16u;
+            else if (nc < cigar_cap) cigar[nc++] = 16u | op;
+            else { rc = ORC_CIGAR_POOL_FULL; break; }
+        }
+    }
+    *n_cigar = nc;
+#undef TB
+    free(unit); free(tb); free(Ly); free(Lx); free(Sn);
+    for (int k = 0; k < 2; k++) { free(Sv[k]); free(Iv[k]); free(Dv[k]); }
+    return rc;
+}

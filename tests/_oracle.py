@@ -100,6 +100,8 @@ def lib():
         L.orc_kmer_votes.restype = C.c_uint32
         L.orc_kmer_votes.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p]
         L.orc_align_batch.argtypes = [C.POINTER(Batch), C.POINTER(Affine), C.POINTER(BatchOut)]
+        L.orc_rustbio_global.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.c_void_p, C.c_size_t]
         L.orc_extract_tagged_sequences.restype = C.c_size_t
         L.orc_extract_tagged_sequences.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.orc_reverse_complement.restype = None
@@ -269,3 +271,16 @@ def reverse_complement(dna):
     buf = C.create_string_buffer(max(1, len(dna)))
     lib().orc_reverse_complement(bytes(dna), len(dna), buf)
     return buf.raw[:len(dna)]
+
+
+RUSTBIO_CLI = (1, -1, -5, -1)  # rust_bio_alignment's hard-coded scoring, alignment_functions.rs:55-57
+
+
+def rustbio_global(ref, read, scoring=RUSTBIO_CLI):
+    """rust-bio Aligner::global as the single-reference branch calls it (PARITY UNPINNED restatement, oracle/clq_oracle.h)."""
+    ref, read = bytes(ref), bytes(read)
+    score, n = C.c_int32(), C.c_uint32()
+    cig = np.zeros(len(ref) + len(read) + 2, dtype=np.uint32)
+    rc = lib().orc_rustbio_global(ref, len(ref), read, len(read), scoring[0], scoring[1], scoring[2], scoring[3],
+                                  C.byref(score), C.byref(n), cig.ctypes.data, len(cig))
+    return {"score": score.value, "status": rc, "cigar": cig[:n.value].copy()}

@@ -5,7 +5,7 @@ import pytest
 
 import _oracle as O
 from clique_b200 import (AffineScoring, Aligner, ClqError, Reference, ReferenceManager, TRACEBACK_DIVERGED,
-                         READ_TOO_LONG, NO_CANDIDATE, CIGAR_POOL_FULL)
+                         READ_TOO_LONG, NO_CANDIDATE, CIGAR_POOL_FULL, SCORING_NOT_REPRESENTABLE)
 from clique_b200 import synth
 from clique_b200.aligner import pack_reads
 
@@ -453,3 +453,76 @@ def test_extract_tags_fused_into_walk(al, goldens):
         o, l = int(want["cigar_off"][i]), int(want["cigar_len"][i])
         ri = int(want["ref_index"][i])
         assert br.tag_strings(i, refs[ri]) == _digit_tags_oracle(refs[ri], rd, want["cigar_pool"][o:o + l]), i
+
+
+# ---------------------------------------------------------------- the single-reference branch: rust-bio global (PARITY UNPINNED)
+def _rb_compare(br, refs, reads, fixed, ctx):
+    bad = 0
+    for i, rd in enumerate(reads):
+        ref = refs[int(fixed[i])]
+        want = O.rustbio_global(ref, rd)
+        assert int(br.status[i]) == 0, (ctx, i, int(br.status[i]))
+        if int(br.score_scaled[i]) != want["score"] or O.cigar_str(br.cigar(i)) != O.cigar_str(want["cigar"]):
+            bad += 1
+            assert bad < 1, (ctx, i, int(br.score_scaled[i]), want["score"], O.cigar_str(br.cigar(i)), O.cigar_str(want["cigar"]), ref, rd)
+        ra, qa = O.apply_cigar(ref, rd, br.cigar(i))
+        assert (int(br.matches[i]), int(br.mismatches[i])) == O.alignment_rate(ra, qa)[1:], (ctx, i, "rm")
+
+
+@pytest.mark.parametrize("no_pack", [0, 1])
+def test_rustbio_single_reference_mode(al, no_pack):
+    """CLQ_RUSTBIO vs the oracle's restatement of rust-bio's Aligner::global (align_to_reference_choices' 1-reference branch,
+    alignment_functions.rs:544-603).  Both the s16x2 PACK kernels and (no_pack) the int32 FAST kernels."""
+    from clique_b200 import RustBioScoring
+    rng = np.random.default_rng(2024 + no_pack)
+    al.set_option("no_pack", no_pack)
+    try:
+        # (1) the C2 lineage amplicon: tag symbols 0/1/2 in the reference, reads with Ns, ragged / empty reads
+        c = synth.config_c2(600)
+        off = c["read_off"]
+        reads = [bytes(c["read_bytes"][int(off[i]):int(off[i + 1])]) for i in range(600)]
+        for i in range(0, 600, 5):
+            reads[i] = mutate(rng, reads[i], 0.2)
+        for i in range(1, 600, 9):
+            b = bytearray(reads[i]); b[int(rng.integers(0, len(b)))] = ord("N"); b[int(rng.integers(0, len(b)))] = ord("N"); reads[i] = bytes(b)
+        reads[2] = b""
+        reads[4] = reads[4][:17]
+        refs = [c["refs"][0]]
+        al.set_references(ReferenceManager([Reference(refs[0], b"amp")]))
+        qb, qo = pack_reads(reads)
+        fixed = np.zeros(len(reads), np.int32)
+        br = al.align_batch(qb, qo, RustBioScoring(), "fixed", "maxlen", fixed_ref=fixed, extract_tags=True)
+        _rb_compare(br, refs, reads, fixed, "c2")
+        for i in (0, 5, 10, 77):
+            exp = _digit_tags_oracle(refs[0], reads[i], br.cigar(i))
+            assert br.tag_strings(i, refs[0]) == exp
+        # (2) several references of different lengths (fixed assignment), every geometry incl. multi-stripe and narrow stripes
+        refs = [rand_seq(rng, n, b"ACGTN") for n in (1, 7, 64, 130, 333, 700, 1500)]
+        reads, fixed = [], []
+        for k, r in enumerate(refs):
+            for _ in range(12):
+                reads.append(mutate(rng, r, float(rng.choice([0.0, 0.05, 0.3]))).replace(b"N", b"A") if rng.random() < 0.8 else rand_seq(rng, int(rng.integers(0, 2 * len(r) + 2)), b"ACGTN"))
+                fixed.append(k)
+        fixed = np.array(fixed, np.int32)
+        al.set_references(ReferenceManager([Reference(r, b"r%d" % i) for i, r in enumerate(refs)]))
+        qb, qo = pack_reads(reads)
+        for cfg in (-1, 0, 2, 3, 4, 5):
+            al.set_option("force_cfg", cfg)
+            br = al.align_batch(qb, qo, RustBioScoring(), "fixed", "maxlen", fixed_ref=fixed)
+            _rb_compare(br, refs, reads, fixed, "multi cfg=%d" % cfg)
+        al.set_option("force_cfg", -1)
+        # (3) a read byte the class table cannot score exactly is refused, not mis-scored
+        ref = b"ACGTACGT01234567ACGT"  # 4 letters + 8 tag symbols: '2'..'7' get rows but no read column
+        al.set_references(ReferenceManager([Reference(ref, b"tags")]))
+        qb, qo = pack_reads([b"ACGTACGTTTTTTTTTACGT", b"ACGTACGT01TTTTTTACGT", b"ACGTACGT0123TTTTACGT"])
+        br = al.align_batch(qb, qo, RustBioScoring(), "fixed", "maxlen", fixed_ref=np.zeros(3, np.int32))
+        assert [int(x) for x in br.status] == [0, 0, SCORING_NOT_REPRESENTABLE]
+        _rb_compare(br, [ref], [b"ACGTACGTTTTTTTTTACGT", b"ACGTACGT01TTTTTTACGT"], [0, 0], "tag symbols")
+        # (4) the host call: score reported as 0.0 and no path, as the reference builds the record (:571-583)
+        al.set_references(ReferenceManager([Reference(c["refs"][0], b"amp")]))
+        w = al.align_to_reference_choices("r", reads[0] if False else bytes(c["read_bytes"][:300]), None, True, AffineScoring(*c["scoring"]), rust_bio=True)
+        want = O.rustbio_global(c["refs"][0], bytes(c["read_bytes"][:300]))
+        assert w.alignment.score == 0.0 and w.alignment.path == [] and w.alignment.cigar() == O.cigar_str(want["cigar"])
+    finally:
+        al.set_option("no_pack", 0)
+        al.set_option("force_cfg", -1)
