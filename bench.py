@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--ref-step-seconds", type=float, default=4.0)
     ap.add_argument("--search", default="", choices=["", "exhaustive", "quick"], help="C4 only: candidate search (default exhaustive)")
     ap.add_argument("--convex", action="store_true", help="two-piece affine gaps o1=-20,e1=-2,o2=-40,e2=-1 (self-pinned semantics)")
+    ap.add_argument("--rustbio", action="store_true", help="C2 only: the reference's current single-reference branch (rust-bio global 1/-1/-5/-1; parity unpinned)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-live-peak", action="store_true", help="use the committed INT32 peak instead of running tools/int_peak")
     args = ap.parse_args()
@@ -187,7 +188,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from clique_b200 import AffineScoring, Aligner, Reference, ReferenceManager, TwoPieceScoring
+    from clique_b200 import AffineScoring, Aligner, Reference, ReferenceManager, RustBioScoring, TwoPieceScoring
 
     if world > 1:
         torch.cuda.set_device(local_rank)
@@ -214,6 +215,10 @@ def main():
     al.set_references(ReferenceManager([Reference(r, nm) for r, nm in zip(c["refs"], c["ref_names"])]))
     sc = TwoPieceScoring(10, -9, 9, -20, -2, -40, -1) if args.convex else AffineScoring(*c["scoring"])
     sci = sc.to_int()
+    if args.rustbio:
+        assert c["search"] == "fixed" and not args.convex, "--rustbio is the single-reference branch"
+        sci = RustBioScoring()   # Aligner.launch adds CLQ_RUSTBIO for this scoring type
+        c["band"] = "maxlen"
     for opt in ("force_cfg", "force_generic", "debug_flags"):     # experiment knobs, e.g. CLQ_FORCE_CFG=3
         if os.environ.get("CLQ_" + opt.upper()):
             al.set_option(opt, int(os.environ["CLQ_" + opt.upper()]))
@@ -317,6 +322,8 @@ def main():
         pack = 2 if (variant & 2) else 1     # s16x2 kernels advance two cells per instruction (peak x pack)
         kernel = {0: "generic int32", 1: "FAST int32 (PRMT profile + DPX)", 3: "PACK s16x2 (two reads per lane group, DPX)",
                   5: "CONVEX int32 (two-piece affine, DPX)"}.get(variant & 7, "variant %d" % (variant & 15))
+        if variant & 16:
+            kernel += " [rust-bio global semantics]"
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -338,7 +345,7 @@ def main():
             "metric": "reads/s", "value": value, "unit": "reads/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "gcups": gcups,
-            "config": {"workload": WORKLOAD_DESC[args.workload].replace("(exhaustive)", "(%s)" % c["search"]) + (" [two-piece affine (convex) gaps, self-pinned]" if args.convex else ""), "reads_per_gpu_per_step": n, "cells_per_gpu_per_step": int(cells),
+            "config": {"workload": WORKLOAD_DESC[args.workload].replace("(exhaustive)", "(%s)" % c["search"]) + (" [two-piece affine (convex) gaps, self-pinned]" if args.convex else "") + (" [rust-bio single-reference branch 1/-1/-5/-1 instead of clique's Gotoh, parity unpinned]" if args.rustbio else ""), "reads_per_gpu_per_step": n, "cells_per_gpu_per_step": int(cells),
                        "parallelism": "read-sharded x%d, no collectives" % n_gpus, "status_ok_reads": n_ok,
                        "l2": "inputs larger than L2 (%.0f MB of reads + %.0f MB of direction bits per step)" % (total_bytes / 1e6, 0.5 * cells / 1e6)},
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"], "power_w_max": clk.get("power_w_max"),
@@ -364,6 +371,20 @@ def main():
                 if w["score"] != int(res.score_scaled[i]) or O.cigar_str(w["cigar"]) != res.cigar_string(i):
                     bad += 1
             line["parity"] = {"checked_reads": ns, "mismatches": bad, "oracle": "orc_convex_align_pair (self-pinned)"}
+        elif args.rustbio and n_gpus == 1:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import _oracle as O
+            bad, ns = 0, min(n, 2000)
+            t0 = time.perf_counter()
+            for i in range(ns):
+                rd = bytes(c["read_bytes"][int(c["read_off"][i]):int(c["read_off"][i + 1])])
+                w = O.rustbio_global(c["refs"][int(c["fixed_ref"][i])], rd)
+                if w["score"] != int(res.score_scaled[i]) or O.cigar_str(w["cigar"]) != res.cigar_string(i):
+                    bad += 1
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": ns / dt, "unit": "reads/s", "cores": 1, "kind": "port",
+                                    "sample": "first %d reads, %.1f s, single-threaded restatement of rust-bio Aligner::global (oracle/, parity unpinned)" % (ns, dt)}
+            line["parity"] = {"checked_reads": ns, "mismatches": bad, "oracle": "orc_rustbio_global (parity unpinned)"}
         elif not args.no_cpu_baseline and n_gpus == 1:
             threads = os.cpu_count() or 1
             probe = min(n, 256 if args.workload == "C2" else 16)

@@ -38,6 +38,13 @@ clq_affine_t AffineScoring::to_int() const {
     return out;
 }
 
+clq_affine_t RustBioScoring::to_int() const {
+    clq_affine_t out;
+    const int32_t rc = clq_rustbio_scoring(match_score, mismatch_score, gap_open, gap_extend, &out);
+    if (rc != CLQ_OK) fail(rc, "rust-bio scoring not representable");
+    return out;
+}
+
 double ConvexScoring::gap(size_t length) const {
     return gap_open + (length > 0 ? std::log10((double)length) : -std::numeric_limits<double>::infinity());
 }
@@ -374,6 +381,7 @@ std::string BatchView::cigar_string(uint32_t i) const {
     return s;
 }
 
+// (score() of a CLQ_RUSTBIO batch is rust-bio's own score; the record the reference builds carries 0.0, see alignment())
 double BatchView::alignment_rate(uint32_t i) const {
     const double m = results[i].matches, mm = results[i].mismatches;
     return m / (m + mm);
@@ -395,7 +403,8 @@ std::optional<AlignmentWithRef> BatchView::alignment(uint32_t i) const {
     const Reference& r = rm->references[ref_index(i)];
     AlignmentWithRef a;
     a.alignment = AlignmentResult::from_cigar(to_string(r.name), batch->name(i), r.sequence.data(), r.sequence.size(), batch->read(i),
-                                              batch->read_len(i), batch->quals(i), cigar(i), cigar_len(i), score(i));
+                                              batch->read_len(i), batch->quals(i), cigar(i), cigar_len(i), rust_bio ? 0.0 : score(i));
+    if (rust_bio) a.alignment->path.clear();  // alignment_functions.rs:571-583: path: vec!(), score: 0.0
     a.ref_name = r.name;
     a.ref_sequence = r.sequence;
     return a;
@@ -411,7 +420,7 @@ TagMap BatchView::align_reads_tags(uint32_t i, const std::string& umi_symbols) c
     t[{'r', 'c'}] = "1";
     t[{'a', 'r'}] = batch->name(i);
     t[{'r', 'm'}] = f64_to_string(alignment_rate(i));
-    t[{'a', 's'}] = f64_to_string(score(i));
+    t[{'a', 's'}] = f64_to_string(rust_bio ? 0.0 : score(i));
     return t;
 }
 
@@ -487,6 +496,7 @@ BatchView Aligner::wait(int slot, const ReadBatch& b) {
     v.cigar_pool = pool_[slot];
     v.scale = scale_[slot];
     v.device = opt_.device;
+    v.rust_bio = (flags_[slot] & CLQ_RUSTBIO) != 0;
     if (flags_[slot] & CLQ_EXTRACT_TAGS) {
         uint32_t stride = 0;
         check(clq_tags_download(ctx_, slot, nullptr, 0, &stride), "clq_tags_download");
@@ -576,8 +586,17 @@ std::optional<AlignmentWithRef> Aligner::quick_alignment_search(const std::strin
 }
 
 std::optional<AlignmentWithRef> Aligner::align_to_reference_choices(const std::string& read_name, const Bytes& read, std::optional<Bytes> qual,
-                                                                    bool fast_lookup, const AffineScoring& scoring) {
+                                                                    bool fast_lookup, const AffineScoring& scoring, bool rust_bio) {
     if (rm_.references.empty()) return std::nullopt;
+    if (rm_.references.size() == 1 && rust_bio) {
+        if (!one_) one_ = std::make_unique<ReadBatch>(1, opt_.max_read_bytes);
+        one_->clear();
+        if (!one_->push(read_name, read.data(), read.size(), qual ? qual->data() : nullptr, 0)) fail(CLQ_E_LIMIT, "read exceeds max_read_bytes");
+        submit(0, *one_, RustBioScoring().to_int(), CLQ_SEARCH_FIXED | CLQ_BAND_MAXLEN | CLQ_RUSTBIO);
+        const BatchView v = wait(0, *one_);
+        if (v.status(0) != CLQ_OK) fail((int32_t)v.status(0), clq_strerror((int32_t)v.status(0)));
+        return v.alignment(0);
+    }
     if (rm_.references.size() == 1) return search(read_name, read, std::move(qual), scoring, CLQ_SEARCH_FIXED, 0.90);
     return search(read_name, read, std::move(qual), scoring, fast_lookup ? CLQ_SEARCH_QUICK : CLQ_SEARCH_EXHAUSTIVE, 0.90);
 }
@@ -597,12 +616,13 @@ void prepare_fixed(ReadBatch& b, uint32_t flags) {
 }  // namespace
 
 AlignReadsStats Aligner::align_reads(const ReadSource& source, const AffineScoring& scoring, bool fast_lookup, const ResultSink& sink,
-                                     bool extract_tags) {
+                                     bool extract_tags, bool rust_bio) {
     const auto t0 = std::chrono::steady_clock::now();
     AlignReadsStats st;
     if (rm_.references.empty()) return st;
-    const clq_affine_t sc = scoring.to_int();
-    const uint32_t flags = search_flags(fast_lookup) | (extract_tags ? CLQ_EXTRACT_TAGS : 0u);
+    const bool rb = rust_bio && rm_.references.size() == 1;
+    const clq_affine_t sc = rb ? RustBioScoring().to_int() : scoring.to_int();
+    const uint32_t flags = search_flags(fast_lookup) | (extract_tags ? CLQ_EXTRACT_TAGS : 0u) | (rb ? CLQ_RUSTBIO : 0u);
     const uint32_t ns = opt_.n_slots;
     std::vector<std::unique_ptr<ReadBatch>> bufs;
     for (uint32_t s = 0; s < ns; s++) bufs.push_back(std::make_unique<ReadBatch>(opt_.max_reads, opt_.max_read_bytes));
@@ -652,7 +672,7 @@ void ShardedAligner::set_references(const ReferenceManager& rm, bool build_kmer_
 }
 
 AlignReadsStats ShardedAligner::align_reads(const ReadSource& source, const AffineScoring& scoring, bool fast_lookup, const ResultSink& sink,
-                                            bool extract_tags) {
+                                            bool extract_tags, bool rust_bio) {
     const auto t0 = std::chrono::steady_clock::now();
     AlignReadsStats total;
     std::mutex src_mu, sink_mu;
@@ -675,7 +695,7 @@ AlignReadsStats ShardedAligner::align_reads(const ReadSource& source, const Affi
     };
     auto work = [&](Aligner* a) {
         try {
-            const AlignReadsStats st = a->align_reads(shared_source, scoring, fast_lookup, locked_sink, extract_tags);
+            const AlignReadsStats st = a->align_reads(shared_source, scoring, fast_lookup, locked_sink, extract_tags, rust_bio);
             std::lock_guard<std::mutex> g(sink_mu);
             total.reads += st.reads; total.aligned += st.aligned; total.dropped += st.dropped; total.batches += st.batches; total.cells += st.cells;
         } catch (...) {

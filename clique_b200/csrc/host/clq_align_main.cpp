@@ -21,7 +21,7 @@ struct Args {
     std::string refs, reads, reads2, out = "-", stats_json, umi_symbols = "0123456789", layout;
     std::vector<int> gpus = {0};
     uint32_t batch = 1u << 18, max_read_len = 1u << 16, cigar_ops_per_read = 32, max_reference_multiplier = 2;
-    bool exhaustive = false, tags = true, quiet_sam = false;
+    bool exhaustive = false, tags = true, quiet_sam = false, rust_bio = false;
     AffineScoring scoring = AffineScoring::align_reads_default();
 };
 
@@ -30,7 +30,7 @@ struct Args {
     std::fprintf(stderr,
                  "usage: clq_align --refs refs.fa --reads reads.fastq|reads.txt [--reads2 r2.fastq --layout 1F,2C] [--out out.sam|-]\n"
                  "                 [--gpus 0,1,..] [--batch N] [--exhaustive] [--scoring match,mismatch,special,open,extend,final_mult]\n"
-                 "                 [--umi-symbols 012] [--no-tags] [--no-sam] [--max-read-len N] [--max-reference-multiplier N]\n"
+                 "                 [--umi-symbols 012] [--no-tags] [--no-sam] [--rust-bio] [--max-read-len N] [--max-reference-multiplier N]\n"
                  "                 [--cigar-ops-per-read N] [--stats-json path]\n");
     std::exit(2);
 }
@@ -53,6 +53,7 @@ Args parse(int argc, char** argv) {
         else if (k == "--max-reference-multiplier") a.max_reference_multiplier = (uint32_t)std::stoul(val());
         else if (k == "--exhaustive") a.exhaustive = true;
         else if (k == "--no-tags") a.tags = false;
+        else if (k == "--rust-bio") a.rust_bio = true;
         else if (k == "--no-sam") a.quiet_sam = true;
         else if (k == "--gpus") {
             a.gpus.clear();
@@ -212,7 +213,7 @@ int main(int argc, char** argv) {
                 n_batches_out++;
             }
         };
-        const AlignReadsStats st = sh.align_reads(source, a.scoring, !a.exhaustive, sink, a.tags);
+        const AlignReadsStats st = sh.align_reads(source, a.scoring, !a.exhaustive, sink, a.tags, a.rust_bio);
         out->flush();
         char js[512];
         std::snprintf(js, sizeof(js),

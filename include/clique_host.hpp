@@ -49,6 +49,13 @@ struct AffineScoring {
     clq_affine_t to_int() const;
 };
 
+/// rust_bio_alignment's hard-coded scoring (alignment_functions.rs:48-61): 1 / -1 (a read 'N' matches anything), gap open -5,
+/// extend -1.  Selects CLQ_RUSTBIO, rust-bio `Aligner::global` semantics -- PARITY UNPINNED (un-vendored `bio = "*"`).
+struct RustBioScoring {
+    int32_t match_score = 1, mismatch_score = -1, gap_open = -5, gap_extend = -1;
+    clq_affine_t to_int() const;
+};
+
 /// ConvexScoring, alignment/scoring_functions.rs:36-53 -- only a gap *function* in the reference (nothing calls it)
 struct ConvexScoring {
     double match_score, mismatch_score, gap_score, gap_open, gap_extend;
@@ -226,6 +233,7 @@ public:
     uint32_t tag_stride = 0;
     int32_t scale = 1;
     int device = 0;
+    bool rust_bio = false;  // CLQ_RUSTBIO batch: the reference reports score 0.0 and an empty path for these records
 
     uint32_t status(uint32_t i) const { return results[i].status; }
     double score(uint32_t i) const { return (double)results[i].score_scaled / (double)scale; }
@@ -292,17 +300,19 @@ public:
     /// quick_alignment_search, alignment_functions.rs:693-767
     std::optional<AlignmentWithRef> quick_alignment_search(const std::string& read_name, const Bytes& read, std::optional<Bytes> qual,
                                                            const AffineScoring& scoring, double match_threshold = 0.90);
-    /// align_to_reference_choices, alignment_functions.rs:520-631: 0 references -> nullopt; 1 -> clique's own Gotoh with
-    /// bandwidth = read.len() (the commented-out intent of :586-597; the rust-bio detour is parity-unpinned);
-    /// > 1 -> quick (fast_lookup) or exhaustive search.
+    /// align_to_reference_choices, alignment_functions.rs:520-631: 0 references -> nullopt; > 1 -> quick (fast_lookup) or
+    /// exhaustive search; 1 -> with `rust_bio` what the reference does today (:544-603: rust-bio global, 1/-1/-5/-1, score
+    /// reported as 0.0, empty path; PARITY UNPINNED), otherwise clique's own Gotoh with bandwidth = read.len() (the call the
+    /// reference has commented out at :586-597; pinned on its goldens).
     std::optional<AlignmentWithRef> align_to_reference_choices(const std::string& read_name, const Bytes& read, std::optional<Bytes> qual,
-                                                               bool fast_lookup, const AffineScoring& scoring);
+                                                               bool fast_lookup, const AffineScoring& scoring, bool rust_bio = false);
 
     // ---- the batch loop ----
     /// align_reads' par_bridge loop (alignment_functions.rs:135-249) up to the writer: drains `source` into pinned batches,
     /// keeps every stream slot busy, hands each finished batch to `sink`.
+    /// `rust_bio`: single-reference panels take the rust-bio branch (see align_to_reference_choices); records then carry score 0.
     AlignReadsStats align_reads(const ReadSource& source, const AffineScoring& scoring, bool fast_lookup, const ResultSink& sink,
-                                bool extract_tags = true);
+                                bool extract_tags = true, bool rust_bio = false);
 
     // ---- raw slot interface (used by ShardedAligner and the bench driver) ----
     uint32_t search_flags(bool fast_lookup) const;
@@ -337,7 +347,7 @@ public:
     ShardedAligner(const std::vector<int>& devices, AlignerOptions opt = AlignerOptions());
     void set_references(const ReferenceManager& rm, bool build_kmer_index = true);
     AlignReadsStats align_reads(const ReadSource& source, const AffineScoring& scoring, bool fast_lookup, const ResultSink& sink,
-                                bool extract_tags = true);
+                                bool extract_tags = true, bool rust_bio = false);
     size_t n_devices() const { return aligners_.size(); }
     Aligner& aligner(size_t k) { return *aligners_[k]; }
 

@@ -283,3 +283,26 @@ def test_clq_align_panel(H, tmp_path, mode):
     exp = _expect_lines(H, want, refs, names, reads, ["read%d" % i for i in range(600)])
     _check(lines, exp)
     assert st["reads"] == 600
+
+
+@pytest.mark.gpu
+def test_clq_align_rust_bio_branch(H, tmp_path):
+    """--rust-bio: the reference's current single-reference branch (alignment_functions.rs:544-603) through the C++ batch loop:
+    rust-bio CIGARs (PARITY UNPINNED restatement), score written as 0, tags extracted from those alignments."""
+    from clique_b200 import synth
+    c = synth.config_c2(500)
+    off = c["read_off"]
+    reads = [bytes(c["read_bytes"][int(off[i]):int(off[i + 1])]) for i in range(500)]
+    refs, names = c["refs"], c["ref_names"]
+    fa, rp = _write_inputs(str(tmp_path), refs, names, reads)
+    head, lines, st = _run_clq_align(str(tmp_path), fa, rp, ["--rust-bio"])
+    assert len(lines) == 500 and st["aligned"] == 500
+    for i, (got, rd) in enumerate(zip(lines, reads)):
+        want = O.rustbio_global(refs[0], rd)
+        ra, qa = O.apply_cigar(refs[0], rd, want["cigar"])
+        tags = {"rc": "1", "ar": "q%d" % i, "rm": h_f64(H, O.alignment_rate(ra, qa)[0]), "as": "0", "rs": "0"}
+        for k, v in O.extract_tagged_sequences(qa, ra).items():
+            if 48 <= k <= 57:
+                tags["e" + chr(k)] = v.decode()
+        assert got[:11] == ["q%d" % i, "0", "lineage_amplicon", "1", "255", O.cigar_str(want["cigar"]), "*", "0", "0", rd.decode(), "i" * len(rd)], i
+        assert dict(x.split(":Z:") for x in got[11:]) == tags, i
