@@ -39,7 +39,7 @@ __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C
             for (int jj = 0; jj < 8; jj++) {
                 const int j = jb * 8 + jj;
                 const uint32_t m = (uint32_t)prmt_s8(tlo, thi, sel[j]);  // [mA, mB] as s16x2
-                const uint32_t Mv = __viaddmax_s16x2(diag, m, 0u);       // per-half add (biased values are > 0)
+                const uint32_t Mv = __viaddmax_s16x2(diag, m, X1);       // per-half add: biased values are > 0 > x1 (X1 is a live register; a literal 0 costs a PRMT per cell)
                 const uint32_t EhU = Eh[j], BU = B[j];
                 const uint32_t Ehn = __viaddmax_s16x2(EhU, LE, BU);
                 uint32_t t2 = 0, u2 = 0;
