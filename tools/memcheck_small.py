@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import _oracle as O
-from clique_b200 import AffineScoring, Aligner, Reference, ReferenceManager, TwoPieceScoring
+from clique_b200 import AffineScoring, Aligner, Reference, ReferenceManager, RustBioScoring, TwoPieceScoring
 from clique_b200.aligner import pack_reads
 
 rng = np.random.default_rng(1)
@@ -42,9 +42,9 @@ for name, refset, sc, search, band, fixed in [
 ]:
     al.set_references(ReferenceManager([Reference(r, b"r%d" % i) for i, r in enumerate(refset)]))
     qb, qo = pack_reads(reads)
-    for cfg in (-1, 0):     # automatic geometry and the narrowest one (multi-stripe for the 700 bp read)
+    for cfg in (-1, 0, 3, 5):     # automatic geometry, the narrowest one (multi-stripe for the 700 bp read), G = 16 / 32 (narrow last stripe)
         al.set_option("force_cfg", cfg)
-        br = al.align_batch(qb, qo, sc, search, band, fixed_ref=fixed, with_stats=True)
+        br = al.align_batch(qb, qo, sc, search, band, fixed_ref=fixed, with_stats=True, extract_tags=True)
         so = al.align_batch(qb, qo, sc, search, band, fixed_ref=fixed, score_only=True)
         rb, ro = O.pack_seqs(refset)
         want = O.align_batch(rb, ro, qb, qo, (sc.match_score, sc.mismatch_score, sc.special_character_score, sc.gap_open, sc.gap_extend,
@@ -57,6 +57,23 @@ for name, refset, sc, search, band, fixed in [
                 bad += 1
         print(name, "cfg", cfg, "variant", br.stats["variant"] & 15, "launches", br.stats["launches"])
     al.set_option("force_cfg", -1)
+# rust-bio single-reference branch (PACK and int32), tags on
+for no_pack in (0, 1):
+    al.set_option("no_pack", no_pack)
+    tagref = rs(40) + b"0000" + rs(30) + b"111" + rs(40, b"ACGTN")
+    al.set_references(ReferenceManager([Reference(tagref, b"t")]))
+    rr = [mut(tagref.replace(b"0", b"A").replace(b"1", b"C")) for _ in range(33)] + [b"", rs(3), rs(200, b"ACGTN")]
+    qb, qo = pack_reads(rr)
+    for cfg in (-1, 0, 3, 5):
+        al.set_option("force_cfg", cfg)
+        br = al.align_batch(qb, qo, RustBioScoring(), "fixed", "maxlen", fixed_ref=np.zeros(len(rr), np.int32), extract_tags=True)
+        for i, rd in enumerate(rr):
+            w = O.rustbio_global(tagref, rd)
+            if w["score"] != int(br.score_scaled[i]) or O.cigar_str(w["cigar"]) != br.cigar_string(i):
+                bad += 1
+    al.set_option("force_cfg", -1)
+al.set_option("no_pack", 0)
+print("rustbio ok")
 cv = TwoPieceScoring(10, -9, 9, -20, -2, -40, -1)
 al.set_references(ReferenceManager([Reference(refs[0], b"r0")]))
 qb, qo = pack_reads(reads)
