@@ -30,7 +30,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
     DevBuf read_bytes, read_off, fixed_ref, order, results, scores, cand_mask, single_ref, ref_of_read, votes;
-    DevBuf cigar_pool, bits, cig_scratch, col_scratch, tb_rec, bits_off, tags;
+    DevBuf cigar_pool, bits, cig_scratch, col_scratch, tb_rec, bits_off, tags, ref_groups;
     std::vector<uint32_t> h_len;     // read lengths in processing order (only when lengths vary: have_order)
     std::vector<int32_t> h_ref;      // fixed_ref in processing order (same condition, when given)
     DevBuf counters;                 // [0..3] task counters (u32, padded to 8 B each), [4] cigar cursor, [5] cells
@@ -63,6 +63,7 @@ struct clq_ctx {
     int force_cfg = -1;
     int debug_flags = 0;
     int no_pack = 0;                 // option "no_pack": never take the s16x2 PACK kernels
+    int no_group = 0;                // option "no_group": multi-reference traceback stays on the int32 kernels (no bucketing by reference)
     int force_generic = 0;           // option "force_generic": never take the FAST (PRMT/DPX) kernel variant
     bool fast_ok = false;            // the reference set has <= 6 distinct non-special bytes
     uint8_t cls[256] = {};           // byte -> class: 0 special, 1 other, 2..7 reference bytes (| row << 3, clq_kernels.cuh)
@@ -369,7 +370,7 @@ void clq_ctx_destroy(clq_ctx* c) {
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
         for (DevBuf* b : {&s.read_bytes, &s.read_off, &s.fixed_ref, &s.order, &s.results, &s.scores, &s.cand_mask, &s.single_ref,
-                          &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.tb_rec, &s.bits_off, &s.tags, &s.counters})
+                          &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.tb_rec, &s.bits_off, &s.tags, &s.ref_groups, &s.counters})
             release(*b);
         if (s.h_counters) cudaFreeHost(s.h_counters);
     }
@@ -385,6 +386,7 @@ int32_t clq_set_option(clq_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "force_generic")) { c->force_generic = (int)value; return CLQ_OK; }
     if (!strcmp(key, "debug_flags")) { c->debug_flags = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_pack")) { c->no_pack = (int)value; return CLQ_OK; }
+    if (!strcmp(key, "no_group")) { c->no_group = (int)value; return CLQ_OK; }
     if (!strcmp(key, "max_scratch_bytes")) { c->max_scratch_bytes = value; return CLQ_OK; }
     return fail(c, CLQ_E_INVALID, std::string("unknown option ") + key);
 }
@@ -677,9 +679,13 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         }
     }
     const bool pack_pairs = pack && c->n_refs == 1;  // pair mode needs one reference for both reads of a task
+    // multi-reference batches: the traceback stage buckets the reads by reference on the device (ref_scatter_kernel) so that
+    // the two reads of a PACK task share theirs; only with the natural read order (uniform lengths, uniform scratch slots)
+    const bool group_pairs = pack && !pack_pairs && !score_only && !s->have_order && n > 0 && c->n_refs > 1 && !c->no_group;
+    const uint64_t n_pos = group_pairs ? (((uint64_t)n + c->n_refs + 2) & ~1ull) : n;  // processing positions incl. bucket padding
     auto launch_dp = [&](bool tb, const KParams& kp, int* grid, bool query) -> cudaError_t {
         if (convex) return tb ? launch_cvx<true>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query) : launch_cvx<false>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query);
-        if (pack && (kp.all_pairs || pack_pairs)) {
+        if (pack && (kp.all_pairs || pack_pairs || (tb && group_pairs))) {
             if (rb) return launch_pack<true, true>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query);
             return tb ? launch_pack<true>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query) : launch_pack<false>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query);
         }
@@ -741,7 +747,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     };
     int32_t rc;
     const uint64_t per_task = bits_stride * 4 + (uint64_t)cig_stride * 4 + sizeof(TbRec);
-    uint64_t sub = std::max<uint64_t>(2, std::min<uint64_t>((uint64_t)n + 1, (uint64_t)c->max_scratch_bytes / per_task)) & ~1ull;  // even: PACK tasks are read pairs
+    uint64_t sub = std::max<uint64_t>(2, std::min<uint64_t>(n_pos + 1, (uint64_t)c->max_scratch_bytes / per_task)) & ~1ull;  // even: PACK tasks are read pairs
     std::vector<uint64_t> cuts;          // sub-batch boundaries in processing positions
     const bool var_slots = !score_only && n && s->have_order && s->h_len.size() == n;
     uint64_t max_sub_words = sub * bits_stride, max_sub_tasks = sub;
@@ -781,8 +787,8 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         CU(c, cudaMemcpyAsync(s->bits_off.p, off.data(), ((size_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
         CU(c, cudaStreamSynchronize(s->stream));  // `off` is a reused host vector
     } else {
-        for (uint64_t b = 0; b < n; b += sub) cuts.push_back(b);
-        cuts.push_back(n);
+        for (uint64_t b = 0; b < n_pos; b += sub) cuts.push_back(b);
+        cuts.push_back(n_pos);
     }
     const uint64_t groups = (uint64_t)std::max(grid_tb, grid_sc) * (kThreads / 32) * GPW;
     if (!score_only && n) {
@@ -810,7 +816,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     }
 
     s->flags = flags;
-    s->stats.variant = (rb ? 16u : 0u) | (fast ? 1u : 0u) | ((pack && (pack_pairs || search != CLQ_SEARCH_FIXED)) ? 2u : 0u) | (convex ? 4u : 0u) | (fin ? 8u : 0u) | ((uint32_t)cfg << 8);
+    s->stats.variant = (rb ? 16u : 0u) | (fast ? 1u : 0u) | ((pack && (pack_pairs || group_pairs || search != CLQ_SEARCH_FIXED)) ? 2u : 0u) | (convex ? 4u : 0u) | (fin ? 8u : 0u) | ((uint32_t)cfg << 8);
     s->stats.sub_batches = 0;
     s->stats.launches = 0;
     s->stats.dp_launches = 0;
@@ -868,6 +874,22 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         q.all_pairs = 0;
         q.ref_of_read = ref_of_read;
         q.task_counter = (unsigned int*)(ctr + 1);
+        if (group_pairs) {
+            const uint32_t nb = c->n_refs + 1;
+            if ((rc = ensure(c, s->ref_groups, (size_t)2 * nb * sizeof(uint32_t))) != CLQ_OK) return rc;
+            if ((rc = ensure(c, s->order, n_pos * sizeof(uint32_t))) != CLQ_OK) return rc;
+            uint32_t* hist = (uint32_t*)s->ref_groups.p;
+            uint32_t* cursor = hist + nb;
+            CU(c, cudaMemsetAsync(hist, 0, (size_t)2 * nb * sizeof(uint32_t), s->stream));
+            CU(c, cudaMemsetAsync(s->order.p, 0xff, n_pos * sizeof(uint32_t), s->stream));
+            ref_hist_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(ref_of_read, n, c->n_refs, hist);
+            ref_scan_kernel<<<1, 32, 0, s->stream>>>(hist, nb, cursor);
+            ref_scatter_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(ref_of_read, n, c->n_refs, cursor, (uint32_t*)s->order.p);
+            CU(c, cudaGetLastError());
+            s->stats.launches += 3;
+            q.order = (const uint32_t*)s->order.p;
+        }
+        const bool tb_pairs = pack_pairs || group_pairs;
         CU(c, cudaEventRecord(s->ev[3], s->stream));
         if (score_only) {
             q.n_tasks = pack_pairs ? (n + 1) / 2 : n;
@@ -884,7 +906,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
                 const uint64_t base = cuts[ci];
                 const uint32_t cnt = (uint32_t)(cuts[ci + 1] - base);
                 if (!cnt) continue;
-                q.n_tasks = pack_pairs ? (cnt + 1) / 2 : cnt;
+                q.n_tasks = tb_pairs ? (cnt + 1) / 2 : cnt;
                 q.task_base = (uint32_t)base;
                 q.task_end = (uint32_t)(base + cnt);
                 if (base) CU(c, cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned long long), s->stream));
@@ -895,7 +917,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
                 s->stats.dp_launches++;
                 s->stats.sub_batches++;
                 if (!(c->debug_flags & 1)) {
-                    if ((ce = convex ? launch_cvx_walk(cfg, q, cnt, s->stream) : launch_walk(cfg, q, pack_pairs ? 2 * q.n_tasks : cnt, s->stream)) != cudaSuccess)
+                    if ((ce = convex ? launch_cvx_walk(cfg, q, cnt, s->stream) : launch_walk(cfg, q, tb_pairs ? 2 * q.n_tasks : cnt, s->stream)) != cudaSuccess)
                         return fail(c, CLQ_E_CUDA, std::string("walk kernel: ") + cudaGetErrorString(ce));
                     s->stats.launches++;
                 }

@@ -625,6 +625,32 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
     r->mismatches = n_mismatch;
 }
 
+// Grouping of a multi-reference batch for the PACK traceback stage: the s16x2 kernels align two reads against ONE reference,
+// so the reads are bucketed by their (selected or fixed) reference; every bucket is padded to an even number of processing
+// positions (padding = 0xffffffff, skipped by the kernel).  Bucket n_refs collects reads without a usable reference.
+__global__ void ref_hist_kernel(const int32_t* ref_of_read, uint32_t n_reads, uint32_t n_refs, uint32_t* hist) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_reads) return;
+    const int32_t r = ref_of_read[i];
+    atomicAdd(hist + ((r >= 0 && (uint32_t)r < n_refs) ? (uint32_t)r : n_refs), 1u);
+}
+
+__global__ void ref_scan_kernel(const uint32_t* hist, uint32_t n_buckets, uint32_t* cursor) {
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t at = 0;
+    for (uint32_t b = 0; b < n_buckets; b++) {
+        cursor[b] = at;
+        at += (hist[b] + 1u) & ~1u;
+    }
+}
+
+__global__ void ref_scatter_kernel(const int32_t* ref_of_read, uint32_t n_reads, uint32_t n_refs, uint32_t* cursor, uint32_t* order) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_reads) return;
+    const int32_t r = ref_of_read[i];
+    order[atomicAdd(cursor + ((r >= 0 && (uint32_t)r < n_refs) ? (uint32_t)r : n_refs), 1u)] = i;
+}
+
 // exhaustive_alignment_search's arg-max: ascending reference index, LAST maximum wins
 // (max_by(partial_cmp), alignment_functions.rs:809-813).  One thread per read.
 __global__ void select_best_kernel(const int32_t* scores, uint32_t n_reads, uint32_t n_refs, const uint32_t* cand_mask,

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, (TB && C >= 32) ? 3 : 1) pack_kernel
                     const uint32_t pos = p.task_base + 2 * task + h;
                     if (pos < p.task_end) {
                         ridx[h] = p.order ? p.order[pos] : pos;
-                        valid[h] = true;
+                        valid[h] = ridx[h] != 0xffffffffu;  // padding position of a reference bucket (ref_scatter_kernel)
                     }
                 }
                 // the reference of the pair = the first usable per-read reference (the host takes this kernel only for
