@@ -321,7 +321,7 @@ def main():
         achieved = alg_ops / (dp / 1e3) / 1e12
         pack = 2 if (variant & 2) else 1     # s16x2 kernels advance two cells per instruction (peak x pack)
         kernel = {0: "generic int32", 1: "FAST int32 (PRMT profile + DPX)", 3: "PACK s16x2 (two reads per lane group, DPX)",
-                  5: "CONVEX int32 (two-piece affine, DPX)"}.get(variant & 7, "variant %d" % (variant & 15))
+                  5: "CONVEX int32 (two-piece affine, DPX)", 7: "CONVEX PACK s16x2 (two-piece affine, two reads per lane group, DPX)"}.get(variant & 7, "variant %d" % (variant & 15))
         if variant & 16:
             kernel += " [rust-bio global semantics]"
         peaks = {}

@@ -11,6 +11,7 @@
 #include "clq_kernels.cuh"
 #include "clq_convex.cuh"
 #include "clq_pack.cuh"
+#include "clq_convex_pack.cuh"
 
 using namespace clq;
 
@@ -177,7 +178,7 @@ cudaError_t launch_pack(int cfg, const KParams& p, const PackParams& pp, int sm,
 }
 
 // two-piece affine ("convex") geometries: C must be a multiple of 16 (8 direction bits per cell, 128-bit row stores)
-const Cfg kCvxCfgs[] = {{8, 16}, {16, 16}, {16, 32}, {32, 32}};
+const Cfg kCvxCfgs[] = {{8, 16}, {16, 16}, {16, 32}, {32, 32}, {32, 16}};  // the last one only by force_cfg (experiments)
 constexpr int kNumCvxCfgs = sizeof(kCvxCfgs) / sizeof(kCvxCfgs[0]);
 
 template <int G, int C, bool TB>
@@ -205,7 +206,38 @@ cudaError_t launch_cvx(int cfg, const KParams& p, const ConvexParams& cp, int sm
         case 0: return launch_cvx_one<8, 16, TB>(p, cp, sm, smem, st, grid, q);
         case 1: return launch_cvx_one<16, 16, TB>(p, cp, sm, smem, st, grid, q);
         case 2: return launch_cvx_one<16, 32, TB>(p, cp, sm, smem, st, grid, q);
+        case 4: return launch_cvx_one<32, 16, TB>(p, cp, sm, smem, st, grid, q);
         default: return launch_cvx_one<32, 32, TB>(p, cp, sm, smem, st, grid, q);
+    }
+}
+
+template <int G, int C, bool TB>
+cudaError_t launch_cvx_pack_one(const KParams& p, const ConvexParams& cp, const PackParams& pp, int sm_count, size_t smem, cudaStream_t st, int* grid_out, bool query_only) {
+    auto kern = convex_pack_kernel<G, C, TB>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int nb = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (nb < 1) return cudaErrorLaunchOutOfResources;
+    int grid = nb * sm_count;
+    if (*grid_out > 0) grid = std::min(grid, *grid_out);
+    *grid_out = grid;
+    if (query_only) return cudaSuccess;
+    kern<<<grid, kThreads, smem, st>>>(p, cp, pp);
+    return cudaGetLastError();
+}
+
+template <bool TB>
+cudaError_t launch_cvx_pack(int cfg, const KParams& p, const ConvexParams& cp, const PackParams& pp, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
+    switch (cfg) {
+        case 0: return launch_cvx_pack_one<8, 16, TB>(p, cp, pp, sm, smem, st, grid, q);
+        case 1: return launch_cvx_pack_one<16, 16, TB>(p, cp, pp, sm, smem, st, grid, q);
+        case 2: return launch_cvx_pack_one<16, 32, TB>(p, cp, pp, sm, smem, st, grid, q);
+        case 4: return launch_cvx_pack_one<32, 16, TB>(p, cp, pp, sm, smem, st, grid, q);
+        default: return launch_cvx_pack_one<32, 32, TB>(p, cp, pp, sm, smem, st, grid, q);
     }
 }
 
@@ -221,6 +253,7 @@ cudaError_t launch_cvx_walk(int cfg, const KParams& p, uint32_t cnt, cudaStream_
         case 0: return launch_cvx_walk_one<8, 16>(p, cnt, st);
         case 1: return launch_cvx_walk_one<16, 16>(p, cnt, st);
         case 2: return launch_cvx_walk_one<16, 32>(p, cnt, st);
+        case 4: return launch_cvx_walk_one<32, 16>(p, cnt, st);
         default: return launch_cvx_walk_one<32, 32>(p, cnt, st);
     }
 }
@@ -648,10 +681,25 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     if ((flags & CLQ_EXTRACT_TAGS) && (convex || score_only)) return fail(c, CLQ_E_UNSUPPORTED, "CLQ_EXTRACT_TAGS needs the affine traceback");
     const uint32_t n = s->n_reads;
     int cfg = pick_cfg(c, s->max_len);
+    // 15-bit window of the two-piece affine PACK kernel for stripe width Wx (clq_convex_pack.cuh)
+    auto cvx_window = [&](int Wx, int32_t* bias_out) -> bool {
+        const clq_convex_t& cv = cp.cv;
+        const int64_t smin = std::min<int64_t>(std::min(cv.match, cv.mismatch), std::min(cv.special, 0));
+        const int64_t smax = std::max<int64_t>(std::max(cv.match, cv.special), 0);
+        const int64_t xa = cv.o1 + cv.e1, xb = cv.o2 + cv.e2;
+        const int64_t emin = std::min(cv.e1, cv.e2), omin = std::min(cv.o1, cv.o2);
+        const int64_t low = 2 * omin + (int64_t)(c->max_ref_len + s->max_len + Wx) * emin + std::min(std::min(smin, emin), std::min(xa, xb)) - 16;
+        const int64_t high = smax * std::min<int64_t>(c->max_ref_len, s->max_len) + std::max(-xa, -xb) + 16;
+        if (bias_out) *bias_out = (int32_t)(64 - low);
+        return high - low + 128 <= 32767;
+    };
     if (convex) {
-        cfg = kNumCvxCfgs - 1;
-        for (int i = 0; i < kNumCvxCfgs; i++)
+        cfg = 3;  // (32,32), multi-stripe beyond 1024 columns
+        for (int i = 0; i < 4; i++)
             if ((uint32_t)(kCvxCfgs[i].G * kCvxCfgs[i].C) >= s->max_len) { cfg = i; break; }
+        // the PACK kernel is fastest on the narrow (8,16) geometry whatever the read length (168 registers, 3 CTAs/SM, four
+        // pairs per warp: C3 990 GCUPS against 837 on (32,32)); the stripe-boundary column costs less than the occupancy
+        if (search == CLQ_SEARCH_FIXED && !c->no_pack && n && cvx_window(128, nullptr)) cfg = 0;
         if (c->force_cfg >= 0 && c->force_cfg < kNumCvxCfgs) cfg = c->force_cfg;
     }
     const int G = convex ? kCvxCfgs[cfg].G : kCfgs[cfg].G, C = convex ? kCvxCfgs[cfg].C : kCfgs[cfg].C, W = G * C, GPW = 32 / G;
@@ -678,13 +726,18 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
             pkp.bias = (int32_t)(64 - low);
         }
     }
+    if (convex && !c->no_pack && n) pack = cvx_window(W, &pkp.bias);  // two-piece affine: same proof with the gap states of both pieces
     const bool pack_pairs = pack && c->n_refs == 1;  // pair mode needs one reference for both reads of a task
     // multi-reference batches: the traceback stage buckets the reads by reference on the device (ref_scatter_kernel) so that
     // the two reads of a PACK task share theirs; only with the natural read order (uniform lengths, uniform scratch slots)
     const bool group_pairs = pack && !pack_pairs && !score_only && !s->have_order && n > 0 && c->n_refs > 1 && !c->no_group;
     const uint64_t n_pos = group_pairs ? (((uint64_t)n + c->n_refs + 2) & ~1ull) : n;  // processing positions incl. bucket padding
     auto launch_dp = [&](bool tb, const KParams& kp, int* grid, bool query) -> cudaError_t {
-        if (convex) return tb ? launch_cvx<true>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query) : launch_cvx<false>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query);
+        if (convex) {
+            if (pack && !kp.all_pairs && (pack_pairs || (tb && group_pairs)))  // the convex PACK kernel is pair-mode only
+                return tb ? launch_cvx_pack<true>(cfg, kp, cp, pkp, c->sm_count, smem, s->stream, grid, query) : launch_cvx_pack<false>(cfg, kp, cp, pkp, c->sm_count, smem, s->stream, grid, query);
+            return tb ? launch_cvx<true>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query) : launch_cvx<false>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query);
+        }
         if (pack && (kp.all_pairs || pack_pairs || (tb && group_pairs))) {
             if (rb) return launch_pack<true, true>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query);
             return tb ? launch_pack<true>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query) : launch_pack<false>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query);
@@ -816,7 +869,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     }
 
     s->flags = flags;
-    s->stats.variant = (rb ? 16u : 0u) | (fast ? 1u : 0u) | ((pack && (pack_pairs || group_pairs || search != CLQ_SEARCH_FIXED)) ? 2u : 0u) | (convex ? 4u : 0u) | (fin ? 8u : 0u) | ((uint32_t)cfg << 8);
+    s->stats.variant = (rb ? 16u : 0u) | (fast ? 1u : 0u) | ((pack && (pack_pairs || group_pairs || (search != CLQ_SEARCH_FIXED && !convex))) ? 2u : 0u) | (convex ? 4u : 0u) | (fin ? 8u : 0u) | ((uint32_t)cfg << 8);
     s->stats.sub_batches = 0;
     s->stats.launches = 0;
     s->stats.dp_launches = 0;
@@ -848,7 +901,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
             if ((rc = ensure(c, s->scores, (size_t)n * nrefs * 4)) != CLQ_OK) return rc;
             KParams q = p;
             q.all_pairs = 1;
-            q.n_tasks = pack ? ((n + 1) / 2) * nrefs : n * nrefs;
+            q.n_tasks = (pack && !convex) ? ((n + 1) / 2) * nrefs : n * nrefs;  // the convex all-pairs stage stays on the int32 kernel
             if ((uint64_t)n * nrefs > 0xfffffff0ull) return fail(c, CLQ_E_LIMIT, "reads x references exceeds 2^32 tasks per batch");
             q.cand_mask = cand;
             q.mask_words = mask_words;
@@ -917,7 +970,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
                 s->stats.dp_launches++;
                 s->stats.sub_batches++;
                 if (!(c->debug_flags & 1)) {
-                    if ((ce = convex ? launch_cvx_walk(cfg, q, cnt, s->stream) : launch_walk(cfg, q, tb_pairs ? 2 * q.n_tasks : cnt, s->stream)) != cudaSuccess)
+                    if ((ce = convex ? launch_cvx_walk(cfg, q, tb_pairs ? 2 * q.n_tasks : cnt, s->stream) : launch_walk(cfg, q, tb_pairs ? 2 * q.n_tasks : cnt, s->stream)) != cudaSuccess)
                         return fail(c, CLQ_E_CUDA, std::string("walk kernel: ") + cudaGetErrorString(ce));
                     s->stats.launches++;
                 }

@@ -243,7 +243,8 @@ __global__ void __launch_bounds__(128) convex_walk_kernel(const TbRec* recs, uin
     const TbRec rec = recs[q];
     if (rec.L1 < 0) return;
     const int L1 = rec.L1, L2 = rec.L2;
-    int z = rec.zK;
+    int z = rec.zK & 7;
+    const int CsL = ((rec.zK >> 20) & 15) * 16, sL = (rec.zK >> 24) & 255;  // narrow last stripe (convex PACK kernel, G >= 16)
     const int T = L1 + G - 1;
     const uint32_t* bits_g = bits + bits_slot(bits_off, bits_stride, task_base, q);
     uint32_t* cig_g = cig_scratch + (size_t)q * cig_stride;
@@ -270,7 +271,8 @@ __global__ void __launch_bounds__(128) convex_walk_kernel(const TbRec* recs, uin
         int c = yy - 1;
         const int s = c / W;
         c -= s * W;
-        const int ln = c / C, j = c - ln * C;
+        const int cs = (G >= 16 && s == sL && CsL > 0) ? CsL : C;
+        const int ln = c / cs, j = c - ln * cs;
         const int k = j >> 2;
         const size_t idx = (size_t)(s * T + (xx + ln - 1)) * (G * WPL) + (k / 4) * (G * 4) + ln * 4 + (k & 3);
         return (__ldg(bits_g + idx) >> (24 - 8 * (j & 3))) & 255u;

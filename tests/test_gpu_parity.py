@@ -367,6 +367,33 @@ def test_convex_two_piece(al):
             assert int(br.status[i]) == 0
             assert int(br.score_scaled[i]) == w["score"] == int(so.score_scaled[i]), (cfg, i)
             assert br.cigar_string(i) == O.cigar_str(w["cigar"]), (cfg, i)
+    # single reference: the s16x2 convex PACK kernel in pair mode (traceback and score-only), every convex geometry, and the
+    # int32 kernel (no_pack) on the same input
+    ref1 = rand_seq(rng, 260, b"ACGTN")
+    rd1 = [mutate(rng, ref1, float(rng.choice([0.02, 0.1, 0.3]))) for _ in range(150)] + [b"", rand_seq(rng, 3), rand_seq(rng, 900)]
+    rd1 += [ref1[:80] + ref1[140:], ref1[:100] + rand_seq(rng, 45) + ref1[100:]]
+    al.set_references(ReferenceManager([Reference(ref1, b"one")]))
+    qb1, qo1 = pack_reads(rd1)
+    f1 = np.zeros(len(rd1), np.int32)
+    want1 = [O.convex_align_pair(ref1, rd, ocv) for rd in rd1]
+    for no_pack in (0, 1):
+        al.set_option("no_pack", no_pack)
+        for cfg in (-1, 0, 1, 2, 3, 4):
+            al.set_option("force_cfg", cfg)
+            try:
+                br = al.align_batch(qb1, qo1, cv, "fixed", "readlen", fixed_ref=f1, with_stats=True)
+                so = al.align_batch(qb1, qo1, cv, "fixed", "readlen", fixed_ref=f1, score_only=True)
+            finally:
+                al.set_option("force_cfg", -1)
+                al.set_option("no_pack", 0)
+            al.set_option("no_pack", no_pack)
+            assert bool(br.stats["variant"] & 2) == (no_pack == 0) and (br.stats["variant"] & 4)
+            for i, w in enumerate(want1):
+                assert int(br.status[i]) == 0
+                assert int(br.score_scaled[i]) == w["score"] == int(so.score_scaled[i]), (no_pack, cfg, i)
+                assert br.cigar_string(i) == O.cigar_str(w["cigar"]), (no_pack, cfg, i)
+    al.set_option("no_pack", 0)
+    al.set_references(ReferenceManager([Reference(r, b"r%d" % i) for i, r in enumerate(refs)]))
     # best-candidate selection under the convex score
     br = al.align_batch(qb[:int(qo[40])], qo[:41], cv, "exhaustive", "readlen")
     for i in range(40):
