@@ -699,9 +699,11 @@ static void* worker_main(void* arg) {
         uint32_t best_ref = 0;
         int have = 0;
         if (in->search_mode == ORC_SEARCH_FIXED) {
-            best_ref = (uint32_t)in->fixed_ref[i];
-            align_pair(w, m, best_ref, read, l2, 1, &best, cig_best, cig_cap);
-            have = 1;
+            if (in->fixed_ref[i] >= 0 && (uint32_t)in->fixed_ref[i] < in->n_refs) { /* otherwise: no candidate (Option::None) */
+                best_ref = (uint32_t)in->fixed_ref[i];
+                align_pair(w, m, best_ref, read, l2, 1, &best, cig_best, cig_cap);
+                have = 1;
+            }
         } else {
             int single = -1;
             memset(cand, 1, in->n_refs);

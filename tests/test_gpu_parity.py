@@ -553,3 +553,44 @@ def test_rustbio_single_reference_mode(al, no_pack):
     finally:
         al.set_option("no_pack", 0)
         al.set_option("force_cfg", -1)
+
+
+def test_grouped_pack_traceback(al):
+    """Multi-reference batches on the PACK traceback kernels: reads bucketed by reference on the device (odd buckets padded),
+    reads without a usable reference, several sub-batches of the bits scratch, tags on."""
+    rng = np.random.default_rng(4242)
+    refs = [rand_seq(rng, 150)[:70] + b"0011" + rand_seq(rng, 76) for _ in range(7)]
+    reads, fixed = [], []
+    for i in range(333):
+        k = int(rng.integers(0, 7)) if i % 5 else 3
+        rd = mutate(rng, refs[k].replace(b"0", b"A").replace(b"1", b"C"), 0.08)
+        rd = (rd + rand_seq(rng, 160))[:150]  # uniform lengths: natural read order, no longest-first permutation
+        reads.append(rd); fixed.append(k)
+    fixed[5], fixed[17], fixed[200] = -1, 99, -7
+    fixed = np.array(fixed, np.int32)
+    al.set_references(ReferenceManager([Reference(r, b"r%d" % i) for i, r in enumerate(refs)]))
+    qb, qo = pack_reads(reads)
+    rb, ro = O.pack_seqs(refs)
+    sc = SCORINGS["cli"]
+    want = O.align_batch(rb, ro, qb, qo, sc, search="fixed", fixed_ref=fixed, band_mode="readlen", threads=8)
+    for scratch in (40 << 30, 1 << 20):
+        al.set_option("max_scratch_bytes", scratch)
+        try:
+            br = al.align_batch(qb, qo, AffineScoring(*sc), "fixed", "readlen", fixed_ref=fixed, with_stats=True, extract_tags=True)
+        finally:
+            al.set_option("max_scratch_bytes", 40 << 30)
+        assert br.stats["variant"] & 2, "the grouped batch should run on the PACK kernels"
+        assert (br.stats["sub_batches"] > 1) == (scratch == 1 << 20)
+        compare(br, want, len(reads), "grouped scratch=%d" % scratch)
+        assert [int(br.status[i]) for i in (5, 17, 200)] == [NO_CANDIDATE] * 3
+        for i in (0, 1, 2, 100, 332):
+            o, l = int(want["cigar_off"][i]), int(want["cigar_len"][i])
+            assert br.tag_strings(i, refs[fixed[i]]) == _digit_tags_oracle(refs[fixed[i]], reads[i], want["cigar_pool"][o:o + l])
+    # the same through the int32 kernels (no_group) gives identical records
+    al.set_option("no_group", 1)
+    try:
+        b2 = al.align_batch(qb, qo, AffineScoring(*sc), "fixed", "readlen", fixed_ref=fixed, with_stats=True)
+    finally:
+        al.set_option("no_group", 0)
+    assert not (b2.stats["variant"] & 2)
+    compare(b2, want, len(reads), "ungrouped")

@@ -306,3 +306,23 @@ def test_clq_align_rust_bio_branch(H, tmp_path):
                 tags["e" + chr(k)] = v.decode()
         assert got[:11] == ["q%d" % i, "0", "lineage_amplicon", "1", "255", O.cigar_str(want["cigar"]), "*", "0", "0", rd.decode(), "i" * len(rd)], i
         assert dict(x.split(":Z:") for x in got[11:]) == tags, i
+
+
+@pytest.mark.gpu
+def test_clq_align_two_gpus(H, tmp_path):
+    """ShardedAligner over two devices (one host thread + context each, shared source, no collective): same records, in input
+    order, as the single-GPU run.  Skipped on a one-GPU box."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "clique_b200", "libclq.so"))
+    if lib.clq_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from clique_b200 import synth
+    c = synth.config_c4(2000, search="quick")
+    off = c["read_off"]
+    reads = [bytes(c["read_bytes"][int(off[i]):int(off[i + 1])]) for i in range(2000)]
+    refs, names = c["refs"][:16], c["ref_names"][:16]
+    fa, rp = _write_inputs(str(tmp_path), refs, names, reads)
+    _, one, st1 = _run_clq_align(str(tmp_path), fa, rp)
+    _, two, st2 = _run_clq_align(str(tmp_path), fa, rp, ["--gpus", "0,1"])
+    assert st2["gpus"] == 2 and st1["reads"] == st2["reads"] == 2000
+    assert one == two
