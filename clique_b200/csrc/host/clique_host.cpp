@@ -294,6 +294,50 @@ MergedSequence merge_reads_by_concatenation(const ReadSetContainer& reads, const
     return m;
 }
 
+double phred_to_prob(uint8_t phred) {
+    const double phred_f64 = (double)((size_t)phred - 33);
+    return std::pow(10.0, (-1.0 * phred_f64) / 10.0);
+}
+
+uint8_t prob_to_phred(double qual) {
+    const double v = ((-10.0) * std::log10(qual)) + 33.0;  // `as u8` saturates, NaN -> 0
+    if (!(v > 0.0)) return 0;
+    if (v >= 255.0) return 255;
+    return (uint8_t)v;
+}
+
+uint8_t combine_phred_scores(uint8_t phred_one, uint8_t phred_two, bool agree) {
+    const double prob1 = phred_to_prob(phred_one), prob2 = phred_to_prob(phred_two);
+    return agree ? prob_to_phred(prob1 * prob2) : prob_to_phred(1.0 - ((1.0 - prob2) * (1.0 * prob1)));
+}
+
+MergedSequence alignment_rate_and_consensus(const Bytes& a1, const Bytes& q1, const Bytes& a2, const Bytes& q2) {
+    if (a1.size() != a2.size()) throw std::logic_error("alignment_rate_and_consensus: the two alignment strings differ in length");
+    MergedSequence m;
+    m.read_bases.reserve(a1.size());
+    m.read_quals.reserve(a1.size());
+    size_t p1 = 0, p2 = 0;
+    for (size_t i = 0; i < a1.size(); i++) {
+        const uint8_t a = a1[i], b = a2[i];
+        if (a == b) {  // includes gap/gap, as in the reference
+            m.read_bases.push_back(a);
+            m.read_quals.push_back(combine_phred_scores(q1.at(p1), q2.at(p2), true));
+            p1++; p2++;
+        } else if (a == '-') {
+            m.read_bases.push_back(b);
+            m.read_quals.push_back(q2.at(p2++));
+        } else if (b == '-') {
+            m.read_bases.push_back(a);
+            m.read_quals.push_back(q1.at(p1++));
+        } else {
+            m.read_bases.push_back(q1.at(p1) >= q2.at(p2) ? a : b);  // bases disagree: the higher quality base
+            m.read_quals.push_back(combine_phred_scores(q1.at(p1), q2.at(p2), false));
+            p1++; p2++;
+        }
+    }
+    return m;
+}
+
 // ------------------------------------------------------------------------------------------------ references
 ReferenceManager::ReferenceManager(std::vector<Reference> refs, size_t ks, size_t kskip) : references(std::move(refs)), kmer_size(ks), kmer_skip(kskip) {
     for (size_t i = 0; i < references.size(); i++) {
@@ -599,6 +643,59 @@ std::optional<AlignmentWithRef> Aligner::align_to_reference_choices(const std::s
     }
     if (rm_.references.size() == 1) return search(read_name, read, std::move(qual), scoring, CLQ_SEARCH_FIXED, 0.90);
     return search(read_name, read, std::move(qual), scoring, fast_lookup ? CLQ_SEARCH_QUICK : CLQ_SEARCH_EXHAUSTIVE, 0.90);
+}
+
+MergedSequence Aligner::merge_reads_by_alignment(const FastqRecord& read1, const FastqRecord& read2, const AffineScoring& sc) {
+    const Bytes rc2 = reverse_complement(read2.seq);
+    Bytes q2(read2.qual.rbegin(), read2.qual.rend());
+    const AlignmentResult r = align_two_strings(read1.seq, rc2, std::nullopt, sc, false, read1.id, read2.id);
+    return alignment_rate_and_consensus(r.reference_aligned, read1.qual, r.read_aligned, q2);
+}
+
+std::vector<std::optional<MergedSequence>> Aligner::merge_read_pairs_by_alignment(const std::vector<ReadSetContainer>& pairs,
+                                                                                  const AffineScoring& sc) {
+    std::vector<std::optional<MergedSequence>> out(pairs.size());
+    if (pairs.empty()) return out;
+    const ReferenceManager saved = rm_;
+    const clq_affine_t sci = sc.to_int();
+    const uint32_t per = std::min<uint32_t>(opt_.max_reads, opt_.max_refs);
+    ReadBatch batch(per, opt_.max_read_bytes);
+    try {
+        for (size_t lo = 0; lo < pairs.size();) {
+            // one launch per chunk: reference k = read1 of pair lo + k, read k = revcomp(read2), fixed_ref[k] = k
+            std::vector<Reference> refs;
+            batch.clear();
+            size_t hi = lo;
+            for (; hi < pairs.size() && hi - lo < per; hi++) {
+                const ReadSetContainer& p = pairs[hi];
+                if (!p.read_two) throw std::logic_error("merge_read_pairs_by_alignment: pair without read2");
+                const Bytes rc2 = reverse_complement(p.read_two->seq);
+                if (!batch.push(p.read_one.id, rc2.data(), rc2.size(), nullptr, (int32_t)(hi - lo))) break;
+                refs.push_back({p.read_one.seq, to_bytes(p.read_one.id)});
+            }
+            if (hi == lo) fail(CLQ_E_LIMIT, "a read pair does not fit an empty batch");
+            set_references(ReferenceManager(std::move(refs)), false);
+            submit(0, batch, sci, CLQ_SEARCH_FIXED | CLQ_BAND_MAXLEN);
+            const BatchView v = wait(0, batch);
+            for (size_t k = 0; k < hi - lo; k++) {
+                const auto al = v.alignment((uint32_t)k);
+                if (!al) continue;
+                const ReadSetContainer& p = pairs[lo + k];
+                const Bytes q2(p.read_two->qual.rbegin(), p.read_two->qual.rend());
+                try {
+                    out[lo + k] = alignment_rate_and_consensus(al->alignment->reference_aligned, p.read_one.qual, al->alignment->read_aligned, q2);
+                } catch (const std::out_of_range&) {
+                    // qualities shorter than the bases: the reference panics here; a batch reports the pair as unmerged
+                }
+            }
+            lo = hi;
+        }
+    } catch (...) {
+        if (!saved.references.empty()) set_references(saved);
+        throw;
+    }
+    if (!saved.references.empty()) set_references(saved);
+    return out;
 }
 
 namespace {

@@ -98,6 +98,61 @@ size_t clqh_sam_line(const char* ref_name, const char* read_name, const uint8_t*
     }
 }
 
+uint8_t clqh_combine_phred_scores(uint8_t a, uint8_t b, int32_t agree) { return combine_phred_scores(a, b, agree != 0); }
+
+size_t clqh_alignment_rate_and_consensus(const uint8_t* a1, const uint8_t* q1, size_t nq1, const uint8_t* a2, const uint8_t* q2, size_t nq2,
+                                         size_t n, uint8_t* out_bases, uint8_t* out_quals) {
+    try {
+        const MergedSequence m = alignment_rate_and_consensus(Bytes(a1, a1 + n), Bytes(q1, q1 + nq1), Bytes(a2, a2 + n), Bytes(q2, q2 + nq2));
+        if (n) { std::memcpy(out_bases, m.read_bases.data(), n); std::memcpy(out_quals, m.read_quals.data(), n); }
+        return n;
+    } catch (const std::exception&) {
+        return (size_t)-1;
+    }
+}
+
+/* GPU: Aligner::merge_read_pairs_by_alignment over n pairs given as packed arrays (read1 / read2 bytes + qualities with
+ * shared offsets per side); merged bases / qualities are written back to back, out_off gets n + 1 offsets, a pair the
+ * reference could not finish has an empty record.  Returns 0 or a negative libclq code. */
+int32_t clqh_merge_read_pairs_by_alignment(int32_t device, uint32_t n, const uint8_t* r1, const uint8_t* q1, const uint64_t* off1,
+                                           const uint8_t* r2, const uint8_t* q2, const uint64_t* off2, double match_score,
+                                           double mismatch_score, double special_score, double gap_open, double gap_extend,
+                                           double final_gap_multiplier, uint8_t* out_bases, uint8_t* out_quals, uint64_t cap,
+                                           uint64_t* out_off) {
+    try {
+        AlignerOptions opt;
+        opt.device = device;
+        opt.max_reads = 1u << 16;
+        opt.max_refs = 1u << 16;
+        opt.max_ref_bytes = 1u << 26;
+        opt.cigar_ops_per_read = 128;
+        opt.n_slots = 1;
+        Aligner al(opt);
+        std::vector<ReadSetContainer> pairs(n);
+        for (uint32_t i = 0; i < n; i++) {
+            pairs[i].read_one = {"r" + std::to_string(i), Bytes(r1 + off1[i], r1 + off1[i + 1]), Bytes(q1 + off1[i], q1 + off1[i + 1])};
+            pairs[i].read_two = FastqRecord{"r" + std::to_string(i), Bytes(r2 + off2[i], r2 + off2[i + 1]), Bytes(q2 + off2[i], q2 + off2[i + 1])};
+        }
+        const auto merged = al.merge_read_pairs_by_alignment(pairs, {match_score, mismatch_score, special_score, gap_open, gap_extend, final_gap_multiplier});
+        uint64_t w = 0;
+        out_off[0] = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            if (merged[i]) {
+                const size_t len = merged[i]->read_bases.size();
+                if (w + len > cap) return CLQ_E_LIMIT;
+                if (len) { std::memcpy(out_bases + w, merged[i]->read_bases.data(), len); std::memcpy(out_quals + w, merged[i]->read_quals.data(), len); }
+                w += len;
+            }
+            out_off[i + 1] = w;
+        }
+        return CLQ_OK;
+    } catch (const ClqError& e) {
+        return e.code < 0 ? e.code : CLQ_E_INVALID;
+    } catch (const std::exception&) {
+        return CLQ_E_INVALID;
+    }
+}
+
 size_t clqh_merge_reads_by_concatenation(const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const char* layout, uint8_t* out,
                                          size_t cap) {
     // layout: comma-separated items "1F" / "2R" / "2C" (read number + Forward / Reverse / reverse-Complement) or "S:ACGT" (spacer)

@@ -161,6 +161,15 @@ Bytes orient_sequence(const uint8_t* sequence, size_t n, AlignedReadOrientation 
 /// merge_reads_by_concatenation, merger.rs:40-105
 MergedSequence merge_reads_by_concatenation(const ReadSetContainer& reads, const std::vector<ReadPosition>& layout);
 
+/// phred helpers, utils/read_utils.rs:6-38 (the disagreement formula is the reference's own, kept as it is)
+double phred_to_prob(uint8_t phred);
+uint8_t prob_to_phred(double qual);
+uint8_t combine_phred_scores(uint8_t phred_one, uint8_t phred_two, bool agree);
+/// alignment_rate_and_consensus, merger.rs:428-498: consensus bases + qualities of two gapped strings; throws std::out_of_range
+/// where the reference panics (a gap/gap column consumes qualities).
+MergedSequence alignment_rate_and_consensus(const Bytes& alignment_1, const Bytes& qual_scores1, const Bytes& alignment_2,
+                                            const Bytes& qual_scores2);
+
 // ------------------------------------------------------------------------------------------------ references
 /// Reference, reference/fasta_reference.rs:41-46 (the suffix table is outside the path)
 struct Reference { Bytes sequence; Bytes name; };
@@ -306,6 +315,14 @@ public:
     /// reference has commented out at :586-597; pinned on its goldens).
     std::optional<AlignmentWithRef> align_to_reference_choices(const std::string& read_name, const Bytes& read, std::optional<Bytes> qual,
                                                                bool fast_lookup, const AffineScoring& scoring, bool rust_bio = false);
+
+    // ---- paired-read merging (MergeStrategy::Align) ----
+    /// merge_reads_by_alignment, merger.rs:348-396: align_two_strings(read1, revcomp(read2)) + alignment_rate_and_consensus
+    MergedSequence merge_reads_by_alignment(const FastqRecord& read1, const FastqRecord& read2, const AffineScoring& merge_initial_scoring);
+    /// the same for a whole batch in one launch: every pair is its own (reference = read1, read = revcomp(read2)) task; the
+    /// caller's reference set is restored afterwards.  Entries whose alignment the reference could not finish are nullopt.
+    std::vector<std::optional<MergedSequence>> merge_read_pairs_by_alignment(const std::vector<ReadSetContainer>& pairs,
+                                                                             const AffineScoring& merge_initial_scoring);
 
     // ---- the batch loop ----
     /// align_reads' par_bridge loop (alignment_functions.rs:135-249) up to the writer: drains `source` into pinned batches,

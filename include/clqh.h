@@ -33,6 +33,17 @@ int32_t clqh_from_cigar(const uint8_t* ref, size_t l1, const uint8_t* read, size
 /* AlignmentResult::to_sam_record as one SAM text line, alignment/alignment_matrix.rs:741-771; extra_tags = "k1=v;k2=v" */
 size_t clqh_sam_line(const char* ref_name, const char* read_name, const uint8_t* ref, size_t l1, const uint8_t* read, size_t l2,
                      const uint32_t* ops, size_t n_ops, double score, int32_t reference_id, const char* extra_tags, char* out, size_t cap);
+/* combine_phred_scores, utils/read_utils.rs:26-38 */
+uint8_t clqh_combine_phred_scores(uint8_t a, uint8_t b, int32_t agree);
+/* alignment_rate_and_consensus, merger.rs:428-498; (size_t)-1 where the reference panics */
+size_t clqh_alignment_rate_and_consensus(const uint8_t* a1, const uint8_t* q1, size_t nq1, const uint8_t* a2, const uint8_t* q2, size_t nq2,
+                                         size_t n, uint8_t* out_bases, uint8_t* out_quals);
+/* merge_reads_by_alignment (merger.rs:348-396) for n read pairs in one GPU launch per chunk: needs a CUDA device */
+int32_t clqh_merge_read_pairs_by_alignment(int32_t device, uint32_t n, const uint8_t* r1, const uint8_t* q1, const uint64_t* off1,
+                                           const uint8_t* r2, const uint8_t* q2, const uint64_t* off2, double match_score,
+                                           double mismatch_score, double special_score, double gap_open, double gap_extend,
+                                           double final_gap_multiplier, uint8_t* out_bases, uint8_t* out_quals, uint64_t cap,
+                                           uint64_t* out_off);
 /* merge_reads_by_concatenation + orient_sequence, merger.rs:40-126; layout items "1F" "2R" "2C" "S:ACGT"; (size_t)-1 = panic */
 size_t clqh_merge_reads_by_concatenation(const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const char* layout, uint8_t* out,
                                          size_t cap);

@@ -1049,3 +1049,52 @@ int orc_rustbio_global(const uint8_t* ref, size_t l1, const uint8_t* read, size_
     for (int k = 0; k < 2; k++) { free(Sv[k]); free(Iv[k]); free(Dv[k]); }
     return rc;
 }
+
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Paired-read merging after align_two_strings: utils/read_utils.rs:6-38, merger.rs:428-498
+ * --------------------------------------------------------------------------------------------------------- */
+double orc_phred_to_prob(uint8_t phred) {
+    const double phred_f64 = (double)((size_t)phred - 33); /* (*phred as usize) - 33: panics below 33 in debug builds */
+    return pow(10.0, (-1.0 * phred_f64) / 10.0);
+}
+
+static uint8_t orc_sat_u8(double v) { /* Rust `as u8`: saturating, NaN -> 0 */
+    if (!(v > 0.0)) return 0;
+    if (v >= 255.0) return 255;
+    return (uint8_t)v;
+}
+
+uint8_t orc_prob_to_phred(double qual) { return orc_sat_u8(((-10.0) * log10(qual)) + 33.0); }
+
+uint8_t orc_combine_phred_scores(uint8_t phred_one, uint8_t phred_two, int agree) {
+    const double prob1 = orc_phred_to_prob(phred_one), prob2 = orc_phred_to_prob(phred_two);
+    if (agree) return orc_prob_to_phred(prob1 * prob2);
+    return orc_prob_to_phred(1.0 - ((1.0 - prob2) * (1.0 * prob1)));
+}
+
+size_t orc_alignment_rate_and_consensus(const uint8_t* a1, const uint8_t* q1, size_t nq1, const uint8_t* a2, const uint8_t* q2,
+                                        size_t nq2, size_t n, uint8_t* out_bases, uint8_t* out_quals) {
+    size_t p1 = 0, p2 = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t a = a1[i], b = a2[i];
+        if (a == b) { /* includes gap/gap, as the reference does */
+            if (p1 >= nq1 || p2 >= nq2) return (size_t)-1;
+            out_bases[i] = a;
+            out_quals[i] = orc_combine_phred_scores(q1[p1], q2[p2], 1);
+            p1++; p2++;
+        } else if (a == '-') {
+            if (p2 >= nq2) return (size_t)-1;
+            out_bases[i] = b; out_quals[i] = q2[p2]; p2++;
+        } else if (b == '-') {
+            if (p1 >= nq1) return (size_t)-1;
+            out_bases[i] = a; out_quals[i] = q1[p1]; p1++;
+        } else {
+            if (p1 >= nq1 || p2 >= nq2) return (size_t)-1;
+            out_bases[i] = q1[p1] >= q2[p2] ? a : b; /* bases disagree: the higher quality base */
+            out_quals[i] = orc_combine_phred_scores(q1[p1], q2[p2], 0);
+            p1++; p2++;
+        }
+    }
+    return n;
+}

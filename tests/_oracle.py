@@ -102,6 +102,15 @@ def lib():
         L.orc_align_batch.argtypes = [C.POINTER(Batch), C.POINTER(Affine), C.POINTER(BatchOut)]
         L.orc_rustbio_global.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.c_void_p, C.c_size_t]
+        L.orc_phred_to_prob.restype = C.c_double
+        L.orc_phred_to_prob.argtypes = [C.c_uint8]
+        L.orc_prob_to_phred.restype = C.c_uint8
+        L.orc_prob_to_phred.argtypes = [C.c_double]
+        L.orc_combine_phred_scores.restype = C.c_uint8
+        L.orc_combine_phred_scores.argtypes = [C.c_uint8, C.c_uint8, C.c_int]
+        L.orc_alignment_rate_and_consensus.restype = C.c_size_t
+        L.orc_alignment_rate_and_consensus.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t,
+                                                       C.c_void_p, C.c_void_p]
         L.orc_extract_tagged_sequences.restype = C.c_size_t
         L.orc_extract_tagged_sequences.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.orc_reverse_complement.restype = None
@@ -284,3 +293,23 @@ def rustbio_global(ref, read, scoring=RUSTBIO_CLI):
     rc = lib().orc_rustbio_global(ref, len(ref), read, len(read), scoring[0], scoring[1], scoring[2], scoring[3],
                                   C.byref(score), C.byref(n), cig.ctypes.data, len(cig))
     return {"score": score.value, "status": rc, "cigar": cig[:n.value].copy()}
+
+
+def alignment_rate_and_consensus(a1, q1, a2, q2):
+    """merger.rs:428-498 -> (bases, quals), or None where the reference panics (quality index out of bounds)"""
+    n = len(a1)
+    assert len(a2) == n
+    ob, oq = C.create_string_buffer(max(1, n)), C.create_string_buffer(max(1, n))
+    r = lib().orc_alignment_rate_and_consensus(bytes(a1), bytes(q1), len(q1), bytes(a2), bytes(q2), len(q2), n, ob, oq)
+    if r == 2 ** 64 - 1:
+        return None
+    return ob.raw[:n], oq.raw[:n]
+
+
+def merge_reads_by_alignment(read1, qual1, read2, qual2, sc):
+    """merge_reads_by_alignment, merger.rs:348-396: align(read1, revcomp(read2)) full matrix, then the consensus"""
+    rc2, q2r = reverse_complement(read2), bytes(qual2)[::-1]
+    a = align_pair(read1, rc2, sc, "maxlen")
+    if a["status"] != OK:
+        return None
+    return alignment_rate_and_consensus(a["ref_aligned"], qual1, a["read_aligned"], q2r)

@@ -273,6 +273,20 @@ for ln in lines(RU, 141, 190):
         revcomp_kats.append({"in": m.group(1), "out": m.group(2)})
 assert len(revcomp_kats) == 24, len(revcomp_kats)
 
+# --- phred helpers, utils/read_utils.rs:119-140 ---
+phred = {"to_prob": [], "to_phred": [], "combine": []}
+for ln in lines(RU, 119, 140):
+    m = re.search(r"phred_to_prob\(&b'(.)'\), ([0-9.e-]+)\)", ln)
+    if m:
+        phred["to_prob"].append({"phred": m.group(1), "prob": float(m.group(2))})
+    m = re.search(r"prob_to_phred\(([0-9.e-]+)\), b'(.)'\)", ln)
+    if m:
+        phred["to_phred"].append({"prob": float(m.group(1)), "phred": m.group(2)})
+    m = re.search(r"combine_phred_scores\(&b'(.)',&b'(.)', (true|false)\), b'(.)'\)", ln)
+    if m:
+        phred["combine"].append({"a": m.group(1), "b": m.group(2), "agree": m.group(3) == "true", "out": m.group(4)})
+assert (len(phred["to_prob"]), len(phred["to_phred"]), len(phred["combine"])) == (4, 4, 2), phred
+
 # --- ConvexScoring::gap KATs, alignment/scoring_functions.rs:200-213 ---
 convex_gap = [{"gap_open": -10.0, "len": 1, "gap": -10.0}, {"gap_open": -10.0, "len": 10, "gap": -9.0}]
 
@@ -300,7 +314,7 @@ out = {
     "pairs": pairs, "mergers": mergers, "best_ref": best_ref, "fastas": fastas, "tie_table": tie_table,
     "match_mismatch_default_dna": mm_table, "simplify_cigar": simplify, "kmers": kmers, "convex_gap": convex_gap, "alignment_rate": alignment_rate,
     "amplicon_c2": amplicon_c2, "amplicon_c3": amplicon_c3, "survey_kats": survey_kats,
-    "tagged_sequences": tagged, "reverse_complement": revcomp_kats,
+    "tagged_sequences": tagged, "reverse_complement": revcomp_kats, "phred": phred,
 }
 with open(OUT, "w") as f:
     json.dump(out, f, indent=1)

@@ -17,7 +17,8 @@ HOST_LIB = os.path.join(ROOT, "clique_b200", "libclq_host.so")
 CLQ_ALIGN = os.path.join(ROOT, "clique_b200", "clq_align")
 
 SYMBOLS = ["clqh_extract_tagged_sequences", "clqh_reverse_complement", "clqh_f64_to_string", "clqh_get_reference_alignment_rate",
-           "clqh_simplify_cigar", "clqh_from_cigar", "clqh_sam_line", "clqh_merge_reads_by_concatenation"]
+           "clqh_simplify_cigar", "clqh_from_cigar", "clqh_sam_line", "clqh_merge_reads_by_concatenation",
+           "clqh_combine_phred_scores", "clqh_alignment_rate_and_consensus", "clqh_merge_read_pairs_by_alignment"]
 
 
 @pytest.fixture(scope="module")
@@ -40,6 +41,14 @@ def H():
     L.clqh_sam_line.restype = C.c_size_t
     L.clqh_sam_line.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                 C.c_double, C.c_int32, C.c_char_p, C.c_void_p, C.c_size_t]
+    L.clqh_combine_phred_scores.restype = C.c_uint8
+    L.clqh_combine_phred_scores.argtypes = [C.c_uint8, C.c_uint8, C.c_int32]
+    L.clqh_alignment_rate_and_consensus.restype = C.c_size_t
+    L.clqh_alignment_rate_and_consensus.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t,
+                                                    C.c_void_p, C.c_void_p]
+    L.clqh_merge_read_pairs_by_alignment.restype = C.c_int32
+    L.clqh_merge_read_pairs_by_alignment.argtypes = [C.c_int32, C.c_uint32] + [C.c_void_p] * 6 + [C.c_double] * 6 + [C.c_void_p, C.c_void_p,
+                                                                                                                  C.c_uint64, C.c_void_p]
     L.clqh_merge_reads_by_concatenation.restype = C.c_size_t
     L.clqh_merge_reads_by_concatenation.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_void_p, C.c_size_t]
     return L
@@ -191,6 +200,30 @@ def test_merge_reads_by_concatenation(H):
     assert merge(b"AACC", b"GG", "1U") is None                                 # Unknown orientation panics
 
 
+def h_consensus(H, a1, q1, a2, q2):
+    n = len(a1)
+    ob, oq = C.create_string_buffer(max(1, n)), C.create_string_buffer(max(1, n))
+    r = H.clqh_alignment_rate_and_consensus(a1, q1, len(q1), a2, q2, len(q2), n, ob, oq)
+    return None if r == 2 ** 64 - 1 else (ob.raw[:n], oq.raw[:n])
+
+
+def test_phred_and_consensus_cpp(H, goldens):
+    # utils/read_utils.rs:26-38, merger.rs:428-498 against the reference's vectors and the oracle
+    for t in goldens["phred"]["combine"]:
+        assert H.clqh_combine_phred_scores(ord(t["a"]), ord(t["b"]), 1 if t["agree"] else 0) == ord(t["out"])
+    L = O.lib()
+    for a in range(33, 127, 3):
+        for b in range(33, 127, 5):
+            for agree in (0, 1):
+                assert H.clqh_combine_phred_scores(a, b, agree) == L.orc_combine_phred_scores(a, b, agree)
+    for m in goldens["mergers"]:
+        r = O.align_pair(m["read1"].encode(), m["read2_revcomp"].encode(), m["scoring"], "maxlen")
+        got = h_consensus(H, r["ref_aligned"], m["qual1"].encode(), r["read_aligned"], m["qual2_rev"].encode())
+        assert got[0].decode() == m["expect_merged"], m["name"]
+        assert got == O.alignment_rate_and_consensus(r["ref_aligned"], m["qual1"].encode(), r["read_aligned"], m["qual2_rev"].encode())
+    assert h_consensus(H, b"A--", b"H", b"A--", b"H") is None
+
+
 # ------------------------------------------------------------------------------------------------ GPU: the batch loop in C++
 def _write_inputs(tmp, refs, names, reads, fastq=True):
     fa = os.path.join(tmp, "refs.fa")
@@ -326,3 +359,42 @@ def test_clq_align_two_gpus(H, tmp_path):
     _, two, st2 = _run_clq_align(str(tmp_path), fa, rp, ["--gpus", "0,1"])
     assert st2["gpus"] == 2 and st1["reads"] == st2["reads"] == 2000
     assert one == two
+
+
+@pytest.mark.gpu
+def test_merge_read_pairs_by_alignment_gpu(H, goldens):
+    """merge_reads_by_alignment (MergeStrategy::Align, merger.rs:348-396) for a batch of read pairs: every pair is its own
+    (reference = read1, read = revcomp(read2)) task on the GPU (merger scoring, x0.25 final-gap multiplier), consensus on the
+    host.  Against the reference's three merger vectors and the oracle on random overlapping pairs."""
+    rng = np.random.default_rng(31)
+    sc = goldens["scorings"]["merger"]
+    pairs = [(m["read1"].encode(), m["qual1"].encode(), O.reverse_complement(m["read2_revcomp"].encode()), m["qual2_rev"].encode()[::-1])
+             for m in goldens["mergers"]]
+    for _ in range(300):  # a fragment of 120-280 bp read from both ends with 150 bp reads and a few errors
+        frag = bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(120, 280))).astype(np.uint8))
+        r1 = bytearray(frag[:150]); r2 = bytearray(O.reverse_complement(frag)[:150])
+        for r in (r1, r2):
+            for k in rng.integers(0, len(r), size=int(rng.integers(0, 4))):
+                r[int(k)] = int(rng.choice(list(b"ACGT")))
+        q1 = bytes(rng.integers(40, 75, size=len(r1)).astype(np.uint8)); q2 = bytes(rng.integers(40, 75, size=len(r2)).astype(np.uint8))
+        pairs.append((bytes(r1), q1, bytes(r2), q2))
+    n = len(pairs)
+    r1b, o1 = O.pack_seqs([p[0] for p in pairs]); q1b, _ = O.pack_seqs([p[1] for p in pairs])
+    r2b, o2 = O.pack_seqs([p[2] for p in pairs]); q2b, _ = O.pack_seqs([p[3] for p in pairs])
+    cap = int(o1[-1] + o2[-1]) + 64
+    ob, oq = np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)
+    off = np.zeros(n + 1, np.uint64)
+    rc = H.clqh_merge_read_pairs_by_alignment(0, n, r1b.ctypes.data, q1b.ctypes.data, o1.ctypes.data, r2b.ctypes.data, q2b.ctypes.data,
+                                              o2.ctypes.data, sc["match_score"], sc["mismatch_score"], sc["special_character_score"],
+                                              sc["gap_open"], sc["gap_extend"], sc["final_gap_multiplier"], ob.ctypes.data, oq.ctypes.data,
+                                              cap, off.ctypes.data)
+    assert rc == 0, rc
+    for i, (r1, q1, r2, q2) in enumerate(pairs):
+        want = O.merge_reads_by_alignment(r1, q1, r2, q2, sc)
+        got = (bytes(ob[int(off[i]):int(off[i + 1])]), bytes(oq[int(off[i]):int(off[i + 1])]))
+        if want is None:
+            assert got == (b"", b""), i
+        else:
+            assert got == want, i
+    for i, m in enumerate(goldens["mergers"]):
+        assert bytes(ob[int(off[i]):int(off[i + 1])]).decode() == m["expect_merged"], m["name"]

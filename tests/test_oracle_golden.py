@@ -199,3 +199,31 @@ def test_reverse_complement_goldens(goldens):
         assert O.reverse_complement(t["in"].encode()).decode() == t["out"], t
     seq = b"ACGTRYSWKMBDHVN"
     assert O.reverse_complement(O.reverse_complement(seq)) == seq
+
+
+def test_phred_goldens(goldens):
+    # utils/read_utils.rs:119-140
+    L = O.lib()
+    for t in goldens["phred"]["to_prob"]:
+        assert L.orc_phred_to_prob(ord(t["phred"])) == t["prob"], t
+    for t in goldens["phred"]["to_phred"]:
+        assert L.orc_prob_to_phred(t["prob"]) == ord(t["phred"]), t
+    for t in goldens["phred"]["combine"]:
+        assert L.orc_combine_phred_scores(ord(t["a"]), ord(t["b"]), 1 if t["agree"] else 0) == ord(t["out"]), t
+    for ph in b"!+5I":  # test_phred_roundtrip, :259-266
+        assert L.orc_prob_to_phred(L.orc_phred_to_prob(ph)) == ph
+    assert L.orc_phred_to_prob(ord("!")) == 1.0
+
+
+def test_merge_reads_by_alignment_goldens(goldens):
+    # merger.rs:527-580 through the C restatement of alignment_rate_and_consensus (bases AND qualities)
+    for m in goldens["mergers"]:
+        r = O.align_pair(m["read1"].encode(), m["read2_revcomp"].encode(), m["scoring"], "maxlen")
+        bases, quals = O.alignment_rate_and_consensus(r["ref_aligned"], m["qual1"].encode(), r["read_aligned"], m["qual2_rev"].encode())
+        assert bases.decode() == m["expect_merged"], m["name"]
+        assert bases == _merge(r["ref_aligned"], m["qual1"].encode(), r["read_aligned"], m["qual2_rev"].encode())
+        assert len(quals) == len(bases)
+    # quality rules: agreement multiplies the error probabilities, a gap passes the other read's quality through
+    b, q = O.alignment_rate_and_consensus(b"AC-T", b"HHH", b"ACG-", b"+++")
+    assert b == b"ACGT" and q == bytes([O.lib().orc_combine_phred_scores(72, 43, 1)] * 2) + b"+H"
+    assert O.alignment_rate_and_consensus(b"A--", b"H", b"A--", b"H") is None  # gap/gap consumes qualities: the reference panics
