@@ -375,7 +375,8 @@ ReadBatch::ReadBatch(uint32_t max_reads, uint64_t max_bytes) : max_reads_(max_re
     bytes_ = pinned<uint8_t>(max_bytes + 16);
     off_ = pinned<uint64_t>((size_t)max_reads + 1);
     fixed_ = pinned<int32_t>(max_reads);
-    names_.reserve(max_reads);
+    name_off_.reserve((size_t)max_reads + 1);
+    name_off_.push_back(0);
     off_[0] = 0;
 }
 
@@ -388,12 +389,13 @@ ReadBatch::~ReadBatch() {
 void ReadBatch::clear() {
     n_ = 0;
     off_[0] = 0;
-    names_.clear();
+    name_bytes_.clear();
+    name_off_.assign(1, 0);
     quals_.clear();
     have_quals_ = false;
 }
 
-bool ReadBatch::push(const std::string& name, const uint8_t* seq, size_t n, const uint8_t* qual, int32_t fixed_ref) {
+bool ReadBatch::push(const char* name, size_t name_len, const uint8_t* seq, size_t n, const uint8_t* qual, int32_t fixed_ref) {
     if (n_ >= max_reads_ || off_[n_] + n > max_bytes_) return false;
     if (n) std::memcpy(bytes_ + off_[n_], seq, n);
     if (qual) {
@@ -404,7 +406,8 @@ bool ReadBatch::push(const std::string& name, const uint8_t* seq, size_t n, cons
     }
     fixed_[n_] = fixed_ref;
     off_[n_ + 1] = off_[n_] + n;
-    names_.push_back(name);
+    name_bytes_.insert(name_bytes_.end(), name, name + name_len);
+    name_off_.push_back(name_bytes_.size());
     n_++;
     return true;
 }
@@ -466,6 +469,65 @@ TagMap BatchView::align_reads_tags(uint32_t i, const std::string& umi_symbols) c
     t[{'r', 'm'}] = f64_to_string(alignment_rate(i));
     t[{'a', 's'}] = f64_to_string(rust_bio ? 0.0 : score(i));
     return t;
+}
+
+namespace {
+inline void append_uint(std::string& s, uint64_t v) {
+    char buf[24];
+    const auto r = std::to_chars(buf, buf + sizeof(buf), v);
+    s.append(buf, r.ptr);
+}
+inline void append_f64(std::string& s, double v) {
+    if (std::isnan(v)) { s += "NaN"; return; }
+    if (std::isinf(v)) { s += v > 0 ? "inf" : "-inf"; return; }
+    char buf[400];
+    const auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::fixed);
+    s.append(buf, r.ptr);
+}
+}  // namespace
+
+bool BatchView::append_sam_line(uint32_t i, const std::string& umi_symbols, const std::vector<std::string>& reference_names,
+                                std::string& out) const {
+    if (status(i) != CLQ_OK) return false;
+    const uint32_t ri = ref_index(i);
+    const size_t l2 = batch->read_len(i);
+    // QNAME FLAG RNAME POS MAPQ
+    if (batch->name_len(i)) out.append(batch->name_data(i), batch->name_len(i)); else out += '*';
+    out += "\t0\t";
+    out += ri < reference_names.size() ? reference_names[ri] : std::string("*");
+    out += "\t1\t255\t";
+    // CIGAR
+    const uint32_t* c = cigar(i);
+    const uint32_t nc = cigar_len(i);
+    if (!nc) out += '*';
+    for (uint32_t k = 0; k < nc; k++) { append_uint(out, c[k] >> 4); out += "MID"[c[k] & 3u]; }
+    out += "\t*\t0\t0\t";
+    // SEQ = the read (read_aligned without gaps), QUAL = raw 'H' per base -> 'i' in SAM text
+    if (l2) { out.append(reinterpret_cast<const char*>(batch->read(i)), l2); out += '\t'; out.append(l2, 'i'); }
+    else out += "*\t*";
+    // the extra set of align_reads in key order (ar, as, e<sym>.., rc, rm); to_sam_record's own rm / as replace those in place, rs is appended
+    const double sc = rust_bio ? 0.0 : score(i);
+    out += "\tar:Z:";
+    out.append(batch->name_data(i), batch->name_len(i));
+    out += "\tas:Z:"; append_f64(out, sc);
+    if (tags && !umi_symbols.empty()) {
+        const Bytes& ref = rm->references[ri].sequence;
+        const uint8_t* row = tags + (size_t)i * tag_stride;
+        bool seen[10] = {};
+        for (uint8_t b : ref) if (b >= '0' && b <= '9') seen[b - '0'] = true;
+        for (int d = 0; d < 10; d++) {   // key order: e0 < e1 < ..
+            if (!seen[d] || umi_symbols.find((char)('0' + d)) == std::string::npos) continue;
+            out += "\te"; out += (char)('0' + d); out += ":Z:";
+            uint32_t k = 0;
+            for (uint8_t b : ref)
+                if (b >= '0' && b <= '9') { if (k < tag_stride && b == '0' + d) out += (char)row[k]; k++; }
+        }
+    }
+    out += "\trc:Z:1\trm:Z:";
+    append_f64(out, alignment_rate(i));
+    out += "\trs:Z:"; append_f64(out, sc);
+    out += '\n';
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------ Aligner
@@ -714,15 +776,17 @@ void prepare_fixed(ReadBatch& b, uint32_t flags) {
 
 AlignReadsStats Aligner::align_reads(const ReadSource& source, const AffineScoring& scoring, bool fast_lookup, const ResultSink& sink,
                                      bool extract_tags, bool rust_bio) {
-    const auto t0 = std::chrono::steady_clock::now();
+    const auto tsetup = std::chrono::steady_clock::now();
     AlignReadsStats st;
     if (rm_.references.empty()) return st;
     const bool rb = rust_bio && rm_.references.size() == 1;
     const clq_affine_t sc = rb ? RustBioScoring().to_int() : scoring.to_int();
     const uint32_t flags = search_flags(fast_lookup) | (extract_tags ? CLQ_EXTRACT_TAGS : 0u) | (rb ? CLQ_RUSTBIO : 0u);
     const uint32_t ns = opt_.n_slots;
-    std::vector<std::unique_ptr<ReadBatch>> bufs;
-    for (uint32_t s = 0; s < ns; s++) bufs.push_back(std::make_unique<ReadBatch>(opt_.max_reads, opt_.max_read_bytes));
+    while (bufs_.size() < ns) bufs_.push_back(std::make_unique<ReadBatch>(opt_.max_reads, opt_.max_read_bytes));  // page-locked once
+    auto& bufs = bufs_;
+    const auto t0 = std::chrono::steady_clock::now();
+    st.setup_seconds = std::chrono::duration<double>(t0 - tsetup).count();
     std::vector<bool> busy(ns, false);
     uint64_t next_index = 0;
     bool more = true;
@@ -795,6 +859,7 @@ AlignReadsStats ShardedAligner::align_reads(const ReadSource& source, const Affi
             const AlignReadsStats st = a->align_reads(shared_source, scoring, fast_lookup, locked_sink, extract_tags, rust_bio);
             std::lock_guard<std::mutex> g(sink_mu);
             total.reads += st.reads; total.aligned += st.aligned; total.dropped += st.dropped; total.batches += st.batches; total.cells += st.cells;
+            total.setup_seconds = std::max(total.setup_seconds, st.setup_seconds);
         } catch (...) {
             std::lock_guard<std::mutex> g(sink_mu);
             if (!err) err = std::current_exception();
@@ -804,7 +869,7 @@ AlignReadsStats ShardedAligner::align_reads(const ReadSource& source, const Affi
     for (auto& a : aligners_) th.emplace_back(work, a.get());
     for (auto& t : th) t.join();
     if (err) std::rethrow_exception(err);
-    total.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    total.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - total.setup_seconds;
     return total;
 }
 

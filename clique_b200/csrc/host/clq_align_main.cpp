@@ -10,6 +10,7 @@
 #include <iostream>
 #include <map>
 #include <sstream>
+#include <thread>
 
 #include "../../../include/clique_host.hpp"
 
@@ -20,8 +21,9 @@ namespace {
 struct Args {
     std::string refs, reads, reads2, out = "-", stats_json, umi_symbols = "0123456789", layout;
     std::vector<int> gpus = {0};
-    uint32_t batch = 1u << 18, max_read_len = 1u << 16, cigar_ops_per_read = 32, max_reference_multiplier = 2;
-    bool exhaustive = false, tags = true, quiet_sam = false, rust_bio = false;
+    uint32_t batch = 1u << 18, max_read_len = 1u << 16, cigar_ops_per_read = 32, max_reference_multiplier = 2, threads = 1;
+    uint64_t synthetic = 0;  // --synthetic N: N in-memory noisy copies of the references instead of a read file
+    bool exhaustive = false, tags = true, quiet_sam = false, rust_bio = false, slow_sam = false;
     AffineScoring scoring = AffineScoring::align_reads_default();
 };
 
@@ -30,8 +32,9 @@ struct Args {
     std::fprintf(stderr,
                  "usage: clq_align --refs refs.fa --reads reads.fastq|reads.txt [--reads2 r2.fastq --layout 1F,2C] [--out out.sam|-]\n"
                  "                 [--gpus 0,1,..] [--batch N] [--exhaustive] [--scoring match,mismatch,special,open,extend,final_mult]\n"
-                 "                 [--umi-symbols 012] [--no-tags] [--no-sam] [--rust-bio] [--max-read-len N] [--max-reference-multiplier N]\n"
-                 "                 [--cigar-ops-per-read N] [--stats-json path]\n");
+                 "                 [--umi-symbols 012] [--no-tags] [--no-sam] [--slow-sam] [--rust-bio] [--max-read-len N] [--max-reference-multiplier N]\n"
+                 "                 [--cigar-ops-per-read N] [--stats-json path] [--threads T (SAM text built by T host threads)]\n"
+                 "                 [--synthetic N (N in-memory noisy copies of the references, 0.3%% substitutions, instead of --reads)]\n");
     std::exit(2);
 }
 
@@ -51,9 +54,12 @@ Args parse(int argc, char** argv) {
         else if (k == "--max-read-len") a.max_read_len = (uint32_t)std::stoul(val());
         else if (k == "--cigar-ops-per-read") a.cigar_ops_per_read = (uint32_t)std::stoul(val());
         else if (k == "--max-reference-multiplier") a.max_reference_multiplier = (uint32_t)std::stoul(val());
+        else if (k == "--threads") a.threads = std::max<uint32_t>(1, (uint32_t)std::stoul(val()));
+        else if (k == "--synthetic") a.synthetic = std::stoull(val());
         else if (k == "--exhaustive") a.exhaustive = true;
         else if (k == "--no-tags") a.tags = false;
         else if (k == "--rust-bio") a.rust_bio = true;
+        else if (k == "--slow-sam") a.slow_sam = true;
         else if (k == "--no-sam") a.quiet_sam = true;
         else if (k == "--gpus") {
             a.gpus.clear();
@@ -70,7 +76,7 @@ Args parse(int argc, char** argv) {
             a.scoring = {v[0], v[1], v[2], v[3], v[4], v[5]};
         } else usage(("unknown option " + k).c_str());
     }
-    if (a.refs.empty() || a.reads.empty()) usage("--refs and --reads are required");
+    if (a.refs.empty() || (a.reads.empty() && !a.synthetic)) usage("--refs and --reads (or --synthetic N) are required");
     return a;
 }
 
@@ -144,9 +150,38 @@ int main(int argc, char** argv) {
         ShardedAligner sh(a.gpus, opt);
         sh.set_references(rm);
 
-        ReadFile f1(a.reads);
+        // --synthetic: reads generated up front in host memory (xorshift, 0.3 % substitutions, tag symbols and N filled with bases)
+        std::vector<Bytes> synth;
+        if (a.synthetic) {
+            uint64_t st = 0x9E3779B97F4A7C15ull;
+            auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+            const size_t pool = (size_t)std::min<uint64_t>(a.synthetic, 1u << 16);
+            for (size_t i = 0; i < pool; i++) {
+                const Bytes& ref = rm.references[rnd() % rm.references.size()].sequence;
+                Bytes r = ref;
+                for (auto& b : r) if (b < 58 || b == 'N' || rnd() % 1000 < 3) b = "ACGT"[rnd() & 3];
+                synth.push_back(std::move(r));
+            }
+        }
+        uint64_t synth_next = 0;
+        const ReadSource synth_source = [&](ReadBatch& b) -> bool {
+            while (synth_next < a.synthetic) {
+                const Bytes& r = synth[synth_next % synth.size()];
+                char nm[24];
+                int nl = 23;
+                uint64_t v = synth_next;
+                do { nm[nl--] = (char)('0' + v % 10); v /= 10; } while (v);
+                nm[nl] = 's';
+                if (!b.push(nm + nl, (size_t)(24 - nl), r.data(), r.size())) return true;
+                synth_next++;
+            }
+            return false;
+        };
+        std::unique_ptr<ReadFile> f1p;
+        if (!a.synthetic) f1p = std::make_unique<ReadFile>(a.reads);
+        ReadFile* f1ptr = f1p.get();
         std::unique_ptr<ReadFile> f2;
-        if (!a.reads2.empty()) f2 = std::make_unique<ReadFile>(a.reads2);
+        if (!a.reads2.empty() && !a.synthetic) f2 = std::make_unique<ReadFile>(a.reads2);
         const std::vector<ReadPosition> layout = a.layout.empty() ? std::vector<ReadPosition>{} : parse_layout(a.layout);
         ReadSetContainer pending;
         bool have_pending = false;
@@ -156,7 +191,7 @@ int main(int argc, char** argv) {
         const ReadSource source = [&](ReadBatch& b) -> bool {
             for (;;) {
                 if (!have_pending) {
-                    if (!f1.next(pending.read_one)) return false;
+                    if (!f1ptr->next(pending.read_one)) return false;
                     if (f2) {
                         FastqRecord r2;
                         if (!f2->next(r2)) return false;
@@ -187,41 +222,57 @@ int main(int argc, char** argv) {
             for (const auto& r : rm.references) *out << "@SQ\tSN:" << to_string(r.name) << "\tLN:" << r.sequence.size() << "\n";
             *out << "@CO\tClique processed\n";
         }
-        // batches complete in any order across GPUs; a small reorder buffer restores input order
-        std::map<uint64_t, std::string> done;
-        uint64_t next_out = 0, n_batches_out = 0;
-        std::map<uint64_t, uint64_t> batch_len;
+        // batches complete in any order across GPUs; a small reorder buffer restores input order.  The SAM text of a batch is
+        // built by `threads` host threads into per-thread buffers (contiguous read ranges) that are written in order and reused.
+        std::map<uint64_t, std::pair<uint64_t, std::vector<std::string>>> done;  // first_index -> (reads, parts)
+        uint64_t next_out = 0;
+        std::vector<std::string> part;
+        double sink_seconds = 0.0;
+        const std::string syms = a.tags ? a.umi_symbols : std::string();
         const ResultSink sink = [&](const BatchView& v) {
-            std::string text;
-            if (!a.quiet_sam) {
-                text.reserve((size_t)v.size() * 700);
-                for (uint32_t i = 0; i < v.size(); i++) {
-                    const auto al = v.alignment(i);
+            const auto t0 = std::chrono::steady_clock::now();
+            const uint32_t nt = a.quiet_sam ? 0 : std::min<uint32_t>(a.threads, std::max<uint32_t>(1, v.size()));
+            part.resize(nt);
+            auto work = [&](uint32_t t) {
+                const uint32_t lo = (uint32_t)((uint64_t)v.size() * t / nt), hi = (uint32_t)((uint64_t)v.size() * (t + 1) / nt);
+                std::string& s = part[t];
+                s.clear();
+                for (uint32_t i = lo; i < hi; i++) {
+                    if (!a.slow_sam) { v.append_sam_line(i, syms, names, s); continue; }
+                    const auto al = v.alignment(i);  // --slow-sam: through the owned AlignmentResult / to_sam_record objects
                     if (!al) continue;
-                    const TagMap tags = v.align_reads_tags(i, a.tags ? a.umi_symbols : std::string());
-                    text += al->alignment->to_sam_record((int32_t)v.ref_index(i), tags, std::nullopt).to_sam_line(names);
-                    text += '\n';
+                    const TagMap tags = v.align_reads_tags(i, syms);
+                    s += al->alignment->to_sam_record((int32_t)v.ref_index(i), tags, std::nullopt).to_sam_line(names);
+                    s += '\n';
                 }
+            };
+            std::vector<std::thread> th;
+            for (uint32_t t = 1; t < nt; t++) th.emplace_back(work, t);
+            if (nt) work(0);
+            for (auto& t : th) t.join();
+            if (v.batch->first_index == next_out) {
+                for (const auto& s : part) out->write(s.data(), (std::streamsize)s.size());
+                next_out += v.size();
+            } else {
+                done[v.batch->first_index] = {v.size(), std::move(part)};
+                part.clear();
             }
-            done[v.batch->first_index] = std::move(text);
-            batch_len[v.batch->first_index] = v.size();
             while (!done.empty() && done.begin()->first == next_out) {
-                *out << done.begin()->second;
-                next_out += batch_len[done.begin()->first];
-                batch_len.erase(done.begin()->first);
+                for (const auto& s : done.begin()->second.second) out->write(s.data(), (std::streamsize)s.size());
+                next_out += done.begin()->second.first;
                 done.erase(done.begin());
-                n_batches_out++;
             }
+            sink_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         };
-        const AlignReadsStats st = sh.align_reads(source, a.scoring, !a.exhaustive, sink, a.tags, a.rust_bio);
+        const AlignReadsStats st = sh.align_reads(a.synthetic ? synth_source : source, a.scoring, !a.exhaustive, sink, a.tags, a.rust_bio);
         out->flush();
-        char js[512];
+        char js[640];
         std::snprintf(js, sizeof(js),
                       "{\"reads\": %llu, \"aligned\": %llu, \"dropped\": %llu, \"batches\": %llu, \"cells\": %llu, \"seconds\": %.6f, "
-                      "\"reads_per_s\": %.1f, \"gcups\": %.3f, \"gpus\": %zu, \"skipped_oversize\": %llu}",
+                      "\"reads_per_s\": %.1f, \"gcups\": %.3f, \"gpus\": %zu, \"skipped_oversize\": %llu, \"sink_seconds\": %.6f, \"threads\": %u, \"setup_seconds\": %.6f}",
                       (unsigned long long)st.reads, (unsigned long long)st.aligned, (unsigned long long)st.dropped,
                       (unsigned long long)st.batches, (unsigned long long)st.cells, st.seconds, st.seconds > 0 ? st.reads / st.seconds : 0.0,
-                      st.seconds > 0 ? st.cells / st.seconds / 1e9 : 0.0, sh.n_devices(), (unsigned long long)too_big);
+                      st.seconds > 0 ? st.cells / st.seconds / 1e9 : 0.0, sh.n_devices(), (unsigned long long)too_big, sink_seconds, a.threads, st.setup_seconds);
         std::fprintf(stderr, "%s\n", js);
         if (!a.stats_json.empty()) { std::ofstream sj(a.stats_json); sj << js << "\n"; }
         return 0;

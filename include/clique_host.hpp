@@ -204,12 +204,18 @@ public:
     ReadBatch& operator=(const ReadBatch&) = delete;
     void clear();
     /// false when the read does not fit any more (the caller keeps it for the next batch)
-    bool push(const std::string& name, const uint8_t* seq, size_t n, const uint8_t* qual = nullptr, int32_t fixed_ref = -1);
+    bool push(const std::string& name, const uint8_t* seq, size_t n, const uint8_t* qual = nullptr, int32_t fixed_ref = -1) {
+        return push(name.data(), name.size(), seq, n, qual, fixed_ref);
+    }
+    /// allocation-free form (names live in one flat buffer): the per-read cost is two memcpys
+    bool push(const char* name, size_t name_len, const uint8_t* seq, size_t n, const uint8_t* qual = nullptr, int32_t fixed_ref = -1);
     uint32_t size() const { return n_; }
     uint32_t capacity() const { return max_reads_; }
     const uint8_t* read(uint32_t i) const { return bytes_ + off_[i]; }
     size_t read_len(uint32_t i) const { return (size_t)(off_[i + 1] - off_[i]); }
-    const std::string& name(uint32_t i) const { return names_[i]; }
+    std::string name(uint32_t i) const { return std::string(name_bytes_.data() + name_off_[i], name_off_[i + 1] - name_off_[i]); }
+    const char* name_data(uint32_t i) const { return name_bytes_.data() + name_off_[i]; }
+    size_t name_len(uint32_t i) const { return name_off_[i + 1] - name_off_[i]; }
     std::optional<Bytes> quals(uint32_t i) const;
     const uint8_t* bytes() const { return bytes_; }
     const uint64_t* offsets() const { return off_; }
@@ -223,7 +229,8 @@ private:
     uint8_t* bytes_ = nullptr;
     uint64_t* off_ = nullptr;
     int32_t* fixed_ = nullptr;
-    std::vector<std::string> names_;
+    std::vector<char> name_bytes_;
+    std::vector<size_t> name_off_;
     Bytes quals_;
     bool have_quals_ = false;
 };
@@ -259,6 +266,10 @@ public:
     /// the tag set align_reads writes (alignment_functions.rs:193-226): e<symbol> for the symbols in `umi_symbols`,
     /// rc = "1", ar = read name, rm, as
     TagMap align_reads_tags(uint32_t i, const std::string& umi_symbols) const;
+    /// Fast path of alignment(i) -> to_sam_record(ref_index, align_reads_tags(i, umi_symbols), None) -> to_sam_line: the same
+    /// text (plus '\n') appended to `out` straight from the raw records, without building the intermediate objects.
+    /// Returns false (nothing appended) for dropped reads.
+    bool append_sam_line(uint32_t i, const std::string& umi_symbols, const std::vector<std::string>& reference_names, std::string& out) const;
 };
 
 struct AlignerOptions {
@@ -278,7 +289,8 @@ using ResultSink = std::function<void(const BatchView& view)>;
 
 struct AlignReadsStats {
     uint64_t reads = 0, aligned = 0, dropped = 0, batches = 0, cells = 0;
-    double seconds = 0.0;
+    double seconds = 0.0;        // the loop itself: first batch filled -> last batch handed to the sink
+    double setup_seconds = 0.0;  // one-time page-locking of the staging buffers (first call on an Aligner)
 };
 
 /// One clq_ctx on one GPU (reference set, stream slots, pinned result buffers).  Not thread-safe; one per device / thread.
@@ -354,6 +366,7 @@ private:
     std::vector<int32_t> scale_;
     uint64_t pool_ops_ = 0, tags_cap_ = 0;
     std::unique_ptr<ReadBatch> one_;  // staging for the single-read calls
+    std::vector<std::unique_ptr<ReadBatch>> bufs_;  // pinned staging of the batch loop, one per stream slot (allocated once)
 };
 
 /// Read-sharded dispatcher over the GPUs of one box: one Aligner + one host thread per device pull

@@ -296,6 +296,11 @@ def test_clq_align_single_amplicon(H, tmp_path):
     exp = _expect_lines(H, want, refs, names, [reads[i] for i in keep], ["q%d" % i for i in keep])
     _check(lines, exp)
     assert st["reads"] == 1500 and st["dropped"] == 1500 - len(exp) and st["batches"] == 6
+    # the fast formatter (BatchView::append_sam_line) and the owned-object path (alignment -> to_sam_record -> to_sam_line)
+    # produce the same text, whatever the thread count
+    _, slow, _ = _run_clq_align(str(tmp_path), fa, rp, ["--slow-sam"])
+    _, threaded, _ = _run_clq_align(str(tmp_path), fa, rp, ["--threads", "5"])
+    assert slow == lines and threaded == lines
     # the lineage amplicon has three tag runs (16 + 12 + 12 columns): e0 / e1 / e2 present on every record
     assert all({"e0", "e1", "e2"} <= {x[:2] for x in ln[11:]} for ln in lines)
 
