@@ -594,3 +594,35 @@ def test_grouped_pack_traceback(al):
         al.set_option("no_group", 0)
     assert not (b2.stats["variant"] & 2)
     compare(b2, want, len(reads), "ungrouped")
+
+
+@pytest.mark.parametrize("cfg", [3, 4, 5])
+@pytest.mark.parametrize("no_pack", [0, 1])
+def test_narrow_last_stripe_boundaries(al, cfg, no_pack):
+    """The narrow last stripe of the G >= 16 geometries (Cs = ceil(R / 8G) * 8 columns per lane): read lengths on both sides of
+    every block boundary of the last stripe, pairs of unequal length in one PACK task, stale band cells (short reads), on the
+    PACK kernels (single reference) and the int32 FAST kernels (no_pack)."""
+    rng = np.random.default_rng(500 + cfg)
+    G, C = [(16, 24), (32, 16), (32, 32)][cfg - 3]
+    W, blk = G * C, G * 8
+    ref = rand_seq(rng, 61)
+    lens = []
+    for s in (0, 1, 2):
+        for b in range(0, W + 1, blk):
+            lens += [s * W + b - 1, s * W + b, s * W + b + 1]
+    lens = sorted(set(l for l in lens if 0 <= l <= 2 * W + blk + 1)) + [1, 2, 3, 7, 60, 61, 62]
+    reads = []
+    for L in lens:
+        rd = mutate(rng, ref, 0.1)
+        reads.append((rd * (L // max(len(rd), 1) + 1))[:L])
+    order = rng.permutation(len(reads))      # unequal neighbours share a PACK task
+    reads = [reads[i] for i in order]
+    al.set_option("force_cfg", cfg)
+    al.set_option("no_pack", no_pack)
+    try:
+        for band in ("readlen", "maxlen"):
+            br, want = run_both(al, [ref], reads, SCORINGS["cli"], "fixed", band, np.zeros(len(reads), np.int32))
+            compare(br, want, len(reads), (cfg, no_pack, band))
+    finally:
+        al.set_option("force_cfg", -1)
+        al.set_option("no_pack", 0)
