@@ -403,3 +403,16 @@ def test_merge_read_pairs_by_alignment_gpu(H, goldens):
             assert got == want, i
     for i, m in enumerate(goldens["mergers"]):
         assert bytes(ob[int(off[i]):int(off[i + 1])]).decode() == m["expect_merged"], m["name"]
+
+
+def test_no_cpu_fallback_in_cpp_layer(tmp_path):
+    """Without a CUDA device the C++ host layer refuses to run: there is no CPU path behind it (skipped where a GPU exists)."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "clique_b200", "libclq.so"))
+    lib.clq_device_count.restype = ctypes.c_int32
+    if lib.clq_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    fa, rp = _write_inputs(str(tmp_path), [b"ACGTACGTACGT"], [b"r"], [b"ACGTACGT"])
+    r = subprocess.run([CLQ_ALIGN, "--refs", fa, "--reads", rp, "--out", os.path.join(str(tmp_path), "o.sam")], capture_output=True, text=True)
+    assert r.returncode == 1
+    assert "no CPU fallback" in r.stderr or "CUDA" in r.stderr, r.stderr
