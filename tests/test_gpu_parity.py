@@ -626,3 +626,29 @@ def test_narrow_last_stripe_boundaries(al, cfg, no_pack):
     finally:
         al.set_option("force_cfg", -1)
         al.set_option("no_pack", 0)
+
+
+def test_grouped_pack_other_modes(al):
+    """Reads bucketed by reference (uniform lengths, several references) on the rust-bio PACK kernel and on the two-piece
+    affine PACK kernel."""
+    from clique_b200 import RustBioScoring, TwoPieceScoring
+    rng = np.random.default_rng(808)
+    refs = [rand_seq(rng, 120, b"ACGTN") for _ in range(5)]
+    reads, fixed = [], []
+    for i in range(171):
+        k = int(rng.integers(0, 5))
+        rd = mutate(rng, refs[k].replace(b"N", b"A"), 0.1)
+        reads.append((rd + rand_seq(rng, 130))[:124]); fixed.append(k)
+    fixed = np.array(fixed, np.int32)
+    al.set_references(ReferenceManager([Reference(r, b"r%d" % i) for i, r in enumerate(refs)]))
+    qb, qo = pack_reads(reads)
+    br = al.align_batch(qb, qo, RustBioScoring(), "fixed", "maxlen", fixed_ref=fixed, with_stats=True)
+    assert (br.stats["variant"] & 18) == 18, "rust-bio on the PACK kernels"
+    _rb_compare(br, refs, reads, fixed, "grouped rust-bio")
+    cv = TwoPieceScoring(10, -9, 9, -20, -2, -40, -1)
+    ocv = O.Convex(10, -9, 9, -20, -2, -40, -1, -100000)
+    br = al.align_batch(qb, qo, cv, "fixed", "readlen", fixed_ref=fixed, with_stats=True)
+    assert (br.stats["variant"] & 6) == 6, "two-piece affine on the PACK kernel"
+    for i, rd in enumerate(reads):
+        w = O.convex_align_pair(refs[fixed[i]], rd, ocv)
+        assert int(br.status[i]) == 0 and int(br.score_scaled[i]) == w["score"] and br.cigar_string(i) == O.cigar_str(w["cigar"]), i
