@@ -8,7 +8,7 @@ _LIB_NAME = "libclq.so"
 CLQ_OK, READ_TOO_LONG, SCORING_NOT_REPRESENTABLE, TRACEBACK_DIVERGED, CIGAR_POOL_FULL, NO_CANDIDATE = range(6)
 E_INVALID, E_CUDA, E_NOMEM, E_LIMIT, E_STATE, E_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 
-BAND_MAXLEN, BAND_READLEN = 0, 1
+BAND_MAXLEN, BAND_READLEN, BAND_K, BAND_K_SHIFT = 0, 1, 2, 8
 SEARCH_FIXED, SEARCH_EXHAUSTIVE, SEARCH_QUICK = 0 << 2, 1 << 2, 2 << 2
 SCORE_ONLY, CONVEX, EXTRACT_TAGS, RUSTBIO = 1 << 4, 1 << 5, 1 << 6, 1 << 7
 

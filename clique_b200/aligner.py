@@ -355,7 +355,10 @@ class Aligner:
     @staticmethod
     def _flags(search, band, score_only):
         f = {"fixed": L.SEARCH_FIXED, "exhaustive": L.SEARCH_EXHAUSTIVE, "quick": L.SEARCH_QUICK}[search]
-        f |= {"maxlen": L.BAND_MAXLEN, "readlen": L.BAND_READLEN}[band]
+        if isinstance(band, int):  # explicit bandwidth (perform_affine_alignment_bandwidth's `bandwidth`)
+            f |= L.BAND_K | (int(band) << L.BAND_K_SHIFT)
+        else:
+            f |= {"maxlen": L.BAND_MAXLEN, "readlen": L.BAND_READLEN}[band]
         if score_only:
             f |= L.SCORE_ONLY
         return f

@@ -262,7 +262,7 @@ template <int G, int C>
 cudaError_t launch_walk_one(const KParams& p, uint32_t cnt, cudaStream_t st) {
     walk_kernel<G, C><<<(cnt + 127) / 128, 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.bits_off, p.task_base, p.cig_scratch, p.cig_stride, p.cigar_pool,
                                                          p.cigar_cap, p.cigar_cursor, p.results, p.ref_bytes, p.ref_off, p.read_bytes, p.read_off,
-                                                         p.tag_slot, p.tags, p.tag_stride, p.rustbio);
+                                                         p.tag_slot, p.tags, p.tag_stride, p.rustbio, p.band_mode, p.band_k);
     return cudaGetLastError();
 }
 
@@ -642,7 +642,8 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     const bool convex = (flags & CLQ_CONVEX) != 0;
     const uint32_t band = flags & CLQ_BAND_MASK;
     const uint32_t search = flags & CLQ_SEARCH_MASK;
-    if (band > CLQ_BAND_READLEN) return fail(c, CLQ_E_UNSUPPORTED, "explicit bandwidth is not supported (the hot path never passes one)");
+    if (band > CLQ_BAND_K) return CLQ_E_INVALID;
+    const uint32_t band_k = band == CLQ_BAND_K ? (flags >> CLQ_BAND_K_SHIFT) : 0u;
     if (search == CLQ_SEARCH_FIXED && !s->have_fixed && s->n_reads) return fail(c, CLQ_E_INVALID, "CLQ_SEARCH_FIXED needs fixed_ref");
     if (search == CLQ_SEARCH_QUICK && c->kmer_k == 0) return fail(c, CLQ_E_STATE, "CLQ_SEARCH_QUICK needs clq_kmer_index_set");
     if (search > CLQ_SEARCH_QUICK) return CLQ_E_INVALID;
@@ -670,11 +671,13 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         if (!(sc.oe_in - sc.e_in < 0) || sc.scale < 1) return fail(c, CLQ_SCORING_NOT_REPRESENTABLE, "gap_open must be negative");
         fin = sc.oe_fin != sc.oe_in || sc.e_fin != sc.e_in;
         fast = c->fast_ok && !c->force_generic && !fin && fits8(sc.match) && fits8(sc.mismatch) && fits8(sc.special);
+        if (band == CLQ_BAND_K) fast = false;  // explicit bandwidth: the generic kernels check every cell against the row's window
         if (rb) {
             if (fin || !fits8(sc.match) || !fits8(sc.mismatch)) return fail(c, CLQ_E_UNSUPPORTED, "CLQ_RUSTBIO needs int8 substitution scores and no final-gap multiplier");
             fast = true;
         }
     }
+    if (band == CLQ_BAND_K && convex) return fail(c, CLQ_E_UNSUPPORTED, "explicit bandwidth with two-piece affine gaps");
     CU(c, cudaSetDevice(c->device));
     const bool score_only = (flags & CLQ_SCORE_ONLY) != 0;
     const bool want_tags = (flags & CLQ_EXTRACT_TAGS) != 0 && c->tag_stride > 0;
@@ -755,6 +758,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     p.order = s->have_order ? (const uint32_t*)s->order.p : nullptr;
     p.sc = sc;
     p.band_mode = rb ? 0xffu : band;  // rust-bio's global alignment is unbanded
+    p.band_k = band_k;
     p.rustbio = rb ? 1u : 0u;
     p.max_read_len = c->lim.max_read_len;
     p.ref_sm_stride = ref_sm_stride;

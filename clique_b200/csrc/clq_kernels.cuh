@@ -61,6 +61,7 @@ struct KParams {
     clq_result_t* results;       // [n_reads]
     clq_affine_t sc;
     uint32_t band_mode;
+    uint32_t band_k;             // CLQ_BAND_K: explicit bandwidth (generic kernels only)
     uint32_t max_read_len;
     uint32_t ref_sm_stride;      // bytes of shared memory per group
     uint32_t* bits;              // traceback bits scratch
@@ -135,6 +136,15 @@ __device__ inline int stale_rows(int L1, int L2, uint32_t band_mode) {
     return K;
 }
 
+// perform_affine_alignment_bandwidth's band of row x (alignment/alignment_matrix.rs:413-424): cells y in [lo, hi] are
+// computed, every other cell of the row keeps the fresh-matrix state (0,0,0) / Up(0).  The centre is computed in f64.
+__device__ __forceinline__ void band_of_row(int x, int L1, int L2, long long bw, int& lo, int& hi) {
+    const long long yc = (long long)(((double)x / (double)(L1 + 1)) * (double)(L2 + 1));
+    const long long a = yc - bw, b = yc + bw;
+    lo = (int)(a > 1 ? a : 1);
+    hi = (int)((b < (long long)L2 + 1 ? b : (long long)L2 + 1) - 1);
+}
+
 // Time-transposed direction-bit store.  The walker follows a path that moves up one row per step, so it wants the
 // words of consecutive steps side by side; the fill produces one row per step.  Each lane therefore parks its WPL words of
 // the last 8 steps in shared memory ([word][step & 7][lane], conflict-free, private to the lane so no barrier) and
@@ -205,10 +215,12 @@ __device__ __forceinline__ size_t bits_index(int s, int T, int t, int ln, int k)
 }
 
 // One wavefront step of one lane: C cells of row x.
-template <int C, bool TB, bool FIN, bool LAST>
+// BAND: columns outside [jlo, jhi] (the explicit band of this row) are not computed: they hold the fresh-matrix state.
+template <int C, bool TB, bool FIN, bool LAST, bool BAND = false>
 __device__ __forceinline__ void row_step(int (&E)[C], int (&B)[C], const int (&bq)[C], uint32_t (&w)[C / 8],
                                          int& Fl, int& El, int& Ml, int& Bl, int diag, int rcode, int mt, int mm,
-                                         const clq_affine_t& sc, bool own_last, int jL, int& capM, int& capE, int& capF) {
+                                         const clq_affine_t& sc, bool own_last, int jL, int& capM, int& capE, int& capF,
+                                         int jlo = 0, int jhi = C) {
     const int x1row = LAST ? sc.oe_fin : sc.oe_in;
     const int lerow = LAST ? sc.e_fin : sc.e_in;
 #pragma unroll
@@ -221,13 +233,16 @@ __device__ __forceinline__ void row_step(int (&E)[C], int (&B)[C], const int (&b
         if (FIN && !LAST) {
             if (own_last && j == jL) { x1c = sc.oe_fin; lec = sc.e_fin; }
         }
-        const int Mv = diag + m;
+        int Mv = diag + m;
         const int Eext = E[j] + lec, Eopen = B[j] + x1c;
-        const int Ev = max(Eext, Eopen);
+        int Ev = max(Eext, Eopen);
         const int Fext = Fl + lec, Fopen = Bl + x1c;
-        const int Fv = max(Fext, Fopen);
+        int Fv = max(Fext, Fopen);
         const int Pv = max(Mv, Fv);
-        const int Bv = max(Pv, Ev);
+        int Bv = max(Pv, Ev);
+        if (BAND) {
+            if (j < jlo || j > jhi) { Mv = 0; Ev = 0; Fv = 0; Bv = 0; }
+        }
         if (TB) {
             const bool ext1 = Eext > Eopen;
             const bool ext2 = (Fext >= El + x1c) && (Fext > Ml + x1c);
@@ -446,7 +461,15 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
                         const int rcode = rsp ? 0x200 : r;
                         const int mt = rsp ? sc.special : sc.match;
                         const int mm = rsp ? sc.special : sc.mismatch;
-                        if (x == L1)
+                        if (p.band_mode == CLQ_BAND_K) {  // explicit bandwidth: per-row column window of this lane
+                            int lo, hi;
+                            band_of_row(x, L1, L2, (long long)p.band_k, lo, hi);
+                            const int jlo = lo - (y0 + 1), jhi = hi - (y0 + 1);
+                            if (x == L1)
+                                row_step<C, TB, FIN, true, true>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, rcode, mt, mm, sc, own_last, jL, capM, capE, capF, jlo, jhi);
+                            else
+                                row_step<C, TB, FIN, false, true>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, rcode, mt, mm, sc, own_last, jL, capM, capE, capF, jlo, jhi);
+                        } else if (x == L1)
                             row_step<C, TB, FIN, true>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, rcode, mt, mm, sc, own_last, jL, capM, capE, capF);
                         else
                             row_step<C, TB, FIN, false>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, rcode, mt, mm, sc, own_last, jL, capM, capE, capF);
@@ -532,7 +555,8 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
                                                    uint32_t* cig_scratch, uint32_t cig_stride, uint32_t* cigar_pool, uint64_t cigar_cap,
                                                    unsigned long long* cigar_cursor, clq_result_t* results, const uint8_t* ref_bytes,
                                                    const uint64_t* ref_off, const uint8_t* read_bytes, const uint64_t* read_off,
-                                                   const uint16_t* tag_slot, uint8_t* tags, uint32_t tag_stride, uint32_t rb) {
+                                                   const uint16_t* tag_slot, uint8_t* tags, uint32_t tag_stride, uint32_t rb,
+                                                   uint32_t band_mode, uint32_t band_k) {
     constexpr int W = G * C;
     constexpr int WPL = C / 8;
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -586,16 +610,28 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
         return (__ldg(bits_g + idx) >> (28 - 4 * (j & 7))) & 15u;
     };
     auto argmax = [](uint32_t nb) -> int { return (nb & 2u) ? 1 : ((nb & 1u) ? 2 : 0); };
+    // cells the fill skipped keep the fresh-matrix state: (x <= K, y == L2) for the two implicit bands, everything outside the
+    // row's window for an explicit bandwidth
+    auto stale = [&](int xx, int yy) -> bool {
+        if (band_mode == CLQ_BAND_K) {
+            int lo, hi;
+            band_of_row(xx, L1, L2, (long long)band_k, lo, hi);
+            return yy < lo || yy > hi;
+        }
+        return yy == L2 && xx <= K;
+    };
     uint32_t nib = (x > 0 && y > 0) ? nibble(x, y) : 0;
+    bool cur_stale = (x > 0 && y > 0) ? stale(x, y) : false;
     while (x > 0 && y > 0) {
-        if (y == L2 && x <= K) { status = CLQ_TRACEBACK_DIVERGED; break; }  // stale Up(0) cell: the reference spins here
+        if (cur_stale) { status = CLQ_TRACEBACK_DIVERGED; break; }  // stale Up(0) cell: the reference spins here
         const uint32_t old = nib;
         if (z == 0) { emit(CLQ_OP_M, 1); count(x, y); x--; y--; }
         else if (z == 1) { emit(CLQ_OP_D, 1); tag(x, '-'); x--; }
         else { emit(CLQ_OP_I, 1); y--; }
         if (x == 0 || y == 0) break;
         nib = nibble(x, y);
-        const int a = (y == L2 && x <= K) ? 0 : argmax(nib);  // a stale source cell holds (0,0,0): Diag
+        cur_stale = stale(x, y);
+        const int a = cur_stale ? 0 : argmax(nib);  // a stale source cell holds (0,0,0): Diag
         if (z == 0) z = a;
         else if (rb) z = (z == 1) ? ((old & 8u) ? 1 : a) : ((old & 4u) ? 2 : a);  // rust-bio: an opened gap resumes in S = argmax
         else if (z == 1) z = (old & 8u) ? 1 : (a == 2 ? 2 : 0);

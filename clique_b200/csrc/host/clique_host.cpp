@@ -662,7 +662,8 @@ AlignmentResult Aligner::align_two_strings_passed_matrix(const std::string& ref_
     uint32_t band;
     if (max_indel == read.size()) band = CLQ_BAND_READLEN;
     else if (max_indel >= std::max(reference.size(), read.size())) band = CLQ_BAND_MAXLEN;  // the band covers the whole matrix
-    else fail(CLQ_E_UNSUPPORTED, "explicit small bandwidths are not supported (no caller of the hot path passes one)");
+    else if (max_indel < (1u << 24)) band = CLQ_BAND_K | ((uint32_t)max_indel << CLQ_BAND_K_SHIFT);  // explicit bandwidth
+    else fail(CLQ_E_UNSUPPORTED, "bandwidth out of range");
     return single(reference, read, std::move(qual), scoring, band, ref_name, read_name);
 }
 

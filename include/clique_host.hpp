@@ -311,7 +311,8 @@ public:
                                       const AffineScoring& scoring_function, bool local, const std::string& ref_name,
                                       const std::string& read_name);
     /// align_two_strings_passed_matrix, alignment_functions.rs:383-449; the caller-owned matrix is gone (scores live in
-    /// registers), `max_indel` must be the read length or cover both sequences -- the only values the reference passes.
+    /// registers); `max_indel` is the bandwidth: the read length and max(L1, L2) take the fast kernels, any other value the
+    /// explicit-band path (CLQ_BAND_K).
     AlignmentResult align_two_strings_passed_matrix(const std::string& ref_name, const std::string& read_name, const Bytes& reference,
                                                     const Bytes& read, std::optional<Bytes> qual, const AffineScoring& scoring,
                                                     size_t max_indel);

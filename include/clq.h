@@ -43,6 +43,12 @@ extern "C" {
 /* ---- flags for clq_submit / clq_launch ---- */
 #define CLQ_BAND_MAXLEN 0u           /* perform_affine_alignment: bandwidth = max(L1,L2); alignment/alignment_matrix.rs:366-372 */
 #define CLQ_BAND_READLEN 1u          /* align_two_strings_passed_matrix(.., &read.len()); alignment_functions.rs:737-746,790-799 */
+#define CLQ_BAND_K 2u                /* perform_affine_alignment_bandwidth(.., &k) with an explicit bandwidth k = flags >> CLQ_BAND_K_SHIFT
+                                        (alignment/alignment_matrix.rs:376-425: row x computes y in [max(1, c - k), min(L2 + 1, c + k)),
+                                        c = trunc(f64(x) / (L1 + 1) * (L2 + 1)); skipped cells keep the fresh-matrix state).  No caller in
+                                        the reference passes one today (the 1-reference call with &100 is commented out, :586-597);
+                                        generic kernels, affine scoring. */
+#define CLQ_BAND_K_SHIFT 8
 #define CLQ_BAND_MASK 3u
 #define CLQ_SEARCH_FIXED (0u << 2)      /* fixed_ref[i] names the reference of read i */
 #define CLQ_SEARCH_EXHAUSTIVE (1u << 2) /* exhaustive_alignment_search; alignment_functions.rs:769-827 */

@@ -652,3 +652,37 @@ def test_grouped_pack_other_modes(al):
     for i, rd in enumerate(reads):
         w = O.convex_align_pair(refs[fixed[i]], rd, ocv)
         assert int(br.status[i]) == 0 and int(br.score_scaled[i]) == w["score"] and br.cigar_string(i) == O.cigar_str(w["cigar"]), i
+
+
+@pytest.mark.parametrize("name", ["cli", "default_dna"])
+def test_explicit_bandwidth(al, name):
+    """perform_affine_alignment_bandwidth with an explicit bandwidth (CLQ_BAND_K, alignment/alignment_matrix.rs:376-425): per-row
+    window around the f64 band centre, skipped cells keep the fresh-matrix state, a traceback that enters one is reported as
+    CLQ_TRACEBACK_DIVERGED (the reference never returns from it).  Also the exhaustive search under an explicit band."""
+    rng = np.random.default_rng(600 + len(name))
+    sc = SCORINGS[name]
+    refs = [rand_seq(rng, int(rng.integers(1, 220)), b"ACGTN") for _ in range(6)]
+    reads, fixed = [], []
+    for it in range(150):
+        r = int(rng.integers(0, len(refs)))
+        rd = mutate(rng, refs[r], float(rng.choice([0.0, 0.05, 0.2]))) if it % 3 else rand_seq(rng, int(rng.integers(0, 400)))
+        reads.append(rd); fixed.append(r)
+    fixed = np.array(fixed, np.int32)
+    al.set_references(ReferenceManager([Reference(r, b"r%d" % i) for i, r in enumerate(refs)]))
+    qb, qo = pack_reads(reads)
+    rb, ro = O.pack_seqs(refs)
+    seen = set()
+    for k in (1, 2, 5, 17, 100, 1000):
+        for cfg in (-1, 0):
+            al.set_option("force_cfg", cfg)
+            try:
+                br = al.align_batch(qb, qo, AffineScoring(*sc), "fixed", k, fixed_ref=fixed)
+            finally:
+                al.set_option("force_cfg", -1)
+            want = O.align_batch(rb, ro, qb, qo, sc, search="fixed", fixed_ref=fixed, band_mode="k", band_k=k, threads=8)
+            compare(br, want, len(reads), (name, k, cfg))
+        seen |= set(int(s) for s in want["status"])
+    assert seen == {0, TRACEBACK_DIVERGED}
+    br = al.align_batch(qb, qo, AffineScoring(*sc), "exhaustive", 40)
+    want = O.align_batch(rb, ro, qb, qo, sc, search="exhaustive", band_mode="k", band_k=40, threads=8, traceback_all=False)
+    compare(br, want, len(reads), (name, "exhaustive k=40"))
