@@ -338,6 +338,100 @@ MergedSequence alignment_rate_and_consensus(const Bytes& a1, const Bytes& q1, co
     return m;
 }
 
+// ------------------------------------------------------------------------------------------------ strand orientation
+namespace {
+inline int acgt(uint8_t b) {
+    switch (b) { case 'A': case 'a': return 1; case 'C': case 'c': return 2; case 'G': case 'g': return 3; case 'T': case 't': return 4; default: return 0; }
+}
+}  // namespace
+
+SuffixTableLookup SuffixTableLookup::find_seeds(const Bytes& reference, size_t seed_size) {
+    SuffixTableLookup s;
+    s.text = reference;
+    s.seed_size = seed_size;
+    s.table.resize(reference.size());
+    for (size_t i = 0; i < reference.size(); i++) s.table[i] = (uint32_t)i;
+    const uint8_t* t = s.text.data();
+    const size_t m = s.text.size();
+    std::sort(s.table.begin(), s.table.end(), [t, m](uint32_t a, uint32_t b) {
+        const size_t la = m - a, lb = m - b;
+        const int c = std::memcmp(t + a, t + b, std::min(la, lb));
+        return c ? c < 0 : la < lb;
+    });
+    return s;
+}
+
+std::pair<const uint32_t*, const uint32_t*> SuffixTableLookup::positions(const uint8_t* query, size_t n) const {
+    const uint8_t* t = text.data();
+    const size_t m = text.size();
+    // first suffix >= query, then first suffix that does not start with query
+    auto lo = std::partition_point(table.begin(), table.end(), [&](uint32_t p) {
+        const size_t l = std::min(n, m - p);
+        const int c = std::memcmp(t + p, query, l);
+        return c ? c < 0 : (m - p) < n;
+    });
+    auto hi = std::partition_point(lo, table.end(), [&](uint32_t p) { return m - p >= n && std::memcmp(t + p, query, n) == 0; });
+    const uint32_t* base = table.data();
+    return {base + (lo - table.begin()), base + (hi - table.begin())};
+}
+
+size_t extend_hit(const uint8_t* search, size_t n, size_t sloc, const uint8_t* reference, size_t m, size_t rloc) {
+    size_t len = 0;
+    while (len + sloc < n && len + rloc < m) {
+        const int a = acgt(search[sloc + len]), b = acgt(reference[rloc + len]);
+        if (!a || a != b) return len;
+        len++;
+    }
+    return len;
+}
+
+SharedSegments find_greedy_non_overlapping_segments(const Bytes& search, const Bytes& reference, const SuffixTableLookup& seeds) {
+    SharedSegments out{reference.size(), {}};
+    size_t position = 0, greatest_ref_pos = 0;
+    while ((int64_t)position <= (int64_t)search.size() - (int64_t)seeds.seed_size) {
+        const auto range = seeds.seed_size ? seeds.positions(search.data() + position, seeds.seed_size)
+                                           : std::pair<const uint32_t*, const uint32_t*>{nullptr, nullptr};
+        size_t longest_hit = 0;
+        for (const uint32_t* it = range.first; it != range.second; ++it) {
+            const size_t ref_position = *it;
+            if (ref_position >= greatest_ref_pos) {
+                const size_t ext = extend_hit(search.data(), search.size(), position, reference.data(), reference.size(), ref_position);
+                if (ext > longest_hit) {
+                    out.alignment_segments.push_back({position, ref_position, ext});
+                    position += ext;
+                    out.start_position = std::min(out.start_position, ref_position);
+                    greatest_ref_pos = std::max(greatest_ref_pos, ref_position + ext);
+                    longest_hit = ext;
+                }
+            }
+        }
+        position += 1;
+    }
+    return out;
+}
+
+Bytes bio_revcomp(const Bytes& text) {
+    static const char from[] = "AGCTYRWSKMDVHBNagctyrwskmdvhbn";
+    static const char to[] = "TCGARYWSMKHBDVNtcgarywsmkhbdvn";
+    uint8_t comp[256];
+    for (int i = 0; i < 256; i++) comp[i] = (uint8_t)i;
+    for (int i = 0; from[i]; i++) comp[(uint8_t)from[i]] = (uint8_t)to[i];
+    Bytes out(text.size());
+    for (size_t i = 0; i < text.size(); i++) out[i] = comp[text[text.size() - 1 - i]];
+    return out;
+}
+
+Orientation orient_by_longest_segment(const Bytes& search, const Bytes& reference, const SuffixTableLookup& seeds) {
+    Orientation o;
+    o.fwd = find_greedy_non_overlapping_segments(search, reference, seeds);
+    o.rev = find_greedy_non_overlapping_segments(bio_revcomp(search), reference, seeds);
+    size_t f = 0, r = 0;
+    for (const auto& p : o.fwd.alignment_segments) f += p.length;
+    for (const auto& p : o.rev.alignment_segments) r += p.length;
+    o.forward = f > r;
+    return o;
+}
+
 // ------------------------------------------------------------------------------------------------ references
 ReferenceManager::ReferenceManager(std::vector<Reference> refs, size_t ks, size_t kskip) : references(std::move(refs)), kmer_size(ks), kmer_skip(kskip) {
     for (size_t i = 0; i < references.size(); i++) {
@@ -692,9 +786,17 @@ std::optional<AlignmentWithRef> Aligner::quick_alignment_search(const std::strin
     return search(read_name, read, std::move(qual), scoring, CLQ_SEARCH_QUICK, match_threshold);
 }
 
-std::optional<AlignmentWithRef> Aligner::align_to_reference_choices(const std::string& read_name, const Bytes& read, std::optional<Bytes> qual,
-                                                                    bool fast_lookup, const AffineScoring& scoring, bool rust_bio) {
+std::optional<AlignmentWithRef> Aligner::align_to_reference_choices(const std::string& read_name, const Bytes& read_in, std::optional<Bytes> qual,
+                                                                    bool fast_lookup, const AffineScoring& scoring, bool rust_bio,
+                                                                    bool known_strand) {
     if (rm_.references.empty()) return std::nullopt;
+    Bytes oriented;
+    if (rm_.references.size() == 1 && !known_strand) {  // alignment_functions.rs:549-558 (seed size = the reference manager's k-mer size, :97)
+        const Bytes& ref = rm_.references[0].sequence;
+        const Orientation o = orient_by_longest_segment(read_in, ref, SuffixTableLookup::find_seeds(ref, rm_.kmer_size));
+        if (!o.forward) oriented = reverse_complement(read_in);
+    }
+    const Bytes& read = oriented.empty() ? read_in : oriented;
     if (rm_.references.size() == 1 && rust_bio) {
         if (!one_) one_ = std::make_unique<ReadBatch>(1, opt_.max_read_bytes);
         one_->clear();

@@ -23,7 +23,7 @@ struct Args {
     std::vector<int> gpus = {0};
     uint32_t batch = 1u << 18, max_read_len = 1u << 16, cigar_ops_per_read = 32, max_reference_multiplier = 2, threads = 1;
     uint64_t synthetic = 0;  // --synthetic N: N in-memory noisy copies of the references instead of a read file
-    bool exhaustive = false, tags = true, quiet_sam = false, rust_bio = false, slow_sam = false;
+    bool exhaustive = false, tags = true, quiet_sam = false, rust_bio = false, slow_sam = false, unknown_strand = false;
     AffineScoring scoring = AffineScoring::align_reads_default();
 };
 
@@ -32,7 +32,7 @@ struct Args {
     std::fprintf(stderr,
                  "usage: clq_align --refs refs.fa --reads reads.fastq|reads.txt [--reads2 r2.fastq --layout 1F,2C] [--out out.sam|-]\n"
                  "                 [--gpus 0,1,..] [--batch N] [--exhaustive] [--scoring match,mismatch,special,open,extend,final_mult]\n"
-                 "                 [--umi-symbols 012] [--no-tags] [--no-sam] [--slow-sam] [--rust-bio] [--max-read-len N] [--max-reference-multiplier N]\n"
+                 "                 [--umi-symbols 012] [--no-tags] [--no-sam] [--slow-sam] [--rust-bio] [--unknown-strand] [--max-read-len N] [--max-reference-multiplier N]\n"
                  "                 [--cigar-ops-per-read N] [--stats-json path] [--threads T (SAM text built by T host threads)]\n"
                  "                 [--synthetic N (N in-memory noisy copies of the references, 0.3%% substitutions, instead of --reads)]\n");
     std::exit(2);
@@ -60,6 +60,7 @@ Args parse(int argc, char** argv) {
         else if (k == "--no-tags") a.tags = false;
         else if (k == "--rust-bio") a.rust_bio = true;
         else if (k == "--slow-sam") a.slow_sam = true;
+        else if (k == "--unknown-strand") a.unknown_strand = true;
         else if (k == "--no-sam") a.quiet_sam = true;
         else if (k == "--gpus") {
             a.gpus.clear();
@@ -183,6 +184,8 @@ int main(int argc, char** argv) {
         std::unique_ptr<ReadFile> f2;
         if (!a.reads2.empty() && !a.synthetic) f2 = std::make_unique<ReadFile>(a.reads2);
         const std::vector<ReadPosition> layout = a.layout.empty() ? std::vector<ReadPosition>{} : parse_layout(a.layout);
+        const bool orient = a.unknown_strand && rm.references.size() == 1;
+        const SuffixTableLookup seeds = orient ? SuffixTableLookup::find_seeds(rm.references[0].sequence, rm.kmer_size) : SuffixTableLookup();
         ReadSetContainer pending;
         bool have_pending = false;
         uint64_t too_big = 0;
@@ -200,6 +203,13 @@ int main(int argc, char** argv) {
                     have_pending = true;
                 }
                 bool ok;
+                if (orient && layout.empty()) {
+                    // known_strand = false, one reference (alignment_functions.rs:549-558): orient_by_longest_segment, then the
+                    // reverse complement when the reverse strand shares more bases with the reference
+                    if (!orient_by_longest_segment(pending.read_one.seq, rm.references[0].sequence, seeds).forward) {
+                        pending.read_one.seq = reverse_complement(pending.read_one.seq);
+                    }
+                }
                 if (layout.empty()) ok = b.push(pending.read_one.id, pending.read_one.seq.data(), pending.read_one.seq.size(), pending.read_one.qual.data());
                 else {
                     const MergedSequence m = merge_reads_by_concatenation(pending, layout);

@@ -153,6 +153,25 @@ int32_t clqh_merge_read_pairs_by_alignment(int32_t device, uint32_t n, const uin
     }
 }
 
+size_t clqh_find_greedy_non_overlapping_segments(const uint8_t* search, size_t n, const uint8_t* reference, size_t m, size_t seed_size,
+                                                 uint32_t* out_xyz, size_t cap, size_t* start_position) {
+    const Bytes ref(reference, reference + m);
+    const SharedSegments sg = find_greedy_non_overlapping_segments(Bytes(search, search + n), ref, SuffixTableLookup::find_seeds(ref, seed_size));
+    if (start_position) *start_position = sg.start_position;
+    const size_t k = std::min(cap, sg.alignment_segments.size());
+    for (size_t i = 0; i < k; i++) {
+        out_xyz[3 * i] = (uint32_t)sg.alignment_segments[i].search_start;
+        out_xyz[3 * i + 1] = (uint32_t)sg.alignment_segments[i].ref_start;
+        out_xyz[3 * i + 2] = (uint32_t)sg.alignment_segments[i].length;
+    }
+    return k;
+}
+
+int32_t clqh_orient_by_longest_segment(const uint8_t* search, size_t n, const uint8_t* reference, size_t m, size_t seed_size) {
+    const Bytes ref(reference, reference + m);
+    return orient_by_longest_segment(Bytes(search, search + n), ref, SuffixTableLookup::find_seeds(ref, seed_size)).forward ? 1 : 0;
+}
+
 size_t clqh_merge_reads_by_concatenation(const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const char* layout, uint8_t* out,
                                          size_t cap) {
     // layout: comma-separated items "1F" / "2R" / "2C" (read number + Forward / Reverse / reverse-Complement) or "S:ACGT" (spacer)

@@ -170,8 +170,33 @@ uint8_t combine_phred_scores(uint8_t phred_one, uint8_t phred_two, bool agree);
 MergedSequence alignment_rate_and_consensus(const Bytes& alignment_1, const Bytes& qual_scores1, const Bytes& alignment_2,
                                             const Bytes& qual_scores2);
 
+// ------------------------------------------------------------------------------------------------ strand orientation
+/// MatchedPosition / SharedSegments, alignment/alignment_matrix.rs (the fields find_greedy_non_overlapping_segments fills)
+struct MatchedPosition { size_t search_start, ref_start, length; };
+struct SharedSegments { size_t start_position; std::vector<MatchedPosition> alignment_segments; };
+/// SuffixTableLookup, reference/fasta_reference.rs:34-38 + ReferenceManager::find_seeds (:155-157): the suffix array of the
+/// reference (what the `suffix` crate's SuffixTable holds) and the seed size
+struct SuffixTableLookup {
+    Bytes text;
+    std::vector<uint32_t> table;  // suffix start positions in lexicographic order of the suffixes
+    size_t seed_size = 0;
+    static SuffixTableLookup find_seeds(const Bytes& reference, size_t seed_size);
+    /// SuffixTable::positions: every occurrence of `query`, in suffix-array order
+    std::pair<const uint32_t*, const uint32_t*> positions(const uint8_t* query, size_t n) const;
+};
+/// extend_hit, linked_alignment.rs:341-362 (plain bases equal up to case; anything else ends the hit)
+size_t extend_hit(const uint8_t* search, size_t n, size_t search_location, const uint8_t* reference, size_t m, size_t reference_location);
+/// find_greedy_non_overlapping_segments, linked_alignment.rs:97-130 (kept as it is, including the cursor that moves inside the
+/// candidate loop)
+SharedSegments find_greedy_non_overlapping_segments(const Bytes& search_string, const Bytes& reference, const SuffixTableLookup& seeds);
+/// bio::alphabets::dna::revcomp (complement table over ACGT + IUPAC in both cases, other bytes unchanged)
+Bytes bio_revcomp(const Bytes& text);
+/// orient_by_longest_segment, linked_alignment.rs:24-32: (forward shares strictly more bases, forward segments, reverse segments)
+struct Orientation { bool forward; SharedSegments fwd, rev; };
+Orientation orient_by_longest_segment(const Bytes& search_string, const Bytes& reference, const SuffixTableLookup& seeds);
+
 // ------------------------------------------------------------------------------------------------ references
-/// Reference, reference/fasta_reference.rs:41-46 (the suffix table is outside the path)
+/// Reference, reference/fasta_reference.rs:41-46
 struct Reference { Bytes sequence; Bytes name; };
 
 /// ReferenceManager, reference/fasta_reference.rs:64-146.  `references` keeps insertion order = ascending index, the
@@ -325,9 +350,11 @@ public:
     /// align_to_reference_choices, alignment_functions.rs:520-631: 0 references -> nullopt; > 1 -> quick (fast_lookup) or
     /// exhaustive search; 1 -> with `rust_bio` what the reference does today (:544-603: rust-bio global, 1/-1/-5/-1, score
     /// reported as 0.0, empty path; PARITY UNPINNED), otherwise clique's own Gotoh with bandwidth = read.len() (the call the
-    /// reference has commented out at :586-597; pinned on its goldens).
+    /// reference has commented out at :586-597; pinned on its goldens).  `known_strand = false` (1 reference only, :549-558):
+    /// the read is oriented by orient_by_longest_segment first and reverse-complemented when the reverse strand shares more.
     std::optional<AlignmentWithRef> align_to_reference_choices(const std::string& read_name, const Bytes& read, std::optional<Bytes> qual,
-                                                               bool fast_lookup, const AffineScoring& scoring, bool rust_bio = false);
+                                                               bool fast_lookup, const AffineScoring& scoring, bool rust_bio = false,
+                                                               bool known_strand = true);
 
     // ---- paired-read merging (MergeStrategy::Align) ----
     /// merge_reads_by_alignment, merger.rs:348-396: align_two_strings(read1, revcomp(read2)) + alignment_rate_and_consensus

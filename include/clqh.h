@@ -44,6 +44,11 @@ int32_t clqh_merge_read_pairs_by_alignment(int32_t device, uint32_t n, const uin
                                            double mismatch_score, double special_score, double gap_open, double gap_extend,
                                            double final_gap_multiplier, uint8_t* out_bases, uint8_t* out_quals, uint64_t cap,
                                            uint64_t* out_off);
+/* find_greedy_non_overlapping_segments / orient_by_longest_segment, linked_alignment.rs:24-32, :97-130 (segments as
+ * (search_start, ref_start, length) triples) */
+size_t clqh_find_greedy_non_overlapping_segments(const uint8_t* search, size_t n, const uint8_t* reference, size_t m, size_t seed_size,
+                                                 uint32_t* out_xyz, size_t cap, size_t* start_position);
+int32_t clqh_orient_by_longest_segment(const uint8_t* search, size_t n, const uint8_t* reference, size_t m, size_t seed_size);
 /* merge_reads_by_concatenation + orient_sequence, merger.rs:40-126; layout items "1F" "2R" "2C" "S:ACGT"; (size_t)-1 = panic */
 size_t clqh_merge_reads_by_concatenation(const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const char* layout, uint8_t* out,
                                          size_t cap);

@@ -1098,3 +1098,89 @@ size_t orc_alignment_rate_and_consensus(const uint8_t* a1, const uint8_t* q1, si
     }
     return n;
 }
+
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Strand orientation: linked_alignment.rs:24-32, :97-130, :341-362
+ * --------------------------------------------------------------------------------------------------------- */
+static int orc_acgt(uint8_t b) { /* DEGENERATEBASES value sets hold only A/C/G/T in both cases, fasta_comparisons.rs:21-67 */
+    switch (b) { case 'A': case 'a': return 1; case 'C': case 'c': return 2; case 'G': case 'g': return 3; case 'T': case 't': return 4; default: return 0; }
+}
+
+/* extend_hit: both lookups must succeed both ways, i.e. plain bases equal up to case */
+static size_t orc_extend_hit(const uint8_t* search, size_t n, size_t sloc, const uint8_t* ref, size_t m, size_t rloc) {
+    size_t len = 0;
+    while (len + sloc < n && len + rloc < m) {
+        const int a = orc_acgt(search[sloc + len]), b = orc_acgt(ref[rloc + len]);
+        if (!a || a != b) return len;
+        len++;
+    }
+    return len;
+}
+
+typedef struct { const uint8_t* ref; size_t m; } orc_sa_ctx_t;
+static orc_sa_ctx_t g_sa_ctx; /* qsort has no context argument; the oracle is single-threaded here */
+static int orc_suffix_cmp(const void* pa, const void* pb) {
+    const uint32_t a = *(const uint32_t*)pa, b = *(const uint32_t*)pb;
+    const size_t la = g_sa_ctx.m - a, lb = g_sa_ctx.m - b, l = la < lb ? la : lb;
+    const int c = memcmp(g_sa_ctx.ref + a, g_sa_ctx.ref + b, l);
+    if (c) return c;
+    return la < lb ? -1 : (la > lb ? 1 : 0);
+}
+
+size_t orc_find_greedy_non_overlapping_segments(const uint8_t* search, size_t n, const uint8_t* reference, size_t m,
+                                                size_t seed_size, orc_segment_t* out, size_t cap, size_t* start_position) {
+    size_t nh = 0, position = 0, least_ref_pos = m, greatest_ref_pos = 0;
+    uint32_t* pos = (uint32_t*)malloc((m + 1) * sizeof(uint32_t));
+    while ((int64_t)position <= (int64_t)n - (int64_t)seed_size) {
+        /* SuffixTable::positions(seed): every occurrence, in suffix-array order */
+        size_t np = 0;
+        for (size_t r = 0; seed_size > 0 && r + seed_size <= m; r++)
+            if (memcmp(reference + r, search + position, seed_size) == 0) pos[np++] = (uint32_t)r;
+        g_sa_ctx.ref = reference; g_sa_ctx.m = m;
+        qsort(pos, np, sizeof(uint32_t), orc_suffix_cmp);
+        size_t longest_hit = 0;
+        for (size_t k = 0; k < np; k++) {
+            const size_t ref_position = pos[k];
+            if (ref_position >= greatest_ref_pos) {
+                const size_t ext = orc_extend_hit(search, n, position, reference, m, ref_position); /* `position` may have moved */
+                if (ext > longest_hit) {
+                    if (nh < cap) { out[nh].search_start = (uint32_t)position; out[nh].ref_start = (uint32_t)ref_position; out[nh].length = (uint32_t)ext; }
+                    nh++;
+                    position += ext;
+                    if (ref_position < least_ref_pos) least_ref_pos = ref_position;
+                    if (ref_position + ext > greatest_ref_pos) greatest_ref_pos = ref_position + ext;
+                    longest_hit = ext;
+                }
+            }
+        }
+        position += 1;
+    }
+    free(pos);
+    if (start_position) *start_position = least_ref_pos;
+    return nh < cap ? nh : cap;
+}
+
+/* bio::alphabets::dna::revcomp: complement over "AGCTYRWSKMDVHBN" <-> "TCGARYWSMKHBDVN" in both cases, other bytes unchanged */
+static uint8_t orc_bio_complement(uint8_t b) {
+    static const char from[] = "AGCTYRWSKMDVHBNagctyrwskmdvhbn";
+    static const char to[] = "TCGARYWSMKHBDVNtcgarywsmkhbdvn";
+    for (int i = 0; from[i]; i++) if ((uint8_t)from[i] == b) return (uint8_t)to[i];
+    return b;
+}
+
+int orc_orient_by_longest_segment(const uint8_t* search, size_t n, const uint8_t* reference, size_t m, size_t seed_size,
+                                  size_t* fwd_score, size_t* rev_score) {
+    const size_t cap = n + 1;
+    orc_segment_t* seg = (orc_segment_t*)malloc(cap * sizeof(orc_segment_t));
+    size_t nf = orc_find_greedy_non_overlapping_segments(search, n, reference, m, seed_size, seg, cap, NULL), f = 0, r = 0;
+    for (size_t i = 0; i < nf; i++) f += seg[i].length;
+    uint8_t* rc = (uint8_t*)malloc(n + 1);
+    for (size_t i = 0; i < n; i++) rc[i] = orc_bio_complement(search[n - 1 - i]);
+    size_t nr = orc_find_greedy_non_overlapping_segments(rc, n, reference, m, seed_size, seg, cap, NULL);
+    for (size_t i = 0; i < nr; i++) r += seg[i].length;
+    free(rc); free(seg);
+    if (fwd_score) *fwd_score = f;
+    if (rev_score) *rev_score = r;
+    return f > r;
+}

@@ -111,6 +111,11 @@ def lib():
         L.orc_alignment_rate_and_consensus.restype = C.c_size_t
         L.orc_alignment_rate_and_consensus.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t,
                                                        C.c_void_p, C.c_void_p]
+        L.orc_find_greedy_non_overlapping_segments.restype = C.c_size_t
+        L.orc_find_greedy_non_overlapping_segments.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                                               C.c_size_t, C.POINTER(C.c_size_t)]
+        L.orc_orient_by_longest_segment.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t),
+                                                    C.POINTER(C.c_size_t)]
         L.orc_extract_tagged_sequences.restype = C.c_size_t
         L.orc_extract_tagged_sequences.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.orc_reverse_complement.restype = None
@@ -313,3 +318,20 @@ def merge_reads_by_alignment(read1, qual1, read2, qual2, sc):
     if a["status"] != OK:
         return None
     return alignment_rate_and_consensus(a["ref_aligned"], qual1, a["read_aligned"], q2r)
+
+
+def find_greedy_non_overlapping_segments(search, reference, seed_size):
+    """linked_alignment.rs:97-130 -> ([(search_start, ref_start, length)], start_position)"""
+    search, reference = bytes(search), bytes(reference)
+    cap = len(search) + 2
+    seg = np.zeros((cap, 3), np.uint32)
+    sp = C.c_size_t()
+    n = lib().orc_find_greedy_non_overlapping_segments(search, len(search), reference, len(reference), seed_size, seg.ctypes.data, cap, C.byref(sp))
+    return [tuple(int(v) for v in seg[i]) for i in range(n)], sp.value
+
+
+def orient_by_longest_segment(search, reference, seed_size):
+    """linked_alignment.rs:24-32 -> (forward?, fwd_score, rev_score)"""
+    f, r = C.c_size_t(), C.c_size_t()
+    fwd = lib().orc_orient_by_longest_segment(bytes(search), len(search), bytes(reference), len(reference), seed_size, C.byref(f), C.byref(r))
+    return bool(fwd), f.value, r.value

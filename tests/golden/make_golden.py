@@ -287,6 +287,18 @@ for ln in lines(RU, 119, 140):
         phred["combine"].append({"a": m.group(1), "b": m.group(2), "agree": m.group(3) == "true", "out": m.group(4)})
 assert (len(phred["to_prob"]), len(phred["to_phred"]), len(phred["combine"])) == (4, 4, 2), phred
 
+# --- orient_by_longest_segment / find_greedy_non_overlapping_segments, linked_alignment.rs:520-540 (+ the print-only inputs of
+#     :591-625 as extra inputs for the C++-vs-oracle comparison) ---
+LA = "linked_alignment.rs"
+L = lits(LA, 521, 540)
+orient = {"kats": [
+    {"cite": LA + ":521-529", "ref": L[0], "read": L[1], "seed_size": 5, "n_segments": 1, "search_starts": [0]},
+    {"cite": LA + ":531-540", "ref": L[2], "read": L[3], "seed_size": 5, "n_segments": 2, "search_starts": [0, 18]}],
+    "inputs": []}
+for lo, hi in ((592, 603), (606, 616)):
+    L = lits(LA, lo, hi)
+    orient["inputs"].append({"cite": "%s:%d-%d" % (LA, lo, hi), "ref": L[0], "read": L[1], "seed_size": 20})
+
 # --- ConvexScoring::gap KATs, alignment/scoring_functions.rs:200-213 ---
 convex_gap = [{"gap_open": -10.0, "len": 1, "gap": -10.0}, {"gap_open": -10.0, "len": 10, "gap": -9.0}]
 
@@ -314,7 +326,7 @@ out = {
     "pairs": pairs, "mergers": mergers, "best_ref": best_ref, "fastas": fastas, "tie_table": tie_table,
     "match_mismatch_default_dna": mm_table, "simplify_cigar": simplify, "kmers": kmers, "convex_gap": convex_gap, "alignment_rate": alignment_rate,
     "amplicon_c2": amplicon_c2, "amplicon_c3": amplicon_c3, "survey_kats": survey_kats,
-    "tagged_sequences": tagged, "reverse_complement": revcomp_kats, "phred": phred,
+    "tagged_sequences": tagged, "reverse_complement": revcomp_kats, "phred": phred, "orient": orient,
 }
 with open(OUT, "w") as f:
     json.dump(out, f, indent=1)

@@ -18,7 +18,8 @@ CLQ_ALIGN = os.path.join(ROOT, "clique_b200", "clq_align")
 
 SYMBOLS = ["clqh_extract_tagged_sequences", "clqh_reverse_complement", "clqh_f64_to_string", "clqh_get_reference_alignment_rate",
            "clqh_simplify_cigar", "clqh_from_cigar", "clqh_sam_line", "clqh_merge_reads_by_concatenation",
-           "clqh_combine_phred_scores", "clqh_alignment_rate_and_consensus", "clqh_merge_read_pairs_by_alignment"]
+           "clqh_combine_phred_scores", "clqh_alignment_rate_and_consensus", "clqh_merge_read_pairs_by_alignment",
+           "clqh_find_greedy_non_overlapping_segments", "clqh_orient_by_longest_segment"]
 
 
 @pytest.fixture(scope="module")
@@ -49,6 +50,11 @@ def H():
     L.clqh_merge_read_pairs_by_alignment.restype = C.c_int32
     L.clqh_merge_read_pairs_by_alignment.argtypes = [C.c_int32, C.c_uint32] + [C.c_void_p] * 6 + [C.c_double] * 6 + [C.c_void_p, C.c_void_p,
                                                                                                                   C.c_uint64, C.c_void_p]
+    L.clqh_find_greedy_non_overlapping_segments.restype = C.c_size_t
+    L.clqh_find_greedy_non_overlapping_segments.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
+                                                            C.POINTER(C.c_size_t)]
+    L.clqh_orient_by_longest_segment.restype = C.c_int32
+    L.clqh_orient_by_longest_segment.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_size_t]
     L.clqh_merge_reads_by_concatenation.restype = C.c_size_t
     L.clqh_merge_reads_by_concatenation.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_void_p, C.c_size_t]
     return L
@@ -222,6 +228,33 @@ def test_phred_and_consensus_cpp(H, goldens):
         assert got[0].decode() == m["expect_merged"], m["name"]
         assert got == O.alignment_rate_and_consensus(r["ref_aligned"], m["qual1"].encode(), r["read_aligned"], m["qual2_rev"].encode())
     assert h_consensus(H, b"A--", b"H", b"A--", b"H") is None
+
+
+def test_orientation_cpp(H, goldens):
+    # orient_by_longest_segment / find_greedy_non_overlapping_segments (linked_alignment.rs:24-32, :97-130): the reference's
+    # two asserted cases, its print-only inputs, and random reads against the oracle (suffix-array order of the seed hits)
+    def segs(read, ref, k):
+        out = np.zeros((len(read) + 2, 3), np.uint32)
+        sp = C.c_size_t()
+        n = H.clqh_find_greedy_non_overlapping_segments(read, len(read), ref, len(ref), k, out.ctypes.data, len(out), C.byref(sp))
+        return [tuple(int(v) for v in out[i]) for i in range(n)], sp.value
+
+    for t in goldens["orient"]["kats"]:
+        s, _ = segs(t["read"].encode(), t["ref"].encode(), t["seed_size"])
+        assert len(s) == t["n_segments"] and [x[0] for x in s] == t["search_starts"]
+    cases = [(t["read"].encode(), t["ref"].encode(), t["seed_size"]) for t in goldens["orient"]["kats"] + goldens["orient"]["inputs"]]
+    rng = np.random.default_rng(17)
+    for _ in range(200):
+        ref = bytes(rng.choice(list(b"ACGTacgtN"), size=int(rng.integers(0, 200)), p=[.2, .2, .2, .2, .04, .04, .04, .04, .04]).astype(np.uint8))
+        ref = ref + ref[:int(rng.integers(0, 40))]          # repeats: several seed hits per k-mer
+        read = bytearray(ref[int(rng.integers(0, 30)):]) if rng.random() < 0.8 else bytearray(rng.choice(list(b"ACGT"), size=60).astype(np.uint8))
+        for k in (rng.integers(0, len(read), size=3) if len(read) else []):
+            read[int(k)] = int(rng.choice(list(b"ACGTN")))
+        read = bytes(read) if rng.random() < 0.5 else O.reverse_complement(bytes(read))
+        cases.append((read, ref, int(rng.choice([3, 5, 8, 20]))))
+    for read, ref, k in cases:
+        assert segs(read, ref, k) == O.find_greedy_non_overlapping_segments(read, ref, k), (read, ref, k)
+        assert bool(H.clqh_orient_by_longest_segment(read, len(read), ref, len(ref), k)) == O.orient_by_longest_segment(read, ref, k)[0]
 
 
 # ------------------------------------------------------------------------------------------------ GPU: the batch loop in C++
@@ -416,3 +449,29 @@ def test_no_cpu_fallback_in_cpp_layer(tmp_path):
     r = subprocess.run([CLQ_ALIGN, "--refs", fa, "--reads", rp, "--out", os.path.join(str(tmp_path), "o.sam")], capture_output=True, text=True)
     assert r.returncode == 1
     assert "no CPU fallback" in r.stderr or "CUDA" in r.stderr, r.stderr
+
+
+@pytest.mark.gpu
+def test_clq_align_unknown_strand(H, tmp_path):
+    """known_strand = false with one reference (alignment_functions.rs:549-558): reads arriving as their reverse complement are
+    oriented by orient_by_longest_segment and reverse-complemented before the alignment."""
+    from clique_b200 import synth
+    c = synth.config_c2(300)
+    off = c["read_off"]
+    reads = [bytes(c["read_bytes"][int(off[i]):int(off[i + 1])]) for i in range(300)]
+    flipped = [O.reverse_complement(r) if i % 2 else r for i, r in enumerate(reads)]
+    refs, names = c["refs"], c["ref_names"]
+    # what the reference would align: the read as it is when the forward strand shares strictly more bases, else its reverse
+    # complement.  (The greedy seed chain is kept as the reference has it: an accidental 8-mer hit far down the reference blocks
+    # every earlier hit, so a few reads are oriented the wrong way -- by the reference too.)
+    decided = [O.orient_by_longest_segment(r, refs[0], 8)[0] for r in flipped]
+    expect_in = [r if fw else O.reverse_complement(r) for r, fw in zip(flipped, decided)]
+    assert sum(1 for i, fw in enumerate(decided) if fw == (i % 2 == 0)) >= 285
+    d1, d2 = tmp_path / "a", tmp_path / "b"
+    d1.mkdir(); d2.mkdir()
+    fa, rp = _write_inputs(str(d1), refs, names, expect_in)
+    _, fwd, _ = _run_clq_align(str(d1), fa, rp)
+    fa2, rp2 = _write_inputs(str(d2), refs, names, flipped)
+    _, ori, _ = _run_clq_align(str(d2), fa2, rp2, ["--unknown-strand"])
+    assert len(ori) == len(fwd) == 300
+    assert ori == fwd

@@ -227,3 +227,20 @@ def test_merge_reads_by_alignment_goldens(goldens):
     b, q = O.alignment_rate_and_consensus(b"AC-T", b"HHH", b"ACG-", b"+++")
     assert b == b"ACGT" and q == bytes([O.lib().orc_combine_phred_scores(72, 43, 1)] * 2) + b"+H"
     assert O.alignment_rate_and_consensus(b"A--", b"H", b"A--", b"H") is None  # gap/gap consumes qualities: the reference panics
+
+
+def test_orientation_goldens(goldens):
+    # linked_alignment.rs:520-540
+    for t in goldens["orient"]["kats"]:
+        segs, start = O.find_greedy_non_overlapping_segments(t["read"].encode(), t["ref"].encode(), t["seed_size"])
+        assert len(segs) == t["n_segments"] and [s[0] for s in segs] == t["search_starts"], t
+        assert O.orient_by_longest_segment(t["read"].encode(), t["ref"].encode(), t["seed_size"])[0] is True
+    for t in goldens["orient"]["inputs"]:  # print-only tests of the reference: sanity properties
+        ref, read = t["ref"].encode(), t["read"].encode()
+        segs, start = O.find_greedy_non_overlapping_segments(read, ref, t["seed_size"])
+        assert segs and start == min(s[1] for s in segs)
+        for ss, rs, ln in segs:
+            assert read[ss:ss + ln].upper() == ref[rs:rs + ln].upper() and ln >= t["seed_size"]
+        fwd, f, r = O.orient_by_longest_segment(read, ref, t["seed_size"])
+        assert fwd and f == sum(s[2] for s in segs) and r < f
+        assert O.orient_by_longest_segment(O.reverse_complement(read), ref, t["seed_size"])[0] is False
