@@ -10,6 +10,8 @@
 #include <limits>
 #include <thread>
 
+#include <zlib.h>
+
 namespace clique {
 
 namespace {
@@ -621,6 +623,150 @@ bool BatchView::append_sam_line(uint32_t i, const std::string& umi_symbols, cons
     append_f64(out, alignment_rate(i));
     out += "\trs:Z:"; append_f64(out, sc);
     out += '\n';
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ BAM
+namespace bam {
+namespace {
+template <class T>
+inline void put(std::string& s, T v) { s.append(reinterpret_cast<const char*>(&v), sizeof(T)); }  // little-endian host
+
+inline int reg2bin(int64_t beg, int64_t end) {  // SAM specification, section 5.3
+    --end;
+    if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
+    if (beg >> 17 == end >> 17) return (int)(((1 << 12) - 1) / 7 + (beg >> 17));
+    if (beg >> 20 == end >> 20) return (int)(((1 << 9) - 1) / 7 + (beg >> 20));
+    if (beg >> 23 == end >> 23) return (int)(((1 << 6) - 1) / 7 + (beg >> 23));
+    if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
+    return 0;
+}
+
+inline uint8_t base_code(uint8_t b) {
+    static const char codes[] = "=ACMGRSVTWYHKDBN";
+    if (b >= 'a' && b <= 'z') b -= 32;
+    for (int i = 0; i < 16; i++) if ((uint8_t)codes[i] == b) return (uint8_t)i;
+    return 15;
+}
+
+// shared by the object path (append_record) and the raw path (BatchView::append_bam_record)
+void record_core(std::string& out, int32_t ref_id, int32_t pos0, const char* name, size_t name_len, const uint32_t* cigar, size_t n_cigar,
+                 const uint8_t* seq, size_t l_seq, uint8_t qual_byte, const std::string& aux) {
+    const size_t start = out.size();
+    put<int32_t>(out, 0);  // block_size, patched below
+    int64_t ref_len = 0;
+    for (size_t k = 0; k < n_cigar; k++) { const uint32_t op = cigar[k] & 15u; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_len += cigar[k] >> 4; }
+    put<int32_t>(out, ref_id);
+    put<int32_t>(out, pos0);
+    const size_t nl = name_len ? name_len : 1;
+    put<uint8_t>(out, (uint8_t)(nl + 1));
+    put<uint8_t>(out, 255);  // mapping quality: missing
+    put<uint16_t>(out, (uint16_t)reg2bin(pos0, pos0 + (ref_len > 0 ? ref_len : 1)));
+    put<uint16_t>(out, (uint16_t)n_cigar);
+    put<uint16_t>(out, 0);  // Flags::empty()
+    put<uint32_t>(out, (uint32_t)l_seq);
+    put<int32_t>(out, -1);  // mate reference
+    put<int32_t>(out, -1);  // mate position
+    put<int32_t>(out, 0);   // template length
+    if (name_len) out.append(name, name_len); else out += '*';
+    out += '\0';
+    out.append(reinterpret_cast<const char*>(cigar), n_cigar * sizeof(uint32_t));  // len << 4 | op: the encoding the C ABI already uses
+    for (size_t i = 0; i < l_seq; i += 2) {
+        const uint8_t hi = base_code(seq[i]), lo = i + 1 < l_seq ? base_code(seq[i + 1]) : 0;
+        out += (char)((hi << 4) | lo);
+    }
+    out.append(l_seq, (char)qual_byte);
+    out += aux;
+    const int32_t block = (int32_t)(out.size() - start - 4);
+    std::memcpy(&out[start], &block, 4);
+}
+
+inline void aux_z(std::string& aux, char a, char b, const std::string& v) { aux += a; aux += b; aux += 'Z'; aux += v; aux += '\0'; }
+}  // namespace
+
+std::string header_text(const std::vector<std::string>& names, const std::vector<size_t>& lengths) {
+    std::string t = "@HD\tVN:1.6\n";
+    for (size_t i = 0; i < names.size(); i++) t += "@SQ\tSN:" + names[i] + "\tLN:" + std::to_string(lengths[i]) + "\n";
+    t += "@CO\tClique processed\n";
+    return t;
+}
+
+void append_header(const std::vector<std::string>& names, const std::vector<size_t>& lengths, std::string& out) {
+    const std::string text = header_text(names, lengths);
+    out += "BAM\1";
+    put<int32_t>(out, (int32_t)text.size());
+    out += text;
+    put<int32_t>(out, (int32_t)names.size());
+    for (size_t i = 0; i < names.size(); i++) {
+        put<int32_t>(out, (int32_t)names[i].size() + 1);
+        out += names[i];
+        out += '\0';
+        put<int32_t>(out, (int32_t)lengths[i]);
+    }
+}
+
+void append_record(const SamRecord& rec, std::string& out) {
+    std::vector<uint32_t> cig;
+    for (const auto& t : rec.cigar) cig.push_back((uint32_t)(t.len << 4) | (uint32_t)t.kind);
+    std::string aux;
+    for (const auto& kv : rec.data) aux_z(aux, kv.first[0], kv.first[1], kv.second);
+    record_core(out, rec.reference_sequence_id, (int32_t)rec.alignment_start - 1, rec.name.data(), rec.name.size(), cig.data(), cig.size(),
+                rec.sequence.data(), rec.sequence.size(), rec.quality_scores.empty() ? 0xff : rec.quality_scores[0], aux);
+}
+
+void bgzf_compress(const char* data, size_t n, std::string& out, int level) {
+    constexpr size_t kBlock = 65280;  // htslib's input block size: the compressed member always fits 64 KiB
+    std::vector<uint8_t> buf(compressBound(kBlock) + 64);
+    for (size_t off = 0; off < n || (n == 0 && off == 0); off += kBlock) {
+        const size_t len = std::min(kBlock, n - off);
+        z_stream zs{};
+        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw std::runtime_error("deflateInit2 failed");
+        zs.next_in = reinterpret_cast<Bytef*>(const_cast<char*>(data + off));
+        zs.avail_in = (uInt)len;
+        zs.next_out = buf.data();
+        zs.avail_out = (uInt)buf.size();
+        const int rc = deflate(&zs, Z_FINISH);
+        const size_t clen = zs.total_out;
+        deflateEnd(&zs);
+        if (rc != Z_STREAM_END) throw std::runtime_error("deflate failed");
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), reinterpret_cast<const Bytef*>(data + off), (uInt)len);
+        const uint16_t bsize = (uint16_t)(clen + 25);  // total block size - 1
+        static const uint8_t head[12] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0};
+        out.append(reinterpret_cast<const char*>(head), 12);
+        out += 'B'; out += 'C';
+        put<uint16_t>(out, 2);
+        put<uint16_t>(out, bsize);
+        out.append(reinterpret_cast<const char*>(buf.data()), clen);
+        put<uint32_t>(out, crc);
+        put<uint32_t>(out, (uint32_t)len);
+        if (n == 0) break;
+    }
+}
+
+void bgzf_eof(std::string& out) {
+    static const uint8_t eof[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    out.append(reinterpret_cast<const char*>(eof), 28);
+}
+}  // namespace bam
+
+bool BatchView::append_bam_record(uint32_t i, const std::string& umi_symbols, std::string& out) const {
+    if (status(i) != CLQ_OK) return false;
+    const uint32_t ri = ref_index(i);
+    const double sc = rust_bio ? 0.0 : score(i);
+    std::string aux, num;
+    bam::aux_z(aux, 'a', 'r', batch->name(i));
+    num.clear(); append_f64(num, sc);
+    bam::aux_z(aux, 'a', 's', num);
+    if (tags && !umi_symbols.empty()) {
+        for (const auto& kv : digit_tags(i))
+            if (umi_symbols.find((char)kv.first) != std::string::npos) bam::aux_z(aux, 'e', (char)kv.first, kv.second);
+    }
+    bam::aux_z(aux, 'r', 'c', "1");
+    std::string rate; append_f64(rate, alignment_rate(i));
+    bam::aux_z(aux, 'r', 'm', rate);
+    bam::aux_z(aux, 'r', 's', num);
+    bam::record_core(out, (int32_t)ri, 0, batch->name_data(i), batch->name_len(i), cigar(i), cigar_len(i), batch->read(i), batch->read_len(i),
+                     (uint8_t)'H', aux);
     return true;
 }
 

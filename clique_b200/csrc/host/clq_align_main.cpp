@@ -22,6 +22,7 @@ struct Args {
     std::string refs, reads, reads2, out = "-", stats_json, umi_symbols = "0123456789", layout;
     std::vector<int> gpus = {0};
     uint32_t batch = 1u << 18, max_read_len = 1u << 16, cigar_ops_per_read = 32, max_reference_multiplier = 2, threads = 1;
+    int bam_level = 6;
     uint64_t synthetic = 0;  // --synthetic N: N in-memory noisy copies of the references instead of a read file
     bool exhaustive = false, tags = true, quiet_sam = false, rust_bio = false, slow_sam = false, unknown_strand = false;
     AffineScoring scoring = AffineScoring::align_reads_default();
@@ -30,7 +31,7 @@ struct Args {
 [[noreturn]] void usage(const char* msg) {
     if (msg) std::fprintf(stderr, "clq_align: %s\n", msg);
     std::fprintf(stderr,
-                 "usage: clq_align --refs refs.fa --reads reads.fastq|reads.txt [--reads2 r2.fastq --layout 1F,2C] [--out out.sam|-]\n"
+                 "usage: clq_align --refs refs.fa --reads reads.fastq|reads.txt [--reads2 r2.fastq --layout 1F,2C] [--out out.sam|out.bam|-] [--bam-level 0..9]\n"
                  "                 [--gpus 0,1,..] [--batch N] [--exhaustive] [--scoring match,mismatch,special,open,extend,final_mult]\n"
                  "                 [--umi-symbols 012] [--no-tags] [--no-sam] [--slow-sam] [--rust-bio] [--unknown-strand] [--max-read-len N] [--max-reference-multiplier N]\n"
                  "                 [--cigar-ops-per-read N] [--stats-json path] [--threads T (SAM text built by T host threads)]\n"
@@ -56,6 +57,7 @@ Args parse(int argc, char** argv) {
         else if (k == "--max-reference-multiplier") a.max_reference_multiplier = (uint32_t)std::stoul(val());
         else if (k == "--threads") a.threads = std::max<uint32_t>(1, (uint32_t)std::stoul(val()));
         else if (k == "--synthetic") a.synthetic = std::stoull(val());
+        else if (k == "--bam-level") a.bam_level = std::stoi(val());
         else if (k == "--exhaustive") a.exhaustive = true;
         else if (k == "--no-tags") a.tags = false;
         else if (k == "--rust-bio") a.rust_bio = true;
@@ -227,7 +229,16 @@ int main(int argc, char** argv) {
         std::ostream* out = &std::cout;
         if (a.out != "-") { fout.open(a.out); if (!fout) throw std::runtime_error("Unable to open " + a.out); out = &fout; }
         const std::vector<std::string> names = rm.names();
-        if (!a.quiet_sam) {
+        // --out x.bam: the BAM container (BamFileAlignmentWriter, alignment_manager.rs:64-209): same records, binary, BGZF
+        const bool as_bam = a.out.size() > 4 && a.out.compare(a.out.size() - 4, 4, ".bam") == 0 && !a.quiet_sam;
+        if (as_bam) {
+            std::vector<size_t> lens;
+            for (const auto& r : rm.references) lens.push_back(r.sequence.size());
+            std::string raw, z;
+            bam::append_header(names, lens, raw);
+            bam::bgzf_compress(raw.data(), raw.size(), z);
+            out->write(z.data(), (std::streamsize)z.size());
+        } else if (!a.quiet_sam) {
             *out << "@HD\tVN:1.6\n";
             for (const auto& r : rm.references) *out << "@SQ\tSN:" << to_string(r.name) << "\tLN:" << r.sequence.size() << "\n";
             *out << "@CO\tClique processed\n";
@@ -247,6 +258,17 @@ int main(int argc, char** argv) {
                 const uint32_t lo = (uint32_t)((uint64_t)v.size() * t / nt), hi = (uint32_t)((uint64_t)v.size() * (t + 1) / nt);
                 std::string& s = part[t];
                 s.clear();
+                if (as_bam) {  // records -> uncompressed BAM blocks -> BGZF members, all on this thread
+                    std::string raw;
+                    raw.reserve((size_t)(hi - lo) * 500);
+                    for (uint32_t i = lo; i < hi; i++) {
+                        if (!a.slow_sam) { v.append_bam_record(i, syms, raw); continue; }
+                        const auto al = v.alignment(i);
+                        if (al) bam::append_record(al->alignment->to_sam_record((int32_t)v.ref_index(i), v.align_reads_tags(i, syms), std::nullopt), raw);
+                    }
+                    if (!raw.empty()) bam::bgzf_compress(raw.data(), raw.size(), s, a.bam_level);
+                    return;
+                }
                 for (uint32_t i = lo; i < hi; i++) {
                     if (!a.slow_sam) { v.append_sam_line(i, syms, names, s); continue; }
                     const auto al = v.alignment(i);  // --slow-sam: through the owned AlignmentResult / to_sam_record objects
@@ -275,6 +297,7 @@ int main(int argc, char** argv) {
             sink_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         };
         const AlignReadsStats st = sh.align_reads(a.synthetic ? synth_source : source, a.scoring, !a.exhaustive, sink, a.tags, a.rust_bio);
+        if (as_bam) { std::string z; bam::bgzf_eof(z); out->write(z.data(), (std::streamsize)z.size()); }
         out->flush();
         char js[640];
         std::snprintf(js, sizeof(js),

@@ -172,6 +172,36 @@ int32_t clqh_orient_by_longest_segment(const uint8_t* search, size_t n, const ui
     return orient_by_longest_segment(Bytes(search, search + n), ref, SuffixTableLookup::find_seeds(ref, seed_size)).forward ? 1 : 0;
 }
 
+size_t clqh_bam_file(const char* ref_name, const char* read_name, const uint8_t* ref, size_t l1, const uint8_t* read, size_t l2,
+                     const uint32_t* ops, size_t n_ops, double score, const char* extra_tags, uint8_t* out, size_t cap) {
+    // a complete BAM file (BGZF: header block, one record, EOF marker) for one alignment, through the object path
+    try {
+        const AlignmentResult r = AlignmentResult::from_cigar(ref_name, read_name, ref, l1, read, l2, std::nullopt, ops, n_ops, score);
+        TagMap extra;
+        std::string s = extra_tags ? extra_tags : "";
+        size_t pos = 0;
+        while (pos < s.size()) {
+            const size_t e = s.find(';', pos);
+            const std::string item = s.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
+            if (item.size() >= 3 && item[2] == '=') extra[{item[0], item[1]}] = item.substr(3);
+            if (e == std::string::npos) break;
+            pos = e + 1;
+        }
+        std::string raw, z;
+        bam::append_header({ref_name}, {l1}, raw);
+        bam::bgzf_compress(raw.data(), raw.size(), z);
+        raw.clear();
+        bam::append_record(r.to_sam_record(0, extra, std::nullopt), raw);
+        bam::bgzf_compress(raw.data(), raw.size(), z);
+        bam::bgzf_eof(z);
+        if (z.size() > cap) return 0;
+        std::memcpy(out, z.data(), z.size());
+        return z.size();
+    } catch (const std::exception&) {
+        return 0;
+    }
+}
+
 size_t clqh_merge_reads_by_concatenation(const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const char* layout, uint8_t* out,
                                          size_t cap) {
     // layout: comma-separated items "1F" / "2R" / "2C" (read number + Forward / Reverse / reverse-Complement) or "S:ACGT" (spacer)

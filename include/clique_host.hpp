@@ -125,6 +125,22 @@ struct AlignmentResult {
     SamRecord to_sam_record(int32_t reference_id, const TagMap& extra_tags, const std::optional<std::vector<std::string>>& read_names) const;
 };
 
+/// BAM wire format of the records (what BamFileAlignmentWriter hands to noodles, alignment_manager.rs:64-209): the header text
+/// ("@HD VN:1.6", one @SQ per reference in index order, "@CO Clique processed"), the binary header and records of the SAM/BAM
+/// specification, BGZF framing.  Encoding is split from compression so that several host threads can prepare blocks.
+namespace bam {
+/// "@HD..@SQ..@CO" text of BamFileAlignmentWriter::new (:76-96)
+std::string header_text(const std::vector<std::string>& reference_names, const std::vector<size_t>& reference_lengths);
+/// uncompressed BAM header: magic, text, reference dictionary
+void append_header(const std::vector<std::string>& reference_names, const std::vector<size_t>& reference_lengths, std::string& out);
+/// one uncompressed alignment record (block_size + fields): flags 0, MAPQ 255, mate fields unset, qualities raw, tags as Z
+void append_record(const SamRecord& rec, std::string& out);
+/// BGZF: `data` cut into blocks of at most 65280 bytes, each a gzip member with the BC extra field; appended to `out`
+void bgzf_compress(const char* data, size_t n, std::string& out, int level = 6);
+/// the 28-byte end-of-file marker block
+void bgzf_eof(std::string& out);
+}  // namespace bam
+
 /// f64 `Display` of Rust (what `score.to_string()` writes into the rm / rs / as tags): shortest round-trip digits, never
 /// scientific notation, integral values without ".0", "NaN", "inf"
 std::string f64_to_string(double v);
@@ -295,6 +311,8 @@ public:
     /// text (plus '\n') appended to `out` straight from the raw records, without building the intermediate objects.
     /// Returns false (nothing appended) for dropped reads.
     bool append_sam_line(uint32_t i, const std::string& umi_symbols, const std::vector<std::string>& reference_names, std::string& out) const;
+    /// the same record as one uncompressed BAM alignment block (== bam::append_record(to_sam_record(..)) of the object path)
+    bool append_bam_record(uint32_t i, const std::string& umi_symbols, std::string& out) const;
 };
 
 struct AlignerOptions {

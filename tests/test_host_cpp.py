@@ -19,7 +19,7 @@ CLQ_ALIGN = os.path.join(ROOT, "clique_b200", "clq_align")
 SYMBOLS = ["clqh_extract_tagged_sequences", "clqh_reverse_complement", "clqh_f64_to_string", "clqh_get_reference_alignment_rate",
            "clqh_simplify_cigar", "clqh_from_cigar", "clqh_sam_line", "clqh_merge_reads_by_concatenation",
            "clqh_combine_phred_scores", "clqh_alignment_rate_and_consensus", "clqh_merge_read_pairs_by_alignment",
-           "clqh_find_greedy_non_overlapping_segments", "clqh_orient_by_longest_segment"]
+           "clqh_find_greedy_non_overlapping_segments", "clqh_orient_by_longest_segment", "clqh_bam_file"]
 
 
 @pytest.fixture(scope="module")
@@ -55,6 +55,9 @@ def H():
                                                             C.POINTER(C.c_size_t)]
     L.clqh_orient_by_longest_segment.restype = C.c_int32
     L.clqh_orient_by_longest_segment.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_size_t]
+    L.clqh_bam_file.restype = C.c_size_t
+    L.clqh_bam_file.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_double,
+                                C.c_char_p, C.c_void_p, C.c_size_t]
     L.clqh_merge_reads_by_concatenation.restype = C.c_size_t
     L.clqh_merge_reads_by_concatenation.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_void_p, C.c_size_t]
     return L
@@ -255,6 +258,70 @@ def test_orientation_cpp(H, goldens):
     for read, ref, k in cases:
         assert segs(read, ref, k) == O.find_greedy_non_overlapping_segments(read, ref, k), (read, ref, k)
         assert bool(H.clqh_orient_by_longest_segment(read, len(read), ref, len(ref), k)) == O.orient_by_longest_segment(read, ref, k)[0]
+
+
+def parse_bam(blob):
+    """Minimal BAM reader for the tests: BGZF framing checks + header + records -> (header_text, refs, SAM-like field lists)."""
+    import gzip
+    import struct
+    # every BGZF member carries the BC extra field with its own size; the file ends with the 28-byte EOF marker
+    off, n_blocks = 0, 0
+    while off < len(blob):
+        assert blob[off:off + 4] == b"\x1f\x8b\x08\x04" and blob[off + 12:off + 14] == b"BC"
+        bsize = struct.unpack_from("<H", blob, off + 16)[0] + 1
+        off += bsize; n_blocks += 1
+    assert off == len(blob) and blob[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    raw = gzip.decompress(blob)
+    assert raw[:4] == b"BAM\x01"
+    l_text = struct.unpack_from("<i", raw, 4)[0]
+    text = raw[8:8 + l_text].decode()
+    p = 8 + l_text
+    n_ref = struct.unpack_from("<i", raw, p)[0]; p += 4
+    refs = []
+    for _ in range(n_ref):
+        ln = struct.unpack_from("<i", raw, p)[0]; p += 4
+        nm = raw[p:p + ln - 1].decode(); p += ln
+        refs.append((nm, struct.unpack_from("<i", raw, p)[0])); p += 4
+    recs = []
+    while p < len(raw):
+        bs = struct.unpack_from("<i", raw, p)[0]; p += 4
+        e = p + bs
+        ref_id, pos, l_name, mapq, bin_, n_cig, flag, l_seq, nref, npos, tlen = struct.unpack_from("<iiBBHHHIiii", raw, p); p += 32
+        name = raw[p:p + l_name - 1].decode(); p += l_name
+        cig = struct.unpack_from("<%dI" % n_cig, raw, p); p += 4 * n_cig
+        seq = "".join("=ACMGRSVTWYHKDBN"[(raw[p + i // 2] >> (4 if i % 2 == 0 else 0)) & 15] for i in range(l_seq)); p += (l_seq + 1) // 2
+        qual = raw[p:p + l_seq]; p += l_seq
+        tags = []
+        while p < e:
+            t = raw[p:p + 2].decode(); assert raw[p + 2:p + 3] == b"Z"; p += 3
+            z = raw.index(b"\0", p)
+            tags.append(t + ":Z:" + raw[p:z].decode()); p = z + 1
+        assert p == e and (nref, npos, tlen) == (-1, -1, 0)
+        cigar = "".join("%d%s" % (c >> 4, "MIDNSHP=X"[c & 15]) for c in cig) or "*"
+        fields = [name, str(flag), refs[ref_id][0], str(pos + 1), str(mapq), cigar, "*", "0", "0", seq or "*",
+                  "".join(chr(q + 33) for q in qual) or "*"] + tags
+        recs.append((fields, bin_))
+    return text, refs, recs, n_blocks
+
+
+def test_bam_wire_format(H, goldens):
+    # BamFileAlignmentWriter (alignment_manager.rs:64-209) + to_sam_record (alignment/alignment_matrix.rs:741-771): header text,
+    # reference dictionary, binary record, BGZF framing -- the record equals the SAM text line field by field
+    p = goldens["pairs"][3]  # affine_alignment_test_favor_non_special_characters: 66M28D26M6D
+    ref, read = p["ref"].encode(), p["read"].encode()
+    a = O.align_pair(ref, read, p["scoring"], "maxlen")
+    ops = np.ascontiguousarray(a["cigar"], dtype=np.uint32)
+    buf = C.create_string_buffer(1 << 16)
+    n = H.clqh_bam_file(b"amp", b"read7", ref, len(ref), read, len(read), ops.ctypes.data, len(ops), a["score"], b"e1=ACGT;rc=1;ar=read7", buf, 1 << 16)
+    assert n > 0
+    text, refs, recs, n_blocks = parse_bam(buf.raw[:n])
+    assert text == "@HD\tVN:1.6\n@SQ\tSN:amp\tLN:%d\n@CO\tClique processed\n" % len(ref)
+    assert refs == [("amp", len(ref))] and n_blocks == 3 and len(recs) == 1
+    line = C.create_string_buffer(8192)
+    m = H.clqh_sam_line(b"amp", b"read7", ref, len(ref), read, len(read), ops.ctypes.data, len(ops), a["score"], 0, b"e1=ACGT;rc=1;ar=read7", line, 8192)
+    assert recs[0][0] == line.raw[:m].decode().split("\t")
+    assert recs[0][1] == 4681  # reg2bin(0, 126): the 16 kb bin of the first window
+    assert recs[0][0][5] == "66M28D26M6D" and recs[0][0][10] == "i" * len(read)
 
 
 # ------------------------------------------------------------------------------------------------ GPU: the batch loop in C++
@@ -475,3 +542,30 @@ def test_clq_align_unknown_strand(H, tmp_path):
     _, ori, _ = _run_clq_align(str(d2), fa2, rp2, ["--unknown-strand"])
     assert len(ori) == len(fwd) == 300
     assert ori == fwd
+
+
+@pytest.mark.gpu
+def test_clq_align_bam_output(H, tmp_path):
+    """--out x.bam: the same records as the SAM text, in BAM (fast raw-record encoder and the object path), BGZF blocks
+    compressed on several threads."""
+    from clique_b200 import synth
+    c = synth.config_c4(700, search="quick")
+    off = c["read_off"]
+    reads = [bytes(c["read_bytes"][int(off[i]):int(off[i + 1])]) for i in range(700)]
+    refs = [r[:100] + b"0123" + r[104:] for r in c["refs"][:8]]
+    names = c["ref_names"][:8]
+    fa, rp = _write_inputs(str(tmp_path), refs, names, reads)
+    head, sam, _ = _run_clq_align(str(tmp_path), fa, rp)
+
+    def run_bam(extra):
+        out = os.path.join(str(tmp_path), "o.bam")
+        r = subprocess.run([CLQ_ALIGN, "--refs", fa, "--reads", rp, "--out", out, "--batch", "257", "--cigar-ops-per-read", "256"] + extra,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        return parse_bam(open(out, "rb").read())
+
+    for extra in ([], ["--threads", "4"], ["--slow-sam"]):
+        text, brefs, recs, n_blocks = run_bam(extra)
+        assert text.rstrip("\n").split("\n") == head
+        assert brefs == [(n.decode(), len(r)) for n, r in zip(names, refs)]
+        assert [r[0] for r in recs] == sam, extra
