@@ -30,6 +30,7 @@ struct DevBuf {
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
+    cudaEvent_t done = nullptr;      // recorded after the last kernel of a launch (see clq_ctx::last_done)
     DevBuf read_bytes, read_off, fixed_ref, order, results, scores, cand_mask, single_ref, ref_of_read, votes;
     DevBuf cigar_pool, bits, cig_scratch, col_scratch, tb_rec, bits_off, tags, ref_groups;
     std::vector<uint32_t> h_len;     // read lengths in processing order (only when lengths vary: have_order)
@@ -73,6 +74,11 @@ struct clq_ctx {
     uint8_t cls_rb[256] = {};        // rust-bio classes: 0 = 'N', 1 other, 2..7 reference bytes; row << 3; bit 7 = unscorable in a read
     DevBuf cls_lut_rb;
     int64_t max_scratch_bytes = 40ll << 30;  // per slot: direction bits of one sub-batch
+    // Kernels of different slots are chained in submission order: every fill kernel is a persistent grid that fills the GPU, so
+    // two launches sharing the SMs only finish together and leave the host nothing to overlap with.  With the chain slot B's
+    // H2D copy runs under slot A's kernels, A finishes first, and its results are handled while B computes.
+    cudaEvent_t last_done = nullptr;
+    int serialize = 1;               // option "serialize_slots"
 };
 
 namespace {
@@ -389,6 +395,7 @@ int32_t clq_ctx_create(int32_t device, const clq_limits_t* limits, clq_ctx** out
     for (auto& s : c->slots) {
         if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { clq_ctx_destroy(c); return CLQ_E_CUDA; }
         for (auto& e : s.ev) cudaEventCreate(&e);
+        cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
         if (cudaHostAlloc((void**)&s.h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) { clq_ctx_destroy(c); return CLQ_E_CUDA; }
         if (ensure(c, s.counters, 8 * sizeof(unsigned long long)) != CLQ_OK) { clq_ctx_destroy(c); return CLQ_E_NOMEM; }
     }
@@ -402,6 +409,7 @@ void clq_ctx_destroy(clq_ctx* c) {
     for (auto& s : c->slots) {
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
+        if (s.done) cudaEventDestroy(s.done);
         for (DevBuf* b : {&s.read_bytes, &s.read_off, &s.fixed_ref, &s.order, &s.results, &s.scores, &s.cand_mask, &s.single_ref,
                           &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.tb_rec, &s.bits_off, &s.tags, &s.ref_groups, &s.counters})
             release(*b);
@@ -420,6 +428,7 @@ int32_t clq_set_option(clq_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "debug_flags")) { c->debug_flags = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_pack")) { c->no_pack = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_group")) { c->no_group = (int)value; return CLQ_OK; }
+    if (!strcmp(key, "serialize_slots")) { c->serialize = (int)value; return CLQ_OK; }
     if (!strcmp(key, "max_scratch_bytes")) { c->max_scratch_bytes = value; return CLQ_OK; }
     return fail(c, CLQ_E_INVALID, std::string("unknown option ") + key);
 }
@@ -878,6 +887,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     s->stats.launches = 0;
     s->stats.dp_launches = 0;
     s->n_dp = 0;
+    if (c->serialize && c->last_done && c->last_done != s->done) CU(c, cudaStreamWaitEvent(s->stream, c->last_done, 0));
     CU(c, cudaMemsetAsync(s->counters.p, 0, 8 * sizeof(unsigned long long), s->stream));
     CU(c, cudaEventRecord(s->ev[0], s->stream));
 
@@ -984,6 +994,8 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         s->n_dp |= 2;
     }
     CU(c, cudaEventRecord(s->ev[5], s->stream));
+    CU(c, cudaEventRecord(s->done, s->stream));
+    c->last_done = s->done;
     s->launched = true;
     s->state = 2;
     return CLQ_OK;
