@@ -35,12 +35,15 @@ __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C
     for (int jb = 0; jb < C / 8; jb++) {
         if (jb < nb) {  // narrow last stripe: only nb blocks of 8 columns per lane are real
             uint32_t acc0 = 0, acc1 = 0;
+            // M of the next cell is issued inside the current one (it needs B[j] of the previous row, which the current cell
+            // overwrites): B[j]'s old value then dies within the cell and no register copy is needed to carry it as `diag`
+            uint32_t Mnext = __viaddmax_s16x2(diag, (uint32_t)prmt_s8(tlo, thi, sel[jb * 8]), X1);  // per-half add: biased values are > 0 > x1
 #pragma unroll
             for (int jj = 0; jj < 8; jj++) {
                 const int j = jb * 8 + jj;
-                const uint32_t m = (uint32_t)prmt_s8(tlo, thi, sel[j]);  // [mA, mB] as s16x2
-                const uint32_t Mv = __viaddmax_s16x2(diag, m, X1);       // per-half add: biased values are > 0 > x1 (X1 is a live register; a literal 0 costs a PRMT per cell)
+                const uint32_t Mv = Mnext;                               // [mA, mB] profile bytes added as s16x2 (X1: a live register; a literal 0 costs a PRMT)
                 const uint32_t EhU = Eh[j], BU = B[j];
+                if (jj < 7) Mnext = __viaddmax_s16x2(BU, (uint32_t)prmt_s8(tlo, thi, sel[j + 1]), X1);
                 const uint32_t Ehn = __viaddmax_s16x2(EhU, LE, BU);
                 uint32_t t2 = 0, u2 = 0;
                 if (TB && !RB) {
@@ -65,7 +68,7 @@ __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C
                         wB[jb] = __byte_perm(acc1, acc0, 0x7632);  // high halves: read B's
                     }
                 }
-                diag = BU;
+                if (jj == 7) diag = BU;  // carried to the next block of 8 columns
                 Eh[j] = Ehn;
                 B[j] = Bn;
                 Fh = Fhn; Ehl = Ehn; Ml = Mv; Bl = Bn;
