@@ -1,5 +1,5 @@
 """Randomised GPU-vs-oracle sweep over kernel families, modes and geometries (run on the GPU box for a fixed time budget):
-   python tools/fuzz_gpu.py [seconds] [seed]"""
+   python tools/fuzz_gpu.py [seconds] [seed] [iterations to replay]      (CLQ_FUZZ_WIDE=1: more option and length draws)"""
 import os
 import re
 import sys
@@ -13,8 +13,14 @@ import _oracle as O
 from clique_b200 import AffineScoring, Aligner, Reference, ReferenceManager, RustBioScoring, TwoPieceScoring
 from clique_b200.aligner import pack_reads
 
+def reset():
+    for k, v in (("force_cfg", -1), ("no_pack", 0), ("max_scratch_bytes", 40 << 30), ("no_group", 0), ("force_generic", 0)):
+        al.set_option(k, v)
+
+
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 12345
+wide = os.environ.get("CLQ_FUZZ_WIDE", "0") == "1"   # also draw scratch sub-batching, no_group, force_generic and 2.6 / 5.2 kb lengths
 only = set(int(x) for x in sys.argv[3].split(",")) if len(sys.argv) > 3 else None   # replay only these iterations (same RNG stream)
 rng = np.random.default_rng(seed)
 SC = [(10.0, -9.0, 9.0, -20.0, -2.0, 1.0), (5.0, -4.0, 4.0, -10.0, -0.5, 0.5), (10.0, -5.0, 8.0, -15.0, -1.0, 0.25), (6.0, -6.0, 5.0, -10.0, -10.0, 1.0),
@@ -45,11 +51,11 @@ while time.time() < t_end:
     it += 1
     nref = int(rng.choice([1, 1, 2, 5]))
     alpha = [b"ACGT", b"ACGTN", b"ACGTN012", b"ACGTacgtN"][int(rng.integers(0, 4))]
-    lmax = int(rng.choice([40, 150, 330, 700, 1300]))
+    lmax = int(rng.choice([40, 150, 330, 700, 1300] + ([2600, 5200] if wide else [])))
     uniform = rng.random() < 0.4
     L0 = int(rng.integers(1, lmax))
     refs = [rs(L0 if uniform else int(rng.integers(1, lmax)), alpha) for _ in range(nref)]
-    n = int(rng.integers(1, 260))
+    n = int(rng.integers(1, 260 if lmax <= 1300 else 24))
     reads, fixed = [], []
     for _ in range(n):
         k = int(rng.integers(0, nref))
@@ -67,6 +73,10 @@ while time.time() < t_end:
     cfg = int(rng.choice([-1, -1, 0, 1, 2, 3, 4, 5]))
     al.set_option("force_cfg", cfg if mode != "convex" else min(cfg, 4))
     al.set_option("no_pack", int(rng.random() < 0.3))
+    if wide:  # sub-batches of the direction-bit scratch, int32 multi-reference traceback, generic kernels
+        al.set_option("max_scratch_bytes", int(rng.choice([40 << 30, 1 << 20, 16 << 20])))
+        al.set_option("no_group", int(rng.random() < 0.3))
+        al.set_option("force_generic", int(rng.random() < 0.15))
     tags = bool(rng.random() < 0.5) and mode not in ("convex",)
     ctx = (it, mode, sc, cfg, nref, n, lmax, uniform)
     if only is not None and it not in only:
@@ -74,7 +84,7 @@ while time.time() < t_end:
             rng.choice(["readlen", "maxlen"])
             if mode == "bandk":
                 rng.choice([1, 3, 10, 50, 400])
-        al.set_option("force_cfg", -1); al.set_option("no_pack", 0)
+        reset()
         if it > max(only):
             break
         continue
@@ -150,7 +160,7 @@ while time.time() < t_end:
                               "oracle", ws, int(want["ref_index"][i]), want["score"][i], O.cigar_str(want["cigar_pool"][o:o + l])[:60], flush=True)
                 n_checked += 1
     finally:
-        al.set_option("force_cfg", -1); al.set_option("no_pack", 0)
+        reset()
 al.close()
 print("iterations", it, "checked pairs", n_checked, "mismatches", bad)
 sys.exit(1 if bad else 0)
