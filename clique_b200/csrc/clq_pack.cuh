@@ -45,10 +45,13 @@ __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C
                 const uint32_t EhU = Eh[j], BU = B[j];
                 if (jj < 7) Mnext = __viaddmax_s16x2(BU, (uint32_t)prmt_s8(tlo, thi, sel[j + 1]), X1);
                 const uint32_t Ehn = __viaddmax_s16x2(EhU, LE, BU);
-                uint32_t t2 = 0, u2 = 0;
+                uint32_t t2 = 0, u2 = 0, f2 = 0;
                 if (TB && !RB) {
+                    // F extends  <=>  F_left + le > max(E_left + x1 - 1, M_left + x1)  (>= the E-open, > the M-open).  LE - t2 is the
+                    // per-half value le - t2 (no borrow crosses the halves: t2 - le is in (0, 65536) per half), so one DPX with
+                    // relu clamps Fh + le - t2 to {0, 1}: the bit itself, without a second max and a subtract + min
                     t2 = __viaddmax_s16x2(Ehl, X1M1, Ml);
-                    u2 = __viaddmax_s16x2(Fh, LE, t2);  // > t2  <=>  F extends (>= E-open, > M-open)
+                    f2 = __viaddmin_s16x2_relu(Fh, LE - t2, ONE);
                 }
                 const uint32_t Fhn = __viaddmax_s16x2(Fh, LE, Bl);
                 if (TB && RB) { u2 = Fhn; t2 = Bl; }  // rust-bio: F extends <=> F_left + e > B_left + o + e
@@ -57,7 +60,7 @@ __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C
                 if (TB) {
                     // nibble pair [ext1 ext2 eP fM] of this cell pair, then 4 cells per 16-bit half
                     uint32_t nib = __vminu2(Ehn - BU, ONE);                 // ext1
-                    nib = nib * 2u + __vminu2(u2 - t2, ONE);                // ext2
+                    nib = nib * 2u + ((TB && !RB) ? f2 : __vminu2(u2 - t2, ONE));  // ext2
                     nib = nib * 2u + __vminu2(Bn - Pv, ONE);                // eP: E > max(M,F)
                     nib = nib * 2u + __vminu2(Pv - Mv, ONE);                // fM: F > M
                     uint32_t a = ((jj & 4) ? acc1 : acc0);

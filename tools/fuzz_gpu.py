@@ -21,6 +21,9 @@ def reset():
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 12345
 wide = os.environ.get("CLQ_FUZZ_WIDE", "0") == "1"   # also draw scratch sub-batching, no_group, force_generic and 2.6 / 5.2 kb lengths
+# CLQ_FUZZ_MODES=fixed,exhaustive,quick restricts the drawn modes; CLQ_FUZZ_NO_PACK_P=0 keeps every batch on the s16x2 kernels when it fits
+MODES = os.environ.get("CLQ_FUZZ_MODES", "fixed,fixed,exhaustive,quick,rustbio,convex,bandk").split(",")
+NO_PACK_P = float(os.environ.get("CLQ_FUZZ_NO_PACK_P", "0.3"))
 only = set(int(x) for x in sys.argv[3].split(",")) if len(sys.argv) > 3 else None   # replay only these iterations (same RNG stream)
 rng = np.random.default_rng(seed)
 SC = [(10.0, -9.0, 9.0, -20.0, -2.0, 1.0), (5.0, -4.0, 4.0, -10.0, -0.5, 0.5), (10.0, -5.0, 8.0, -15.0, -1.0, 0.25), (6.0, -6.0, 5.0, -10.0, -10.0, 1.0),
@@ -68,11 +71,11 @@ while time.time() < t_end:
     al.set_references(ReferenceManager([Reference(r, b"r%d" % i) for i, r in enumerate(refs)]))
     qb, qo = pack_reads(reads)
     rb, ro = O.pack_seqs(refs)
-    mode = str(rng.choice(["fixed", "fixed", "exhaustive", "quick", "rustbio", "convex", "bandk"]))
+    mode = str(rng.choice(MODES))
     sc = SC[int(rng.integers(0, len(SC)))]
     cfg = int(rng.choice([-1, -1, 0, 1, 2, 3, 4, 5]))
     al.set_option("force_cfg", cfg if mode != "convex" else min(cfg, 4))
-    al.set_option("no_pack", int(rng.random() < 0.3))
+    al.set_option("no_pack", int(rng.random() < NO_PACK_P))
     if wide:  # sub-batches of the direction-bit scratch, int32 multi-reference traceback, generic kernels
         al.set_option("max_scratch_bytes", int(rng.choice([40 << 30, 1 << 20, 16 << 20])))
         al.set_option("no_group", int(rng.random() < 0.3))
