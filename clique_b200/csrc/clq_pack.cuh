@@ -13,6 +13,13 @@
 
 #include "clq_kernels.cuh"
 
+// Experiment switch (default off; DESIGN.md "next experiments", identity checked on the CPU in tests/test_pack_bit_identities.py):
+// the ext2 bit from the left cell's B and eP bit instead of max(E_left - 1, M_left) -- one DPX less per cell pair, the carried
+// E_left / M_left registers and one shuffle per row go away.  Not yet measured or parity-tested on a GPU.
+#ifndef CLQ_PACK_EXT2_VIA_EP
+#define CLQ_PACK_EXT2_VIA_EP 0
+#endif
+
 namespace clq {
 
 __device__ __forceinline__ uint32_t dup16(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }
@@ -50,8 +57,14 @@ __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C
                     // F extends  <=>  F_left + le > max(E_left + x1 - 1, M_left + x1)  (>= the E-open, > the M-open).  LE - t2 is the
                     // per-half value le - t2 (no borrow crosses the halves: t2 - le is in (0, 65536) per half), so one DPX with
                     // relu clamps Fh + le - t2 to {0, 1}: the bit itself, without a second max and a subtract + min
+#if CLQ_PACK_EXT2_VIA_EP
+                    // Ehl carries eP of the left cell (0/1 per half): under "F_left + le - x1 > ." max(E_left - 1, M_left) equals
+                    // max(E_left - 1, M_left, F_left) = B_left - eP_left
+                    f2 = __viaddmin_s16x2_relu(Fh, LE - (Bl - Ehl), ONE);
+#else
                     t2 = __viaddmax_s16x2(Ehl, X1M1, Ml);
                     f2 = __viaddmin_s16x2_relu(Fh, LE - t2, ONE);
+#endif
                 }
                 const uint32_t Fhn = __viaddmax_s16x2(Fh, LE, Bl);
                 if (TB && RB) { u2 = Fhn; t2 = Bl; }  // rust-bio: F extends <=> F_left + e > B_left + o + e
@@ -61,7 +74,12 @@ __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C
                     // nibble pair [ext1 ext2 eP fM] of this cell pair, then 4 cells per 16-bit half
                     uint32_t nib = __vminu2(Ehn - BU, ONE);                 // ext1
                     nib = nib * 2u + ((TB && !RB) ? f2 : __vminu2(u2 - t2, ONE));  // ext2
+#if CLQ_PACK_EXT2_VIA_EP
+                    const uint32_t ePv = __vminu2(Bn - Pv, ONE);
+                    nib = nib * 2u + ePv;
+#else
                     nib = nib * 2u + __vminu2(Bn - Pv, ONE);                // eP: E > max(M,F)
+#endif
                     nib = nib * 2u + __vminu2(Pv - Mv, ONE);                // fM: F > M
                     uint32_t a = ((jj & 4) ? acc1 : acc0);
                     a = ((jj & 3) == 0) ? nib : a * 16u + nib;
@@ -70,11 +88,19 @@ __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C
                         wA[jb] = __byte_perm(acc1, acc0, 0x5410);  // low halves: read A's 8 nibbles
                         wB[jb] = __byte_perm(acc1, acc0, 0x7632);  // high halves: read B's
                     }
+#if CLQ_PACK_EXT2_VIA_EP
+                    if (!RB) Ehl = ePv;
+#endif
                 }
                 if (jj == 7) diag = BU;  // carried to the next block of 8 columns
                 Eh[j] = Ehn;
                 B[j] = Bn;
+#if CLQ_PACK_EXT2_VIA_EP
+                Fh = Fhn; Bl = Bn;
+                if (!(TB && !RB)) { Ehl = Ehn; Ml = Mv; }
+#else
                 Fh = Fhn; Ehl = Ehn; Ml = Mv; Bl = Bn;
+#endif
                 if (LAST) {
                     if (ownA && j == jA) { cap[0] = set_lo(cap[0], get_lo(Mv)); cap[1] = set_lo(cap[1], get_lo(Ehn)); cap[2] = set_lo(cap[2], get_lo(Fhn)); }
                     if (ownB && j == jB) { cap[0] = set_hi(cap[0], get_hi(Mv)); cap[1] = set_hi(cap[1], get_hi(Ehn)); cap[2] = set_hi(cap[2], get_hi(Fhn)); }
@@ -252,8 +278,8 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
                 uint32_t Bl = __shfl_up_sync(FULL, oB, 1, G);
                 uint32_t El = 0, Ml = 0;
                 if (TB && !RB) {
-                    El = __shfl_up_sync(FULL, oE, 1, G);
-                    Ml = __shfl_up_sync(FULL, oM, 1, G);
+                    El = __shfl_up_sync(FULL, oE, 1, G);  // CLQ_PACK_EXT2_VIA_EP: the eP bit of the left lane's last cell
+                    if (!CLQ_PACK_EXT2_VIA_EP) Ml = __shfl_up_sync(FULL, oM, 1, G);
                 }
                 const bool act = act_s && x >= 1 && x <= L1;
                 if (act) {
@@ -263,6 +289,7 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
                             Bl = dup16(g);
                             Fl = El = dup16(g - x1);
                             Ml = 0;  // the sentinel: below every biased value
+                            if (CLQ_PACK_EXT2_VIA_EP && TB && !RB) El = 0;  // boundary column: E = F = g(x), eP = 0
                             if (RB) Fl = 0;  // rust-bio: I[i][0] = MIN_SCORE on the empty-read boundary
                         } else {
                             Fl = nF; El = nE; Ml = nM; Bl = nB;
@@ -291,8 +318,9 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
                             if (sa && j == jLh[0]) { Eh[j] = set_lo(Eh[j], e0); B[j] = set_lo(B[j], b0v); }
                             if (sb && j == jLh[1]) { Eh[j] = set_hi(Eh[j], e0); B[j] = set_hi(B[j], b0v); }
                         }
-                        if (sa && jLh[0] == Cs - 1) { oF = set_lo(oF, e0); oE = set_lo(oE, e0); oM = set_lo(oM, b0v); oB = set_lo(oB, b0v); }
-                        if (sb && jLh[1] == Cs - 1) { oF = set_hi(oF, e0); oE = set_hi(oE, e0); oM = set_hi(oM, b0v); oB = set_hi(oB, b0v); }
+                        const int oe0 = (CLQ_PACK_EXT2_VIA_EP && TB && !RB) ? 0 : e0;  // fresh-matrix cell: E = M = F, eP = 0
+                        if (sa && jLh[0] == Cs - 1) { oF = set_lo(oF, e0); oE = set_lo(oE, oe0); oM = set_lo(oM, b0v); oB = set_lo(oB, b0v); }
+                        if (sb && jLh[1] == Cs - 1) { oF = set_hi(oF, e0); oE = set_hi(oE, oe0); oM = set_hi(oM, b0v); oB = set_hi(oB, b0v); }
                         if (x == L1) {
                             if (sa) { cap[0] = set_lo(cap[0], bias); cap[1] = set_lo(cap[1], e0); cap[2] = set_lo(cap[2], e0); }
                             if (sb) { cap[0] = set_hi(cap[0], bias); cap[1] = set_hi(cap[1], e0); cap[2] = set_hi(cap[2], e0); }
