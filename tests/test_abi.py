@@ -75,3 +75,50 @@ def test_strerror():
     lib = L.load_library()
     assert lib.clq_strerror(L.TRACEBACK_DIVERGED).decode().startswith("traceback diverged")
     assert lib.clq_strerror(-2).decode() == "CUDA error"
+
+
+def _c_header_model():
+    """functions (name -> parameter count), structs (name -> field names in order) and #define constants of include/clq.h"""
+    src = open(os.path.join(ROOT, "include", "clq.h")).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    funcs = {}
+    for m in re.finditer(r"\b(clq_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src):
+        args = m.group(2).strip()
+        funcs[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    structs = {}
+    for m in re.finditer(r"typedef struct \{(.*?)\}\s*(clq_[a-z_]+_t)\s*;", src, flags=re.S):
+        fields = []
+        for decl in m.group(1).split(";"):
+            decl = decl.strip()
+            if decl:
+                fields += [f.strip().lstrip("*") for f in decl.split(None, 1)[1].split(",")]
+        structs[m.group(2)] = fields
+    consts = {}
+    for m in re.finditer(r"#define (CLQ_[A-Z0-9_]+)[ \t]+(\S.*)", src):
+        expr = m.group(2).strip().replace("u", "")
+        consts[m.group(1)] = int(eval(expr, {"__builtins__": {}}))
+    return funcs, structs, consts
+
+
+def test_rust_sys_crate_matches_header():
+    """rust/clq-sys is source only (no Rust toolchain in this image): keep its extern block, #[repr(C)] structs and constants
+    in step with include/clq.h mechanically."""
+    rs = open(os.path.join(ROOT, "rust", "clq-sys", "src", "lib.rs")).read()
+    rs = re.sub(r"//.*", "", rs)
+    funcs, structs, consts = _c_header_model()
+    assert len(funcs) == len(L.SYMBOLS)
+    ext = rs[rs.index('extern "C" {'):]
+    rust_funcs = {}
+    for m in re.finditer(r"pub fn (clq_[a-z0-9_]+)\s*\((.*?)\)\s*(->\s*[^;]+)?;", ext, flags=re.S):
+        args = m.group(2).strip()
+        rust_funcs[m.group(1)] = 0 if not args else len([a for a in args.split(",") if a.strip()])
+    assert rust_funcs == funcs
+    for name, fields in structs.items():
+        m = re.search(r"pub struct %s \{(.*?)\}" % name, rs, flags=re.S)
+        assert m, name
+        rust_fields = [f.strip().split(":")[0].replace("pub ", "").strip() for f in m.group(1).split(",") if f.strip()]
+        assert [f.rstrip("_") for f in rust_fields] == fields, name      # `match` is a Rust keyword: match_
+    rust_consts = {m.group(1): m.group(3) for m in re.finditer(r"pub const (CLQ_[A-Z0-9_]+): (u32|i32) = ([^;]+);", rs)}
+    for name, value in consts.items():
+        assert name in rust_consts, name
+        assert int(eval(rust_consts[name], {"__builtins__": {}})) == value, name
