@@ -147,6 +147,29 @@ def test_simplify_cigar_cpp(H, goldens):
         assert O.cigar_str(out[:n]) == t["out"], t
 
 
+# cigar_to_alignment (alignment_functions.rs:830-872): unit Match / Subst / Del / Ins ops -> gapped strings + merged tags.  Here
+# that is simplify_cigar_string + AlignmentResult::from_cigar; the reference's four unit tests (:1149-1214), op lists as CIGAR
+# letters (Subst is a MatchMismatch step).
+CIGAR_TO_ALIGNMENT = [
+    (b"ACGT", b"ACGT", "MMMM", b"ACGT", b"ACGT", "4M"),          # :1150-1163
+    (b"ACGT", b"AT", "MDDM", b"ACGT", b"A--T", "1M2D1M"),        # :1165-1181 (asserts ref_aln, read_aln[0], read_aln[3], 3 tags)
+    (b"AT", b"ACGT", "MIIM", b"A--T", b"ACGT", "1M2I1M"),        # :1183-1199
+    (b"ACGT", b"ATGT", "MMMM", b"ACGT", b"ATGT", "4M"),          # :1201-1214 (Match, Subst, Match, Match)
+]
+
+
+def test_cigar_to_alignment_reference_vectors(H):
+    for ref, read, unit, want_ref, want_read, want_cigar in CIGAR_TO_ALIGNMENT:
+        ops = np.array([(1 << 4) | "MID".index(c) for c in unit], dtype=np.uint32)
+        out = np.zeros(len(ops), np.uint32)
+        n = H.clqh_simplify_cigar(ops.ctypes.data, len(ops), out.ctypes.data)
+        assert O.cigar_str(out[:n]) == want_cigar
+        ra, qa, _ = h_from_cigar(H, ref, read, out[:n])
+        assert (ra, qa) == (want_ref, want_read)
+        assert O.apply_cigar(ref, read, out[:n]) == (want_ref, want_read)       # the oracle-side helper the GPU tests use
+        assert O.apply_cigar(ref, read, ops) == (want_ref, want_read)           # unit ops give the same strings
+
+
 def test_f64_display(H):
     # Rust `Display` for f64 (score.to_string() / rate.to_string() in the BAM tags)
     for v, s in [(979.0, "979"), (391.5, "391.5"), (13.75, "13.75"), (-40.0, "-40"), (0.0, "0"), (1.0, "1"), (0.5, "0.5"),
