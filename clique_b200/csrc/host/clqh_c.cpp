@@ -172,6 +172,10 @@ int32_t clqh_orient_by_longest_segment(const uint8_t* search, size_t n, const ui
     return orient_by_longest_segment(Bytes(search, search + n), ref, SuffixTableLookup::find_seeds(ref, seed_size)).forward ? 1 : 0;
 }
 
+size_t clqh_extend_hit(const uint8_t* search, size_t n, size_t search_location, const uint8_t* reference, size_t m, size_t reference_location) {
+    return extend_hit(search, n, search_location, reference, m, reference_location);
+}
+
 size_t clqh_bam_file(const char* ref_name, const char* read_name, const uint8_t* ref, size_t l1, const uint8_t* read, size_t l2,
                      const uint32_t* ops, size_t n_ops, double score, const char* extra_tags, uint8_t* out, size_t cap) {
     // a complete BAM file (BGZF: header block, one record, EOF marker) for one alignment, through the object path

@@ -49,6 +49,8 @@ int32_t clqh_merge_read_pairs_by_alignment(int32_t device, uint32_t n, const uin
 size_t clqh_find_greedy_non_overlapping_segments(const uint8_t* search, size_t n, const uint8_t* reference, size_t m, size_t seed_size,
                                                  uint32_t* out_xyz, size_t cap, size_t* start_position);
 int32_t clqh_orient_by_longest_segment(const uint8_t* search, size_t n, const uint8_t* reference, size_t m, size_t seed_size);
+/* extend_hit, linked_alignment.rs:341-362 */
+size_t clqh_extend_hit(const uint8_t* search, size_t n, size_t search_location, const uint8_t* reference, size_t m, size_t reference_location);
 /* BamFileAlignmentWriter's wire format (alignment_manager.rs:64-209) for one alignment: BGZF header block + record + EOF */
 size_t clqh_bam_file(const char* ref_name, const char* read_name, const uint8_t* ref, size_t l1, const uint8_t* read, size_t l2,
                      const uint32_t* ops, size_t n_ops, double score, const char* extra_tags, uint8_t* out, size_t cap);

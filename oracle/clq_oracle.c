@@ -1108,7 +1108,7 @@ static int orc_acgt(uint8_t b) { /* DEGENERATEBASES value sets hold only A/C/G/T
 }
 
 /* extend_hit: both lookups must succeed both ways, i.e. plain bases equal up to case */
-static size_t orc_extend_hit(const uint8_t* search, size_t n, size_t sloc, const uint8_t* ref, size_t m, size_t rloc) {
+size_t orc_extend_hit(const uint8_t* search, size_t n, size_t sloc, const uint8_t* ref, size_t m, size_t rloc) {
     size_t len = 0;
     while (len + sloc < n && len + rloc < m) {
         const int a = orc_acgt(search[sloc + len]), b = orc_acgt(ref[rloc + len]);

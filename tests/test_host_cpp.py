@@ -19,7 +19,7 @@ CLQ_ALIGN = os.path.join(ROOT, "clique_b200", "clq_align")
 SYMBOLS = ["clqh_extract_tagged_sequences", "clqh_reverse_complement", "clqh_f64_to_string", "clqh_get_reference_alignment_rate",
            "clqh_simplify_cigar", "clqh_from_cigar", "clqh_sam_line", "clqh_merge_reads_by_concatenation",
            "clqh_combine_phred_scores", "clqh_alignment_rate_and_consensus", "clqh_merge_read_pairs_by_alignment",
-           "clqh_find_greedy_non_overlapping_segments", "clqh_orient_by_longest_segment", "clqh_bam_file"]
+           "clqh_find_greedy_non_overlapping_segments", "clqh_orient_by_longest_segment", "clqh_bam_file", "clqh_extend_hit"]
 
 
 @pytest.fixture(scope="module")
@@ -55,6 +55,8 @@ def H():
                                                             C.POINTER(C.c_size_t)]
     L.clqh_orient_by_longest_segment.restype = C.c_int32
     L.clqh_orient_by_longest_segment.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_size_t]
+    L.clqh_extend_hit.restype = C.c_size_t
+    L.clqh_extend_hit.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_char_p, C.c_size_t, C.c_size_t]
     L.clqh_bam_file.restype = C.c_size_t
     L.clqh_bam_file.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_double,
                                 C.c_char_p, C.c_void_p, C.c_size_t]
@@ -230,6 +232,40 @@ def test_merge_reads_by_concatenation(H):
     assert merge(b"AACC", None, "1F") == b"AACC"
     assert merge(b"AACC", None, "1F,2F") is None                               # assert!(reads.read_two.is_some()) panics
     assert merge(b"AACC", b"GG", "1U") is None                                 # Unknown orientation panics
+
+
+def test_orient_sequence_reference_vectors(H):
+    # merger.rs:689-730, through the single-read layout items 1F / 1R / 1C / 1U
+    def orient(seq, item):
+        buf = C.create_string_buffer(64)
+        n = H.clqh_merge_reads_by_concatenation(seq, len(seq), None, 0, item.encode(), buf, 64)
+        return None if n == 2 ** 64 - 1 else buf.raw[:n]
+
+    assert orient(b"ACGT", "1F") == b"ACGT"        # :690-695
+    assert orient(b"ACGT", "1R") == b"TGCA"        # :697-702
+    assert orient(b"ACGT", "1C") == b"ACGT"        # :704-709 (its own reverse complement)
+    assert orient(b"AAAA", "1C") == b"TTTT"        # :711-716
+    assert orient(b"ACGT", "1U") is None           # :718-723 panics with "Unknown"
+    for item in ("1F", "1R", "1C"):                # :725-730
+        assert orient(b"", item) == b""
+
+
+# extend_hit's assertions: linked_alignment.rs:370-412 and :544-582  (search, search_location, reference, reference_location, length)
+EXTEND_HIT = [
+    (b"ACGTACGT", 0, b"ACGTACGT", 0, 8), (b"ACGTTTTT", 0, b"ACGTACGT", 0, 4), (b"TTTT", 0, b"ACGT", 0, 0),
+    (b"TTACGT", 2, b"ACGT", 0, 4), (b"ACGT", 0, b"TTACGT", 2, 4), (b"RCGT", 0, b"ACGT", 0, 0),
+    (b"AATGATACGG", 0, b"AATGATACGG", 0, 10), (b"AATGATACGG", 0, b"AATGATACGGAAA", 0, 10),
+    (b"AATGATACGG", 0, b"GGAATGATACGGAAA", 2, 10), (b"AATGATACGG", 0, b"AAA", 0, 2),
+]
+
+
+def test_extend_hit_reference_vectors(H):
+    orc = O.lib()
+    orc.orc_extend_hit.restype = C.c_size_t
+    orc.orc_extend_hit.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_char_p, C.c_size_t, C.c_size_t]
+    for s, sl, r, rl, want in EXTEND_HIT:
+        assert H.clqh_extend_hit(s, len(s), sl, r, len(r), rl) == want, (s, r)
+        assert orc.orc_extend_hit(s, len(s), sl, r, len(r), rl) == want, (s, r)
 
 
 def h_consensus(H, a1, q1, a2, q2):
