@@ -387,6 +387,7 @@ int32_t clq_ctx_create(int32_t device, const clq_limits_t* limits, clq_ctx** out
     c->lim = *limits;
     if (c->lim.n_slots < 1) c->lim.n_slots = 1;
     if (c->lim.n_slots > 4) c->lim.n_slots = 4;
+    if (c->lim.cigar_pool_ops > 0xffffffffull) c->lim.cigar_pool_ops = 0xffffffffull;  // clq_result_t.cigar_off is 32 bits
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return CLQ_E_CUDA; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return CLQ_E_CUDA; }

@@ -99,7 +99,7 @@ typedef struct {
     uint32_t max_read_len;    /* reads >= this are dropped with CLQ_READ_TOO_LONG (align_reads' rule)   */
     uint32_t max_refs;
     uint64_t max_ref_bytes;
-    uint64_t cigar_pool_ops;  /* CIGAR pool capacity per slot, in uint32 ops                            */
+    uint64_t cigar_pool_ops;  /* CIGAR pool capacity per slot, in uint32 ops (clamped to 2^32 - 1)       */
     uint32_t n_slots;         /* independent stream slots for double buffering (1..4)                   */
 } clq_limits_t;
 
