@@ -123,3 +123,69 @@ def test_ext2_from_left_cell_B_and_eP(x1, le):
     got = viaddmin_s16x2_relu(Fh, d, ONE)                # clamp(F - x1 + le - (B - eP), 0, 1)
     gl, gh = halves(got)
     assert np.array_equal(gl, want[0]) and np.array_equal(gh, want[1])
+
+
+def byte_perm(x, y, sel):
+    """__byte_perm(x, y, s): byte k of the result = byte s[k] of the 8-byte value {y, x} (x = bytes 0..3, y = bytes 4..7)"""
+    src = [(int(x) >> (8 * i)) & 0xFF for i in range(4)] + [(int(y) >> (8 * i)) & 0xFF for i in range(4)]
+    return sum(src[(sel >> (4 * k)) & 7] << (8 * k) for k in range(4))
+
+
+def test_nibble_packing_matches_the_walkers_layout():
+    """pack_row_step shifts four clamp results per cell pair into `nib`, four nibble pairs into acc0 / acc1 and unzips them with
+    two PRMTs; walk_kernel reads column j of a word as (w >> (28 - 4 * (j & 7))) & 15 = [ext1 ext2 eP fM]."""
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        flags = rng.integers(0, 2, size=(8, 4, 2))            # [column][ext1, ext2, eP, fM][read A, read B]
+        acc = [0, 0]
+        for jj in range(8):
+            nib = 0
+            for k in range(4):
+                nib = (nib * 2 + (int(flags[jj, k, 0]) | (int(flags[jj, k, 1]) << 16))) & 0xFFFFFFFF
+            a = acc[jj >> 2]
+            a = nib if (jj & 3) == 0 else (a * 16 + nib) & 0xFFFFFFFF
+            acc[jj >> 2] = a
+        wA = byte_perm(acc[1], acc[0], 0x5410)                # low halves: read A
+        wB = byte_perm(acc[1], acc[0], 0x7632)                # high halves: read B
+        for jj in range(8):
+            for h, w in ((0, wA), (1, wB)):
+                nibble = (w >> (28 - 4 * jj)) & 15
+                want = sum(int(flags[jj, k, h]) << (3 - k) for k in range(4))
+                assert nibble == want, (jj, h)
+
+
+@pytest.mark.parametrize("x1,le", GAPS)
+def test_other_three_bits(x1, le):
+    """ext1 / eP / fM as pack_row_step derives them: min_u16x2(x - y, 1) with x >= y per half (no borrow), against the tie order of
+    three_way_max_and_direction (alignment/alignment_matrix.rs:671-683: Diag > Left > Up on ties)."""
+    rng = np.random.default_rng(9 - x1)
+    n = 100000
+    top = 32767 + x1
+    base = rng.integers(200, top - 200, size=(2, n))
+    sp = lambda: rng.integers(-60, 61, size=(2, n))
+    E_up, B_up = np.clip(base + sp(), 64, top), np.clip(base + sp(), 64, top)     # upper neighbour: E layer and best
+    M, F = np.clip(base + sp(), 64, top), np.clip(base + sp(), 64, top)           # this cell: M and F (true values)
+    r = rng.random((2, n))
+    E_up = np.where(r < 0.15, B_up + x1 - le, E_up)                                # tie: extension == opening
+    F = np.where((r > 0.8), M, F)                                                  # tie: F == M
+    EhU, BU = pack(E_up[0] - x1, E_up[1] - x1), pack(B_up[0], B_up[1])
+    LE, X1 = dup16(le), dup16(x1)
+    Ehn = viaddmax_s16x2(EhU, LE, BU)                                              # E - x1 = max(E_up + le - x1, B_up)
+    E = np.maximum(E_up + le, B_up + x1)
+    el, eh = halves(Ehn)
+    assert np.array_equal(el, E[0] - x1) and np.array_equal(eh, E[1] - x1)
+    ext1 = vminu2(sub32(Ehn, BU), ONE)                                             # E extends: E_up + le > B_up + x1
+    l, h = halves(ext1)
+    assert np.array_equal(l, (E_up[0] + le > B_up[0] + x1).astype(np.int64)) and np.array_equal(h, (E_up[1] + le > B_up[1] + x1).astype(np.int64))
+    Fhn, Mv = pack(F[0] - x1, F[1] - x1), pack(M[0], M[1])
+    Pv = viaddmax_s16x2(Fhn, X1, Mv)                                               # max(F, M)
+    Bn = viaddmax_s16x2(Ehn, X1, Pv)                                               # max(E, F, M)
+    fM = vminu2(sub32(Pv, Mv), ONE)                                                # F > M   (tie: Diag)
+    eP = vminu2(sub32(Bn, Pv), ONE)                                                # E > max(M, F)   (tie: not Up)
+    l, h = halves(fM)
+    assert np.array_equal(l, (F[0] > M[0]).astype(np.int64)) and np.array_equal(h, (F[1] > M[1]).astype(np.int64))
+    l, h = halves(eP)
+    mf = np.maximum(M, F)
+    assert np.array_equal(l, (E[0] > mf[0]).astype(np.int64)) and np.array_equal(h, (E[1] > mf[1]).astype(np.int64))
+    bl, bh = halves(Bn)
+    assert np.array_equal(bl, np.maximum(E, mf)[0]) and np.array_equal(bh, np.maximum(E, mf)[1])
