@@ -86,7 +86,9 @@ unsafe impl<T: Copy + Send> Send for PinnedBuf<T> {}
 impl<T: Copy> PinnedBuf<T> {
     pub fn new(cap: usize) -> Result<Self> {
         let mut p: *mut c_void = ptr::null_mut();
-        check(unsafe { clq_host_alloc(cap.max(1) * std::mem::size_of::<T>(), &mut p) }, ptr::null())?;
+        let bytes = cap.max(1) * std::mem::size_of::<T>();
+        check(unsafe { clq_host_alloc(bytes, &mut p) }, ptr::null())?;
+        unsafe { ptr::write_bytes(p as *mut u8, 0, bytes) }; // the slices below hand out initialised memory
         Ok(PinnedBuf { ptr: p as *mut T, cap, _own: PhantomData })
     }
     pub fn capacity(&self) -> usize {
