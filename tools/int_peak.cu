@@ -9,15 +9,19 @@
 #define ITER 4096
 
 enum Op { ADD, MAX, VIADDMAX, VIMAX3, VIBMAX, PRMT, ADDMAX16, MAX3_16, ADDMAXU16, IMAD, LOP3, SHF, SEL, SHFL,
-          MIX_DPX_IMAD, MIX_CELL, MIX_CELL16, NOPS };
+          MIX_DPX_IMAD, MIX_CELL, MIX_CELL16, UMULHI, IADD3, VMINU2, LDS_RAND, MIX_ALU2_FMA2, NOPS };
 static const char* names[] = {"iadd", "imax", "viaddmax_s32", "vimax3_s32", "vibmax_s32", "prmt", "viaddmax_s16x2",
           "vimax3_s16x2", "viaddmax_u16x2", "imad", "lop3", "shf", "isetp+sel", "shfl_up",
-          "mix(viaddmax+imad)", "cell6(int32)", "cell6(s16x2)"};
+          "mix(viaddmax+imad)", "cell6(int32)", "cell6(s16x2)",
+          "umulhi(imad.hi)", "iadd3", "vminu2", "lds_rand_u32", "mix(2dpx+2imad)"};
 // ops counted per accumulator per iteration
-static const int opcount[] = {1,1,1,1,1,1,1,1,1,1,1,1,2,1,2,6,6};
+static const int opcount[] = {1,1,1,1,1,1,1,1,1,1,1,1,2,1,2,6,6,1,1,1,1,4};
 
 template <int OP>
 __global__ void __launch_bounds__(256) k(int* out, int b, int c, int d, unsigned long long* cyc) {
+    __shared__ int lds_tab[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) lds_tab[i] = i * 2654435761u >> 23;
+    __syncthreads();
     int a[NACC];
     int e[NACC];
 #pragma unroll
@@ -51,7 +55,12 @@ __global__ void __launch_bounds__(256) k(int* out, int b, int c, int d, unsigned
                 int t = max(E, F);
                 a[i] = __viaddmax_s32(t, c, M);
                 e[i] = E;
-            } else if (OP == MIX_CELL16) {
+            } else if (OP == UMULHI) a[i] = __umulhi((unsigned)a[i], (unsigned)b << 16) + i;
+            else if (OP == IADD3) a[i] = a[i] + e[i] + b;
+            else if (OP == VMINU2) a[i] = __vminu2(a[i], e[i]) + 0;
+            else if (OP == LDS_RAND) a[i] = lds_tab[(a[i] + i) & 511];
+            else if (OP == MIX_ALU2_FMA2) { a[i] = __viaddmax_s16x2(a[i], b, c); e[i] = e[i] * b + d; a[i] = __viaddmax_s16x2(a[i], d, e[i]); e[i] = e[i] * c + a[i]; }
+            else if (OP == MIX_CELL16) {
                 int m = __byte_perm(b, c, e[i]);
                 int M = a[i] + m;
                 int E = __viaddmax_s16x2(e[i], d, a[i]);
@@ -118,6 +127,11 @@ int main() {
     run<MIX_DPX_IMAD>(nsm, out, cyc, b, c, d);
     run<MIX_CELL>(nsm, out, cyc, b, c, d);
     run<MIX_CELL16>(nsm, out, cyc, b, c, d);
+    run<UMULHI>(nsm, out, cyc, b, c, d);
+    run<IADD3>(nsm, out, cyc, b, c, d);
+    run<VMINU2>(nsm, out, cyc, b, c, d);
+    run<LDS_RAND>(nsm, out, cyc, b, c, d);
+    run<MIX_ALU2_FMA2>(nsm, out, cyc, b, c, d);
     cudaError_t err = cudaDeviceSynchronize();
     if (err != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(err)); return 1; }
     return 0;
