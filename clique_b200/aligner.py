@@ -440,9 +440,12 @@ class Aligner:
         try:
             rb, ro = pack_reads([read])
             br = self.align_batch(rb, ro, scoring_function, "fixed", "maxlen", fixed_ref=[0])
-        finally:
+        finally:  # always restore: an aligner that had no references must not keep the caller's last pairwise reference
             if saved is not None:
                 self.set_references(saved)
+            else:
+                self._check(self.lib.clq_refs_set(self.ctx, 0, None, None))
+                self.rm = None
         return self._result(br, 0, ref, read, read_qual, ref_name, read_name)
 
     def _result(self, br: BatchResult, i, ref, read, quals, ref_name, read_name) -> AlignmentResult:
@@ -460,8 +463,11 @@ class Aligner:
         read = _b(read)
         rb, ro = pack_reads([read])
         br = self.align_batch(rb, ro, scoring, search, "readlen", threshold=threshold)
-        if int(br.status[0]) == L.NO_CANDIDATE:
+        st = int(br.status[0])
+        if st == L.NO_CANDIDATE:
             return None
+        if st != L.CLQ_OK:  # ref_index is only meaningful for CLQ_OK records (clique_host.cpp: Aligner::search)
+            self._result(br, 0, b"", read, qual, "", read_name)  # raises ClqError with the status
         r = rm.references[int(br.ref_index[0])]
         al = self._result(br, 0, r.sequence, read, qual, r.name.decode(), read_name)
         return AlignmentWithRef(al, r.name, r.sequence)

@@ -395,8 +395,9 @@ int32_t clq_ctx_create(int32_t device, const clq_limits_t* limits, clq_ctx** out
     c->slots.resize(c->lim.n_slots);
     for (auto& s : c->slots) {
         if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { clq_ctx_destroy(c); return CLQ_E_CUDA; }
-        for (auto& e : s.ev) cudaEventCreate(&e);
-        cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+        for (auto& e : s.ev)
+            if (cudaEventCreate(&e) != cudaSuccess) { clq_ctx_destroy(c); return CLQ_E_CUDA; }
+        if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) { clq_ctx_destroy(c); return CLQ_E_CUDA; }
         if (cudaHostAlloc((void**)&s.h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) { clq_ctx_destroy(c); return CLQ_E_CUDA; }
         if (ensure(c, s.counters, 8 * sizeof(unsigned long long)) != CLQ_OK) { clq_ctx_destroy(c); return CLQ_E_NOMEM; }
     }
@@ -430,7 +431,11 @@ int32_t clq_set_option(clq_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "no_pack")) { c->no_pack = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_group")) { c->no_group = (int)value; return CLQ_OK; }
     if (!strcmp(key, "serialize_slots")) { c->serialize = (int)value; return CLQ_OK; }
-    if (!strcmp(key, "max_scratch_bytes")) { c->max_scratch_bytes = value; return CLQ_OK; }
+    if (!strcmp(key, "max_scratch_bytes")) {
+        if (value < (1 << 20)) return fail(c, CLQ_E_INVALID, "max_scratch_bytes must be at least 1 MiB");
+        c->max_scratch_bytes = value;
+        return CLQ_OK;
+    }
     return fail(c, CLQ_E_INVALID, std::string("unknown option ") + key);
 }
 
@@ -440,9 +445,13 @@ int32_t clq_refs_set(clq_ctx* c, uint32_t n_refs, const uint8_t* bytes, const ui
     const uint64_t total = n_refs ? off[n_refs] : 0;
     if (total > c->lim.max_ref_bytes) return fail(c, CLQ_E_LIMIT, "reference bytes exceed limit");
     CU(c, cudaSetDevice(c->device));
-    c->h_ref_bytes.assign(bytes, bytes + total);
-    c->h_ref_off.assign(off, off + n_refs + 1);
-    if (!n_refs) c->h_ref_off.assign(1, 0);
+    if (n_refs) {
+        c->h_ref_bytes.assign(bytes, bytes + total);
+        c->h_ref_off.assign(off, off + n_refs + 1);
+    } else {  // empty set (bytes / off may be NULL)
+        c->h_ref_bytes.clear();
+        c->h_ref_off.assign(1, 0);
+    }
     c->n_refs = n_refs;
     c->max_ref_len = 0;
     for (uint32_t r = 0; r < n_refs; r++) {
@@ -553,6 +562,7 @@ int32_t clq_kmer_index_set(clq_ctx* c, uint32_t k, uint32_t skip) {
         i = j;
     }
     int32_t rc;
+    for (auto& s : c->slots) CU(c, cudaStreamSynchronize(s.stream));  // the slot streams are non-blocking: an in-flight CLQ_SEARCH_QUICK launch reads the old table
     if ((rc = ensure(c, c->kmer_keys, keys.size() + 16)) != CLQ_OK) return rc;
     if ((rc = ensure(c, c->kmer_owner, (owner.size() + 1) * sizeof(uint32_t))) != CLQ_OK) return rc;
     if (!keys.empty()) {

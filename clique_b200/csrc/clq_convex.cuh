@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kThreads) convex_kernel(const KParams p, const
             if (!TB && p.all_pairs) p.scores[(size_t)ridx * p.n_refs + ref] = ok ? score : INT32_MIN;
             else {
                 clq_result_t r;
-                r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = 0; r.cigar_len = 0; r.status = status; r.matches = 0; r.mismatches = 0;
+                r.score_scaled = score; r.ref_index = (status != CLQ_NO_CANDIDATE && ref >= 0 && (uint32_t)ref < p.n_refs) ? (uint32_t)ref : 0xffffffffu; r.cigar_off = 0; r.cigar_len = 0; r.status = status; r.matches = 0; r.mismatches = 0;
                 p.results[ridx] = r;
                 if (TB) {
                     TbRec rec;

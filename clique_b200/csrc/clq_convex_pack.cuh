@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) convex_pack_kernel(const KParams p, 
             }
             if (valid[h] && gl == 0) {
                 clq_result_t r;
-                r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = 0; r.cigar_len = 0; r.status = status[h]; r.matches = 0; r.mismatches = 0;
+                r.score_scaled = score; r.ref_index = (status[h] != CLQ_NO_CANDIDATE && ref >= 0 && (uint32_t)ref < p.n_refs) ? (uint32_t)ref : 0xffffffffu; r.cigar_off = 0; r.cigar_len = 0; r.status = status[h]; r.matches = 0; r.mismatches = 0;
                 p.results[ridx[h]] = r;
                 if (run[h]) atomicAdd(p.cells, (unsigned long long)L1 * (unsigned long long)L2[h]);
             }

@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
                 if (p.all_pairs) p.scores[(size_t)ridx * p.n_refs + ref] = ok ? score : INT32_MIN;
                 else {
                     clq_result_t r;
-                    r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = 0; r.cigar_len = 0; r.status = status; r.matches = 0; r.mismatches = 0;
+                    r.score_scaled = score; r.ref_index = (status != CLQ_NO_CANDIDATE && ref >= 0 && (uint32_t)ref < p.n_refs) ? (uint32_t)ref : 0xffffffffu; r.cigar_off = 0; r.cigar_len = 0; r.status = status; r.matches = 0; r.mismatches = 0;
                     p.results[ridx] = r;
                 }
                 if (run) atomicAdd(p.cells, (unsigned long long)L1 * (unsigned long long)L2);
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
         // ---- leave the start layer for walk_kernel ----
         if (valid && gl == 0) {
             clq_result_t r;
-            r.score_scaled = score; r.ref_index = (uint32_t)ref; r.cigar_off = 0; r.cigar_len = 0; r.status = status; r.matches = 0; r.mismatches = 0;
+            r.score_scaled = score; r.ref_index = (status != CLQ_NO_CANDIDATE && ref >= 0 && (uint32_t)ref < p.n_refs) ? (uint32_t)ref : 0xffffffffu; r.cigar_off = 0; r.cigar_len = 0; r.status = status; r.matches = 0; r.mismatches = 0;
             p.results[ridx] = r;
             TbRec rec;
             rec.ridx = ridx; rec.L1 = (ok && status == CLQ_OK) ? L1 : -1; rec.L2 = L2;

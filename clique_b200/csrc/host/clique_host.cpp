@@ -790,6 +790,7 @@ Aligner::Aligner(const AlignerOptions& opt) : opt_(opt) {
         res_.push_back(pinned<clq_result_t>(opt_.max_reads));
         pool_.push_back(pinned<uint32_t>(pool_ops_));
         tags_.push_back(nullptr);
+        tags_cap_.push_back(0);
     }
     flags_.assign(opt_.n_slots, 0);
     scale_.assign(opt_.n_slots, 1);
@@ -847,11 +848,12 @@ BatchView Aligner::wait(int slot, const ReadBatch& b) {
         uint32_t stride = 0;
         check(clq_tags_download(ctx_, slot, nullptr, 0, &stride), "clq_tags_download");
         const uint64_t need = (uint64_t)opt_.max_reads * stride;
-        if (need > tags_cap_) {
-            for (auto*& p : tags_) { if (p) clq_host_free(p); p = pinned<uint8_t>(need); }
-            tags_cap_ = need;
+        if (need > tags_cap_[slot]) {  // per slot: a BatchView of another slot may still point into its buffer
+            if (tags_[slot]) clq_host_free(tags_[slot]);
+            tags_[slot] = pinned<uint8_t>(need);
+            tags_cap_[slot] = need;
         }
-        if (stride && b.size()) check(clq_tags_download(ctx_, slot, tags_[slot], tags_cap_, &stride), "clq_tags_download");
+        if (stride && b.size()) check(clq_tags_download(ctx_, slot, tags_[slot], tags_cap_[slot], &stride), "clq_tags_download");
         v.tags = stride ? tags_[slot] : nullptr;
         v.tag_stride = stride;
     }
@@ -880,10 +882,10 @@ AlignmentResult Aligner::single(const Bytes& reference, const Bytes& read, std::
         st = v.status(0);
         out = v.alignment(0);
     } catch (...) {
-        if (!saved.references.empty()) set_references(saved);
+        set_references(saved);  // also when the aligner had no references: the temporary one must not stay installed
         throw;
     }
-    if (!saved.references.empty()) set_references(saved);
+    set_references(saved);
     if (st == CLQ_TRACEBACK_DIVERGED) fail((int32_t)st, "the reference's traceback does not terminate for this pair (stale band cell)");
     if (st != CLQ_OK || !out) fail((int32_t)st, clq_strerror((int32_t)st));
     return std::move(*out->alignment);
@@ -1002,10 +1004,10 @@ std::vector<std::optional<MergedSequence>> Aligner::merge_read_pairs_by_alignmen
             lo = hi;
         }
     } catch (...) {
-        if (!saved.references.empty()) set_references(saved);
+        set_references(saved);
         throw;
     }
-    if (!saved.references.empty()) set_references(saved);
+    set_references(saved);
     return out;
 }
 
@@ -1024,13 +1026,16 @@ void prepare_fixed(ReadBatch& b, uint32_t flags) {
 }  // namespace
 
 AlignReadsStats Aligner::align_reads(const ReadSource& source, const AffineScoring& scoring, bool fast_lookup, const ResultSink& sink,
-                                     bool extract_tags, bool rust_bio) {
+                                     bool extract_tags, bool rust_bio, bool known_strand) {
     const auto tsetup = std::chrono::steady_clock::now();
     AlignReadsStats st;
     if (rm_.references.empty()) return st;
     const bool rb = rust_bio && rm_.references.size() == 1;
     const clq_affine_t sc = rb ? RustBioScoring().to_int() : scoring.to_int();
     const uint32_t flags = search_flags(fast_lookup) | (extract_tags ? CLQ_EXTRACT_TAGS : 0u) | (rb ? CLQ_RUSTBIO : 0u);
+    // known_strand = false with one reference (alignment_functions.rs:549-558): orient on the host before the batch goes out
+    const bool orient = !known_strand && rm_.references.size() == 1;
+    const SuffixTableLookup seeds = orient ? SuffixTableLookup::find_seeds(rm_.references[0].sequence, rm_.kmer_size) : SuffixTableLookup();
     const uint32_t ns = opt_.n_slots;
     while (bufs_.size() < ns) bufs_.push_back(std::make_unique<ReadBatch>(opt_.max_reads, opt_.max_read_bytes));  // page-locked once
     auto& bufs = bufs_;
@@ -1055,6 +1060,16 @@ AlignReadsStats Aligner::align_reads(const ReadSource& source, const AffineScori
         more = source(b);
         if (b.size()) {
             prepare_fixed(b, flags);
+            if (orient) {
+                Bytes tmp;
+                for (uint32_t i = 0; i < b.size(); i++) {
+                    tmp.assign(b.read(i), b.read(i) + b.read_len(i));
+                    if (!orient_by_longest_segment(tmp, rm_.references[0].sequence, seeds).forward) {
+                        const Bytes rc = reverse_complement(tmp);
+                        std::memcpy(b.read_mut(i), rc.data(), rc.size());
+                    }
+                }
+            }
             submit((int)slot, b, sc, flags);
             busy[slot] = true;
             next_index += b.size();
@@ -1082,7 +1097,7 @@ void ShardedAligner::set_references(const ReferenceManager& rm, bool build_kmer_
 }
 
 AlignReadsStats ShardedAligner::align_reads(const ReadSource& source, const AffineScoring& scoring, bool fast_lookup, const ResultSink& sink,
-                                            bool extract_tags, bool rust_bio) {
+                                            bool extract_tags, bool rust_bio, bool known_strand) {
     const auto t0 = std::chrono::steady_clock::now();
     AlignReadsStats total;
     std::mutex src_mu, sink_mu;
@@ -1105,7 +1120,7 @@ AlignReadsStats ShardedAligner::align_reads(const ReadSource& source, const Affi
     };
     auto work = [&](Aligner* a) {
         try {
-            const AlignReadsStats st = a->align_reads(shared_source, scoring, fast_lookup, locked_sink, extract_tags, rust_bio);
+            const AlignReadsStats st = a->align_reads(shared_source, scoring, fast_lookup, locked_sink, extract_tags, rust_bio, known_strand);
             std::lock_guard<std::mutex> g(sink_mu);
             total.reads += st.reads; total.aligned += st.aligned; total.dropped += st.dropped; total.batches += st.batches; total.cells += st.cells;
             total.setup_seconds = std::max(total.setup_seconds, st.setup_seconds);

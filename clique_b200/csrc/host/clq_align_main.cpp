@@ -186,8 +186,6 @@ int main(int argc, char** argv) {
         std::unique_ptr<ReadFile> f2;
         if (!a.reads2.empty() && !a.synthetic) f2 = std::make_unique<ReadFile>(a.reads2);
         const std::vector<ReadPosition> layout = a.layout.empty() ? std::vector<ReadPosition>{} : parse_layout(a.layout);
-        const bool orient = a.unknown_strand && rm.references.size() == 1;
-        const SuffixTableLookup seeds = orient ? SuffixTableLookup::find_seeds(rm.references[0].sequence, rm.kmer_size) : SuffixTableLookup();
         ReadSetContainer pending;
         bool have_pending = false;
         uint64_t too_big = 0;
@@ -205,13 +203,6 @@ int main(int argc, char** argv) {
                     have_pending = true;
                 }
                 bool ok;
-                if (orient && layout.empty()) {
-                    // known_strand = false, one reference (alignment_functions.rs:549-558): orient_by_longest_segment, then the
-                    // reverse complement when the reverse strand shares more bases with the reference
-                    if (!orient_by_longest_segment(pending.read_one.seq, rm.references[0].sequence, seeds).forward) {
-                        pending.read_one.seq = reverse_complement(pending.read_one.seq);
-                    }
-                }
                 if (layout.empty()) ok = b.push(pending.read_one.id, pending.read_one.seq.data(), pending.read_one.seq.size(), pending.read_one.qual.data());
                 else {
                     const MergedSequence m = merge_reads_by_concatenation(pending, layout);
@@ -296,7 +287,8 @@ int main(int argc, char** argv) {
             }
             sink_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         };
-        const AlignReadsStats st = sh.align_reads(a.synthetic ? synth_source : source, a.scoring, !a.exhaustive, sink, a.tags, a.rust_bio);
+        const AlignReadsStats st = sh.align_reads(a.synthetic ? synth_source : source, a.scoring, !a.exhaustive, sink, a.tags, a.rust_bio,
+                                                  /*known_strand=*/!a.unknown_strand);  // the library orients the reads (alignment_functions.rs:549-558)
         if (as_bam) { std::string z; bam::bgzf_eof(z); out->write(z.data(), (std::streamsize)z.size()); }
         out->flush();
         char js[640];

@@ -253,6 +253,7 @@ public:
     uint32_t size() const { return n_; }
     uint32_t capacity() const { return max_reads_; }
     const uint8_t* read(uint32_t i) const { return bytes_ + off_[i]; }
+    uint8_t* read_mut(uint32_t i) { return bytes_ + off_[i]; }  // in-place re-orientation (same length) before the batch is submitted
     size_t read_len(uint32_t i) const { return (size_t)(off_[i + 1] - off_[i]); }
     std::string name(uint32_t i) const { return std::string(name_bytes_.data() + name_off_[i], name_off_[i + 1] - name_off_[i]); }
     const char* name_data(uint32_t i) const { return name_bytes_.data() + name_off_[i]; }
@@ -386,8 +387,10 @@ public:
     /// align_reads' par_bridge loop (alignment_functions.rs:135-249) up to the writer: drains `source` into pinned batches,
     /// keeps every stream slot busy, hands each finished batch to `sink`.
     /// `rust_bio`: single-reference panels take the rust-bio branch (see align_to_reference_choices); records then carry score 0.
+    /// `known_strand = false` (single-reference panels only, alignment_functions.rs:549-558): every read is oriented on the host
+    /// by orient_by_longest_segment and reverse-complemented in the pinned batch when the reverse strand shares more bases.
     AlignReadsStats align_reads(const ReadSource& source, const AffineScoring& scoring, bool fast_lookup, const ResultSink& sink,
-                                bool extract_tags = true, bool rust_bio = false);
+                                bool extract_tags = true, bool rust_bio = false, bool known_strand = true);
 
     // ---- raw slot interface (used by ShardedAligner and the bench driver) ----
     uint32_t search_flags(bool fast_lookup) const;
@@ -410,7 +413,8 @@ private:
     std::vector<uint8_t*> tags_;
     std::vector<uint32_t> flags_;
     std::vector<int32_t> scale_;
-    uint64_t pool_ops_ = 0, tags_cap_ = 0;
+    uint64_t pool_ops_ = 0;
+    std::vector<uint64_t> tags_cap_;
     std::unique_ptr<ReadBatch> one_;  // staging for the single-read calls
     std::vector<std::unique_ptr<ReadBatch>> bufs_;  // pinned staging of the batch loop, one per stream slot (allocated once)
 };
@@ -423,7 +427,7 @@ public:
     ShardedAligner(const std::vector<int>& devices, AlignerOptions opt = AlignerOptions());
     void set_references(const ReferenceManager& rm, bool build_kmer_index = true);
     AlignReadsStats align_reads(const ReadSource& source, const AffineScoring& scoring, bool fast_lookup, const ResultSink& sink,
-                                bool extract_tags = true, bool rust_bio = false);
+                                bool extract_tags = true, bool rust_bio = false, bool known_strand = true);
     size_t n_devices() const { return aligners_.size(); }
     Aligner& aligner(size_t k) { return *aligners_[k]; }
 

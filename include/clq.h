@@ -107,7 +107,7 @@ typedef struct {
  * (alignment/alignment_matrix.rs:694-706, alignment_functions.rs:451-456) */
 typedef struct {
     int32_t score_scaled; /* AlignmentResult.score * scale (exact) */
-    uint32_t ref_index;   /* index into the clq_refs_set order     */
+    uint32_t ref_index;   /* index into the clq_refs_set order; 0xffffffff when no usable reference (CLQ_NO_CANDIDATE) */
     uint32_t cigar_off;   /* first op in the CIGAR pool            */
     uint32_t cigar_len;   /* run-length merged ops                 */
     uint32_t status;

@@ -19,6 +19,8 @@ use clq::{affine_scoring, rustbio_scoring, BatchResults, CigarOp, Context, Mode,
 use crate::alignment::alignment_matrix::{AlignmentLocation, AlignmentResult, AlignmentTag};
 use crate::alignment::scoring_functions::AffineScoring;
 use crate::alignment_manager::{BamFileAlignmentWriter, OutputAlignmentWriter};
+use crate::linked_alignment::orient_by_longest_segment;
+use crate::utils::read_utils::reverse_complement;
 use crate::read_strategies::read_disk_sorter::SortingReadSetContainer;
 use crate::read_strategies::sequence_layout::SequenceLayout;
 use crate::reference::fasta_reference::ReferenceManager;
@@ -138,14 +140,36 @@ where
         let batch = ctx.batch_mut(slot).expect("slot is idle");
         batch.clear();
         while let Some(r) = reads.peek() {
-            if !batch.push(r.seq(), if single { Some(0) } else { None }) {
+            // align_to_reference_choices, :549-558: with one reference and an unknown strand the read is oriented on the host
+            // first (orient_by_longest_segment against the reference's suffix table) and reverse-complemented when the
+            // reverse strand shares more bases; the GPU then aligns the oriented bytes
+            let oriented: Option<Vec<u8>> = if single && !read_structure.known_strand {
+                let reference = &rm.references[&order[0]];
+                let read_vec: Vec<u8> = r.seq().to_vec(); // the reference's helpers take &Vec<u8>
+                let (forward, _, _) = orient_by_longest_segment(&read_vec, &reference.sequence, &reference.suffix_table);
+                if forward { None } else { Some(reverse_complement(&read_vec)) }
+            } else {
+                None
+            };
+            let seq: &[u8] = oriented.as_deref().unwrap_or_else(|| r.seq());
+            if !batch.push(seq, if single { Some(0) } else { None }) {
+                if batch.len() == 0 {
+                    // a read that does not fit an EMPTY batch never will (longer than the slot's max_read_bytes): drop it with
+                    // the reference's own message (:240-247) instead of submitting empty batches forever
+                    let r = reads.next().unwrap();
+                    warn!("Dropped read {} is it's length {} exceeds 2x the reference length {}",
+                          String::from_utf8_lossy(r.name()), r.seq().len(), max_read_size);
+                    continue;
+                }
                 break;
             }
             let r = reads.next().unwrap();
             m.names.push(String::from_utf8(r.name().clone()).unwrap());
             m.quals.push(r.quals.clone());
         }
-        ctx.submit(slot, &scoring, mode).expect("clq_submit");
+        if batch.len() > 0 {
+            ctx.submit(slot, &scoring, mode).expect("clq_submit");
+        }
         slot = (slot + 1) % n_slots;
     }
 }
