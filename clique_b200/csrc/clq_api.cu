@@ -17,6 +17,17 @@ using namespace clq;
 
 namespace {
 
+// -DCLQ_LEAN=1: development build that instantiates only the (8,40) and (32,32) geometries (convex: (8,16), (32,32)); any other
+// geometry falls through to (32,32).  Cuts the compile time of a kernel experiment from ~90 s to ~25 s.  Never shipped.
+#ifndef CLQ_LEAN
+#define CLQ_LEAN 0
+#endif
+#if CLQ_LEAN
+#define CLQ_FULL_CASE(n, stmt)
+#else
+#define CLQ_FULL_CASE(n, stmt) case n: stmt;
+#endif
+
 struct Cfg { int G, C; };
 // wavefront geometries: G lanes per pair x C columns per lane (stripe width W = G*C)
 const Cfg kCfgs[] = {{8, 16}, {8, 24}, {8, 40}, {16, 24}, {32, 16}, {32, 32}};
@@ -135,11 +146,11 @@ cudaError_t launch_one(const KParams& p, int sm_count, size_t smem, cudaStream_t
 template <bool TB, bool FIN, bool FAST, bool RB = false>
 cudaError_t launch_cfg(int cfg, const KParams& p, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
     switch (cfg) {
-        case 0: return launch_one<8, 16, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q);
-        case 1: return launch_one<8, 24, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q);
+        CLQ_FULL_CASE(0, return (launch_one<8, 16, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q)))
+        CLQ_FULL_CASE(1, return (launch_one<8, 24, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q)))
         case 2: return launch_one<8, 40, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q);
-        case 3: return launch_one<16, 24, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q);
-        case 4: return launch_one<32, 16, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q);
+        CLQ_FULL_CASE(3, return (launch_one<16, 24, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q)))
+        CLQ_FULL_CASE(4, return (launch_one<32, 16, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q)))
         default: return launch_one<32, 32, TB, FIN, FAST, RB>(p, sm, smem, st, grid, q);
     }
 }
@@ -174,11 +185,11 @@ cudaError_t launch_pack_one(const KParams& p, const PackParams& pp, int sm_count
 template <bool TB, bool RB = false>
 cudaError_t launch_pack(int cfg, const KParams& p, const PackParams& pp, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
     switch (cfg) {
-        case 0: return launch_pack_one<8, 16, TB, RB>(p, pp, sm, smem, st, grid, q);
-        case 1: return launch_pack_one<8, 24, TB, RB>(p, pp, sm, smem, st, grid, q);
+        CLQ_FULL_CASE(0, return (launch_pack_one<8, 16, TB, RB>(p, pp, sm, smem, st, grid, q)))
+        CLQ_FULL_CASE(1, return (launch_pack_one<8, 24, TB, RB>(p, pp, sm, smem, st, grid, q)))
         case 2: return launch_pack_one<8, 40, TB, RB>(p, pp, sm, smem, st, grid, q);
-        case 3: return launch_pack_one<16, 24, TB, RB>(p, pp, sm, smem, st, grid, q);
-        case 4: return launch_pack_one<32, 16, TB, RB>(p, pp, sm, smem, st, grid, q);
+        CLQ_FULL_CASE(3, return (launch_pack_one<16, 24, TB, RB>(p, pp, sm, smem, st, grid, q)))
+        CLQ_FULL_CASE(4, return (launch_pack_one<32, 16, TB, RB>(p, pp, sm, smem, st, grid, q)))
         default: return launch_pack_one<32, 32, TB, RB>(p, pp, sm, smem, st, grid, q);
     }
 }
@@ -210,9 +221,9 @@ template <bool TB>
 cudaError_t launch_cvx(int cfg, const KParams& p, const ConvexParams& cp, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
     switch (cfg) {
         case 0: return launch_cvx_one<8, 16, TB>(p, cp, sm, smem, st, grid, q);
-        case 1: return launch_cvx_one<16, 16, TB>(p, cp, sm, smem, st, grid, q);
-        case 2: return launch_cvx_one<16, 32, TB>(p, cp, sm, smem, st, grid, q);
-        case 4: return launch_cvx_one<32, 16, TB>(p, cp, sm, smem, st, grid, q);
+        CLQ_FULL_CASE(1, return (launch_cvx_one<16, 16, TB>(p, cp, sm, smem, st, grid, q)))
+        CLQ_FULL_CASE(2, return (launch_cvx_one<16, 32, TB>(p, cp, sm, smem, st, grid, q)))
+        CLQ_FULL_CASE(4, return (launch_cvx_one<32, 16, TB>(p, cp, sm, smem, st, grid, q)))
         default: return launch_cvx_one<32, 32, TB>(p, cp, sm, smem, st, grid, q);
     }
 }
@@ -240,9 +251,9 @@ template <bool TB>
 cudaError_t launch_cvx_pack(int cfg, const KParams& p, const ConvexParams& cp, const PackParams& pp, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
     switch (cfg) {
         case 0: return launch_cvx_pack_one<8, 16, TB>(p, cp, pp, sm, smem, st, grid, q);
-        case 1: return launch_cvx_pack_one<16, 16, TB>(p, cp, pp, sm, smem, st, grid, q);
-        case 2: return launch_cvx_pack_one<16, 32, TB>(p, cp, pp, sm, smem, st, grid, q);
-        case 4: return launch_cvx_pack_one<32, 16, TB>(p, cp, pp, sm, smem, st, grid, q);
+        CLQ_FULL_CASE(1, return (launch_cvx_pack_one<16, 16, TB>(p, cp, pp, sm, smem, st, grid, q)))
+        CLQ_FULL_CASE(2, return (launch_cvx_pack_one<16, 32, TB>(p, cp, pp, sm, smem, st, grid, q)))
+        CLQ_FULL_CASE(4, return (launch_cvx_pack_one<32, 16, TB>(p, cp, pp, sm, smem, st, grid, q)))
         default: return launch_cvx_pack_one<32, 32, TB>(p, cp, pp, sm, smem, st, grid, q);
     }
 }
@@ -257,9 +268,9 @@ cudaError_t launch_cvx_walk_one(const KParams& p, uint32_t cnt, cudaStream_t st)
 cudaError_t launch_cvx_walk(int cfg, const KParams& p, uint32_t cnt, cudaStream_t st) {
     switch (cfg) {
         case 0: return launch_cvx_walk_one<8, 16>(p, cnt, st);
-        case 1: return launch_cvx_walk_one<16, 16>(p, cnt, st);
-        case 2: return launch_cvx_walk_one<16, 32>(p, cnt, st);
-        case 4: return launch_cvx_walk_one<32, 16>(p, cnt, st);
+        CLQ_FULL_CASE(1, return (launch_cvx_walk_one<16, 16>(p, cnt, st)))
+        CLQ_FULL_CASE(2, return (launch_cvx_walk_one<16, 32>(p, cnt, st)))
+        CLQ_FULL_CASE(4, return (launch_cvx_walk_one<32, 16>(p, cnt, st)))
         default: return launch_cvx_walk_one<32, 32>(p, cnt, st);
     }
 }
@@ -274,19 +285,21 @@ cudaError_t launch_walk_one(const KParams& p, uint32_t cnt, cudaStream_t st) {
 
 cudaError_t launch_walk(int cfg, const KParams& p, uint32_t cnt, cudaStream_t st) {
     switch (cfg) {
-        case 0: return launch_walk_one<8, 16>(p, cnt, st);
-        case 1: return launch_walk_one<8, 24>(p, cnt, st);
+        CLQ_FULL_CASE(0, return (launch_walk_one<8, 16>(p, cnt, st)))
+        CLQ_FULL_CASE(1, return (launch_walk_one<8, 24>(p, cnt, st)))
         case 2: return launch_walk_one<8, 40>(p, cnt, st);
-        case 3: return launch_walk_one<16, 24>(p, cnt, st);
-        case 4: return launch_walk_one<32, 16>(p, cnt, st);
+        CLQ_FULL_CASE(3, return (launch_walk_one<16, 24>(p, cnt, st)))
+        CLQ_FULL_CASE(4, return (launch_walk_one<32, 16>(p, cnt, st)))
         default: return launch_walk_one<32, 32>(p, cnt, st);
     }
 }
 
 int pick_cfg(const clq_ctx* c, uint32_t max_len) {
     if (c->force_cfg >= 0 && c->force_cfg < kNumCfgs) return c->force_cfg;
-    for (int i = 0; i < kNumCfgs; i++)
+    for (int i = 0; i < kNumCfgs; i++) {
+        if (CLQ_LEAN && i != 2 && i != kNumCfgs - 1) continue;
         if ((uint32_t)(kCfgs[i].G * kCfgs[i].C) >= max_len) return i;
+    }
     return kNumCfgs - 1;
 }
 
@@ -724,7 +737,8 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         // pairs per warp: C3 990 GCUPS against 837 on (32,32)); the stripe-boundary column costs less than the occupancy
         if (search == CLQ_SEARCH_FIXED && !c->no_pack && n && cvx_window(128, nullptr)) cfg = 0;
         if (c->force_cfg >= 0 && c->force_cfg < kNumCvxCfgs) cfg = c->force_cfg;
-    }
+        if (CLQ_LEAN && cfg != 0) cfg = 3;
+    } else if (CLQ_LEAN && cfg != 2) cfg = kNumCfgs - 1;
     const int G = convex ? kCvxCfgs[cfg].G : kCfgs[cfg].G, C = convex ? kCvxCfgs[cfg].C : kCfgs[cfg].C, W = G * C, GPW = 32 / G;
     const int bits_per_cell = convex ? 8 : 4;
     const uint32_t L1max = c->max_ref_len, L2max = s->max_len;
