@@ -543,18 +543,28 @@ class Aligner:
             yield from drain(*it)
 
 
-def shard_bounds(read_off, n_shards, ref_len=1):
-    """Contiguous read ranges balanced by sum(L1*L2) ~ sum(L2).  Returns n_shards+1 boundaries."""
+def shard_bounds(read_off, n_shards, ref_len=1, fixed_ref=None):
+    """Contiguous read ranges balanced by cells, sum(L1 * L2), not by bytes: on length-sorted input a byte
+    split gives the shard of long reads many times the work of the shard of short ones.  `ref_len`: one reference length, or a
+    sequence of reference lengths indexed by `fixed_ref` (reads without a usable reference count with the longest).  Returns
+    n_shards + 1 boundaries."""
     read_off = np.asarray(read_off, dtype=np.uint64)
     n = len(read_off) - 1
-    total = int(read_off[-1] - read_off[0]) if n else 0
+    lens = (read_off[1:] - read_off[:-1]).astype(np.float64)
+    rl = np.atleast_1d(np.asarray(ref_len, dtype=np.float64))
+    if fixed_ref is not None and rl.size > 1:
+        fr = np.asarray(fixed_ref, dtype=np.int64)
+        ok = (fr >= 0) & (fr < rl.size)
+        l1 = np.where(ok, rl[np.clip(fr, 0, rl.size - 1)], rl.max())
+    else:
+        l1 = np.full(n, rl.max() if rl.size else 1.0)
+    cum = np.concatenate([[0.0], np.cumsum(np.maximum(l1, 1.0) * lens)])
     bounds = [0]
     for k in range(1, n_shards):
-        target = int(read_off[0]) + total * k // n_shards
-        bounds.append(int(np.searchsorted(read_off, target, side="left")))
+        bounds.append(int(np.searchsorted(cum, cum[-1] * k / n_shards, side="left")))
     bounds.append(n)
     for k in range(1, len(bounds)):
-        bounds[k] = max(bounds[k], bounds[k - 1])
+        bounds[k] = min(n, max(bounds[k], bounds[k - 1]))
     return bounds
 
 
@@ -575,7 +585,8 @@ class ShardedAligner:
 
     def align_batch(self, read_bytes, read_off, scoring, search="fixed", band="readlen", fixed_ref=None, score_only=False) -> BatchResult:
         read_off = np.asarray(read_off, dtype=np.uint64)
-        bounds = shard_bounds(read_off, len(self.aligners))
+        ref_lens = [len(r.sequence) for r in self.aligners[0].rm.references] if self.aligners[0].rm is not None else [1]
+        bounds = shard_bounds(read_off, len(self.aligners), ref_lens or [1], fixed_ref)
         outs = [None] * len(self.aligners)
         errs = []
 

@@ -11,6 +11,8 @@
 // into packed accumulators (low half = read A, high half = read B) and unzipped with PRMT into each read's row word.
 #pragma once
 
+#include <type_traits>
+
 #include "clq_kernels.cuh"
 
 // Experiment switch (default off; DESIGN.md "next experiments", identity checked on the CPU in tests/test_pack_bit_identities.py):
@@ -27,6 +29,53 @@ __device__ __forceinline__ uint32_t set_lo(uint32_t w, int v) { return (w & 0xff
 __device__ __forceinline__ uint32_t set_hi(uint32_t w, int v) { return (w & 0x0000ffffu) | ((uint32_t)v << 16); }
 __device__ __forceinline__ int get_lo(uint32_t w) { return (int)(w & 0xffffu); }
 __device__ __forceinline__ int get_hi(uint32_t w) { return (int)(w >> 16); }
+
+// shared-memory accessors on 32-bit shared addresses (the generic-pointer form re-derives the CTA's shared window -- S2UR
+// SR_CgaCtaId + ULEA -- at every use inside the step loop)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint2 lds_u64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+// Direction-bit store of both reads of a PACK task: one flush branch per step for the pair (bits_store per read costs two).
+// The words are parked unconditionally (the buffer is private to the lane); only the global stores depend on the read.
+template <int G, int WPL>
+__device__ __forceinline__ void bits_store2(uint32_t* tt, uint32_t* bitsA, uint32_t* bitsB, const uint32_t (&wA)[WPL], const uint32_t (&wB)[WPL],
+                                            bool stA, bool stB, int s, int T, int t, int lane, int gl, bool last_row, int nb) {
+    if constexpr (BitsLayout<G>::transposed) {
+        const int Tb = (T + 7) >> 3;
+        const int ph = (t - 1) & 7;
+        uint32_t* ttB = tt + WPL * 256;
+#pragma unroll
+        for (int k = 0; k < WPL; k++) { tt[(k * 8 + ph) * 32 + lane] = wA[k]; ttB[(k * 8 + ph) * 32 + lane] = wB[k]; }
+        if (ph == 7 || last_row) {
+            const size_t at = ((size_t)(s * Tb + ((t - 1) >> 3)) * (G * WPL) + gl * WPL) * 8;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (h ? stB : stA) {
+                    uint32_t* dst = (h ? bitsB : bitsA) + at;
+                    const uint32_t* buf = h ? ttB : tt;
+#pragma unroll
+                    for (int k = 0; k < WPL; k++) {
+                        const uint32_t* src = buf + (k * 8) * 32 + lane;
+                        *reinterpret_cast<uint4*>(dst + k * 8) = make_uint4(src[0], src[32], src[64], src[96]);
+                        *reinterpret_cast<uint4*>(dst + k * 8 + 4) = make_uint4(src[128], src[160], src[192], src[224]);
+                    }
+                }
+            }
+        }
+    } else {
+        if (stA) row_store<G, WPL>(bitsA, wA, s, T, t, gl, nb);
+        if (stB) row_store<G, WPL>(bitsB, wB, s, T, t, gl, nb);
+    }
+}
 
 struct PackParams {
     int32_t bias;  // added to every stored score
@@ -242,6 +291,15 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
         uint32_t* bitsA = TB ? p.bits + bits_slot(p.bits_off, p.bits_stride, p.task_base, 2 * task) : nullptr;
         uint32_t* bitsB = (TB && valid[1]) ? p.bits + bits_slot(p.bits_off, p.bits_stride, p.task_base, 2 * task + 1) : nullptr;
 
+        // Warp-uniform fast path: one column stripe and no band-skipped cells anywhere in the warp.  The step loop is compiled
+        // twice (steps<SIMPLE>): per-step branches cost ~12 issue slots each on a 2-warps-per-scheduler kernel (ncu source page,
+        // profiles/ncu_r02_s1_pack_and_walk.txt: 40 % of the warp samples sat in the 17 % of instructions around the row step),
+        // so the common case keeps only four: the loop, `act`, the last-row capture and the 8-step bit flush.
+        // (short-read geometries only: a long-read warp would alternate between the two copies from task to task and the second
+        // copy costs more instruction-cache misses than the branches it removes -- C3 1510 -> 1383 GCUPS when both were compiled)
+        const bool simple = G <= 8 && NSmax <= 1 && __reduce_max_sync(FULL, (unsigned)(K[0] | K[1])) == 0u;
+        const uint32_t NB1 = dup16(-sc.b1), NX1 = dup16(-x1);  // boundary column g(x): plain packed arithmetic on positive halves
+
         for (int s = 0; s < NSmax; s++) {
             const bool act_s = anyrun && s < NS;
             const bool ownA = run[0] && s == NSh[0] - 1 && gl == lLh[0];
@@ -270,71 +328,95 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
             if (s > 0 && gl == 0 && act_s) {
                 nF = col_g[1]; nE = col_g[p.col_stride + 1]; nM = col_g[2 * p.col_stride + 1]; nB = col_g[3 * p.col_stride + 1];
             }
-            int rnext = act_s ? ref_sm[0] : 0;
-
-            for (int t = 1; t <= Tmax; t++) {
-                const int x = t - gl;
-                uint32_t Fl = __shfl_up_sync(FULL, oF, 1, G);
-                uint32_t Bl = __shfl_up_sync(FULL, oB, 1, G);
-                uint32_t El = 0, Ml = 0;
-                if (TB && !RB) {
-                    El = __shfl_up_sync(FULL, oE, 1, G);  // CLQ_PACK_EXT2_VIA_EP: the eP bit of the left lane's last cell
-                    if (!CLQ_PACK_EXT2_VIA_EP) Ml = __shfl_up_sync(FULL, oM, 1, G);
-                }
-                const bool act = act_s && x >= 1 && x <= L1;
-                if (act) {
-                    if (gl == 0) {
-                        if (s == 0) {
-                            const int g = sc.b0 + x * sc.b1 + bias;  // S[x,0] = (MAXNEG, g(x), g(x))
-                            Bl = dup16(g);
-                            Fl = El = dup16(g - x1);
+            // per-step conditions as single integer compares (predicates do not survive the 900-instruction row step, so a
+            // compound condition is re-evaluated from its parts every step)
+            const uint32_t L1act = act_s ? (uint32_t)L1 : 0u;          // act  <=>  (unsigned)(x - 1) < L1act
+            const int xcap = (ownA || ownB) ? L1 : -1;                 // the capture variant: only the lane(s) owning column L2, at row L1
+            const bool first_col = (gl == 0) && (s == 0);
+            const bool stA = TB && run[0] && s < NSh[0], stB = TB && run[1] && s < NSh[1];
+            // the profile row of the current reference class comes from a lane shuffle (lane k holds row k of the 16-row table):
+            // no shared-memory address arithmetic in the loop; the class of the next row is read one step ahead
+            // (the long-read geometries run at 3 CTAs/SM on 168 registers and cannot spare the two table registers: they load
+            // the row from shared memory instead)
+            constexpr bool TAB_SHFL = G <= 8;
+            const uint2 tab_row = TAB_SHFL ? *(const uint2*)(tab_sm + (lane & 15) * 8) : make_uint2(0u, 0u);
+            uint32_t rcur = act_s ? (uint32_t)ref_sm[0] : 0u;
+            auto steps = [&](auto simple_tag) {
+                constexpr bool SIMPLE = decltype(simple_tag)::value;
+                uint32_t gB = dup16(sc.b0 + bias);  // lane 0 of stripe 0: g(x) + bias, advanced by one row per step (x = t there)
+                int t = 1;
+                if (Tmax >= 1) do {
+                    const int x = t - gl;
+                    uint32_t Fl = __shfl_up_sync(FULL, oF, 1, G);
+                    uint32_t Bl = __shfl_up_sync(FULL, oB, 1, G);
+                    uint32_t El = 0, Ml = 0;
+                    if (TB && !RB) {
+                        El = __shfl_up_sync(FULL, oE, 1, G);  // CLQ_PACK_EXT2_VIA_EP: the eP bit of the left lane's last cell
+                        if (!CLQ_PACK_EXT2_VIA_EP) Ml = __shfl_up_sync(FULL, oM, 1, G);
+                    }
+                    uint2 tr;
+                    if (TAB_SHFL) {
+                        tr.x = __shfl_sync(FULL, tab_row.x, (int)rcur);
+                        tr.y = __shfl_sync(FULL, tab_row.y, (int)rcur);
+                    } else {
+                        tr = *(const uint2*)(tab_sm + rcur * 8);
+                    }
+                    gB -= NB1;
+                    if ((uint32_t)(x - 1) < L1act) {
+                        if (first_col) {  // S[x,0] = (MAXNEG, g(x), g(x)); selects, not a branch
+                            Bl = gB;
+                            Fl = El = gB + NX1;
                             Ml = 0;  // the sentinel: below every biased value
                             if (CLQ_PACK_EXT2_VIA_EP && TB && !RB) El = 0;  // boundary column: E = F = g(x), eP = 0
                             if (RB) Fl = 0;  // rust-bio: I[i][0] = MIN_SCORE on the empty-read boundary
-                        } else {
-                            Fl = nF; El = nE; Ml = nM; Bl = nB;
-                            if (x < L1) {
-                                nF = col_g[x + 1]; nE = col_g[p.col_stride + x + 1];
-                                nM = col_g[2 * p.col_stride + x + 1]; nB = col_g[3 * p.col_stride + x + 1];
+                        }
+                        if (!SIMPLE) {
+                            if (gl == 0 && s > 0) {
+                                Fl = nF; El = nE; Ml = nM; Bl = nB;
+                                if (x < L1) {
+                                    nF = col_g[x + 1]; nE = col_g[p.col_stride + x + 1];
+                                    nM = col_g[2 * p.col_stride + x + 1]; nB = col_g[3 * p.col_stride + x + 1];
+                                }
+                            }
+                        }
+                        rcur = ref_sm[x < L1 ? x : L1 - 1];  // class of row x + 1 (clamped on the last row: unused)
+                        const uint32_t BlIn = Bl;
+                        // the capture variant only runs on the lane(s) that own column L2, at their last row: once per task
+                        if (x == xcap)
+                            pack_row_step<C, TB, true, RB>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap, nb);
+                        else
+                            pack_row_step<C, TB, false, RB>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap, nb);
+                        prevBl = BlIn;
+                        oF = Fl; oE = El; oM = Ml; oB = Bl;
+                        if (!SIMPLE) {
+                            // band-skipped cells (x <= K, y == L2): fresh-matrix state (0,0,0), per read
+                            if ((ownA && x <= K[0]) || (ownB && x <= K[1])) {
+                                const bool sa = ownA && x <= K[0], sb = ownB && x <= K[1];
+                                const int e0 = -x1 + bias, b0v = bias;
+#pragma unroll
+                                for (int j = 0; j < C; j++) {
+                                    if (sa && j == jLh[0]) { Eh[j] = set_lo(Eh[j], e0); B[j] = set_lo(B[j], b0v); }
+                                    if (sb && j == jLh[1]) { Eh[j] = set_hi(Eh[j], e0); B[j] = set_hi(B[j], b0v); }
+                                }
+                                const int oe0 = (CLQ_PACK_EXT2_VIA_EP && TB && !RB) ? 0 : e0;  // fresh-matrix cell: E = M = F, eP = 0
+                                if (sa && jLh[0] == Cs - 1) { oF = set_lo(oF, e0); oE = set_lo(oE, oe0); oM = set_lo(oM, b0v); oB = set_lo(oB, b0v); }
+                                if (sb && jLh[1] == Cs - 1) { oF = set_hi(oF, e0); oE = set_hi(oE, oe0); oM = set_hi(oM, b0v); oB = set_hi(oB, b0v); }
+                                if (x == L1) {
+                                    if (sa) { cap[0] = set_lo(cap[0], bias); cap[1] = set_lo(cap[1], e0); cap[2] = set_lo(cap[2], e0); }
+                                    if (sb) { cap[0] = set_hi(cap[0], bias); cap[1] = set_hi(cap[1], e0); cap[2] = set_hi(cap[2], e0); }
+                                }
+                            }
+                        }
+                        if (TB) bits_store2<G, WPL>(tt_sm, bitsA, bitsB, wA, wB, stA, stB, s, T, t, lane, gl, x == L1, nb);
+                        if (!SIMPLE) {
+                            if (gl == G - 1 && s < NS - 1) {
+                                col_g[x] = oF; col_g[p.col_stride + x] = oE; col_g[2 * p.col_stride + x] = oM; col_g[3 * p.col_stride + x] = oB;
                             }
                         }
                     }
-                    const int r = rnext;
-                    if (x < L1) rnext = ref_sm[x];
-                    const uint32_t BlIn = Bl;
-                    const uint2 tr = *(const uint2*)(tab_sm + r * 8);
-                    if (x == L1)
-                        pack_row_step<C, TB, true, RB>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap, nb);
-                    else
-                        pack_row_step<C, TB, false, RB>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap, nb);
-                    prevBl = BlIn;
-                    oF = Fl; oE = El; oM = Ml; oB = Bl;
-                    // band-skipped cells (x <= K, y == L2): fresh-matrix state (0,0,0), per read
-                    if ((ownA && x <= K[0]) || (ownB && x <= K[1])) {
-                        const bool sa = ownA && x <= K[0], sb = ownB && x <= K[1];
-                        const int e0 = -x1 + bias, b0v = bias;
-#pragma unroll
-                        for (int j = 0; j < C; j++) {
-                            if (sa && j == jLh[0]) { Eh[j] = set_lo(Eh[j], e0); B[j] = set_lo(B[j], b0v); }
-                            if (sb && j == jLh[1]) { Eh[j] = set_hi(Eh[j], e0); B[j] = set_hi(B[j], b0v); }
-                        }
-                        const int oe0 = (CLQ_PACK_EXT2_VIA_EP && TB && !RB) ? 0 : e0;  // fresh-matrix cell: E = M = F, eP = 0
-                        if (sa && jLh[0] == Cs - 1) { oF = set_lo(oF, e0); oE = set_lo(oE, oe0); oM = set_lo(oM, b0v); oB = set_lo(oB, b0v); }
-                        if (sb && jLh[1] == Cs - 1) { oF = set_hi(oF, e0); oE = set_hi(oE, oe0); oM = set_hi(oM, b0v); oB = set_hi(oB, b0v); }
-                        if (x == L1) {
-                            if (sa) { cap[0] = set_lo(cap[0], bias); cap[1] = set_lo(cap[1], e0); cap[2] = set_lo(cap[2], e0); }
-                            if (sb) { cap[0] = set_hi(cap[0], bias); cap[1] = set_hi(cap[1], e0); cap[2] = set_hi(cap[2], e0); }
-                        }
-                    }
-                    if (TB) {
-                        if (run[0] && s < NSh[0]) bits_store<G, WPL>(tt_sm, bitsA, wA, s, T, t, lane, gl, x == L1, nb);
-                        if (run[1] && s < NSh[1]) bits_store<G, WPL>(tt_sm + WPL * 256, bitsB, wB, s, T, t, lane, gl, x == L1, nb);
-                    }
-                    if (gl == G - 1 && s < NS - 1) {
-                        col_g[x] = oF; col_g[p.col_stride + x] = oE; col_g[2 * p.col_stride + x] = oM; col_g[3 * p.col_stride + x] = oB;
-                    }
-                }
-            }
+                } while (++t <= Tmax);
+            };
+            if (G <= 8 && simple) steps(std::true_type{}); else steps(std::false_type{});
             __syncwarp();
         }
 

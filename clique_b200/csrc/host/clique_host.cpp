@@ -3,7 +3,10 @@
 
 #include <algorithm>
 #include <charconv>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -508,6 +511,20 @@ bool ReadBatch::push(const char* name, size_t name_len, const uint8_t* seq, size
     return true;
 }
 
+bool ReadBatch::assign_span(const uint8_t* bytes, const uint64_t* off, uint64_t lo, uint64_t hi, const int32_t* fixed_ref) {
+    const uint64_t n = hi - lo, nb = off[hi] - off[lo];
+    if (n > max_reads_ || nb > max_bytes_) return false;
+    clear();
+    if (nb) std::memcpy(bytes_, bytes + off[lo], nb);
+    const uint64_t base = off[lo];
+    for (uint64_t i = 0; i <= n; i++) off_[i] = off[lo + i] - base;
+    if (fixed_ref) std::memcpy(fixed_, fixed_ref + lo, n * sizeof(int32_t));
+    else std::fill(fixed_, fixed_ + n, -1);
+    name_off_.assign((size_t)n + 1, 0);
+    n_ = (uint32_t)n;
+    return true;
+}
+
 std::optional<Bytes> ReadBatch::quals(uint32_t i) const {
     if (!have_quals_) return std::nullopt;
     return Bytes(quals_.begin() + (size_t)off_[i], quals_.begin() + (size_t)off_[i + 1]);
@@ -844,6 +861,7 @@ BatchView Aligner::wait(int slot, const ReadBatch& b) {
     v.scale = scale_[slot];
     v.device = opt_.device;
     v.rust_bio = (flags_[slot] & CLQ_RUSTBIO) != 0;
+    v.cigar_used = used;
     if (flags_[slot] & CLQ_EXTRACT_TAGS) {
         uint32_t stride = 0;
         check(clq_tags_download(ctx_, slot, nullptr, 0, &stride), "clq_tags_download");
@@ -1135,6 +1153,201 @@ AlignReadsStats ShardedAligner::align_reads(const ReadSource& source, const Affi
     if (err) std::rethrow_exception(err);
     total.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - total.setup_seconds;
     return total;
+}
+
+// ------------------------------------------------------------------------------------------------ span feed
+namespace {
+// a tiny blocking queue of batch buffers (indices into the device's buffer pool)
+struct IdxQueue {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<int> q;
+    bool closed = false;
+    void push(int v) { { std::lock_guard<std::mutex> g(mu); q.push_back(v); } cv.notify_one(); }
+    void close() { { std::lock_guard<std::mutex> g(mu); closed = true; } cv.notify_all(); }
+    bool pop(int& v) {  // false once closed and drained
+        std::unique_lock<std::mutex> g(mu);
+        cv.wait(g, [&] { return !q.empty() || closed; });
+        if (q.empty()) return false;
+        v = q.front(); q.pop_front();
+        return true;
+    }
+};
+}  // namespace
+
+SpanStats ShardedAligner::align_reads_span(const ReadSpan& span, const AffineScoring& scoring, bool fast_lookup, SpanOutput& out,
+                                           int fillers_per_device, bool extract_tags, bool rust_bio) {
+    SpanStats stats;
+    const size_t nd = aligners_.size();
+    stats.device_kernel_ms.assign(nd, 0.0);
+    stats.device_reads.assign(nd, 0); stats.device_cells.assign(nd, 0); stats.device_batches.assign(nd, 0);
+    out.cigar_used = 0;
+    if (!nd || !span.n) return stats;
+    const ReferenceManager& rm = aligners_[0]->references();
+    if (rm.references.empty()) return stats;
+    if (!span.bytes || !span.off || !out.results) fail(CLQ_E_INVALID, "align_reads_span: null span or result array");
+    const AlignerOptions& opt = aligners_[0]->options();
+    const bool rb = rust_bio && rm.references.size() == 1;
+    const clq_affine_t sc = rb ? RustBioScoring().to_int() : scoring.to_int();
+    out.scale = sc.scale;
+    uint32_t flags = aligners_[0]->search_flags(fast_lookup) | (extract_tags ? CLQ_EXTRACT_TAGS : 0u) | (rb ? CLQ_RUSTBIO : 0u);
+    if (span.fixed_ref && rm.references.size() > 1) flags = (flags & ~CLQ_SEARCH_MASK) | CLQ_SEARCH_FIXED;  // the caller knows the reference of every read
+    const int nf = std::max(1, fillers_per_device);
+    const uint32_t ns = opt.n_slots;
+    const int nbuf = (int)ns + nf;  // per device: one batch per stream slot in flight + one per filler being staged
+
+    const auto tsetup = std::chrono::steady_clock::now();
+    struct Dev {
+        std::vector<std::unique_ptr<ReadBatch>>* pool = nullptr;
+        IdxQueue free_q, ready_q;
+        std::atomic<int> fillers_left{0};
+    };
+    std::vector<std::unique_ptr<Dev>> devs;
+    span_bufs_.resize(nd);
+    for (size_t d = 0; d < nd; d++) {
+        devs.push_back(std::make_unique<Dev>());
+        while ((int)span_bufs_[d].size() < nbuf) span_bufs_[d].push_back(std::make_unique<ReadBatch>(opt.max_reads, opt.max_read_bytes));  // page-locked once
+        devs[d]->pool = &span_bufs_[d];
+        for (int b = 0; b < nbuf; b++) devs[d]->free_q.push(b);
+        devs[d]->fillers_left = nf;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    stats.total.setup_seconds = std::chrono::duration<double>(t0 - tsetup).count();
+
+    // one cursor over the whole span: a claim takes up to a full batch, but never more than 1 / (4 * devices) of what is left
+    // (guided self-scheduling), so the last batches are small and the devices drain together even on length-sorted input
+    std::mutex claim_mu;
+    uint64_t cursor = 0;
+    const uint64_t min_claim = std::min<uint64_t>(opt.max_reads, 4096);
+    auto claim = [&](uint64_t& lo, uint64_t& hi) -> bool {
+        std::lock_guard<std::mutex> g(claim_mu);
+        if (cursor >= span.n) return false;
+        lo = cursor;
+        const uint64_t left_bytes = span.off[span.n] - span.off[lo];
+        uint64_t want_bytes = std::min<uint64_t>(opt.max_read_bytes, std::max<uint64_t>(left_bytes / (4 * nd), 1));
+        // last read whose end stays within want_bytes (binary search over the offsets), at least min_claim reads when they fit
+        const uint64_t* first = span.off + lo + 1;
+        const uint64_t* last = span.off + span.n + 1;
+        uint64_t by_bytes = (uint64_t)(std::upper_bound(first, last, span.off[lo] + want_bytes) - first);
+        uint64_t cap_bytes = (uint64_t)(std::upper_bound(first, last, span.off[lo] + opt.max_read_bytes) - first);
+        uint64_t n = std::max<uint64_t>(by_bytes, std::min<uint64_t>(min_claim, cap_bytes));
+        n = std::min<uint64_t>(n, std::min<uint64_t>(opt.max_reads, span.n - lo));
+        if (n == 0) n = 1;  // a read larger than a whole batch: handed over alone, reported CLQ_READ_TOO_LONG below
+        hi = lo + n;
+        cursor = hi;
+        return true;
+    };
+
+    std::mutex stat_mu, pool_mu;
+    std::exception_ptr err;
+    std::atomic<bool> failed{false};
+    auto fail_with = [&](std::exception_ptr e) {
+        std::lock_guard<std::mutex> g(stat_mu);
+        if (!err) err = e;
+        failed = true;
+    };
+
+    auto filler = [&](size_t d) {
+        Dev& D = *devs[d];
+        double secs = 0.0;
+        try {
+            uint64_t lo, hi;
+            while (!failed && claim(lo, hi)) {
+                int b;
+                if (!D.free_q.pop(b)) break;
+                const auto f0 = std::chrono::steady_clock::now();
+                ReadBatch& rbuf = *(*D.pool)[b];
+                if (!rbuf.assign_span(span.bytes, span.off, lo, hi, span.fixed_ref)) {
+                    // does not fit even an empty batch (one read beyond max_read_bytes): the reference drops such reads (:240-247)
+                    for (uint64_t i = lo; i < hi; i++) { clq_result_t r = {}; r.status = CLQ_READ_TOO_LONG; r.ref_index = 0xffffffffu; out.results[i] = r; }
+                    D.free_q.push(b);
+                    std::lock_guard<std::mutex> g(stat_mu);
+                    stats.total.reads += hi - lo; stats.total.dropped += hi - lo;
+                    continue;
+                }
+                rbuf.first_index = lo;
+                secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - f0).count();
+                D.ready_q.push(b);
+            }
+        } catch (...) { fail_with(std::current_exception()); }
+        if (--D.fillers_left == 0) D.ready_q.close();
+        std::lock_guard<std::mutex> g(stat_mu);
+        stats.fill_seconds += secs;
+    };
+
+    auto device = [&](size_t d) {
+        Dev& D = *devs[d];
+        Aligner& a = *aligners_[d];
+        double sink_secs = 0.0, kernel_ms = 0.0;
+        uint64_t reads = 0, cells = 0, batches = 0, aligned = 0, dropped = 0;
+        std::vector<int> in_slot(ns, -1);
+        auto drain = [&](uint32_t s) {
+            const int b = in_slot[s];
+            const BatchView v = a.wait((int)s, *(*D.pool)[b]);
+            const clq_stats_t st = a.stats((int)s);
+            kernel_ms += st.kernel_ms; cells += st.cells;
+            const auto s0 = std::chrono::steady_clock::now();
+            const uint64_t first = v.batch->first_index, n = v.size();
+            uint64_t base;
+            {
+                std::lock_guard<std::mutex> g(pool_mu);
+                base = out.cigar_used; out.cigar_used += v.cigar_used;
+                if (v.tags && v.tag_stride) out.tag_stride = v.tag_stride;
+            }
+            if (base + v.cigar_used > out.cigar_cap || base + v.cigar_used > 0xffffffffull) fail(CLQ_E_LIMIT, "align_reads_span: the caller's CIGAR pool is too small");
+            if (v.cigar_used) std::memcpy(out.cigar_pool + base, v.cigar_pool, v.cigar_used * sizeof(uint32_t));
+            clq_result_t* dst = out.results + first;
+            for (uint64_t i = 0; i < n; i++) {
+                clq_result_t r = v.results[i];
+                r.cigar_off += (uint32_t)base;
+                dst[i] = r;
+                (r.status == CLQ_OK ? aligned : dropped)++;
+            }
+            if (out.tags && v.tags && v.tag_stride) {
+                std::memcpy(out.tags + first * v.tag_stride, v.tags, n * v.tag_stride);
+            }
+            sink_secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
+            reads += n; batches++;
+            in_slot[s] = -1;
+            D.free_q.push(b);
+        };
+        try {
+            uint32_t slot = 0;
+            int b;
+            while (D.ready_q.pop(b)) {
+                if (failed) { D.free_q.push(b); continue; }
+                if (in_slot[slot] >= 0) drain(slot);
+                ReadBatch& rbuf = *(*D.pool)[b];
+                prepare_fixed(rbuf, flags);
+                a.submit((int)slot, rbuf, sc, flags);
+                in_slot[slot] = b;
+                slot = (slot + 1) % ns;
+            }
+            for (uint32_t k = 0; k < ns; k++) {
+                const uint32_t s = (slot + k) % ns;
+                if (in_slot[s] >= 0) drain(s);
+            }
+        } catch (...) {
+            fail_with(std::current_exception());
+            D.free_q.close();  // unblock this device's fillers
+            int b;
+            while (D.ready_q.pop(b)) {}
+        }
+        std::lock_guard<std::mutex> g(stat_mu);
+        stats.device_kernel_ms[d] = kernel_ms; stats.device_reads[d] = reads; stats.device_cells[d] = cells; stats.device_batches[d] = batches;
+        stats.total.reads += reads; stats.total.cells += cells; stats.total.batches += batches; stats.total.aligned += aligned; stats.total.dropped += dropped;
+        stats.sink_seconds += sink_secs;
+    };
+
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < nd; d++) {
+        th.emplace_back(device, d);
+        for (int f = 0; f < nf; f++) th.emplace_back(filler, d);
+    }
+    for (auto& t : th) t.join();
+    if (err) std::rethrow_exception(err);
+    stats.total.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return stats;
 }
 
 }  // namespace clique

@@ -240,4 +240,53 @@ size_t clqh_merge_reads_by_concatenation(const uint8_t* r1, size_t n1, const uin
     }
 }
 
+
+int32_t clqh_align_reads_span(const int32_t* devices, uint32_t n_devices, const clqh_span_options_t* o, const uint8_t* ref_bytes,
+                              const uint64_t* ref_off, uint32_t n_refs, const uint8_t* read_bytes, const uint64_t* read_off, uint64_t n_reads,
+                              const int32_t* fixed_ref, double match_score, double mismatch_score, double special_score, double gap_open,
+                              double gap_extend, double final_gap_multiplier, uint32_t passes, void* results, uint32_t* cigar_pool,
+                              uint64_t cigar_cap, uint64_t* cigar_used, int32_t* scale, double* stats, char* err, size_t err_cap) {
+    try {
+        if (!devices || !n_devices || !o) throw ClqError(CLQ_E_INVALID, "clqh_align_reads_span: no devices / options");
+        AlignerOptions opt;
+        opt.max_reads = o->max_reads;
+        opt.max_read_bytes = o->max_read_bytes;
+        opt.max_read_len = o->max_read_len;
+        opt.cigar_ops_per_read = o->cigar_ops_per_read;
+        opt.n_slots = o->n_slots;
+        opt.max_refs = std::max<uint32_t>(64, n_refs);
+        ShardedAligner sh(std::vector<int>(devices, devices + n_devices), opt);
+        std::vector<Reference> refs;
+        for (uint32_t r = 0; r < n_refs; r++)
+            refs.push_back({Bytes(ref_bytes + ref_off[r], ref_bytes + ref_off[r + 1]), to_bytes("ref" + std::to_string(r))});
+        sh.set_references(ReferenceManager(std::move(refs)));
+        ReadSpan span;
+        span.bytes = read_bytes; span.off = read_off; span.n = n_reads; span.fixed_ref = fixed_ref;
+        SpanOutput out;
+        out.results = static_cast<clq_result_t*>(results);
+        out.cigar_pool = cigar_pool;
+        out.cigar_cap = cigar_cap;
+        const AffineScoring sc{match_score, mismatch_score, special_score, gap_open, gap_extend, final_gap_multiplier};
+        SpanStats st;
+        // pass 0 warms up (page-locks the staging buffers, sizes the device scratch); the last pass is the one reported
+        for (uint32_t k = 0; k < std::max<uint32_t>(1, passes); k++) st = sh.align_reads_span(span, sc, o->fast_lookup != 0, out, o->fillers_per_device, o->extract_tags != 0);
+        if (cigar_used) *cigar_used = out.cigar_used;
+        if (scale) *scale = out.scale;
+        if (stats) {
+            stats[0] = st.total.seconds; stats[1] = st.total.setup_seconds; stats[2] = st.fill_seconds; stats[3] = st.sink_seconds;
+            stats[4] = (double)st.total.reads; stats[5] = (double)st.total.aligned; stats[6] = (double)st.total.dropped; stats[7] = (double)st.total.batches;
+            for (uint32_t d = 0; d < n_devices; d++) {
+                stats[8 + 3 * d] = st.device_kernel_ms[d]; stats[9 + 3 * d] = (double)st.device_reads[d]; stats[10 + 3 * d] = (double)st.device_cells[d];
+            }
+        }
+        return CLQ_OK;
+    } catch (const ClqError& e) {
+        if (err && err_cap) { std::strncpy(err, e.what(), err_cap - 1); err[err_cap - 1] = 0; }
+        return e.code ? e.code : CLQ_E_INVALID;
+    } catch (const std::exception& e) {
+        if (err && err_cap) { std::strncpy(err, e.what(), err_cap - 1); err[err_cap - 1] = 0; }
+        return CLQ_E_INVALID;
+    }
+}
+
 }  // extern "C"

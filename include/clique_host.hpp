@@ -250,8 +250,12 @@ public:
     }
     /// allocation-free form (names live in one flat buffer): the per-read cost is two memcpys
     bool push(const char* name, size_t name_len, const uint8_t* seq, size_t n, const uint8_t* qual = nullptr, int32_t fixed_ref = -1);
+    /// replaces the batch by reads [lo, hi) of a caller-owned span (bytes + offsets, any host memory): one memcpy of the bytes,
+    /// offsets rebased, unnamed reads, no qualities.  false when the range exceeds the batch's capacity.
+    bool assign_span(const uint8_t* bytes, const uint64_t* off, uint64_t lo, uint64_t hi, const int32_t* fixed_ref);
     uint32_t size() const { return n_; }
     uint32_t capacity() const { return max_reads_; }
+    uint64_t byte_capacity() const { return max_bytes_; }
     const uint8_t* read(uint32_t i) const { return bytes_ + off_[i]; }
     uint8_t* read_mut(uint32_t i) { return bytes_ + off_[i]; }  // in-place re-orientation (same length) before the batch is submitted
     size_t read_len(uint32_t i) const { return (size_t)(off_[i + 1] - off_[i]); }
@@ -292,6 +296,7 @@ public:
     int32_t scale = 1;
     int device = 0;
     bool rust_bio = false;  // CLQ_RUSTBIO batch: the reference reports score 0.0 and an empty path for these records
+    uint64_t cigar_used = 0;  // ops of cigar_pool this batch filled
 
     uint32_t status(uint32_t i) const { return results[i].status; }
     double score(uint32_t i) const { return (double)results[i].score_scaled / (double)scale; }
@@ -419,6 +424,36 @@ private:
     std::vector<std::unique_ptr<ReadBatch>> bufs_;  // pinned staging of the batch loop, one per stream slot (allocated once)
 };
 
+/// A contiguous span of reads already in host memory -- what a FASTQ block decoder (or the stage before align_reads) hands
+/// over: read i = bytes[off[i] .. off[i+1]).  The memory need not be page-locked.  fixed_ref (nullable): per-read reference for
+/// multi-reference inputs whose assignment is known; single-reference panels need none.
+struct ReadSpan {
+    const uint8_t* bytes = nullptr;
+    const uint64_t* off = nullptr;
+    uint64_t n = 0;
+    const int32_t* fixed_ref = nullptr;
+};
+
+/// Caller-owned result arrays of ShardedAligner::align_reads_span, in input order: results[i] for read i (cigar_off indexes
+/// cigar_pool), tags (nullable) n * tag_stride bytes.
+struct SpanOutput {
+    clq_result_t* results = nullptr;
+    uint32_t* cigar_pool = nullptr;
+    uint64_t cigar_cap = 0;
+    uint64_t cigar_used = 0;      // out
+    uint8_t* tags = nullptr;      // optional, n * tag_stride bytes (tag_stride from the reference set)
+    uint32_t tag_stride = 0;      // out
+    int32_t scale = 1;            // out: score = score_scaled / scale
+};
+
+struct SpanStats {
+    AlignReadsStats total;
+    std::vector<double> device_kernel_ms;     // sum of the kernels' device time per GPU (CUDA events)
+    std::vector<uint64_t> device_reads, device_cells, device_batches;
+    double fill_seconds = 0.0;                // sum over filler threads: staging copies into pinned batches
+    double sink_seconds = 0.0;                // sum over device threads: results copied out to the caller's arrays
+};
+
 /// Read-sharded dispatcher over the GPUs of one box: one Aligner + one host thread per device pull
 /// batches from the shared source; no collective, no peer traffic.  The sink is called under a mutex (the reference's
 /// writer is behind Arc<Mutex<..>> too) in completion order; BatchView::batch->first_index places a batch in the input.
@@ -428,11 +463,19 @@ public:
     void set_references(const ReferenceManager& rm, bool build_kmer_index = true);
     AlignReadsStats align_reads(const ReadSource& source, const AffineScoring& scoring, bool fast_lookup, const ResultSink& sink,
                                 bool extract_tags = true, bool rust_bio = false, bool known_strand = true);
+    /// The same loop fed from an in-memory span (the analogue of `read_iterator.par_bridge().for_each`, alignment_functions.rs:135,
+    /// for input that is already decoded): batches are cut dynamically from one shared cursor (shrinking towards the end of
+    /// the input so that the GPUs finish together, whatever the read-length order), `fillers_per_device` host threads per GPU
+    /// stage them into page-locked batches (the only copy of the read bytes on the host), one thread per GPU submits / waits
+    /// and writes the records into `out` in input order.  No collective, no peer traffic.
+    SpanStats align_reads_span(const ReadSpan& span, const AffineScoring& scoring, bool fast_lookup, SpanOutput& out,
+                               int fillers_per_device = 2, bool extract_tags = false, bool rust_bio = false);
     size_t n_devices() const { return aligners_.size(); }
     Aligner& aligner(size_t k) { return *aligners_[k]; }
 
 private:
     std::vector<std::unique_ptr<Aligner>> aligners_;
+    std::vector<std::vector<std::unique_ptr<ReadBatch>>> span_bufs_;  // page-locked staging of align_reads_span, per device (allocated once)
 };
 
 }  // namespace clique

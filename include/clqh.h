@@ -58,6 +58,27 @@ size_t clqh_bam_file(const char* ref_name, const char* read_name, const uint8_t*
 size_t clqh_merge_reads_by_concatenation(const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const char* layout, uint8_t* out,
                                          size_t cap);
 
+/* align_reads over an in-memory span through clique::ShardedAligner::align_reads_span (one clq_ctx + host threads per device;
+ * the analogue of the par_bridge loop, alignment_functions.rs:135): reads from plain (unpinned) host memory, results into the
+ * caller's arrays in input order.  Needs CUDA devices.  stats (nullable, >= 8 + 3 * n_devices doubles): [seconds, setup_seconds,
+ * fill_seconds, sink_seconds, reads, aligned, dropped, batches], then per device kernel_ms, reads, cells. */
+typedef struct {
+    uint32_t max_reads;            /* per batch / stream slot */
+    uint64_t max_read_bytes;       /* per batch; 0: max_reads * 512 */
+    uint32_t max_read_len;
+    uint32_t cigar_ops_per_read;
+    uint32_t n_slots;
+    int32_t fillers_per_device;
+    int32_t fast_lookup;           /* > 1 reference without fixed_ref: quick (1) or exhaustive (0) search */
+    int32_t extract_tags;
+} clqh_span_options_t;
+int32_t clqh_align_reads_span(const int32_t* devices, uint32_t n_devices, const clqh_span_options_t* opt, const uint8_t* ref_bytes,
+                              const uint64_t* ref_off, uint32_t n_refs, const uint8_t* read_bytes, const uint64_t* read_off, uint64_t n_reads,
+                              const int32_t* fixed_ref, double match_score, double mismatch_score, double special_score, double gap_open,
+                              double gap_extend, double final_gap_multiplier, uint32_t passes, void* results /* clq_result_t[n_reads] */,
+                              uint32_t* cigar_pool, uint64_t cigar_cap, uint64_t* cigar_used, int32_t* scale, double* stats, char* err,
+                              size_t err_cap);
+
 #ifdef __cplusplus
 }
 #endif

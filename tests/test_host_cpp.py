@@ -19,7 +19,8 @@ CLQ_ALIGN = os.path.join(ROOT, "clique_b200", "clq_align")
 SYMBOLS = ["clqh_extract_tagged_sequences", "clqh_reverse_complement", "clqh_f64_to_string", "clqh_get_reference_alignment_rate",
            "clqh_simplify_cigar", "clqh_from_cigar", "clqh_sam_line", "clqh_merge_reads_by_concatenation",
            "clqh_combine_phred_scores", "clqh_alignment_rate_and_consensus", "clqh_merge_read_pairs_by_alignment",
-           "clqh_find_greedy_non_overlapping_segments", "clqh_orient_by_longest_segment", "clqh_bam_file", "clqh_extend_hit"]
+           "clqh_find_greedy_non_overlapping_segments", "clqh_orient_by_longest_segment", "clqh_bam_file", "clqh_extend_hit",
+           "clqh_align_reads_span"]
 
 
 @pytest.fixture(scope="module")
@@ -523,6 +524,67 @@ def test_clq_align_two_gpus(H, tmp_path):
     _, two, st2 = _run_clq_align(str(tmp_path), fa, rp, ["--gpus", "0,1"])
     assert st2["gpus"] == 2 and st1["reads"] == st2["reads"] == 2000
     assert one == two
+
+
+def _span_case(n=6000):
+    """length-sorted mixed-length input (the hard case for a contiguous byte split): C5 reads, shortest first"""
+    from clique_b200 import synth
+    c = synth.config_c5(n, unique_per_amplicon=32)
+    off = c["read_off"]
+    lens = (off[1:] - off[:-1]).astype(np.int64)
+    order = np.argsort(lens, kind="stable")
+    reads = [bytes(c["read_bytes"][int(off[i]):int(off[i + 1])]) for i in order]
+    qb, qo = O.pack_seqs(reads)
+    return c, qb, qo, c["fixed_ref"][order].astype(np.int32)
+
+
+def _check_span(br, c, qb, qo, fixed, n_check):
+    rb, ro = O.pack_seqs(c["refs"])
+    idx = np.unique(np.linspace(0, len(qo) - 2, n_check).astype(np.int64))
+    reads = [bytes(qb[int(qo[i]):int(qo[i + 1])]) for i in idx]
+    sb, so = O.pack_seqs(reads)
+    want = O.align_batch(rb, ro, sb, so, c["scoring"], search="fixed", fixed_ref=fixed[idx], band_mode="readlen", threads=8)
+    for k, i in enumerate(idx):
+        assert int(br.status[i]) == int(want["status"][k]) == 0, (i, int(br.status[i]))
+        assert int(br.ref_index[i]) == int(want["ref_index"][k]), i
+        assert int(br.score_scaled[i]) == want["score"][k] * br.scale, i
+        o, l = int(want["cigar_off"][k]), int(want["cigar_len"][k])
+        assert O.cigar_str(br.cigar(int(i))) == O.cigar_str(want["cigar_pool"][o:o + l]), i
+
+
+@pytest.mark.gpu
+def test_align_reads_span_one_gpu():
+    """ShardedAligner::align_reads_span on one device: reads in plain host memory, dynamic batches (much smaller than the
+    input, so the guided claims, the buffer pool and the CIGAR-pool rebasing all run), records in input order == oracle."""
+    from clique_b200 import AffineScoring
+    from clique_b200.host import align_reads_span
+    c, qb, qo, fixed = _span_case(3000)
+    br, st = align_reads_span([0], c["refs"], qb, qo, AffineScoring(*c["scoring"]), fixed_ref=fixed, batch_reads=512, batch_bytes=1 << 20,
+                              max_read_len=1 << 15, cigar_ops_per_read=700, fillers_per_device=2, passes=2)
+    assert st["reads"] == 3000 and st["aligned"] == 3000 and st["batches"] > 4
+    assert int(br.cigar_len.sum()) == len(br.cigar_pool)
+    _check_span(br, c, qb, qo, fixed, 40)
+
+
+@pytest.mark.gpu
+def test_align_reads_span_all_gpus():
+    """the same stream sharded over every visible GPU by the product dispatcher (one process, one cursor, no collective):
+    every device takes part, the union of the records == the single-device run.  Skipped on a one-GPU box."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "clique_b200", "libclq.so"))
+    ng = lib.clq_device_count()
+    if ng < 2:
+        pytest.skip("needs two GPUs")
+    from clique_b200 import AffineScoring
+    from clique_b200.host import align_reads_span
+    c, qb, qo, fixed = _span_case(6000)
+    kw = dict(fixed_ref=fixed, batch_reads=256, batch_bytes=1 << 19, max_read_len=1 << 15, cigar_ops_per_read=700, fillers_per_device=2)
+    one, _ = align_reads_span([0], c["refs"], qb, qo, AffineScoring(*c["scoring"]), **kw)
+    many, st = align_reads_span(list(range(ng)), c["refs"], qb, qo, AffineScoring(*c["scoring"]), **kw)
+    assert st["reads"] == 6000 and all(r > 0 for r in st["device_reads"]), st
+    assert (one.score_scaled == many.score_scaled).all() and (one.status == many.status).all() and (one.cigar_len == many.cigar_len).all()
+    for i in range(0, 6000, 97):
+        assert one.cigar_string(i) == many.cigar_string(i), i
 
 
 @pytest.mark.gpu

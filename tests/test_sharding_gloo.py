@@ -65,3 +65,18 @@ def test_shard_bounds_edges():
     b = shard_bounds(off, 8)
     assert b[0] == 0 and b[-1] == 4 and all(b[i] <= b[i + 1] for i in range(8))
     assert shard_bounds(np.array([0], dtype=np.uint64), 3) == [0, 0, 0, 0]
+
+
+def test_shard_bounds_balance_cells_not_bytes():
+    """contiguous ranges balanced by sum(L1 * L2).  On length-sorted mixed input (C5: 300 bp reads then
+    5 kb reads, each against its own amplicon) a byte split would give the last shard ~16x the cells per byte of the first."""
+    sys.path.insert(0, ROOT)
+    from clique_b200.aligner import shard_bounds
+    lens = np.concatenate([np.full(1000, 300), np.full(1000, 5000)])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    fixed = np.concatenate([np.zeros(1000, np.int32), np.ones(1000, np.int32)])
+    b = shard_bounds(off, 4, [300, 5000], fixed)
+    cells = np.where(fixed == 0, 300, 5000) * lens
+    share = [cells[b[i]:b[i + 1]].sum() / cells.sum() for i in range(4)]
+    assert max(share) - min(share) < 0.01, share
+    assert b[1] > 1000  # the whole block of short reads is far less than a quarter of the work

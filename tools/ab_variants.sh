@@ -23,10 +23,12 @@ run)
         cp tools/_v/libclq_$name.so clique_b200/libclq.so
         echo "== $name"
         CLQ_FUZZ_MODES=fixed,fixed,exhaustive,quick CLQ_FUZZ_NO_PACK_P=0.1 timeout 60 python tools/fuzz_gpu.py ${FUZZ_SECONDS:-25} 4711 2>&1 | tail -2
-        timeout 60 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-live-peak 2>/dev/null | python -c '
+        for wl in ${AB_WORKLOADS:-C2}; do
+        timeout 120 python bench.py --workload $wl --steps ${AB_STEPS:-6} --warmup 3 --no-cpu-baseline --no-live-peak --no-extra 2>/dev/null | python -c '
 import sys, json
 d = json.loads(sys.stdin.readline())
-print("ms_per_step %.3f  reads/s %.4g  e2e %.4g  dp_kernel_ms %.3f  ok_reads %d" % (d["ms_per_step"], d["value"], d["e2e"]["value"], d["roofline"]["kernel_ms"], d["config"]["status_ok_reads"]))'
+print("%s ms_per_step %.3f  reads/s %.4g  gcups %.1f  e2e %.4g  dp_kernel_ms %.3f  ok_reads %d" % (sys.argv[1], d["ms_per_step"], d["value"], d["gcups"], d["e2e"]["value"], d["roofline"]["kernel_ms"], d["config"]["status_ok_reads"]))' $wl
+        done
     done ;;
 *) echo "usage: $0 build name=flags... | run name..."; exit 2 ;;
 esac
