@@ -246,7 +246,7 @@ def run_config(args, workload, n, search, convex, rustbio, steps, warmup, e2e_ch
         assert c["search"] == "fixed" and not convex, "--rustbio is the single-reference branch"
         sci = RustBioScoring()   # Aligner.launch adds CLQ_RUSTBIO for this scoring type
         c["band"] = "maxlen"
-    for opt in ("force_cfg", "force_generic", "debug_flags", "no_pack"):     # experiment knobs, e.g. CLQ_FORCE_CFG=3
+    for opt in ("force_cfg", "force_generic", "debug_flags", "no_pack", "no_madd"):     # experiment knobs, e.g. CLQ_FORCE_CFG=3
         if os.environ.get("CLQ_" + opt.upper()):
             al.set_option(opt, int(os.environ["CLQ_" + opt.upper()]))
     score_only = bool(int(os.environ.get("CLQ_SCORE_ONLY", "0")))
@@ -351,7 +351,7 @@ def run_config(args, workload, n, search, convex, rustbio, steps, warmup, e2e_ch
             "e2e_ms": e2e_ms, "h2d": int(h2d), "d2h": int(d2h), "nch": nch}
 
 
-def api_pass(c, devices, n_reads_total, passes=3, batch_reads=1 << 18, fillers=2):
+def api_pass(c, devices, n_reads_total, passes=3, batch_reads=1 << 18, fillers=2, repeat=1):
     """The product's batch loop (C++ clique::ShardedAligner::align_reads_span, the analogue of align_reads' par_bridge loop,
     alignment_functions.rs:135) over `devices`, fed from plain UNPINNED host memory: staging copy into page-locked batches, H2D,
     kernels, D2H and the copy of the records into the caller's arrays are all inside the timed region (C++ steady_clock around
@@ -362,8 +362,14 @@ def api_pass(c, devices, n_reads_total, passes=3, batch_reads=1 << 18, fillers=2
     mean_len = float(lens.mean()) if len(lens) else 1.0
     ops_per_read = int(max(16, 12 if mean_len < 400 else mean_len * 0.7))
     batch_bytes = int(min(1 << 30, max(1 << 22, batch_reads * mean_len * 1.25)))
-    br, st = align_reads_span(devices, c["refs"], c["read_bytes"][:int(c["read_off"][-1])], c["read_off"], AffineScoring(*c["scoring"]),
-                              fixed_ref=c["fixed_ref"] if len(c["refs"]) > 1 else None, batch_reads=batch_reads, batch_bytes=batch_bytes,
+    rbytes, roff, fixed = c["read_bytes"][:int(c["read_off"][-1])], c["read_off"], c["fixed_ref"]
+    if repeat > 1:   # one longer stream: the same reads `repeat` times over (the pipeline's fill / drain latency is paid once per stream)
+        n0, tot = len(roff) - 1, int(roff[-1])
+        rbytes = np.tile(rbytes, repeat)
+        roff = np.concatenate([roff[:-1].astype(np.uint64) + np.uint64(tot * k) for k in range(repeat)] + [np.array([tot * repeat], np.uint64)])
+        fixed = None if fixed is None else np.tile(fixed, repeat)
+    br, st = align_reads_span(devices, c["refs"], rbytes, roff, AffineScoring(*c["scoring"]),
+                              fixed_ref=fixed if len(c["refs"]) > 1 else None, batch_reads=batch_reads, batch_bytes=batch_bytes,
                               max_read_len=1 << 15, cigar_ops_per_read=ops_per_read, n_slots=2, fillers_per_device=fillers,
                               fast_lookup=(c["search"] == "quick"), passes=passes)
     return br, st
@@ -481,19 +487,21 @@ def main():
     e2e_api, sharded = None, None
     if not args.no_api and not args.convex and not args.rustbio:
         try:
-            br_api, st_api = api_pass(c, [dev], n, passes=3)
+            rep = max(1, min(8, 4_000_000 // max(n, 1)))
+            br_api, st_api = api_pass(c, [dev], n, passes=3, repeat=rep)
             barrier()
             t = torch.tensor([st_api["seconds"]], dtype=torch.float64, device="cuda")
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             api_s = float(t[0])
-            same = bool((br_api.score_scaled == res.score_scaled).all() and (br_api.cigar_len == res.cigar_len).all() and (br_api.status == res.status).all())
-            e2e_api = {"value": n * n_gpus / api_s, "unit": "reads/s", "ms_per_step": 1e3 * api_s, "batches": st_api["batches"],
+            same = all(bool((br_api.score_scaled[k * n:(k + 1) * n] == res.score_scaled).all() and (br_api.cigar_len[k * n:(k + 1) * n] == res.cigar_len).all()
+                            and (br_api.status[k * n:(k + 1) * n] == res.status).all()) for k in range(rep))
+            e2e_api = {"value": n * rep * n_gpus / api_s, "unit": "reads/s", "ms_per_step": 1e3 * api_s / rep, "reads_per_stream": n * rep, "batches": st_api["batches"],
                        "fill_thread_seconds": st_api["fill_seconds"], "sink_thread_seconds": st_api["sink_seconds"],
                        "identical_to_device_resident_results": same,
                        "how": "clique::ShardedAligner::align_reads_span (C++ align_reads loop) on 1 GPU per rank: reads in plain unpinned host memory, "
                               "2 filler threads stage 262144-read batches into page-locked buffers, double-buffered submit / wait, records copied out "
-                              "to the caller's arrays; staging copy + H2D + kernels + D2H + copy-out inside the timer (third pass reported)"}
+                              "to the caller's arrays; staging copy + H2D + kernels + D2H + copy-out inside the timer; one stream of %d x the step's reads (third pass reported)" % rep}
         except Exception as e:  # noqa: BLE001
             e2e_api = {"error": "%s: %s" % (type(e).__name__, e)}
         if world > 1:

@@ -66,7 +66,7 @@ struct clq_ctx {
     int sm_count = 0;
     clq_limits_t lim = {};
     std::string err;
-    DevBuf ref_bytes, ref_off, kmer_keys, kmer_owner, tag_slot;
+    DevBuf ref_bytes, ref_off, kmer_keys, kmer_owner, kmer_keys64, tag_slot;
     uint32_t tag_stride = 0;         // most tag columns ('0'..'9') of any reference, rounded up to 4
     std::vector<uint8_t> h_ref_bytes;
     std::vector<uint64_t> h_ref_off;
@@ -76,6 +76,7 @@ struct clq_ctx {
     int force_cfg = -1;
     int debug_flags = 0;
     int no_pack = 0;                 // option "no_pack": never take the s16x2 PACK kernels
+    int no_madd = 0;                 // option "no_madd": PACK kernels without the static row slope (M step on the ALU pipe)
     int no_group = 0;                // option "no_group": multi-reference traceback stays on the int32 kernels (no bucketing by reference)
     int force_generic = 0;           // option "force_generic": never take the FAST (PRMT/DPX) kernel variant
     bool fast_ok = false;            // the reference set has <= 6 distinct non-special bytes
@@ -163,9 +164,9 @@ cudaError_t launch_any(int cfg, bool tb, bool fin, bool fast, bool rb, const KPa
     return fin ? launch_cfg<false, true, false>(cfg, p, sm, smem, st, grid, q) : launch_cfg<false, false, false>(cfg, p, sm, smem, st, grid, q);
 }
 
-template <int G, int C, bool TB, bool RB = false>
+template <int G, int C, bool TB, bool RB = false, bool MADD = false>
 cudaError_t launch_pack_one(const KParams& p, const PackParams& pp, int sm_count, size_t smem, cudaStream_t st, int* grid_out, bool query_only) {
-    auto kern = pack_kernel<G, C, TB, RB>;
+    auto kern = pack_kernel<G, C, TB, RB, MADD>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -182,15 +183,15 @@ cudaError_t launch_pack_one(const KParams& p, const PackParams& pp, int sm_count
     return cudaGetLastError();
 }
 
-template <bool TB, bool RB = false>
+template <bool TB, bool RB = false, bool MADD = false>
 cudaError_t launch_pack(int cfg, const KParams& p, const PackParams& pp, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
     switch (cfg) {
-        CLQ_FULL_CASE(0, return (launch_pack_one<8, 16, TB, RB>(p, pp, sm, smem, st, grid, q)))
-        CLQ_FULL_CASE(1, return (launch_pack_one<8, 24, TB, RB>(p, pp, sm, smem, st, grid, q)))
-        case 2: return launch_pack_one<8, 40, TB, RB>(p, pp, sm, smem, st, grid, q);
-        CLQ_FULL_CASE(3, return (launch_pack_one<16, 24, TB, RB>(p, pp, sm, smem, st, grid, q)))
-        CLQ_FULL_CASE(4, return (launch_pack_one<32, 16, TB, RB>(p, pp, sm, smem, st, grid, q)))
-        default: return launch_pack_one<32, 32, TB, RB>(p, pp, sm, smem, st, grid, q);
+        CLQ_FULL_CASE(0, return (launch_pack_one<8, 16, TB, RB, MADD>(p, pp, sm, smem, st, grid, q)))
+        CLQ_FULL_CASE(1, return (launch_pack_one<8, 24, TB, RB, MADD>(p, pp, sm, smem, st, grid, q)))
+        case 2: return launch_pack_one<8, 40, TB, RB, MADD>(p, pp, sm, smem, st, grid, q);
+        CLQ_FULL_CASE(3, return (launch_pack_one<16, 24, TB, RB, false>(p, pp, sm, smem, st, grid, q)))  // MADD: G <= 8 only (clq_launch)
+        CLQ_FULL_CASE(4, return (launch_pack_one<32, 16, TB, RB, false>(p, pp, sm, smem, st, grid, q)))
+        default: return launch_pack_one<32, 32, TB, RB, false>(p, pp, sm, smem, st, grid, q);
     }
 }
 
@@ -430,7 +431,7 @@ void clq_ctx_destroy(clq_ctx* c) {
             release(*b);
         if (s.h_counters) cudaFreeHost(s.h_counters);
     }
-    release(c->ref_bytes); release(c->ref_off); release(c->kmer_keys); release(c->kmer_owner); release(c->cls_lut); release(c->cls_lut_rb); release(c->tag_slot);
+    release(c->ref_bytes); release(c->ref_off); release(c->kmer_keys); release(c->kmer_owner); release(c->kmer_keys64); release(c->cls_lut); release(c->cls_lut_rb); release(c->tag_slot);
     delete c;
 }
 
@@ -442,6 +443,7 @@ int32_t clq_set_option(clq_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "force_generic")) { c->force_generic = (int)value; return CLQ_OK; }
     if (!strcmp(key, "debug_flags")) { c->debug_flags = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_pack")) { c->no_pack = (int)value; return CLQ_OK; }
+    if (!strcmp(key, "no_madd")) { c->no_madd = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_group")) { c->no_group = (int)value; return CLQ_OK; }
     if (!strcmp(key, "serialize_slots")) { c->serialize = (int)value; return CLQ_OK; }
     if (!strcmp(key, "max_scratch_bytes")) {
@@ -581,6 +583,16 @@ int32_t clq_kmer_index_set(clq_ctx* c, uint32_t k, uint32_t skip) {
     if (!keys.empty()) {
         CU(c, cudaMemcpy(c->kmer_keys.p, keys.data(), keys.size(), cudaMemcpyHostToDevice));
         CU(c, cudaMemcpy(c->kmer_owner.p, owner.data(), owner.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    if (k <= 8) {  // packed big-endian copy for kmer_vote_packed_kernel (same order: memcmp order == numeric order)
+        std::vector<uint64_t> k64(owner.size() + 1, 0);
+        for (size_t i = 0; i < owner.size(); i++) {
+            uint64_t v = 0;
+            for (uint32_t b = 0; b < k; b++) v = (v << 8) | keys[i * k + b];
+            k64[i] = v;
+        }
+        if ((rc = ensure(c, c->kmer_keys64, k64.size() * sizeof(uint64_t))) != CLQ_OK) return rc;
+        CU(c, cudaMemcpy(c->kmer_keys64.p, k64.data(), k64.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
     }
     c->kmer_k = k;
     c->kmer_skip = skip;
@@ -746,13 +758,13 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     const uint32_t ref_sm_stride = (L1max + 15) / 16 * 16 + 16;
     // + per-warp transposition buffers of the direction bits (C/8 KiB per warp, twice for the PACK kernels); the
     // convex kernels keep the plain row layout
-    const size_t smem = (size_t)(kThreads / 32) * GPW * ref_sm_stride + (fast ? kLutBytes + kTabBytes : 0) + ((!convex && G <= 8) ? (size_t)(kThreads / 32) * (C / 8) * 1024 * 2 : 0);
+    const size_t smem = (size_t)(kThreads / 32) * GPW * ref_sm_stride + (fast ? kLutBytes + kTabBytes : 0) + ((!convex && G <= kTransposeMaxG) ? (size_t)(kThreads / 32) * (C / 8) * 1024 * 2 : 0);
     if (smem > 200 * 1024) return fail(c, CLQ_E_LIMIT, "references too long for this geometry's shared-memory staging");
     // s16x2 PACK kernels: two reads per lane group.  Needs the FAST preconditions plus a proof that every cell value of
     // this batch fits a 15-bit window: B >= 2*g(0) + (L1+L2)*e (the all-gap corner path), everything else is within a gap
     // open / one substitution of B, and nothing exceeds max(match, special) * min(L1, L2).
     PackParams pkp = {};
-    bool pack = false;
+    bool pack = false, madd = false;
     if (fast && !convex && !c->no_pack && n) {
         const int64_t smin = std::min<int64_t>(std::min(sc.match, sc.mismatch), std::min(sc.special, 0));
         const int64_t smax = std::max<int64_t>(std::max(sc.match, sc.special), 0);
@@ -761,6 +773,17 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         if (sc.b1 <= 0 && high - low + 128 <= 32767) {
             pack = true;
             pkp.bias = (int32_t)(64 - low);
+            // static row slope (MADD kernels, clq_pack.cuh): row x stored with x * slope more, slope = -min(substitution score, 0), so
+            // that the profile bytes are >= 0 and M = diag + m is a plain add.  Needs L1 * slope more head-room (Eh' of row 0 sits
+            // one slope lower) and bytes that still fit int8.
+            const int64_t slope = -smin;
+            // (short-read geometries only: on the long-read ones, 168 registers at 3 CTAs/SM, the two extra constants cost more
+            // than the ALU-pipe relief gains -- C3 1485 -> 1452 GCUPS with it)
+            if (!rb && !c->no_madd && G <= 8 && slope > 0 && smax + slope <= 127 && high + slope * (int64_t)L1max - (low - slope) + 128 <= 32767) {
+                madd = true;
+                pkp.slope = (int32_t)slope;
+                pkp.bias = (int32_t)(64 - (low - slope));
+            }
         }
     }
     if (convex && !c->no_pack && n) pack = cvx_window(W, &pkp.bias);  // two-piece affine: same proof with the gap states of both pieces
@@ -769,6 +792,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     // the two reads of a PACK task share theirs; only with the natural read order (uniform lengths, uniform scratch slots)
     const bool group_pairs = pack && !pack_pairs && !score_only && !s->have_order && n > 0 && c->n_refs > 1 && !c->no_group;
     const uint64_t n_pos = group_pairs ? (((uint64_t)n + c->n_refs + 2) & ~1ull) : n;  // processing positions incl. bucket padding
+    uint32_t madd_tab[32] = {};  // the MADD kernels take the profile table with the row slope already added (every byte >= 0)
     auto launch_dp = [&](bool tb, const KParams& kp, int* grid, bool query) -> cudaError_t {
         if (convex) {
             if (pack && !kp.all_pairs && (pack_pairs || (tb && group_pairs)))  // the convex PACK kernel is pair-mode only
@@ -777,6 +801,11 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         }
         if (pack && (kp.all_pairs || pack_pairs || (tb && group_pairs))) {
             if (rb) return launch_pack<true, true>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query);
+            if (madd) {
+                KParams km = kp;
+                memcpy(km.tab, madd_tab, sizeof(madd_tab));
+                return tb ? launch_pack<true, false, true>(cfg, km, pkp, c->sm_count, smem, s->stream, grid, query) : launch_pack<false, false, true>(cfg, km, pkp, c->sm_count, smem, s->stream, grid, query);
+            }
             return tb ? launch_pack<true>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query) : launch_pack<false>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query);
         }
         return launch_any(cfg, tb, fin, fast, rb && tb, kp, c->sm_count, smem, s->stream, grid, query);
@@ -811,6 +840,13 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
             }
         memcpy(p.tab, tab, 128);
     }
+    if (madd) {
+        int8_t tab[16][8];
+        memcpy(tab, p.tab, 128);
+        for (int r = 0; r < 16; r++)
+            for (int q = 0; q < 8; q++) tab[r][q] = (int8_t)(tab[r][q] + pkp.slope);
+        memcpy(madd_tab, tab, 128);
+    }
 
     // grid + scratch sizing (per resident group)
     int grid_tb = 0, grid_sc = 0;
@@ -823,7 +859,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         return fail(c, CLQ_E_CUDA, std::string("occupancy(score): ") + cudaGetErrorString(ce));
     // direction bits per pair: G <= 8 geometries store blocks of 8 steps x G lanes x WPL words x 8 (time-transposed,
     // BitsLayout in clq_kernels.cuh), the others and the convex kernels one row per step
-    const bool transposed = !convex && G <= 8;
+    const bool transposed = !convex && G <= kTransposeMaxG;
     const uint64_t bits_stride = transposed ? (uint64_t)ns_max * ((L1max + G + 7) / 8) * G * (C / 8) * 8
                                             : ((uint64_t)ns_max * (L1max + G) * G * (C * bits_per_cell / 32) + 7) / 8 * 8;
     const uint32_t cig_stride = L1max + L2max + 8;
@@ -907,7 +943,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     }
 
     s->flags = flags;
-    s->stats.variant = (rb ? 16u : 0u) | (fast ? 1u : 0u) | ((pack && (pack_pairs || group_pairs || (search != CLQ_SEARCH_FIXED && !convex))) ? 2u : 0u) | (convex ? 4u : 0u) | (fin ? 8u : 0u) | ((uint32_t)cfg << 8);
+    s->stats.variant = (rb ? 16u : 0u) | (fast ? 1u : 0u) | ((pack && (pack_pairs || group_pairs || (search != CLQ_SEARCH_FIXED && !convex))) ? 2u : 0u) | (convex ? 4u : 0u) | (fin ? 8u : 0u) | (madd ? 32u : 0u) | ((uint32_t)cfg << 8);
     s->stats.sub_batches = 0;
     s->stats.launches = 0;
     s->stats.dp_launches = 0;
@@ -928,6 +964,13 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
             if ((rc = ensure(c, s->votes, (size_t)n * nrefs * 4)) != CLQ_OK) return rc;
             if ((rc = ensure(c, s->cand_mask, (size_t)n * mask_words * 4)) != CLQ_OK) return rc;
             if ((rc = ensure(c, s->single_ref, (size_t)n * 4)) != CLQ_OK) return rc;
+            const size_t vote_smem = (size_t)c->n_keys * 12 + (size_t)nrefs * 128 * 2;
+            if (c->kmer_k <= 8 && vote_smem <= 160 * 1024 && !c->force_generic) {
+                if (vote_smem > 48 * 1024) CU(c, cudaFuncSetAttribute(kmer_vote_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vote_smem));
+                kmer_vote_packed_kernel<<<(n + 127) / 128, 128, vote_smem, s->stream>>>(
+                    p.read_bytes, p.read_off, n, (const uint64_t*)c->kmer_keys64.p, (const uint32_t*)c->kmer_owner.p, c->n_keys, c->kmer_k,
+                    c->kmer_skip, nrefs, match_threshold, (uint32_t*)s->cand_mask.p, mask_words, (int32_t*)s->single_ref.p);
+            } else
             kmer_vote_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(
                 p.read_bytes, p.read_off, n, (const uint8_t*)c->kmer_keys.p, (const uint32_t*)c->kmer_owner.p, c->n_keys, c->kmer_k,
                 c->kmer_skip, nrefs, match_threshold, (uint32_t*)s->votes.p, (uint32_t*)s->cand_mask.p, mask_words, (int32_t*)s->single_ref.p);

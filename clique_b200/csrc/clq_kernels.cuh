@@ -198,8 +198,12 @@ __device__ __forceinline__ size_t row_index(int s, int T, int t, int ln, int k) 
 }
 
 // which layout a geometry uses (host: clq_api.cu::bits_words_per_pair must agree)
+#ifndef CLQ_TRANSPOSE_MAX_G
+#define CLQ_TRANSPOSE_MAX_G 8
+#endif
+constexpr int kTransposeMaxG = CLQ_TRANSPOSE_MAX_G;
 template <int G>
-struct BitsLayout { static constexpr bool transposed = (G <= 8); };
+struct BitsLayout { static constexpr bool transposed = (G <= kTransposeMaxG); };
 
 template <int G, int WPL>
 __device__ __forceinline__ void bits_store(uint32_t* tt, uint32_t* bits_g, const uint32_t (&w)[WPL], int s, int T, int t, int lane, int gl,
@@ -546,6 +550,11 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
     }
 }
 
+#ifndef CLQ_WALK_PREFETCH
+#define CLQ_WALK_PREFETCH 12
+#endif
+constexpr int kWalkPrefetch = CLQ_WALK_PREFETCH;  // steps ahead along the diagonal (0 = off)
+
 // perform_3d_global_traceback (alignment/alignment_matrix.rs:941-1086) + simplify_cigar_string (alignment_manager.rs:386-423)
 // over the direction bits gotoh_kernel<.., TB=true, ..> stored.  One thread per pair: the walk is a chain of dependent
 // loads (one 32-byte sector per step), so it is spread over as many threads as there are pairs in the sub-batch.
@@ -609,6 +618,19 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
         const size_t idx = bits_index<G, WPL>(s, T, xx + ln, ln, j >> 3);
         return (__ldg(bits_g + idx) >> (28 - 4 * (j & 7))) & 15u;
     };
+    // The walk is a chain of dependent sector loads (ncu: long-scoreboard stall 15 per issue, 5.4 KB of DRAM reads per C2 read
+    // = 168 sectors for a 515-step path).  Alignment paths run along diagonals, so every step also prefetches the word of the cell
+    // kWalkPrefetch steps further up the diagonal into L1: the demand load then finds its sector on chip and the misses of
+    // consecutive sectors overlap instead of queueing behind one another.  A wrong guess (indels move the path off the diagonal)
+    // costs one extra sector, never a wrong result.
+    auto prefetch = [&](int xx, int yy) {
+        int c = yy - 1;
+        const int s = c / W;
+        c -= s * W;
+        const int cs = (G >= 16 && s == sL && CsL > 0) ? CsL : C;
+        const int ln = c / cs, j = c - ln * cs;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(bits_g + bits_index<G, WPL>(s, T, xx + ln, ln, j >> 3)));
+    };
     auto argmax = [](uint32_t nb) -> int { return (nb & 2u) ? 1 : ((nb & 1u) ? 2 : 0); };
     // cells the fill skipped keep the fresh-matrix state: (x <= K, y == L2) for the two implicit bands, everything outside the
     // row's window for an explicit bandwidth
@@ -629,6 +651,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
         else if (z == 1) { emit(CLQ_OP_D, 1); tag(x, '-'); x--; }
         else { emit(CLQ_OP_I, 1); y--; }
         if (x == 0 || y == 0) break;
+        if (kWalkPrefetch > 0 && x > kWalkPrefetch && y > kWalkPrefetch) prefetch(x - kWalkPrefetch, y - kWalkPrefetch);
         nib = nibble(x, y);
         cur_stale = stale(x, y);
         const int a = cur_stale ? 0 : argmax(nib);  // a stale source cell holds (0,0,0): Diag
@@ -760,6 +783,75 @@ __global__ void kmer_vote_kernel(const uint8_t* read_bytes, const uint64_t* read
             if (!votes[r]) continue;
             mask[r >> 5] |= 1u << (r & 31);
             const double pr = (double)votes[r] / count;
+            if (pr >= bestp) { bestp = pr; bi = (int)r; }
+        }
+        if (bestp > threshold) single = bi;
+    }
+    single_ref[i] = single;
+    if (single >= 0) {
+        for (uint32_t wd = 0; wd < mask_words; wd++) mask[wd] = 0;  // no exhaustive fill for this read
+    }
+}
+
+// Fast form of kmer_vote_kernel for k <= 8 (clique's CLI uses k = 8, skip = 4, main.rs:271): the unique k-mers are packed
+// big-endian into uint64 (numeric order == the byte-wise order of the host's sort), the table and the per-thread vote counters
+// live in shared memory, the read's window is a rolling 64-bit register and the run-length de-duplication one compare.  Same
+// votes, same candidate masks, same single_ref as the generic kernel (the host falls back to that one when the table or the
+// counters do not fit).  Dynamic shared memory: n_keys * 12 bytes (keys, owners) + n_refs * blockDim.x * 2 (u16 counters).
+__global__ void __launch_bounds__(128) kmer_vote_packed_kernel(const uint8_t* read_bytes, const uint64_t* read_off, uint32_t n_reads,
+                                                                const uint64_t* keys64, const uint32_t* owner, uint32_t n_keys, uint32_t k,
+                                                                uint32_t skip, uint32_t n_refs, double threshold, uint32_t* cand_mask,
+                                                                uint32_t mask_words, int32_t* single_ref) {
+    extern __shared__ __align__(16) uint8_t vote_sm[];
+    uint64_t* keys_sm = reinterpret_cast<uint64_t*>(vote_sm);
+    uint32_t* own_sm = reinterpret_cast<uint32_t*>(vote_sm + (size_t)n_keys * 8);
+    uint16_t* cnt_sm = reinterpret_cast<uint16_t*>(vote_sm + (size_t)n_keys * 12);
+    for (uint32_t i = threadIdx.x; i < n_keys; i += blockDim.x) { keys_sm[i] = keys64[i]; own_sm[i] = owner[i]; }
+    for (uint32_t r = 0; r < n_refs; r++) cnt_sm[r * blockDim.x + threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_reads) return;
+    const uint8_t* rd = read_bytes + read_off[i];
+    const uint32_t L2 = (uint32_t)(read_off[i + 1] - read_off[i]);
+    uint16_t* votes = cnt_sm + threadIdx.x;  // votes[r * blockDim.x]
+    const uint64_t kmask = k >= 8 ? ~0ull : ((1ull << (8 * k)) - 1ull);
+    uint32_t total = 0;
+    uint64_t win = 0, prev = 0;
+    bool have_prev = false;
+    uint32_t filled = 0;  // bytes of the read already shifted into the window
+    for (uint32_t pos = 0; pos + k <= L2; pos += skip) {
+        // advance the window to cover read[pos .. pos + k)
+        for (; filled < pos + k; filled++) {
+            uint8_t b = __ldg(rd + filled);
+            b = (b >= 'a' && b <= 'z') ? b - 32 : b;
+            win = (win << 8) | b;
+        }
+        const uint64_t key = win & kmask;
+        const bool same = have_prev && key == prev;  // consecutive dedup_with_count: one vote per run
+        prev = key; have_prev = true;
+        if (same) continue;
+        uint32_t lo = 0, hi = n_keys;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint64_t a = keys_sm[mid];
+            if (a == key) { votes[own_sm[mid] * blockDim.x]++; total++; break; }
+            if (a < key) lo = mid + 1; else hi = mid;
+        }
+    }
+    uint32_t* mask = cand_mask + (size_t)i * mask_words;
+    for (uint32_t wd = 0; wd < mask_words; wd++) mask[wd] = 0;
+    int single = -1;
+    if (total == 0) {
+        for (uint32_t r = 0; r < n_refs; r++) mask[r >> 5] |= 1u << (r & 31);
+    } else {
+        const double count = (double)total;
+        double bestp = -1.0;
+        int bi = -1;
+        for (uint32_t r = 0; r < n_refs; r++) {
+            const uint32_t v = votes[r * blockDim.x];
+            if (!v) continue;
+            mask[r >> 5] |= 1u << (r & 31);
+            const double pr = (double)v / count;
             if (pr >= bestp) { bestp = pr; bi = (int)r; }
         }
         if (bestp > threshold) single = bi;

@@ -15,13 +15,6 @@
 
 #include "clq_kernels.cuh"
 
-// Experiment switch (default off; DESIGN.md "next experiments", identity checked on the CPU in tests/test_pack_bit_identities.py):
-// the ext2 bit from the left cell's B and eP bit instead of max(E_left - 1, M_left) -- one DPX less per cell pair, the carried
-// E_left / M_left registers and one shuffle per row go away.  Not yet measured or parity-tested on a GPU.
-#ifndef CLQ_PACK_EXT2_VIA_EP
-#define CLQ_PACK_EXT2_VIA_EP 0
-#endif
-
 namespace clq {
 
 __device__ __forceinline__ uint32_t dup16(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }
@@ -77,15 +70,32 @@ __device__ __forceinline__ void bits_store2(uint32_t* tt, uint32_t* bitsA, uint3
     }
 }
 
+#ifndef CLQ_PACK_PIN_NIBBLE
+#define CLQ_PACK_PIN_NIBBLE 1
+#endif
+__device__ __forceinline__ uint32_t mad2(uint32_t a, uint32_t b) {
+#if CLQ_PACK_PIN_NIBBLE
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+#else
+    return a * 2u + b;
+#endif
+}
+
 struct PackParams {
-    int32_t bias;  // added to every stored score
+    int32_t bias;   // added to every stored score
+    int32_t slope;  // MADD kernels: row x is stored with x * slope more (slope = -min(substitution score, 0) >= 0)
 };
 
-template <int C, bool TB, bool LAST, bool RB = false>
+// MADD (static row slope, see pack_kernel): the profile bytes are >= 0, so M = diag + m is a plain 32-bit add of packed halves
+// (no carry can cross them) and leaves the ALU pipe; LEe / X1b are the E-step extend and the B-step open constants, which then
+// differ from the F-step / P-step ones (LE, X1) by the slope.
+template <int C, bool TB, bool LAST, bool RB = false, bool MADD = false>
 __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C], const uint32_t (&sel)[C], uint32_t (&wA)[C / 8],
                                               uint32_t (&wB)[C / 8], uint32_t& Fh, uint32_t& Ehl, uint32_t& Ml, uint32_t& Bl, uint32_t diag,
-                                              uint32_t tlo, uint32_t thi, uint32_t LE, uint32_t X1, uint32_t X1M1, bool ownA, int jA,
-                                              bool ownB, int jB, uint32_t (&cap)[3], int nb) {
+                                              uint32_t tlo, uint32_t thi, uint32_t LE, uint32_t X1, uint32_t X1M1, uint32_t LEe, uint32_t X1b,
+                                              bool ownA, int jA, bool ownB, int jB, uint32_t (&cap)[3], int nb) {
     const uint32_t ONE = 0x00010001u;
 #pragma unroll
     for (int jb = 0; jb < C / 8; jb++) {
@@ -93,63 +103,47 @@ __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C
             uint32_t acc0 = 0, acc1 = 0;
             // M of the next cell is issued inside the current one (it needs B[j] of the previous row, which the current cell
             // overwrites): B[j]'s old value then dies within the cell and no register copy is needed to carry it as `diag`
-            uint32_t Mnext = __viaddmax_s16x2(diag, (uint32_t)prmt_s8(tlo, thi, sel[jb * 8]), X1);  // per-half add: biased values are > 0 > x1
+            uint32_t Mnext = MADD ? diag + (uint32_t)prmt_s8(tlo, thi, sel[jb * 8])
+                                  : __viaddmax_s16x2(diag, (uint32_t)prmt_s8(tlo, thi, sel[jb * 8]), X1);  // per-half add: biased values are > 0 > x1
 #pragma unroll
             for (int jj = 0; jj < 8; jj++) {
                 const int j = jb * 8 + jj;
                 const uint32_t Mv = Mnext;                               // [mA, mB] profile bytes added as s16x2 (X1: a live register; a literal 0 costs a PRMT)
                 const uint32_t EhU = Eh[j], BU = B[j];
-                if (jj < 7) Mnext = __viaddmax_s16x2(BU, (uint32_t)prmt_s8(tlo, thi, sel[j + 1]), X1);
-                const uint32_t Ehn = __viaddmax_s16x2(EhU, LE, BU);
+                if (jj < 7) Mnext = MADD ? BU + (uint32_t)prmt_s8(tlo, thi, sel[j + 1]) : __viaddmax_s16x2(BU, (uint32_t)prmt_s8(tlo, thi, sel[j + 1]), X1);
+                const uint32_t Ehn = __viaddmax_s16x2(EhU, LEe, BU);
                 uint32_t t2 = 0, u2 = 0, f2 = 0;
                 if (TB && !RB) {
                     // F extends  <=>  F_left + le > max(E_left + x1 - 1, M_left + x1)  (>= the E-open, > the M-open).  LE - t2 is the
                     // per-half value le - t2 (no borrow crosses the halves: t2 - le is in (0, 65536) per half), so one DPX with
                     // relu clamps Fh + le - t2 to {0, 1}: the bit itself, without a second max and a subtract + min
-#if CLQ_PACK_EXT2_VIA_EP
-                    // Ehl carries eP of the left cell (0/1 per half): under "F_left + le - x1 > ." max(E_left - 1, M_left) equals
-                    // max(E_left - 1, M_left, F_left) = B_left - eP_left
-                    f2 = __viaddmin_s16x2_relu(Fh, LE - (Bl - Ehl), ONE);
-#else
                     t2 = __viaddmax_s16x2(Ehl, X1M1, Ml);
                     f2 = __viaddmin_s16x2_relu(Fh, LE - t2, ONE);
-#endif
                 }
                 const uint32_t Fhn = __viaddmax_s16x2(Fh, LE, Bl);
                 if (TB && RB) { u2 = Fhn; t2 = Bl; }  // rust-bio: F extends <=> F_left + e > B_left + o + e
                 const uint32_t Pv = __viaddmax_s16x2(Fhn, X1, Mv);
-                const uint32_t Bn = __viaddmax_s16x2(Ehn, X1, Pv);
+                const uint32_t Bn = __viaddmax_s16x2(Ehn, X1b, Pv);
                 if (TB) {
                     // nibble pair [ext1 ext2 eP fM] of this cell pair, then 4 cells per 16-bit half
-                    uint32_t nib = __vminu2(Ehn - BU, ONE);                 // ext1
-                    nib = nib * 2u + ((TB && !RB) ? f2 : __vminu2(u2 - t2, ONE));  // ext2
-#if CLQ_PACK_EXT2_VIA_EP
-                    const uint32_t ePv = __vminu2(Bn - Pv, ONE);
-                    nib = nib * 2u + ePv;
-#else
-                    nib = nib * 2u + __vminu2(Bn - Pv, ONE);                // eP: E > max(M,F)
-#endif
-                    nib = nib * 2u + __vminu2(Pv - Mv, ONE);                // fM: F > M
+                    // every flag is shifted into the accumulator by one multiply-add (mad2: an opaque a * 2 + b, so that the compiler
+                    // cannot re-associate the chain into a tree of ~4.75 adds and multiply-adds per cell for the sake of its depth)
                     uint32_t a = ((jj & 4) ? acc1 : acc0);
-                    a = ((jj & 3) == 0) ? nib : a * 16u + nib;
+                    const uint32_t e1 = __vminu2(Ehn - BU, ONE);           // ext1
+                    a = ((jj & 3) == 0) ? e1 : mad2(a, e1);
+                    a = mad2(a, (TB && !RB) ? f2 : __vminu2(u2 - t2, ONE));  // ext2
+                    a = mad2(a, __vminu2(Bn - Pv, ONE));                     // eP: E > max(M,F)
+                    a = mad2(a, __vminu2(Pv - Mv, ONE));                     // fM: F > M
                     if (jj & 4) acc1 = a; else acc0 = a;
                     if (jj == 7) {
                         wA[jb] = __byte_perm(acc1, acc0, 0x5410);  // low halves: read A's 8 nibbles
                         wB[jb] = __byte_perm(acc1, acc0, 0x7632);  // high halves: read B's
                     }
-#if CLQ_PACK_EXT2_VIA_EP
-                    if (!RB) Ehl = ePv;
-#endif
                 }
                 if (jj == 7) diag = BU;  // carried to the next block of 8 columns
                 Eh[j] = Ehn;
                 B[j] = Bn;
-#if CLQ_PACK_EXT2_VIA_EP
-                Fh = Fhn; Bl = Bn;
-                if (!(TB && !RB)) { Ehl = Ehn; Ml = Mv; }
-#else
                 Fh = Fhn; Ehl = Ehn; Ml = Mv; Bl = Bn;
-#endif
                 if (LAST) {
                     if (ownA && j == jA) { cap[0] = set_lo(cap[0], get_lo(Mv)); cap[1] = set_lo(cap[1], get_lo(Ehn)); cap[2] = set_lo(cap[2], get_lo(Fhn)); }
                     if (ownB && j == jB) { cap[0] = set_hi(cap[0], get_hi(Mv)); cap[1] = set_hi(cap[1], get_hi(Ehn)); cap[2] = set_hi(cap[2], get_hi(Fhn)); }
@@ -168,8 +162,18 @@ __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C
 template <int G, int C, bool TB>
 constexpr int pack_min_blocks() { return (TB && C >= 32) ? (G <= 8 ? 2 : 3) : 1; }
 
-template <int G, int C, bool TB, bool RB = false>
+//
+// MADD ("static row slope"): row x is stored as v + bias + x * s with s = -min(substitution score) >= 0.  Only constants of
+// the recurrence change (derivation with B' = B + s x, M' = M + s x, Fh' = Fh + s x, Eh'(x,.) = Eh(x,.) + s (x - 1)):
+//   M'  = B'[x-1,y-1] + (m + s)              profile bytes m + s >= 0: a plain packed add, off the ALU pipe
+//   Eh' = max(Eh'_up + (le + s), B'_up)      Fh' = max(Fh'_left + le, B'_left)
+//   P'  = max(Fh' + x1, M')                  B'  = max(Eh' + (x1 + s), P')
+//   ext2: t2' = max(Eh'_left + (x1 - 1 + s), M'_left); every direction bit compares two values of the same row: unchanged.
+// The host takes these kernels when the 15-bit window still holds with L1 * s more head-room (clq_api.cu) and hands over the
+// profile table with s already added.
+template <int G, int C, bool TB, bool RB = false, bool MADD = false>
 __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_kernel(const KParams p, const PackParams pp) {
+    static_assert(!(RB && MADD), "the rust-bio variant keeps the unsloped form");
     static_assert(C % 8 == 0, "C must be a multiple of 8");
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + kLutBytes + kTabBytes;
@@ -192,7 +196,9 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
     const clq_affine_t sc = p.sc;
     const int bias = pp.bias;
     const int x1 = sc.oe_in, le = sc.e_in;
-    const uint32_t LE = dup16(le), X1 = dup16(x1), X1M1 = dup16(x1 - 1);
+    const int slope = MADD ? pp.slope : 0;
+    const uint32_t LE = dup16(le), X1 = dup16(x1), X1M1 = dup16(x1 - 1 + slope);
+    const uint32_t LEe = dup16(le + slope), X1b = dup16(x1 + slope);  // E-step extend / B-step open of a sloped row
     int staged_ref = -1;
 
     for (;;) {
@@ -298,7 +304,8 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
         // (short-read geometries only: a long-read warp would alternate between the two copies from task to task and the second
         // copy costs more instruction-cache misses than the branches it removes -- C3 1510 -> 1383 GCUPS when both were compiled)
         const bool simple = G <= 8 && NSmax <= 1 && __reduce_max_sync(FULL, (unsigned)(K[0] | K[1])) == 0u;
-        const uint32_t NB1 = dup16(-sc.b1), NX1 = dup16(-x1);  // boundary column g(x): plain packed arithmetic on positive halves
+        // boundary column g(x) + s x: plain packed arithmetic; (b1 + s) * 0x10001 mod 2^32 adds b1 + s to both halves, whatever its sign
+        const uint32_t GD = (uint32_t)((sc.b1 + slope) * 0x10001), NX1 = dup16(-x1), SL = dup16(slope);
 
         for (int s = 0; s < NSmax; s++) {
             const bool act_s = anyrun && s < NS;
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
                 sel[j] = (ca * 0x11u | 0x80u) | ((cb * 0x11u | 0x80u) << 8);  // bytes [mA, sign(mA), mB, sign(mB)]
                 const int g = sc.b0 + y * sc.b1 + bias;                        // row 0: S[0,y] = (MAXNEG, g(y), g(y))
                 B[j] = dup16(g);
-                Eh[j] = RB ? 0u : dup16(g - x1);                               // rust-bio: D[0][j] = MIN_SCORE (the sentinel 0)
+                Eh[j] = RB ? 0u : dup16(g - x1 - slope);                       // rust-bio: D[0][j] = MIN_SCORE (the sentinel 0); Eh' of row x carries s (x - 1)
             }
             uint32_t prevBl = dup16(((y0 == 0) ? 0 : sc.b0 + y0 * sc.b1) + bias);
             uint32_t oF = 0, oE = 0, oM = 0, oB = 0;
@@ -351,8 +358,8 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
                     uint32_t Bl = __shfl_up_sync(FULL, oB, 1, G);
                     uint32_t El = 0, Ml = 0;
                     if (TB && !RB) {
-                        El = __shfl_up_sync(FULL, oE, 1, G);  // CLQ_PACK_EXT2_VIA_EP: the eP bit of the left lane's last cell
-                        if (!CLQ_PACK_EXT2_VIA_EP) Ml = __shfl_up_sync(FULL, oM, 1, G);
+                        El = __shfl_up_sync(FULL, oE, 1, G);
+                        Ml = __shfl_up_sync(FULL, oM, 1, G);
                     }
                     uint2 tr;
                     if (TAB_SHFL) {
@@ -361,13 +368,13 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
                     } else {
                         tr = *(const uint2*)(tab_sm + rcur * 8);
                     }
-                    gB -= NB1;
+                    gB += GD;
                     if ((uint32_t)(x - 1) < L1act) {
                         if (first_col) {  // S[x,0] = (MAXNEG, g(x), g(x)); selects, not a branch
                             Bl = gB;
-                            Fl = El = gB + NX1;
-                            Ml = 0;  // the sentinel: below every biased value
-                            if (CLQ_PACK_EXT2_VIA_EP && TB && !RB) El = 0;  // boundary column: E = F = g(x), eP = 0
+                            Fl = gB + NX1;
+                            El = Fl - SL;  // Eh' of row x carries s (x - 1)
+                            Ml = 0;        // the sentinel: below every biased value
                             if (RB) Fl = 0;  // rust-bio: I[i][0] = MIN_SCORE on the empty-read boundary
                         }
                         if (!SIMPLE) {
@@ -383,27 +390,27 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
                         const uint32_t BlIn = Bl;
                         // the capture variant only runs on the lane(s) that own column L2, at their last row: once per task
                         if (x == xcap)
-                            pack_row_step<C, TB, true, RB>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap, nb);
+                            pack_row_step<C, TB, true, RB, MADD>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, LEe, X1b, ownA, jLh[0], ownB, jLh[1], cap, nb);
                         else
-                            pack_row_step<C, TB, false, RB>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, ownA, jLh[0], ownB, jLh[1], cap, nb);
+                            pack_row_step<C, TB, false, RB, MADD>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, LEe, X1b, ownA, jLh[0], ownB, jLh[1], cap, nb);
                         prevBl = BlIn;
                         oF = Fl; oE = El; oM = Ml; oB = Bl;
                         if (!SIMPLE) {
                             // band-skipped cells (x <= K, y == L2): fresh-matrix state (0,0,0), per read
                             if ((ownA && x <= K[0]) || (ownB && x <= K[1])) {
                                 const bool sa = ownA && x <= K[0], sb = ownB && x <= K[1];
-                                const int e0 = -x1 + bias, b0v = bias;
+                                // true values (0,0,0): stored with this row's slope terms (Eh' carries s (x - 1), the rest s x)
+                                const int b0v = bias + slope * x, f0 = -x1 + b0v, e0 = f0 - slope;
 #pragma unroll
                                 for (int j = 0; j < C; j++) {
                                     if (sa && j == jLh[0]) { Eh[j] = set_lo(Eh[j], e0); B[j] = set_lo(B[j], b0v); }
                                     if (sb && j == jLh[1]) { Eh[j] = set_hi(Eh[j], e0); B[j] = set_hi(B[j], b0v); }
                                 }
-                                const int oe0 = (CLQ_PACK_EXT2_VIA_EP && TB && !RB) ? 0 : e0;  // fresh-matrix cell: E = M = F, eP = 0
-                                if (sa && jLh[0] == Cs - 1) { oF = set_lo(oF, e0); oE = set_lo(oE, oe0); oM = set_lo(oM, b0v); oB = set_lo(oB, b0v); }
-                                if (sb && jLh[1] == Cs - 1) { oF = set_hi(oF, e0); oE = set_hi(oE, oe0); oM = set_hi(oM, b0v); oB = set_hi(oB, b0v); }
+                                if (sa && jLh[0] == Cs - 1) { oF = set_lo(oF, f0); oE = set_lo(oE, e0); oM = set_lo(oM, b0v); oB = set_lo(oB, b0v); }
+                                if (sb && jLh[1] == Cs - 1) { oF = set_hi(oF, f0); oE = set_hi(oE, e0); oM = set_hi(oM, b0v); oB = set_hi(oB, b0v); }
                                 if (x == L1) {
-                                    if (sa) { cap[0] = set_lo(cap[0], bias); cap[1] = set_lo(cap[1], e0); cap[2] = set_lo(cap[2], e0); }
-                                    if (sb) { cap[0] = set_hi(cap[0], bias); cap[1] = set_hi(cap[1], e0); cap[2] = set_hi(cap[2], e0); }
+                                    if (sa) { cap[0] = set_lo(cap[0], b0v); cap[1] = set_lo(cap[1], e0); cap[2] = set_lo(cap[2], f0); }
+                                    if (sb) { cap[0] = set_hi(cap[0], b0v); cap[1] = set_hi(cap[1], e0); cap[2] = set_hi(cap[2], f0); }
                                 }
                             }
                         }
@@ -433,9 +440,9 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
             const uint32_t c0 = __shfl_sync(FULL, cap[0], src), c1 = __shfl_sync(FULL, cap[1], src), c2 = __shfl_sync(FULL, cap[2], src);
             int score = 0, z = 0;
             if (run[h]) {
-                const int cM = (h ? get_hi(c0) : get_lo(c0)) - bias;
-                const int cE = (h ? get_hi(c1) : get_lo(c1)) - bias + x1;
-                const int cF = (h ? get_hi(c2) : get_lo(c2)) - bias + x1;
+                const int cM = (h ? get_hi(c0) : get_lo(c0)) - bias - slope * L1;
+                const int cE = (h ? get_hi(c1) : get_lo(c1)) - bias - slope * (L1 - 1) + x1;
+                const int cF = (h ? get_hi(c2) : get_lo(c2)) - bias - slope * L1 + x1;
                 score = cM; z = 0;
                 if (RB) {  // rust-bio: match first, then insertion, then deletion, each only when strictly better
                     if (cF > score) { score = cF; z = 2; }

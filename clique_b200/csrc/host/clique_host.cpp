@@ -1214,17 +1214,20 @@ SpanStats ShardedAligner::align_reads_span(const ReadSpan& span, const AffineSco
     const auto t0 = std::chrono::steady_clock::now();
     stats.total.setup_seconds = std::chrono::duration<double>(t0 - tsetup).count();
 
-    // one cursor over the whole span: a claim takes up to a full batch, but never more than 1 / (4 * devices) of what is left
-    // (guided self-scheduling), so the last batches are small and the devices drain together even on length-sorted input
+    // one cursor over the whole span: a claim takes up to a full batch, but with several devices never more than 1 / (2 * devices)
+    // of what is left (guided self-scheduling), so the last batches are small and the devices drain together even on
+    // length-sorted input
     std::mutex claim_mu;
-    uint64_t cursor = 0;
+    uint64_t cursor = 0, n_claims = 0;
     const uint64_t min_claim = std::min<uint64_t>(opt.max_reads, 4096);
     auto claim = [&](uint64_t& lo, uint64_t& hi) -> bool {
         std::lock_guard<std::mutex> g(claim_mu);
         if (cursor >= span.n) return false;
         lo = cursor;
         const uint64_t left_bytes = span.off[span.n] - span.off[lo];
-        uint64_t want_bytes = std::min<uint64_t>(opt.max_read_bytes, std::max<uint64_t>(left_bytes / (4 * nd), 1));
+        // one device: nothing to balance, full batches.  Several: a claim is at most half of an equal share of what is left
+        const uint64_t share = nd > 1 ? left_bytes / (2 * nd) : left_bytes;
+        uint64_t want_bytes = std::min<uint64_t>(opt.max_read_bytes, std::max<uint64_t>(share, 1));
         // last read whose end stays within want_bytes (binary search over the offsets), at least min_claim reads when they fit
         const uint64_t* first = span.off + lo + 1;
         const uint64_t* last = span.off + span.n + 1;
@@ -1232,6 +1235,10 @@ SpanStats ShardedAligner::align_reads_span(const ReadSpan& span, const AffineSco
         uint64_t cap_bytes = (uint64_t)(std::upper_bound(first, last, span.off[lo] + opt.max_read_bytes) - first);
         uint64_t n = std::max<uint64_t>(by_bytes, std::min<uint64_t>(min_claim, cap_bytes));
         n = std::min<uint64_t>(n, std::min<uint64_t>(opt.max_reads, span.n - lo));
+        // ramp-up: the first claims are small (32 Ki reads, doubling per round of claims) so that every GPU starts computing
+        // after about a millisecond of staging instead of after a whole batch
+        const uint64_t round = n_claims++ / (uint64_t)(nd * (size_t)nf);
+        n = std::min<uint64_t>(n, 32768ull << std::min<uint64_t>(round, 10));
         if (n == 0) n = 1;  // a read larger than a whole batch: handed over alone, reported CLQ_READ_TOO_LONG below
         hi = lo + n;
         cursor = hi;

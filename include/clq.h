@@ -125,7 +125,8 @@ typedef struct {
     uint64_t h2d_bytes;    /* bytes copied host->device by clq_upload                               */
     uint64_t d2h_bytes;    /* bytes copied device->host by clq_download + clq_wait                  */
     uint32_t variant;      /* kernel family of the last launch: bit0 FAST (PRMT/DPX), bit1 PACK (s16x2, two reads per
-                              lane group), bit2 CONVEX, bit3 final-gap multiplier variant; bits 8.. = geometry index */
+                              lane group), bit2 CONVEX, bit3 final-gap multiplier variant, bit4 rust-bio semantics, bit5 PACK with the static
+                              row slope (M step off the ALU pipe); bits 8.. = geometry index */
     uint32_t sub_batches;  /* fill + walk rounds the traceback scratch budget split the batch into  */
 } clq_stats_t;
 

@@ -222,7 +222,7 @@ def test_quick_search_vote_paths(al):
             reads.append(rand_seq(rng, int(rng.integers(5, 200))))           # no votes -> exhaustive over all
         else:
             reads.append(core)                                               # shared core only: no unique k-mer
-    for kmer in ((8, 4), (15, 5), (8, 8)):
+    for kmer in ((8, 4), (15, 5), (8, 8), (5, 3)):  # k <= 8: packed shared-memory vote kernel; k > 8: the generic one
         br, want = run_both(al, refs, reads, SCORINGS["cli"], "quick", "readlen", kmer=kmer)
         compare(br, want, len(reads), ("quick", kmer))
 
