@@ -48,7 +48,7 @@ class Result(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_ms", C.c_float), ("dp_ms", C.c_float), ("launches", C.c_uint32), ("dp_launches", C.c_uint32),
                 ("cells", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("variant", C.c_uint32),
-                ("sub_batches", C.c_uint32)]
+                ("sub_batches", C.c_uint32), ("pack_retries", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
 def library_path():

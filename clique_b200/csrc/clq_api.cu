@@ -12,6 +12,7 @@
 #include "clq_convex.cuh"
 #include "clq_pack.cuh"
 #include "clq_convex_pack.cuh"
+#include "clq_pack_adapt.cuh"
 
 using namespace clq;
 
@@ -52,6 +53,10 @@ struct Slot {
     uint64_t n_read_bytes = 0;
     uint32_t max_len = 0, min_len = 0;
     bool have_order = false, have_fixed = false;
+    bool order_by_ref = false;       // the processing order groups the reads by their fixed reference (each group padded to an even
+                                     // number of positions with 0xffffffff) so that the reads of a PACK pair share theirs
+    uint32_t n_pos = 0;              // processing positions incl. that padding (== n_reads otherwise)
+    DevBuf retry_list;               // pack_adapt_kernel -> int32 retry pass
     int state = 0;  // 0 empty, 1 uploaded, 2 launched, 3 downloaded
     uint32_t flags = 0;
     clq_stats_t stats = {};
@@ -77,6 +82,8 @@ struct clq_ctx {
     int debug_flags = 0;
     int no_pack = 0;                 // option "no_pack": never take the s16x2 PACK kernels
     int no_madd = 0;                 // option "no_madd": PACK kernels without the static row slope (M step on the ALU pipe)
+    int no_adapt = 0;                // option "no_adapt": long pairs beyond the static 15-bit window stay on the int32 kernels
+    int adapt_guard = 0;             // option "adapt_guard" (tests): overrides the guard band of pack_adapt_kernel; a huge value forces every pair through the retry pass
     int no_group = 0;                // option "no_group": multi-reference traceback stays on the int32 kernels (no bucketing by reference)
     int force_generic = 0;           // option "force_generic": never take the FAST (PRMT/DPX) kernel variant
     bool fast_ok = false;            // the reference set has <= 6 distinct non-special bytes
@@ -195,6 +202,34 @@ cudaError_t launch_pack(int cfg, const KParams& p, const PackParams& pp, int sm,
     }
 }
 
+template <int G, int C>
+cudaError_t launch_adapt_one(const KParams& p, const AdaptParams& ap, int sm_count, size_t smem, cudaStream_t st, int* grid_out, bool query_only) {
+    auto kern = pack_adapt_kernel<G, C>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int nb = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (nb < 1) return cudaErrorLaunchOutOfResources;
+    int grid = nb * sm_count;
+    if (*grid_out > 0) grid = std::min(grid, *grid_out);
+    *grid_out = grid;
+    if (query_only) return cudaSuccess;
+    kern<<<grid, kThreads, smem, st>>>(p, ap);
+    return cudaGetLastError();
+}
+
+// adaptive-bias PACK: long-read geometries only
+cudaError_t launch_adapt(int cfg, const KParams& p, const AdaptParams& ap, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
+    switch (cfg) {
+        CLQ_FULL_CASE(3, return (launch_adapt_one<16, 24>(p, ap, sm, smem, st, grid, q)))
+        CLQ_FULL_CASE(4, return (launch_adapt_one<32, 16>(p, ap, sm, smem, st, grid, q)))
+        default: return launch_adapt_one<32, 32>(p, ap, sm, smem, st, grid, q);
+    }
+}
+
 // two-piece affine ("convex") geometries: C must be a multiple of 16 (8 direction bits per cell, 128-bit row stores)
 const Cfg kCvxCfgs[] = {{8, 16}, {16, 16}, {16, 32}, {32, 32}, {32, 16}};  // the last one only by force_cfg (experiments)
 constexpr int kNumCvxCfgs = sizeof(kCvxCfgs) / sizeof(kCvxCfgs[0]);
@@ -278,7 +313,8 @@ cudaError_t launch_cvx_walk(int cfg, const KParams& p, uint32_t cnt, cudaStream_
 
 template <int G, int C>
 cudaError_t launch_walk_one(const KParams& p, uint32_t cnt, cudaStream_t st) {
-    walk_kernel<G, C><<<(cnt + 127) / 128, 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.bits_off, p.task_base, p.cig_scratch, p.cig_stride, p.cigar_pool,
+    constexpr bool WARP = G >= 16;  // long-read geometries: one warp per pair (clq_kernels.cuh)
+    walk_kernel<G, C, WARP><<<(uint32_t)(((uint64_t)cnt * (WARP ? 32 : 1) + 127) / 128), 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.bits_off, p.task_base, p.cig_scratch, p.cig_stride, p.cigar_pool,
                                                          p.cigar_cap, p.cigar_cursor, p.results, p.ref_bytes, p.ref_off, p.read_bytes, p.read_off,
                                                          p.tag_slot, p.tags, p.tag_stride, p.rustbio, p.band_mode, p.band_k);
     return cudaGetLastError();
@@ -427,7 +463,7 @@ void clq_ctx_destroy(clq_ctx* c) {
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
         if (s.done) cudaEventDestroy(s.done);
         for (DevBuf* b : {&s.read_bytes, &s.read_off, &s.fixed_ref, &s.order, &s.results, &s.scores, &s.cand_mask, &s.single_ref,
-                          &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.tb_rec, &s.bits_off, &s.tags, &s.ref_groups, &s.counters})
+                          &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.tb_rec, &s.bits_off, &s.tags, &s.ref_groups, &s.retry_list, &s.counters})
             release(*b);
         if (s.h_counters) cudaFreeHost(s.h_counters);
     }
@@ -444,6 +480,8 @@ int32_t clq_set_option(clq_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "debug_flags")) { c->debug_flags = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_pack")) { c->no_pack = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_madd")) { c->no_madd = (int)value; return CLQ_OK; }
+    if (!strcmp(key, "no_adapt")) { c->no_adapt = (int)value; return CLQ_OK; }
+    if (!strcmp(key, "adapt_guard")) { c->adapt_guard = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_group")) { c->no_group = (int)value; return CLQ_OK; }
     if (!strcmp(key, "serialize_slots")) { c->serialize = (int)value; return CLQ_OK; }
     if (!strcmp(key, "max_scratch_bytes")) {
@@ -628,30 +666,69 @@ int32_t clq_upload(clq_ctx* c, int32_t slot, uint32_t n_reads, const uint8_t* re
     s->max_len = mx;
     s->min_len = mn;
     s->have_order = false;
-    static thread_local std::vector<uint32_t> order, bucket;
+    s->order_by_ref = false;
+    s->n_pos = n_reads;
+    static thread_local std::vector<uint32_t> order, bucket, padded;
     if (n_reads && mx > mn + mn / 8 + 16) {
         const uint32_t nb = mx / 16 + 2;
-        bucket.assign(nb + 1, 0);
+        // multi-reference batches with a known reference per read: group by reference first (longest reference first), then
+        // longest read first inside a group, so that the two reads of a PACK task share their reference
+        const bool by_ref = fixed_ref != nullptr && c->n_refs > 1;
+        std::vector<uint32_t> ref_rank;
+        uint32_t n_groups = 1;
+        if (by_ref) {
+            std::vector<uint32_t> idx(c->n_refs);
+            for (uint32_t r = 0; r < c->n_refs; r++) idx[r] = r;
+            std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
+                return c->h_ref_off[a + 1] - c->h_ref_off[a] > c->h_ref_off[b + 1] - c->h_ref_off[b];
+            });
+            ref_rank.assign(c->n_refs + 1, 0);
+            for (uint32_t k = 0; k < c->n_refs; k++) ref_rank[idx[k]] = k;
+            ref_rank[c->n_refs] = c->n_refs;  // reads without a usable reference come last
+            n_groups = c->n_refs + 1;
+        }
+        auto group_of = [&](uint32_t i) -> uint32_t {
+            if (!by_ref) return 0;
+            const int32_t r = fixed_ref[i];
+            return ref_rank[(r >= 0 && (uint32_t)r < c->n_refs) ? (uint32_t)r : c->n_refs];
+        };
+        bucket.assign((size_t)nb * n_groups + 1, 0);
         auto key = [&](uint32_t i) -> uint32_t {
             const uint64_t l = read_off[i + 1] - read_off[i];
             const uint32_t b = l >= c->lim.max_read_len ? 0 : (uint32_t)l / 16 + 1;
-            return nb - 1 - std::min(b, nb - 1);  // longest first
+            return group_of(i) * nb + (nb - 1 - std::min(b, nb - 1));  // longest first
         };
         for (uint32_t i = 0; i < n_reads; i++) bucket[key(i) + 1]++;
-        for (uint32_t b = 0; b < nb; b++) bucket[b + 1] += bucket[b];
+        for (size_t b = 0; b < (size_t)nb * n_groups; b++) bucket[b + 1] += bucket[b];
         order.resize(n_reads);
         for (uint32_t i = 0; i < n_reads; i++) order[bucket[key(i)]++] = i;
-        if ((rc = ensure(c, s->order, (size_t)n_reads * sizeof(uint32_t))) != CLQ_OK) return rc;
-        CU(c, cudaMemcpyAsync(s->order.p, order.data(), (size_t)n_reads * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
-        CU(c, cudaStreamSynchronize(s->stream));  // `order` is a reused host vector
+        const std::vector<uint32_t>* use = &order;
+        if (by_ref) {  // pad every group to an even number of positions
+            padded.clear();
+            padded.reserve((size_t)n_reads + n_groups);
+            uint32_t prev_g = 0xffffffffu;
+            for (uint32_t i = 0; i < n_reads; i++) {
+                const uint32_t g = group_of(order[i]);
+                if (g != prev_g && (padded.size() & 1)) padded.push_back(0xffffffffu);
+                prev_g = g;
+                padded.push_back(order[i]);
+            }
+            use = &padded;
+            s->order_by_ref = true;
+        }
+        const size_t npos = use->size();
+        s->n_pos = (uint32_t)npos;
+        if ((rc = ensure(c, s->order, (npos + 2) * sizeof(uint32_t))) != CLQ_OK) return rc;
+        CU(c, cudaMemcpyAsync(s->order.p, use->data(), npos * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+        CU(c, cudaStreamSynchronize(s->stream));  // the host vectors are reused
         s->have_order = true;
-        s->h_len.resize(n_reads);
+        s->h_len.resize(npos);
         s->h_ref.clear();
-        if (fixed_ref) s->h_ref.resize(n_reads);
-        for (uint32_t i = 0; i < n_reads; i++) {
-            const uint32_t r = order[i];
-            s->h_len[i] = (uint32_t)(read_off[r + 1] - read_off[r]);
-            if (fixed_ref) s->h_ref[i] = fixed_ref[r];
+        if (fixed_ref) s->h_ref.resize(npos);
+        for (size_t i = 0; i < npos; i++) {
+            const uint32_t r = (*use)[i];
+            s->h_len[i] = r == 0xffffffffu ? 0u : (uint32_t)(read_off[r + 1] - read_off[r]);
+            if (fixed_ref) s->h_ref[i] = r == 0xffffffffu ? -1 : fixed_ref[r];
         }
     }
     uint64_t h2d = 0;
@@ -670,7 +747,7 @@ int32_t clq_upload(clq_ctx* c, int32_t slot, uint32_t n_reads, const uint8_t* re
         h2d += (size_t)n_reads * sizeof(int32_t);
         s->have_fixed = true;
     }
-    if (s->have_order) h2d += (size_t)n_reads * sizeof(uint32_t);
+    if (s->have_order) h2d += (size_t)s->n_pos * sizeof(uint32_t);
     s->n_reads = n_reads;
     s->n_read_bytes = total;
     s->stats = clq_stats_t{};
@@ -692,6 +769,8 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     if (search == CLQ_SEARCH_FIXED && !s->have_fixed && s->n_reads) return fail(c, CLQ_E_INVALID, "CLQ_SEARCH_FIXED needs fixed_ref");
     if (search == CLQ_SEARCH_QUICK && c->kmer_k == 0) return fail(c, CLQ_E_STATE, "CLQ_SEARCH_QUICK needs clq_kmer_index_set");
     if (search > CLQ_SEARCH_QUICK) return CLQ_E_INVALID;
+    if (search != CLQ_SEARCH_FIXED && s->order_by_ref)
+        return fail(c, CLQ_E_STATE, "this batch was uploaded with fixed_ref (its processing order groups the reads by reference): launch it with CLQ_SEARCH_FIXED or upload it without fixed_ref");
     clq_affine_t sc = {};
     ConvexParams cp = {};
     auto fits8 = [](int v) { return v >= -128 && v <= 127; };
@@ -760,6 +839,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     // convex kernels keep the plain row layout
     const size_t smem = (size_t)(kThreads / 32) * GPW * ref_sm_stride + (fast ? kLutBytes + kTabBytes : 0) + ((!convex && G <= kTransposeMaxG) ? (size_t)(kThreads / 32) * (C / 8) * 1024 * 2 : 0);
     if (smem > 200 * 1024) return fail(c, CLQ_E_LIMIT, "references too long for this geometry's shared-memory staging");
+    const size_t smem_adapt = (size_t)(kThreads / 32) * GPW * ref_sm_stride + kLutBytes + (size_t)kAdaptTabs * kTabBytes;  // pack_adapt_kernel: one profile table per slope
     // s16x2 PACK kernels: two reads per lane group.  Needs the FAST preconditions plus a proof that every cell value of
     // this batch fits a 15-bit window: B >= 2*g(0) + (L1+L2)*e (the all-gap corner path), everything else is within a gap
     // open / one substitution of B, and nothing exceeds max(match, special) * min(L1, L2).
@@ -787,11 +867,25 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         }
     }
     if (convex && !c->no_pack && n) pack = cvx_window(W, &pkp.bias);  // two-piece affine: same proof with the gap states of both pieces
-    const bool pack_pairs = pack && c->n_refs == 1;  // pair mode needs one reference for both reads of a task
+    // Pairs beyond the static window (long reads): s16x2 with an adaptive per-row bias, overflow detection and an int32 retry pass
+    // (clq_pack_adapt.cuh).  Traceback stage only, pair mode: one reference, or a fixed assignment the upload grouped by reference.
+    AdaptParams adp = {};
+    bool adapt = false;
+    if (fast && !convex && !rb && !pack && !c->no_pack && !c->no_adapt && !score_only && n && G >= 16 && sc.b1 <= 0 && search == CLQ_SEARCH_FIXED &&
+        (c->n_refs == 1 || s->order_by_ref)) {
+        const int smin = std::min(std::min(sc.match, sc.mismatch), sc.special), smax = std::max(std::max(sc.match, sc.special), 0);
+        // adjacent cells of a row differ by at most smax - 2 * x1 (clq_pack_adapt.cuh); a lane holds C columns, E / F / M sit within a few opens of B
+        const int guard = c->adapt_guard > 0 ? c->adapt_guard : (C + 4) * (smax - 2 * sc.oe_in) + 64;
+        if (fits8(smax + kAdaptSigmaMax) && fits8(smin + kAdaptSigmaMin) && sc.oe_in >= -512 && (c->adapt_guard > 0 || 2 * guard + 64 + 16384 <= 32767)) {
+            adapt = true;
+            adp.guard = guard;
+        }
+    }
+    const bool pack_pairs = (pack && c->n_refs == 1) || adapt;  // pair mode needs one reference for both reads of a task
     // multi-reference batches: the traceback stage buckets the reads by reference on the device (ref_scatter_kernel) so that
     // the two reads of a PACK task share theirs; only with the natural read order (uniform lengths, uniform scratch slots)
     const bool group_pairs = pack && !pack_pairs && !score_only && !s->have_order && n > 0 && c->n_refs > 1 && !c->no_group;
-    const uint64_t n_pos = group_pairs ? (((uint64_t)n + c->n_refs + 2) & ~1ull) : n;  // processing positions incl. bucket padding
+    const uint64_t n_pos = group_pairs ? (((uint64_t)n + c->n_refs + 2) & ~1ull) : (s->have_order ? s->n_pos : n);  // processing positions incl. group padding
     uint32_t madd_tab[32] = {};  // the MADD kernels take the profile table with the row slope already added (every byte >= 0)
     auto launch_dp = [&](bool tb, const KParams& kp, int* grid, bool query) -> cudaError_t {
         if (convex) {
@@ -799,6 +893,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
                 return tb ? launch_cvx_pack<true>(cfg, kp, cp, pkp, c->sm_count, smem, s->stream, grid, query) : launch_cvx_pack<false>(cfg, kp, cp, pkp, c->sm_count, smem, s->stream, grid, query);
             return tb ? launch_cvx<true>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query) : launch_cvx<false>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query);
         }
+        if (adapt && tb && !kp.all_pairs) return launch_adapt(cfg, kp, adp, c->sm_count, smem_adapt, s->stream, grid, query);
         if (pack && (kp.all_pairs || pack_pairs || (tb && group_pairs))) {
             if (rb) return launch_pack<true, true>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query);
             if (madd) {
@@ -857,6 +952,9 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         return fail(c, CLQ_E_CUDA, std::string("occupancy(tb): ") + cudaGetErrorString(ce));
     if ((ce = launch_dp(false, pq, &grid_sc, true)) != cudaSuccess)
         return fail(c, CLQ_E_CUDA, std::string("occupancy(score): ") + cudaGetErrorString(ce));
+    int grid_retry = 0;
+    if (adapt && (ce = launch_any(cfg, true, false, true, false, p, c->sm_count, smem, s->stream, &grid_retry, true)) != cudaSuccess)
+        return fail(c, CLQ_E_CUDA, std::string("occupancy(retry): ") + cudaGetErrorString(ce));
     // direction bits per pair: G <= 8 geometries store blocks of 8 steps x G lanes x WPL words x 8 (time-transposed,
     // BitsLayout in clq_kernels.cuh), the others and the convex kernels one row per step
     const bool transposed = !convex && G <= kTransposeMaxG;
@@ -876,27 +974,28 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     const uint64_t per_task = bits_stride * 4 + (uint64_t)cig_stride * 4 + sizeof(TbRec);
     uint64_t sub = std::max<uint64_t>(2, std::min<uint64_t>(n_pos + 1, (uint64_t)c->max_scratch_bytes / per_task)) & ~1ull;  // even: PACK tasks are read pairs
     std::vector<uint64_t> cuts;          // sub-batch boundaries in processing positions
-    const bool var_slots = !score_only && n && s->have_order && s->h_len.size() == n;
+    const uint64_t np = s->have_order ? s->n_pos : n;  // processing positions of a host-ordered batch (incl. reference-group padding)
+    const bool var_slots = !score_only && n && s->have_order && s->h_len.size() == np;
     uint64_t max_sub_words = sub * bits_stride, max_sub_tasks = sub;
     if (var_slots) {
         static thread_local std::vector<uint64_t> off;
-        off.resize((size_t)n + 1);
+        off.resize((size_t)np + 1);
         off[0] = 0;
-        const bool fixed_known = search == CLQ_SEARCH_FIXED && s->h_ref.size() == n;
-        for (uint32_t i = 0; i < n; i++) {
+        const bool fixed_known = search == CLQ_SEARCH_FIXED && s->h_ref.size() == np;
+        for (uint64_t i = 0; i < np; i++) {
             uint64_t l1 = L1max;
             if (fixed_known && s->h_ref[i] >= 0 && (uint32_t)s->h_ref[i] < c->n_refs)
                 l1 = c->h_ref_off[s->h_ref[i] + 1] - c->h_ref_off[s->h_ref[i]];
             const uint64_t l2 = s->h_len[i] >= c->lim.max_read_len ? 0 : s->h_len[i];
-            off[i + 1] = off[i] + bits_words(l1, l2);
+            off[i + 1] = off[i] + (l2 ? bits_words(l1, l2) : 0);  // empty reads and padding positions store nothing
         }
         const uint64_t budget_words = (uint64_t)c->max_scratch_bytes / 4;
         cuts.push_back(0);
         max_sub_words = 0; max_sub_tasks = 0;
         uint64_t start = 0;
-        for (uint64_t i = 0; i < n;) {
+        for (uint64_t i = 0; i < np;) {
             // grow [start, i) while it fits; always an even number of positions except for the last sub-batch
-            uint64_t j = i + 2 <= n ? i + 2 : n;
+            uint64_t j = i + 2 <= np ? i + 2 : np;
             if (off[j] - off[start] + (j - start) * (cig_stride + 4) > budget_words && i > start) {
                 cuts.push_back(i);
                 max_sub_words = std::max(max_sub_words, off[i] - off[start]);
@@ -906,25 +1005,26 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
             }
             i = j;
         }
-        cuts.push_back(n);
-        max_sub_words = std::max(max_sub_words, off[n] - off[start]);
-        max_sub_tasks = std::max<uint64_t>(max_sub_tasks, n - start);
+        cuts.push_back(np);
+        max_sub_words = std::max(max_sub_words, off[np] - off[start]);
+        max_sub_tasks = std::max<uint64_t>(max_sub_tasks, np - start);
         max_sub_tasks = (max_sub_tasks + 1) & ~1ull;
-        if ((rc = ensure(c, s->bits_off, ((size_t)n + 1) * sizeof(uint64_t))) != CLQ_OK) return rc;
-        CU(c, cudaMemcpyAsync(s->bits_off.p, off.data(), ((size_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+        if ((rc = ensure(c, s->bits_off, ((size_t)np + 1) * sizeof(uint64_t))) != CLQ_OK) return rc;
+        CU(c, cudaMemcpyAsync(s->bits_off.p, off.data(), ((size_t)np + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
         CU(c, cudaStreamSynchronize(s->stream));  // `off` is a reused host vector
     } else {
         for (uint64_t b = 0; b < n_pos; b += sub) cuts.push_back(b);
         cuts.push_back(n_pos);
     }
-    const uint64_t groups = (uint64_t)std::max(grid_tb, grid_sc) * (kThreads / 32) * GPW;
+    const uint64_t groups = (uint64_t)std::max(std::max(grid_tb, grid_sc), grid_retry) * (kThreads / 32) * GPW;
     if (!score_only && n) {
         if ((rc = ensure(c, s->bits, max_sub_words * 4 + 64)) != CLQ_OK) return rc;
         if ((rc = ensure(c, s->cig_scratch, max_sub_tasks * cig_stride * 4)) != CLQ_OK) return rc;
         if ((rc = ensure(c, s->tb_rec, max_sub_tasks * sizeof(TbRec))) != CLQ_OK) return rc;
         if ((rc = ensure(c, s->cigar_pool, (size_t)c->lim.cigar_pool_ops * 4 + 16)) != CLQ_OK) return rc;
     }
-    if ((rc = ensure(c, s->col_scratch, groups * col_stride * 16)) != CLQ_OK) return rc;
+    if ((rc = ensure(c, s->col_scratch, groups * col_stride * (adapt ? 20 : 16))) != CLQ_OK) return rc;  // pack_adapt_kernel keeps a fifth array (the bias of every row)
+    if (adapt && (rc = ensure(c, s->retry_list, (max_sub_tasks + 2) * sizeof(uint32_t))) != CLQ_OK) return rc;
     p.bits = (uint32_t*)s->bits.p;
     p.bits_stride = bits_stride;
     p.bits_off = var_slots ? (const uint64_t*)s->bits_off.p : nullptr;
@@ -943,7 +1043,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     }
 
     s->flags = flags;
-    s->stats.variant = (rb ? 16u : 0u) | (fast ? 1u : 0u) | ((pack && (pack_pairs || group_pairs || (search != CLQ_SEARCH_FIXED && !convex))) ? 2u : 0u) | (convex ? 4u : 0u) | (fin ? 8u : 0u) | (madd ? 32u : 0u) | ((uint32_t)cfg << 8);
+    s->stats.variant = (rb ? 16u : 0u) | (fast ? 1u : 0u) | ((pack && (pack_pairs || group_pairs || (search != CLQ_SEARCH_FIXED && !convex))) ? 2u : 0u) | (convex ? 4u : 0u) | (fin ? 8u : 0u) | (madd ? 32u : 0u) | (adapt ? (2u | 64u) : 0u) | ((uint32_t)cfg << 8);
     s->stats.sub_batches = 0;
     s->stats.launches = 0;
     s->stats.dp_launches = 0;
@@ -1045,12 +1145,35 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
                 q.task_base = (uint32_t)base;
                 q.task_end = (uint32_t)(base + cnt);
                 if (base) CU(c, cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned long long), s->stream));
+                if (adapt) {  // retry pass bookkeeping: its task counter (ctr[2]) and the number of listed positions (ctr[6])
+                    if (base) {
+                        CU(c, cudaMemsetAsync(ctr + 2, 0, sizeof(unsigned long long), s->stream));
+                        CU(c, cudaMemsetAsync(ctr + 6, 0, sizeof(unsigned long long), s->stream));
+                    }
+                    adp.retry_list = (uint32_t*)s->retry_list.p;
+                    adp.retry_count = (unsigned int*)(ctr + 6);
+                    adp.retry_total = (unsigned int*)(ctr + 7);
+                }
                 int g = grid_tb;
                 if ((ce = launch_dp(true, q, &g, false)) != cudaSuccess)
                     return fail(c, CLQ_E_CUDA, std::string("fill kernel: ") + cudaGetErrorString(ce));
                 s->stats.launches++;
                 s->stats.dp_launches++;
                 s->stats.sub_batches++;
+                if (adapt) {
+                    // pairs that left the guarded window are redone by the int32 kernel, which writes their records, walker records and
+                    // direction bits into the same slots (same geometry); the number of tasks is read on the device
+                    KParams q2 = q;
+                    q2.retry_list = (const uint32_t*)s->retry_list.p;
+                    q2.n_tasks_dev = (const unsigned int*)(ctr + 6);
+                    q2.n_tasks = 0;
+                    q2.task_counter = (unsigned int*)(ctr + 2);
+                    int g2 = grid_retry;
+                    if ((ce = launch_any(cfg, true, false, true, false, q2, c->sm_count, smem, s->stream, &g2, false)) != cudaSuccess)
+                        return fail(c, CLQ_E_CUDA, std::string("retry kernel: ") + cudaGetErrorString(ce));
+                    s->stats.launches++;
+                    s->stats.dp_launches++;
+                }
                 if (!(c->debug_flags & 1)) {
                     if ((ce = convex ? launch_cvx_walk(cfg, q, tb_pairs ? 2 * q.n_tasks : cnt, s->stream) : launch_walk(cfg, q, tb_pairs ? 2 * q.n_tasks : cnt, s->stream)) != cudaSuccess)
                         return fail(c, CLQ_E_CUDA, std::string("walk kernel: ") + cudaGetErrorString(ce));
@@ -1118,6 +1241,7 @@ int32_t clq_wait(clq_ctx* c, int32_t slot, clq_result_t* results, uint32_t* ciga
     const uint64_t cursor = s->h_counters[4];
     const uint64_t used = std::min<uint64_t>(cursor, c->lim.cigar_pool_ops);
     s->stats.cells = s->h_counters[5];
+    s->stats.pack_retries = (uint32_t)(s->h_counters[7] & 0xffffffffull);
     uint64_t d2h = 8 * sizeof(unsigned long long);
     if (results && s->n_reads) {
         CU(c, cudaMemcpyAsync(results, s->results.p, (size_t)s->n_reads * sizeof(clq_result_t), cudaMemcpyDeviceToHost, s->stream));

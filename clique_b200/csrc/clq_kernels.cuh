@@ -87,6 +87,10 @@ struct KParams {
     const uint16_t* tag_slot;    // CLQ_EXTRACT_TAGS: per reference byte, rank among the reference's tag columns (0xffff = none)
     uint8_t* tags;               // [n_reads * tag_stride] read bytes aligned to the tag columns ('-' = deleted)
     uint32_t tag_stride;
+    // retry pass after pack_adapt_kernel (clq_pack_adapt.cuh): the tasks are the sub-batch positions listed in retry_list, their
+    // number is read from device memory (the host does not know it when it queues the launch)
+    const uint32_t* retry_list;
+    const unsigned int* n_tasks_dev;
 };
 
 // what the fill kernel leaves for the walker: one record per task of the sub-batch
@@ -268,14 +272,16 @@ constexpr int kLutBytes = 256, kTabBytes = 128;  // FAST kernels: class LUT + 16
 // FAST wavefront step: Eh/Fh are E/F shifted by -x1 (uniform gap constants), m by PRMT, max-plus by DPX, bits by SHF.
 // RB (rust-bio global, oracle/clq_oracle.h::orc_rustbio_global): same values, but a gap extends only when strictly better
 // than opening from the best state S = max(M, I, D) of the neighbour: ext2 <=> F_left + e > B_left + o + e.
-template <int C, bool TB, bool LAST, bool RB = false>
-__device__ __forceinline__ void row_step_fast(int (&Eh)[C], int (&B)[C], const int (&sel)[C], uint32_t (&w)[C / 8], int& Fh,
-                                              int& Ehl, int& Ml, int& Bl, int diag, uint32_t tlo, uint32_t thi, int le, int x1,
-                                              bool own_last, int jL, int& capM, int& capE, int& capF, int nb) {
-    const int x1m1 = x1 - 1;
-#pragma unroll
-    for (int jb = 0; jb < C / 8; jb++) {
-        if (jb < nb) {  // narrow last stripe: only nb blocks of 8 columns per lane are real
+template <int C, bool TB, bool LAST, bool RB, int JB>
+__device__ __forceinline__ void row_blocks_fast(int (&Eh)[C], int (&B)[C], const int (&sel)[C], uint32_t (&w)[C / 8], int& Fh, int& Ehl, int& Ml,
+                                                int& Bl, int diag, uint32_t tlo, uint32_t thi, int le, int x1, bool own_last, int jL, int& capM,
+                                                int& capE, int& capF, int nb) {
+    // blocks of 8 columns, nested (block JB + 1 inside block JB's `if`): a narrow last stripe (only nb blocks per lane are real)
+    // leaves through one forward branch instead of a reconvergence region per block
+    if constexpr (JB < C / 8) {
+        if (JB < nb) {
+            constexpr int jb = JB;
+            const int x1m1 = x1 - 1;
 #pragma unroll
             for (int jj = 0; jj < 8; jj++) {
                 const int j = jb * 8 + jj;
@@ -304,8 +310,26 @@ __device__ __forceinline__ void row_step_fast(int (&Eh)[C], int (&B)[C], const i
                     if (own_last && j == jL) { capM = Mv; capE = Ehn + x1; capF = Fhn + x1; }
                 }
             }
+            row_blocks_fast<C, TB, LAST, RB, JB + 1>(Eh, B, sel, w, Fh, Ehl, Ml, Bl, diag, tlo, thi, le, x1, own_last, jL, capM, capE, capF, nb);
         }
     }
+}
+
+template <int C, bool TB, bool LAST, bool RB = false>
+__device__ __forceinline__ void row_step_fast(int (&Eh)[C], int (&B)[C], const int (&sel)[C], uint32_t (&w)[C / 8], int& Fh,
+                                              int& Ehl, int& Ml, int& Bl, int diag, uint32_t tlo, uint32_t thi, int le, int x1,
+                                              bool own_last, int jL, int& capM, int& capE, int& capF, int nb) {
+    row_blocks_fast<C, TB, LAST, RB, 0>(Eh, B, sel, w, Fh, Ehl, Ml, Bl, diag, tlo, thi, le, x1, own_last, jL, capM, capE, capF, nb);
+}
+
+// predicated global accesses for the stripe-boundary column (a branch around four loads / stores costs more issue slots in the
+// step loop than executing the address arithmetic on every lane)
+__device__ __forceinline__ int ldg_if_s32(const int32_t* ptr, bool cond, int keep) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.s32 %0, [%1];\n\t}" : "+r"(keep) : "l"(ptr), "r"((uint32_t)cond));
+    return keep;
+}
+__device__ __forceinline__ void stg_if_s32(int32_t* ptr, bool cond, int v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.s32 [%0], %1;\n\t}" ::"l"(ptr), "r"(v), "r"((uint32_t)cond) : "memory");
 }
 
 template <int G, int C, bool TB, bool FIN, bool FAST, bool RB = false>
@@ -337,16 +361,18 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
     const clq_affine_t sc = p.sc;
     int staged_ref = -1;
 
+    const uint32_t n_tasks = p.n_tasks_dev ? *p.n_tasks_dev : p.n_tasks;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(p.task_counter, (unsigned)GPW);
         base = __shfl_sync(FULL, base, 0);
-        if (base >= p.n_tasks) break;
-        const uint32_t task = base + gw;
-        bool valid = task < p.n_tasks;
+        if (base >= n_tasks) break;
+        uint32_t task = base + gw;
+        bool valid = task < n_tasks;
+        if (valid && p.retry_list) task = p.retry_list[task];  // retry pass: the task is a sub-batch position some earlier kernel gave up on
         uint32_t ridx = 0;
         int ref = -1;
-        uint32_t* bits_g = TB ? p.bits + bits_slot(p.bits_off, p.bits_stride, p.task_base, task) : nullptr;
+        uint32_t* bits_g = (TB && valid) ? p.bits + bits_slot(p.bits_off, p.bits_stride, p.task_base, task) : nullptr;
         if (valid) {
             if (p.all_pairs) {
                 const uint32_t q = task / p.n_refs;
@@ -355,7 +381,11 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
                 if (p.cand_mask && !((p.cand_mask[(size_t)ridx * p.mask_words + (ref >> 5)] >> (ref & 31)) & 1u)) valid = false;
             } else {
                 ridx = p.order ? p.order[p.task_base + task] : p.task_base + task;
-                ref = p.ref_of_read[ridx];
+                if (ridx == 0xffffffffu) {  // padding position of a reference group (host order / ref_scatter_kernel): nothing to align
+                    if (TB && gl == 0) { TbRec rec; rec.ridx = 0; rec.L1 = -1; rec.L2 = 0; rec.zK = 0; p.tb_rec[task] = rec; }
+                    valid = false;
+                } else
+                    ref = p.ref_of_read[ridx];
             }
         }
         int L1 = 0, L2 = 0;
@@ -425,6 +455,13 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
                 nF = col_g[1]; nE = col_g[p.col_stride + 1]; nM = col_g[2 * p.col_stride + 1]; nB = col_g[3 * p.col_stride + 1];
             }
             int rnext = act_s ? ref_sm[0] : 0;  // every lane starts at row 1 (lane gl at step t = 1 + gl)
+            // per-step conditions as single compares / loop-invariant flags (a compound condition is re-evaluated from its parts on
+            // every step: predicates do not survive the row step)
+            const uint32_t L1act = act_s ? (uint32_t)L1 : 0u;                      // act  <=>  (unsigned)(x - 1) < L1act
+            const int xlast = FAST ? (own_last ? L1 : -1) : L1;                     // FAST: the capture variant only on the lane owning column L2
+            const bool first_col = (gl == 0) && (s == 0);
+            const bool ld_col = (gl == 0) && (s > 0), st_col = (gl == G - 1) && (s < NS - 1);
+            const int k_own = own_last ? K : 0;
 
             for (int t = 1; t <= Tmax; t++) {
                 const int x = t - gl;
@@ -435,28 +472,25 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
                     El = __shfl_up_sync(FULL, oE, 1, G);
                     Ml = __shfl_up_sync(FULL, oM, 1, G);
                 }
-                const bool act = act_s && x >= 1 && x <= L1;
-                if (act) {
-                    if (gl == 0) {
-                        if (s == 0) {
-                            Bl = sc.b0 + x * sc.b1;  // S[x,0] = (MAXNEG, g(x), g(x))
-                            Fl = El = Bl - (FAST ? sc.oe_in : 0);
-                            Ml = sc.max_neg;
-                            if (RB) Fl = sc.max_neg;  // rust-bio: I[i][0] = MIN_SCORE on the empty-read boundary
-                        } else {
-                            Fl = nF; El = nE; Ml = nM; Bl = nB;
-                            if (x < L1) {
-                                nF = col_g[x + 1]; nE = col_g[p.col_stride + x + 1];
-                                nM = col_g[2 * p.col_stride + x + 1]; nB = col_g[3 * p.col_stride + x + 1];
-                            }
-                        }
+                if ((uint32_t)(x - 1) < L1act) {
+                    if (first_col) {  // S[x,0] = (MAXNEG, g(x), g(x)); selects
+                        Bl = sc.b0 + x * sc.b1;
+                        Fl = El = Bl - (FAST ? sc.oe_in : 0);
+                        Ml = sc.max_neg;
+                        if (RB) Fl = sc.max_neg;  // rust-bio: I[i][0] = MIN_SCORE on the empty-read boundary
+                    }
+                    if (ld_col) { Fl = nF; El = nE; Ml = nM; Bl = nB; }
+                    {
+                        const bool nx = ld_col && x < L1;  // the next row's boundary values, one step ahead
+                        nF = ldg_if_s32(col_g + x + 1, nx, nF); nE = ldg_if_s32(col_g + p.col_stride + x + 1, nx, nE);
+                        nM = ldg_if_s32(col_g + 2 * p.col_stride + x + 1, nx, nM); nB = ldg_if_s32(col_g + 3 * p.col_stride + x + 1, nx, nB);
                     }
                     const int r = rnext;
-                    if (x < L1) rnext = ref_sm[x];
+                    rnext = ref_sm[x < L1 ? x : L1 - 1];
                     const int BlIn = Bl;
                     if (FAST) {
                         const uint2 tr = *(const uint2*)(tab_sm + r * 8);
-                        if (x == L1)
+                        if (x == xlast)
                             row_step_fast<C, TB, true, RB>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, sc.e_in, sc.oe_in, own_last, jL, capM, capE, capF, nb);
                         else
                             row_step_fast<C, TB, false, RB>(E, B, bq, w, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, sc.e_in, sc.oe_in, own_last, jL, capM, capE, capF, nb);
@@ -480,7 +514,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
                     }
                     prevBl = BlIn;
                     oF = Fl; oE = El; oM = Ml; oB = Bl;
-                    if (K > 0 && own_last && x <= K) {
+                    if (x <= k_own) {
                         // band-skipped cell (x, L2): fresh-matrix state (0,0,0) / Up(0)
                         const int e0 = FAST ? -sc.oe_in : 0;
 #pragma unroll
@@ -490,9 +524,8 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
                         if (x == L1) { capM = 0; capE = 0; capF = 0; }
                     }
                     if (TB) bits_store<G, WPL>(tt_sm, bits_g, w, s, T, t, lane, gl, x == L1, nb);
-                    if (gl == G - 1 && s < NS - 1) {
-                        col_g[x] = oF; col_g[p.col_stride + x] = oE; col_g[2 * p.col_stride + x] = oM; col_g[3 * p.col_stride + x] = oB;
-                    }
+                    stg_if_s32(col_g + x, st_col, oF); stg_if_s32(col_g + p.col_stride + x, st_col, oE);
+                    stg_if_s32(col_g + 2 * p.col_stride + x, st_col, oM); stg_if_s32(col_g + 3 * p.col_stride + x, st_col, oB);
                 }
             }
             __syncwarp();
@@ -558,7 +591,13 @@ constexpr int kWalkPrefetch = CLQ_WALK_PREFETCH;  // steps ahead along the diago
 // perform_3d_global_traceback (alignment/alignment_matrix.rs:941-1086) + simplify_cigar_string (alignment_manager.rs:386-423)
 // over the direction bits gotoh_kernel<.., TB=true, ..> stored.  One thread per pair: the walk is a chain of dependent
 // loads (one 32-byte sector per step), so it is spread over as many threads as there are pairs in the sub-batch.
-template <int G, int C>
+// WARP (the long-read geometries, G >= 16): one WARP per pair instead of one thread.  A sub-batch of long reads holds only a few
+// thousand pairs with paths of ~10^4 steps, and with one thread per pair the walk is that many dependent DRAM round trips with
+// the GPU nearly idle (C5: 14 % of the step).  All 32 lanes carry the same walk state; when the word of the current cell is not
+// in the warp's window, lane i loads the word of the cell i steps further up the diagonal, and the following steps take
+// their words from the lanes by shuffle as long as the path stays inside those words: one memory round trip per ~20-30
+// steps instead of one per step.  Lane 0 alone writes.
+template <int G, int C, bool WARP = false>
 __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n_tasks, const uint32_t* bits, uint64_t bits_stride,
                                                    const uint64_t* bits_off, uint32_t task_base,
                                                    uint32_t* cig_scratch, uint32_t cig_stride, uint32_t* cigar_pool, uint64_t cigar_cap,
@@ -568,8 +607,11 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
                                                    uint32_t band_mode, uint32_t band_k) {
     constexpr int W = G * C;
     constexpr int WPL = C / 8;
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_tasks) return;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t q = WARP ? (gtid >> 5) : gtid;
+    const int wlane = threadIdx.x & 31;
+    const bool writer = !WARP || wlane == 0;
+    if (q >= n_tasks) return;  // warp-uniform with WARP
     const TbRec rec = recs[q];
     if (rec.L1 < 0) return;
     const int L1 = rec.L1, L2 = rec.L2, K = (rec.zK >> 2) & 0x3ffff;
@@ -592,7 +634,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
     auto tag = [&](int xx, uint8_t b) {
         if (slotp) {
             const uint16_t sl = __ldg(slotp + xx - 1);
-            if (sl != 0xffffu) tagp[sl] = b;
+            if (sl != 0xffffu && writer) tagp[sl] = b;
         }
     };
     auto count = [&](int xx, int yy) {
@@ -605,18 +647,46 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
     auto emit = [&](uint32_t op, uint32_t n) {
         if (op == cur_op) cur_len += n;
         else {
-            if (cur_len) cig_g[--cpos] = (cur_len << 4) | cur_op;
+            if (cur_len) { --cpos; if (writer) cig_g[cpos] = (cur_len << 4) | cur_op; }
             cur_op = op; cur_len = n;
         }
     };
-    auto nibble = [&](int xx, int yy) -> uint32_t {
+    // word index of cell (xx, yy) in the task's slot and the shift of its nibble
+    auto locate = [&](int xx, int yy, int& shift) -> size_t {
         int c = yy - 1;
         const int s = c / W;
         c -= s * W;
         const int cs = (G >= 16 && s == sL && CsL > 0) ? CsL : C;
         const int ln = c / cs, j = c - ln * cs;
-        const size_t idx = bits_index<G, WPL>(s, T, xx + ln, ln, j >> 3);
-        return (__ldg(bits_g + idx) >> (28 - 4 * (j & 7))) & 15u;
+        shift = 28 - 4 * (j & 7);
+        return bits_index<G, WPL>(s, T, xx + ln, ln, j >> 3);
+    };
+    int win_x = -1;                 // WARP: lane i holds the word of cell (win_x - i, win_y - i) and its index
+    uint32_t win_word = 0, win_idx = 0xffffffffu;
+    auto nibble = [&](int xx, int yy) -> uint32_t {
+        int shift;
+        const size_t idx = locate(xx, yy, shift);
+        if (!WARP) return (__ldg(bits_g + idx) >> shift) & 15u;
+        const int d = win_x - xx;   // every lane walks the same path: all of this is warp-uniform
+        uint32_t v = 0;
+        bool hit = false;
+        if (d >= 0 && d < 32) {
+            v = __shfl_sync(FULL, win_word, d);
+            hit = __shfl_sync(FULL, win_idx, d) == (uint32_t)idx;
+        }
+        if (!hit) {
+            win_x = xx;
+            const int px = xx - wlane, py = yy - wlane;
+            win_idx = 0xffffffffu;
+            if (px >= 1 && py >= 1) {
+                int sh;
+                const size_t pi = locate(px, py, sh);
+                win_idx = (uint32_t)pi;
+                win_word = __ldg(bits_g + pi);
+            }
+            v = __shfl_sync(FULL, win_word, 0);
+        }
+        return (v >> shift) & 15u;
     };
     // The walk is a chain of dependent sector loads (ncu: long-scoreboard stall 15 per issue, 5.4 KB of DRAM reads per C2 read
     // = 168 sectors for a 515-step path).  Alignment paths run along diagonals, so every step also prefetches the word of the cell
@@ -651,7 +721,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
         else if (z == 1) { emit(CLQ_OP_D, 1); tag(x, '-'); x--; }
         else { emit(CLQ_OP_I, 1); y--; }
         if (x == 0 || y == 0) break;
-        if (kWalkPrefetch > 0 && x > kWalkPrefetch && y > kWalkPrefetch) prefetch(x - kWalkPrefetch, y - kWalkPrefetch);
+        if (!WARP && G >= 16 && kWalkPrefetch > 0 && x > kWalkPrefetch && y > kWalkPrefetch) prefetch(x - kWalkPrefetch, y - kWalkPrefetch);
         nib = nibble(x, y);
         cur_stale = stale(x, y);
         const int a = cur_stale ? 0 : argmax(nib);  // a stale source cell holds (0,0,0): Diag
@@ -667,21 +737,27 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
         }
         if (y > 0) emit(CLQ_OP_I, (uint32_t)y);
     }
-    if (cur_len) cig_g[--cpos] = (cur_len << 4) | cur_op;
+    if (cur_len) { --cpos; if (writer) cig_g[cpos] = (cur_len << 4) | cur_op; }
     int nops = (int)cig_stride - cpos;
     unsigned long long off = 0;
     if (status != CLQ_OK) nops = 0;
     if (nops > 0) {
-        off = atomicAdd(cigar_cursor, (unsigned long long)nops);
+        if (writer) off = atomicAdd(cigar_cursor, (unsigned long long)nops);
+        if (WARP) {
+            off = __shfl_sync(FULL, off, 0);
+            __syncwarp();  // lane 0's scratch writes, read by every lane below
+        }
         if (off + (unsigned long long)nops > cigar_cap) { status = CLQ_CIGAR_POOL_FULL; nops = 0; }
     }
-    for (int i = 0; i < nops; i++) cigar_pool[off + i] = cig_g[cpos + i];
-    clq_result_t* r = results + rec.ridx;
-    r->cigar_off = (uint32_t)off;
-    r->cigar_len = (uint32_t)nops;
-    r->status = status;
-    r->matches = n_match;
-    r->mismatches = n_mismatch;
+    for (int i = WARP ? wlane : 0; i < nops; i += WARP ? 32 : 1) cigar_pool[off + i] = cig_g[cpos + i];
+    if (writer) {
+        clq_result_t* r = results + rec.ridx;
+        r->cigar_off = (uint32_t)off;
+        r->cigar_len = (uint32_t)nops;
+        r->status = status;
+        r->matches = n_match;
+        r->mismatches = n_mismatch;
+    }
 }
 
 // Grouping of a multi-reference batch for the PACK traceback stage: the s16x2 kernels align two reads against ONE reference,

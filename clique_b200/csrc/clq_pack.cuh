@@ -70,6 +70,16 @@ __device__ __forceinline__ void bits_store2(uint32_t* tt, uint32_t* bitsA, uint3
     }
 }
 
+// predicated global accesses for the stripe-boundary column: a branch around four loads / stores costs more issue slots on this
+// kernel than executing the address arithmetic on every lane
+__device__ __forceinline__ uint32_t ldg_if(const uint32_t* ptr, bool cond, uint32_t keep) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.u32 %0, [%1];\n\t}" : "+r"(keep) : "l"(ptr), "r"((uint32_t)cond));
+    return keep;
+}
+__device__ __forceinline__ void stg_if(uint32_t* ptr, bool cond, uint32_t v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u32 [%0], %1;\n\t}" ::"l"(ptr), "r"(v), "r"((uint32_t)cond) : "memory");
+}
+
 #ifndef CLQ_PACK_PIN_NIBBLE
 #define CLQ_PACK_PIN_NIBBLE 1
 #endif
@@ -91,15 +101,17 @@ struct PackParams {
 // MADD (static row slope, see pack_kernel): the profile bytes are >= 0, so M = diag + m is a plain 32-bit add of packed halves
 // (no carry can cross them) and leaves the ALU pipe; LEe / X1b are the E-step extend and the B-step open constants, which then
 // differ from the F-step / P-step ones (LE, X1) by the slope.
-template <int C, bool TB, bool LAST, bool RB = false, bool MADD = false>
-__device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C], const uint32_t (&sel)[C], uint32_t (&wA)[C / 8],
-                                              uint32_t (&wB)[C / 8], uint32_t& Fh, uint32_t& Ehl, uint32_t& Ml, uint32_t& Bl, uint32_t diag,
-                                              uint32_t tlo, uint32_t thi, uint32_t LE, uint32_t X1, uint32_t X1M1, uint32_t LEe, uint32_t X1b,
-                                              bool ownA, int jA, bool ownB, int jB, uint32_t (&cap)[3], int nb) {
-    const uint32_t ONE = 0x00010001u;
-#pragma unroll
-    for (int jb = 0; jb < C / 8; jb++) {
-        if (jb < nb) {  // narrow last stripe: only nb blocks of 8 columns per lane are real
+template <int C, bool TB, bool LAST, bool RB, bool MADD, int JB>
+__device__ __forceinline__ void pack_row_blocks(uint32_t (&Eh)[C], uint32_t (&B)[C], const uint32_t (&sel)[C], uint32_t (&wA)[C / 8],
+                                                uint32_t (&wB)[C / 8], uint32_t& Fh, uint32_t& Ehl, uint32_t& Ml, uint32_t& Bl, uint32_t diag,
+                                                uint32_t tlo, uint32_t thi, uint32_t LE, uint32_t X1, uint32_t X1M1, uint32_t LEe, uint32_t X1b,
+                                                bool ownA, int jA, bool ownB, int jB, uint32_t (&cap)[3], int nb) {
+    // Blocks of 8 columns, nested: block JB + 1 only runs inside block JB's `if`, so a narrow last stripe (only nb blocks per lane
+    // are real, G >= 16 geometries) leaves through ONE forward branch instead of a reconvergence region per block.
+    if constexpr (JB < C / 8) {
+        if (JB < nb) {
+            constexpr int jb = JB;
+            const uint32_t ONE = 0x00010001u;
             uint32_t acc0 = 0, acc1 = 0;
             // M of the next cell is issued inside the current one (it needs B[j] of the previous row, which the current cell
             // overwrites): B[j]'s old value then dies within the cell and no register copy is needed to carry it as `diag`
@@ -149,8 +161,17 @@ __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C
                     if (ownB && j == jB) { cap[0] = set_hi(cap[0], get_hi(Mv)); cap[1] = set_hi(cap[1], get_hi(Ehn)); cap[2] = set_hi(cap[2], get_hi(Fhn)); }
                 }
             }
+            pack_row_blocks<C, TB, LAST, RB, MADD, JB + 1>(Eh, B, sel, wA, wB, Fh, Ehl, Ml, Bl, diag, tlo, thi, LE, X1, X1M1, LEe, X1b, ownA, jA, ownB, jB, cap, nb);
         }
     }
+}
+
+template <int C, bool TB, bool LAST, bool RB = false, bool MADD = false>
+__device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C], const uint32_t (&sel)[C], uint32_t (&wA)[C / 8],
+                                              uint32_t (&wB)[C / 8], uint32_t& Fh, uint32_t& Ehl, uint32_t& Ml, uint32_t& Bl, uint32_t diag,
+                                              uint32_t tlo, uint32_t thi, uint32_t LE, uint32_t X1, uint32_t X1M1, uint32_t LEe, uint32_t X1b,
+                                              bool ownA, int jA, bool ownB, int jB, uint32_t (&cap)[3], int nb) {
+    pack_row_blocks<C, TB, LAST, RB, MADD, 0>(Eh, B, sel, wA, wB, Fh, Ehl, Ml, Bl, diag, tlo, thi, LE, X1, X1M1, LEe, X1b, ownA, jA, ownB, jB, cap, nb);
 }
 
 // Tasks are read PAIRS.  Pair mode (all_pairs == 0): pair t = reads at processing positions task_base + 2t, +1, all against
@@ -340,6 +361,8 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
             const uint32_t L1act = act_s ? (uint32_t)L1 : 0u;          // act  <=>  (unsigned)(x - 1) < L1act
             const int xcap = (ownA || ownB) ? L1 : -1;                 // the capture variant: only the lane(s) owning column L2, at row L1
             const bool first_col = (gl == 0) && (s == 0);
+            const bool ld_col = (gl == 0) && (s > 0), st_col = (gl == G - 1) && (s < NS - 1);  // stripe-boundary column: consumer / producer lane
+            const int k_own = max(ownA ? K[0] : 0, ownB ? K[1] : 0);  // band-skipped cell (x <= K, L2) of this lane's reads, if it owns column L2
             const bool stA = TB && run[0] && s < NSh[0], stB = TB && run[1] && s < NSh[1];
             // the profile row of the current reference class comes from a lane shuffle (lane k holds row k of the 16-row table):
             // no shared-memory address arithmetic in the loop; the class of the next row is read one step ahead
@@ -378,13 +401,10 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
                             if (RB) Fl = 0;  // rust-bio: I[i][0] = MIN_SCORE on the empty-read boundary
                         }
                         if (!SIMPLE) {
-                            if (gl == 0 && s > 0) {
-                                Fl = nF; El = nE; Ml = nM; Bl = nB;
-                                if (x < L1) {
-                                    nF = col_g[x + 1]; nE = col_g[p.col_stride + x + 1];
-                                    nM = col_g[2 * p.col_stride + x + 1]; nB = col_g[3 * p.col_stride + x + 1];
-                                }
-                            }
+                            if (ld_col) { Fl = nF; El = nE; Ml = nM; Bl = nB; }  // selects; the next row's values are fetched one step ahead
+                            const bool nx = ld_col && x < L1;
+                            nF = ldg_if(col_g + x + 1, nx, nF); nE = ldg_if(col_g + p.col_stride + x + 1, nx, nE);
+                            nM = ldg_if(col_g + 2 * p.col_stride + x + 1, nx, nM); nB = ldg_if(col_g + 3 * p.col_stride + x + 1, nx, nB);
                         }
                         rcur = ref_sm[x < L1 ? x : L1 - 1];  // class of row x + 1 (clamped on the last row: unused)
                         const uint32_t BlIn = Bl;
@@ -397,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
                         oF = Fl; oE = El; oM = Ml; oB = Bl;
                         if (!SIMPLE) {
                             // band-skipped cells (x <= K, y == L2): fresh-matrix state (0,0,0), per read
-                            if ((ownA && x <= K[0]) || (ownB && x <= K[1])) {
+                            if (x <= k_own) {
                                 const bool sa = ownA && x <= K[0], sb = ownB && x <= K[1];
                                 // true values (0,0,0): stored with this row's slope terms (Eh' carries s (x - 1), the rest s x)
                                 const int b0v = bias + slope * x, f0 = -x1 + b0v, e0 = f0 - slope;
@@ -416,9 +436,8 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
                         }
                         if (TB) bits_store2<G, WPL>(tt_sm, bitsA, bitsB, wA, wB, stA, stB, s, T, t, lane, gl, x == L1, nb);
                         if (!SIMPLE) {
-                            if (gl == G - 1 && s < NS - 1) {
-                                col_g[x] = oF; col_g[p.col_stride + x] = oE; col_g[2 * p.col_stride + x] = oM; col_g[3 * p.col_stride + x] = oB;
-                            }
+                            stg_if(col_g + x, st_col, oF); stg_if(col_g + p.col_stride + x, st_col, oE);
+                            stg_if(col_g + 2 * p.col_stride + x, st_col, oM); stg_if(col_g + 3 * p.col_stride + x, st_col, oB);
                         }
                     }
                 } while (++t <= Tmax);

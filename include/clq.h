@@ -126,8 +126,11 @@ typedef struct {
     uint64_t d2h_bytes;    /* bytes copied device->host by clq_download + clq_wait                  */
     uint32_t variant;      /* kernel family of the last launch: bit0 FAST (PRMT/DPX), bit1 PACK (s16x2, two reads per
                               lane group), bit2 CONVEX, bit3 final-gap multiplier variant, bit4 rust-bio semantics, bit5 PACK with the static
-                              row slope (M step off the ALU pipe); bits 8.. = geometry index */
+                              row slope (M step off the ALU pipe), bit6 PACK with the adaptive per-row bias + int32 retry pass (long reads);
+                              bits 8.. = geometry index */
     uint32_t sub_batches;  /* fill + walk rounds the traceback scratch budget split the batch into  */
+    uint32_t pack_retries; /* reads the adaptive s16x2 kernel (variant bit6) handed to the int32 retry pass; set by clq_wait */
+    uint32_t reserved0;
 } clq_stats_t;
 
 int32_t clq_version(void);

@@ -114,6 +114,8 @@ pub struct clq_stats_t {
     pub d2h_bytes: u64,
     pub variant: u32,
     pub sub_batches: u32,
+    pub pack_retries: u32,
+    pub reserved0: u32,
 }
 
 extern "C" {

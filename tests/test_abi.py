@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_header_structs_match_ctypes():
     assert C.sizeof(L.AffineInt) == 44 and C.sizeof(L.Result) == 28
-    assert C.sizeof(L.Limits) == 48 and C.sizeof(L.Stats) == 48
+    assert C.sizeof(L.Limits) == 48 and C.sizeof(L.Stats) == 56
 
 
 def test_affine_from_f64():
