@@ -371,6 +371,16 @@ const char* clq_strerror(int32_t code) {
     }
 }
 
+/* debug builds (-DCLQ_PACK_CANARY=1): tasks whose stored s16 values were tracked / tasks with a value outside [64, 32767] that
+ * no retry pass covered; {0, 0} in production builds.  Not part of include/clq.h. */
+int32_t clq_debug_canary(unsigned long long* checked, unsigned long long* violations) {
+    unsigned long long h[2] = {0, 0};
+    if (cudaMemcpyFromSymbol(h, g_pack_canary, sizeof(h)) != cudaSuccess) return CLQ_E_CUDA;
+    if (checked) *checked = h[0];
+    if (violations) *violations = h[1];
+    return CLQ_PACK_CANARY ? CLQ_OK : CLQ_E_UNSUPPORTED;
+}
+
 int32_t clq_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;

@@ -80,6 +80,30 @@ __device__ __forceinline__ void stg_if(uint32_t* ptr, bool cond, uint32_t v) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u32 [%0], %1;\n\t}" ::"l"(ptr), "r"(v), "r"((uint32_t)cond) : "memory");
 }
 
+// -DCLQ_PACK_CANARY=1 (debug builds, tools/canary_gpu.sh): every value a PACK kernel stores (M, Eh, Fh, B of every cell) is
+// tracked per task; a task whose values left [64, 32767] WITHOUT being handed to the retry pass is counted here and reported by
+// clq_debug_canary().  Must stay 0: it is the run-time check of the window proofs (static, sloped, adaptive guard band).
+#ifndef CLQ_PACK_CANARY
+#define CLQ_PACK_CANARY 0
+#endif
+__device__ unsigned long long g_pack_canary[2];  // [0] tasks checked, [1] violations
+struct Canary {
+    uint32_t mn = 0xffffffffu, mx = 0u;
+    __device__ __forceinline__ void see(uint32_t v) {
+#if CLQ_PACK_CANARY
+        mn = __vminu2(mn, v); mx = __vmaxu2(mx, v);
+#endif
+    }
+    // call with full-warp convergence; `skip`: the task is redone elsewhere (its values do not matter)
+    __device__ __forceinline__ void report(bool active, bool skip) {
+#if CLQ_PACK_CANARY
+        const bool bad = active && !skip && ((mn & 0xffffu) < 64u || (mn >> 16) < 64u || (mx & 0xffffu) > 32767u || (mx >> 16) > 32767u);
+        const unsigned nbad = __popc(__ballot_sync(0xffffffffu, bad)), nact = __popc(__ballot_sync(0xffffffffu, active && !skip));
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&g_pack_canary[0], (unsigned long long)nact); if (nbad) atomicAdd(&g_pack_canary[1], (unsigned long long)nbad); }
+#endif
+    }
+};
+
 #ifndef CLQ_PACK_PIN_NIBBLE
 #define CLQ_PACK_PIN_NIBBLE 1
 #endif
@@ -105,7 +129,7 @@ template <int C, bool TB, bool LAST, bool RB, bool MADD, int JB>
 __device__ __forceinline__ void pack_row_blocks(uint32_t (&Eh)[C], uint32_t (&B)[C], const uint32_t (&sel)[C], uint32_t (&wA)[C / 8],
                                                 uint32_t (&wB)[C / 8], uint32_t& Fh, uint32_t& Ehl, uint32_t& Ml, uint32_t& Bl, uint32_t diag,
                                                 uint32_t tlo, uint32_t thi, uint32_t LE, uint32_t X1, uint32_t X1M1, uint32_t LEe, uint32_t X1b,
-                                                bool ownA, int jA, bool ownB, int jB, uint32_t (&cap)[3], int nb) {
+                                                bool ownA, int jA, bool ownB, int jB, uint32_t (&cap)[3], int nb, Canary& cy) {
     // Blocks of 8 columns, nested: block JB + 1 only runs inside block JB's `if`, so a narrow last stripe (only nb blocks per lane
     // are real, G >= 16 geometries) leaves through ONE forward branch instead of a reconvergence region per block.
     if constexpr (JB < C / 8) {
@@ -156,12 +180,13 @@ __device__ __forceinline__ void pack_row_blocks(uint32_t (&Eh)[C], uint32_t (&B)
                 Eh[j] = Ehn;
                 B[j] = Bn;
                 Fh = Fhn; Ehl = Ehn; Ml = Mv; Bl = Bn;
+                if (CLQ_PACK_CANARY) { cy.see(Mv); cy.see(Ehn); cy.see(Fhn); cy.see(Bn); }
                 if (LAST) {
                     if (ownA && j == jA) { cap[0] = set_lo(cap[0], get_lo(Mv)); cap[1] = set_lo(cap[1], get_lo(Ehn)); cap[2] = set_lo(cap[2], get_lo(Fhn)); }
                     if (ownB && j == jB) { cap[0] = set_hi(cap[0], get_hi(Mv)); cap[1] = set_hi(cap[1], get_hi(Ehn)); cap[2] = set_hi(cap[2], get_hi(Fhn)); }
                 }
             }
-            pack_row_blocks<C, TB, LAST, RB, MADD, JB + 1>(Eh, B, sel, wA, wB, Fh, Ehl, Ml, Bl, diag, tlo, thi, LE, X1, X1M1, LEe, X1b, ownA, jA, ownB, jB, cap, nb);
+            pack_row_blocks<C, TB, LAST, RB, MADD, JB + 1>(Eh, B, sel, wA, wB, Fh, Ehl, Ml, Bl, diag, tlo, thi, LE, X1, X1M1, LEe, X1b, ownA, jA, ownB, jB, cap, nb, cy);
         }
     }
 }
@@ -170,8 +195,8 @@ template <int C, bool TB, bool LAST, bool RB = false, bool MADD = false>
 __device__ __forceinline__ void pack_row_step(uint32_t (&Eh)[C], uint32_t (&B)[C], const uint32_t (&sel)[C], uint32_t (&wA)[C / 8],
                                               uint32_t (&wB)[C / 8], uint32_t& Fh, uint32_t& Ehl, uint32_t& Ml, uint32_t& Bl, uint32_t diag,
                                               uint32_t tlo, uint32_t thi, uint32_t LE, uint32_t X1, uint32_t X1M1, uint32_t LEe, uint32_t X1b,
-                                              bool ownA, int jA, bool ownB, int jB, uint32_t (&cap)[3], int nb) {
-    pack_row_blocks<C, TB, LAST, RB, MADD, 0>(Eh, B, sel, wA, wB, Fh, Ehl, Ml, Bl, diag, tlo, thi, LE, X1, X1M1, LEe, X1b, ownA, jA, ownB, jB, cap, nb);
+                                              bool ownA, int jA, bool ownB, int jB, uint32_t (&cap)[3], int nb, Canary& cy) {
+    pack_row_blocks<C, TB, LAST, RB, MADD, 0>(Eh, B, sel, wA, wB, Fh, Ehl, Ml, Bl, diag, tlo, thi, LE, X1, X1M1, LEe, X1b, ownA, jA, ownB, jB, cap, nb, cy);
 }
 
 // Tasks are read PAIRS.  Pair mode (all_pairs == 0): pair t = reads at processing positions task_base + 2t, +1, all against
@@ -313,6 +338,7 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
         const int NSmax = __reduce_max_sync(FULL, NS);
         const int T = anyrun ? L1 + G - 1 : 0;
         const int Tmax = __reduce_max_sync(FULL, T);
+        Canary cy;
         uint32_t cap[3] = {0, 0, 0};
         uint32_t bad = 0;  // RB: bit h = read h holds a byte the class table cannot score exactly
         uint32_t* bitsA = TB ? p.bits + bits_slot(p.bits_off, p.bits_stride, p.task_base, 2 * task) : nullptr;
@@ -410,9 +436,9 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
                         const uint32_t BlIn = Bl;
                         // the capture variant only runs on the lane(s) that own column L2, at their last row: once per task
                         if (x == xcap)
-                            pack_row_step<C, TB, true, RB, MADD>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, LEe, X1b, ownA, jLh[0], ownB, jLh[1], cap, nb);
+                            pack_row_step<C, TB, true, RB, MADD>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, LEe, X1b, ownA, jLh[0], ownB, jLh[1], cap, nb, cy);
                         else
-                            pack_row_step<C, TB, false, RB, MADD>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, LEe, X1b, ownA, jLh[0], ownB, jLh[1], cap, nb);
+                            pack_row_step<C, TB, false, RB, MADD>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, LEe, X1b, ownA, jLh[0], ownB, jLh[1], cap, nb, cy);
                         prevBl = BlIn;
                         oF = Fl; oE = El; oM = Ml; oB = Bl;
                         if (!SIMPLE) {
@@ -446,6 +472,7 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
             __syncwarp();
         }
 
+        cy.report(anyrun, false);
         // ---- final cells: score + start layer = LAST maximum of (M, E, F) per read ----
         if (RB) {
             const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (gw * G));

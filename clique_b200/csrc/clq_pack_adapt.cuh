@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(kThreads, 3) pack_adapt_kernel(const KParams p
         const int NSmax = __reduce_max_sync(FULL, NS);
         const int T = anyrun ? L1 + G - 1 : 0;
         const int Tmax = __reduce_max_sync(FULL, T);
+        Canary cy;
         uint32_t cap[3] = {0, 0, 0};
         int cap_beta[2] = {0, 0}, cap_beta_prev[2] = {0, 0};  // beta(L1), beta(L1 - 1) of the stripe that holds column L2 of read h
         uint32_t* bitsA = p.bits + bits_slot(p.bits_off, p.bits_stride, p.task_base, 2 * task);
@@ -255,11 +256,11 @@ __global__ void __launch_bounds__(kThreads, 3) pack_adapt_kernel(const KParams p
                     rcur = ref_sm[x < L1 ? x : L1 - 1];
                     const uint32_t BlIn = Bl;
                     if (x == xcap) {
-                        pack_row_step<C, true, true, false, false>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, LEe, X1b, ownA, jLh[0], ownB, jLh[1], cap, nb);
+                        pack_row_step<C, true, true, false, false>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, LEe, X1b, ownA, jLh[0], ownB, jLh[1], cap, nb, cy);
                         if (ownA) { cap_beta[0] = beta; cap_beta_prev[0] = beta_prev; }
                         if (ownB) { cap_beta[1] = beta; cap_beta_prev[1] = beta_prev; }
                     } else
-                        pack_row_step<C, true, false, false, false>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, LEe, X1b, ownA, jLh[0], ownB, jLh[1], cap, nb);
+                        pack_row_step<C, true, false, false, false>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, LEe, X1b, ownA, jLh[0], ownB, jLh[1], cap, nb, cy);
                     prevBl = BlIn;
                     oF = Fl; oE = El; oM = Ml; oB = Bl;
                     if (x <= k_own) {
@@ -325,6 +326,7 @@ __global__ void __launch_bounds__(kThreads, 3) pack_adapt_kernel(const KParams p
         }
         const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (gw * G));
         const bool redo = anyrun && (__ballot_sync(FULL, fault) & gm) != 0u;
+        cy.report(anyrun, redo);  // a pair that is NOT redone must never have left the window: the guard band's soundness, checked
 
         // ---- final cells: score + start layer = LAST maximum of (M, E, F) per read ----
 #pragma unroll

@@ -14,7 +14,7 @@ from clique_b200 import AffineScoring, Aligner, Reference, ReferenceManager, Rus
 from clique_b200.aligner import pack_reads
 
 def reset():
-    for k, v in (("force_cfg", -1), ("no_pack", 0), ("max_scratch_bytes", 40 << 30), ("no_group", 0), ("force_generic", 0)):
+    for k, v in (("force_cfg", -1), ("no_pack", 0), ("max_scratch_bytes", 40 << 30), ("no_group", 0), ("force_generic", 0), ("no_madd", 0), ("no_adapt", 0)):
         al.set_option(k, v)
 
 
@@ -80,6 +80,8 @@ while time.time() < t_end:
         al.set_option("max_scratch_bytes", int(rng.choice([40 << 30, 1 << 20, 16 << 20])))
         al.set_option("no_group", int(rng.random() < 0.3))
         al.set_option("force_generic", int(rng.random() < 0.15))
+        al.set_option("no_madd", int(rng.random() < 0.3))
+        al.set_option("no_adapt", int(rng.random() < 0.2))
     tags = bool(rng.random() < 0.5) and mode not in ("convex",)
     ctx = (it, mode, sc, cfg, nref, n, lmax, uniform)
     if only is not None and it not in only:
@@ -166,4 +168,14 @@ while time.time() < t_end:
         reset()
 al.close()
 print("iterations", it, "checked pairs", n_checked, "mismatches", bad)
+# debug builds (-DCLQ_PACK_CANARY=1, tools/canary_gpu.sh): s16x2 tasks whose stored values were tracked / tasks that left [64, 32767]
+# without being covered by the retry pass
+import ctypes
+from clique_b200 import load_library
+_lib = load_library()
+if hasattr(_lib, "clq_debug_canary"):
+    chk, vio = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    if _lib.clq_debug_canary(ctypes.byref(chk), ctypes.byref(vio)) == 0:
+        print("canary: s16x2 tasks checked", chk.value, "window violations", vio.value)
+        bad += vio.value
 sys.exit(1 if bad else 0)
