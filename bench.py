@@ -166,11 +166,13 @@ def run_reference_arm(args, rank, world):
 
 
 KERNEL_NAMES = {0: "generic int32", 1: "FAST int32 (PRMT profile + DPX)", 3: "PACK s16x2 (two reads per lane group, DPX)",
+                35: "PACK s16x2 with static row slope (two reads per lane group, DPX; M step off the ALU pipe)",
+                67: "PACK s16x2 with adaptive row bias + int32 retry pass (two reads per lane group, DPX)",
                 5: "CONVEX int32 (two-piece affine, DPX)", 7: "CONVEX PACK s16x2 (two-piece affine, two reads per lane group, DPX)"}
 
 
 def kernel_name(variant):
-    k = KERNEL_NAMES.get(variant & 7, "variant %d" % (variant & 15))
+    k = KERNEL_NAMES.get(variant & 103, KERNEL_NAMES.get(variant & 7, "variant %d" % (variant & 127)))
     if variant & 16:
         k += " [rust-bio global semantics]"
     return k
@@ -277,16 +279,18 @@ def run_config(args, workload, n, search, convex, rustbio, steps, warmup, e2e_ch
     if clocks:
         clocks.start()
     barrier()
-    step_ms, dp_ms, launches, cells, variant = [], [], 0, 0, 0
+    step_ms, dp_ms, launches, cells, variant, sub_batches = [], [], 0, 0, 0, 0
     t0 = time.perf_counter()
     for _ in range(steps):
         al.launch(0, sci, c["search"], c["band"], score_only)
         st = al.stats(0)       # synchronises the slot's stream; times come from CUDA events on that stream
         step_ms.append(st["kernel_ms"]); dp_ms.append(st["dp_ms"]); launches += st["launches"]; cells = st["cells"]; variant = st["variant"]
+        sub_batches = st["sub_batches"]
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     clk = clocks.stop() if clocks else None
     res = al.wait(0, copy=True)
+    pack_retries = al.stats(0).get("pack_retries", 0)   # set by clq_wait: reads the adaptive s16x2 kernel handed to the int32 retry pass
     n_ok = int((res.status == 0).sum())
     dev_ms_total = float(np.sum(step_ms))
     t = torch.tensor([dev_ms_total, wall_ms], dtype=torch.float64, device="cuda")
@@ -348,7 +352,7 @@ def run_config(args, workload, n, search, convex, rustbio, steps, warmup, e2e_ch
     al.close()
     return {"c": c, "n": n, "total_bytes": total_bytes, "res": res, "n_ok": n_ok, "ms_per_step": ms_per_step, "wall_ms": wall_ms,
             "dp_ms": float(np.mean(dp_ms)), "launches": int(launches), "cells": int(cells), "variant": int(variant), "clk": clk,
-            "e2e_ms": e2e_ms, "h2d": int(h2d), "d2h": int(d2h), "nch": nch}
+            "e2e_ms": e2e_ms, "h2d": int(h2d), "d2h": int(d2h), "nch": nch, "pack_retries": int(pack_retries), "sub_batches": int(sub_batches)}
 
 
 def api_pass(c, devices, n_reads_total, passes=3, batch_reads=1 << 18, fillers=2, repeat=1):
@@ -477,7 +481,7 @@ def main():
                        "gcups": x["cells"] * n_gpus / (x["ms_per_step"] / 1e3) / 1e9, "ms_per_step": x["ms_per_step"],
                        "e2e_reads_s": n_x * n_gpus / (x["e2e_ms"] / 1e3), "kernel": kernel_name(x["variant"]), "kernel_ms": x["dp_ms"],
                        "ops_per_cell": ops, "pack": pack, "frac": achieved / (peak * pack), "frac_vs_packed_peak": achieved / (peak * 2),
-                       "status_ok_reads": x["n_ok"], "gpu_launches": x["launches"]}
+                       "status_ok_reads": x["n_ok"], "gpu_launches": x["launches"], "sub_batches": x["sub_batches"], "pack_retries": x["pack_retries"]}
                 if n_gpus == 1:
                     ent["parity"] = oracle_parity(x["c"], x["res"], min(n_chk, n_x), convex=convex)
                     ent["parity"].pop("oracle_seconds", None); ent["parity"].pop("oracle_cells", None)
@@ -551,7 +555,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "gcups": gcups,
             "config": {"workload": WORKLOAD_DESC[args.workload].replace("(exhaustive)", "(%s)" % c["search"]) + (" [two-piece affine (convex) gaps, self-pinned]" if args.convex else "") + (" [rust-bio single-reference branch 1/-1/-5/-1 instead of clique's Gotoh, parity unpinned]" if args.rustbio else ""), "reads_per_gpu_per_step": n, "cells_per_gpu_per_step": int(cells),
-                       "parallelism": "read-sharded x%d, no collectives" % n_gpus, "status_ok_reads": r["n_ok"],
+                       "parallelism": "read-sharded x%d, no collectives" % n_gpus, "status_ok_reads": r["n_ok"], "sub_batches": r["sub_batches"], "pack_retries": r["pack_retries"],
                        "l2": "inputs larger than L2 (%.0f MB of reads + %.0f MB of direction bits per step)" % (total_bytes / 1e6, 0.5 * cells / 1e6)},
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"], "power_w_max": clk.get("power_w_max"),
                        "samples": clk.get("samples")},

@@ -47,6 +47,8 @@ struct Slot {
     DevBuf cigar_pool, bits, cig_scratch, col_scratch, tb_rec, bits_off, tags, ref_groups;
     std::vector<uint32_t> h_len;     // read lengths in processing order (only when lengths vary: have_order)
     std::vector<int32_t> h_ref;      // fixed_ref in processing order (same condition, when given)
+    std::vector<uint32_t> h_order;   // the processing order itself (read index per position, 0xffffffff = padding)
+    DevBuf order2;                   // the order of one launch after its sub-batches were dealt (clq_launch)
     DevBuf counters;                 // [0..3] task counters (u32, padded to 8 B each), [4] cigar cursor, [5] cells
     unsigned long long* h_counters = nullptr;  // pinned mirror
     uint32_t n_reads = 0;
@@ -313,8 +315,17 @@ cudaError_t launch_cvx_walk(int cfg, const KParams& p, uint32_t cnt, cudaStream_
 
 template <int G, int C>
 cudaError_t launch_walk_one(const KParams& p, uint32_t cnt, cudaStream_t st) {
-    constexpr bool WARP = G >= 16;  // long-read geometries: one warp per pair (clq_kernels.cuh)
-    walk_kernel<G, C, WARP><<<(uint32_t)(((uint64_t)cnt * (WARP ? 32 : 1) + 127) / 128), 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.bits_off, p.task_base, p.cig_scratch, p.cig_stride, p.cigar_pool,
+    // one thread per pair.  (The warp-per-pair mode of walk_kernel -- a window of 32 diagonal cells fetched at once -- was measured
+    // on the long-read geometries: C5 unchanged, C3 15 % slower: with 10^4..10^5 pairs per sub-batch the 32x instruction count
+    // costs more than the latency it hides.  It stays in the kernel for sub-batches of very few, very long pairs.)
+    const bool warp_mode = G >= 16 && cnt <= 1024;
+    if (warp_mode) {
+        walk_kernel<G, C, (G >= 16)><<<(uint32_t)(((uint64_t)cnt * 32 + 127) / 128), 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.bits_off, p.task_base, p.cig_scratch, p.cig_stride, p.cigar_pool,
+                                                         p.cigar_cap, p.cigar_cursor, p.results, p.ref_bytes, p.ref_off, p.read_bytes, p.read_off,
+                                                         p.tag_slot, p.tags, p.tag_stride, p.rustbio, p.band_mode, p.band_k);
+        return cudaGetLastError();
+    }
+    walk_kernel<G, C, false><<<(cnt + 127) / 128, 128, 0, st>>>(p.tb_rec, cnt, p.bits, p.bits_stride, p.bits_off, p.task_base, p.cig_scratch, p.cig_stride, p.cigar_pool,
                                                          p.cigar_cap, p.cigar_cursor, p.results, p.ref_bytes, p.ref_off, p.read_bytes, p.read_off,
                                                          p.tag_slot, p.tags, p.tag_stride, p.rustbio, p.band_mode, p.band_k);
     return cudaGetLastError();
@@ -473,7 +484,7 @@ void clq_ctx_destroy(clq_ctx* c) {
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
         if (s.done) cudaEventDestroy(s.done);
         for (DevBuf* b : {&s.read_bytes, &s.read_off, &s.fixed_ref, &s.order, &s.results, &s.scores, &s.cand_mask, &s.single_ref,
-                          &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.tb_rec, &s.bits_off, &s.tags, &s.ref_groups, &s.retry_list, &s.counters})
+                          &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.tb_rec, &s.bits_off, &s.tags, &s.ref_groups, &s.retry_list, &s.order2, &s.counters})
             release(*b);
         if (s.h_counters) cudaFreeHost(s.h_counters);
     }
@@ -732,6 +743,7 @@ int32_t clq_upload(clq_ctx* c, int32_t slot, uint32_t n_reads, const uint8_t* re
         CU(c, cudaMemcpyAsync(s->order.p, use->data(), npos * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
         CU(c, cudaStreamSynchronize(s->stream));  // the host vectors are reused
         s->have_order = true;
+        s->h_order.assign(use->begin(), use->end());
         s->h_len.resize(npos);
         s->h_ref.clear();
         if (fixed_ref) s->h_ref.resize(npos);
@@ -891,7 +903,9 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
             adp.guard = guard;
         }
     }
-    const bool pack_pairs = (pack && c->n_refs == 1) || adapt;  // pair mode needs one reference for both reads of a task
+    // pair mode needs one reference for both reads of a task: a single-reference panel, or a fixed assignment that the upload
+    // grouped by reference (every group padded to whole pairs)
+    const bool pack_pairs = (pack && (c->n_refs == 1 || (s->order_by_ref && search == CLQ_SEARCH_FIXED))) || adapt;
     // multi-reference batches: the traceback stage buckets the reads by reference on the device (ref_scatter_kernel) so that
     // the two reads of a PACK task share theirs; only with the natural read order (uniform lengths, uniform scratch slots)
     const bool group_pairs = pack && !pack_pairs && !score_only && !s->have_order && n > 0 && c->n_refs > 1 && !c->no_group;
@@ -1000,28 +1014,53 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
             off[i + 1] = off[i] + (l2 ? bits_words(l1, l2) : 0);  // empty reads and padding positions store nothing
         }
         const uint64_t budget_words = (uint64_t)c->max_scratch_bytes / 4;
-        cuts.push_back(0);
-        max_sub_words = 0; max_sub_tasks = 0;
-        uint64_t start = 0;
-        for (uint64_t i = 0; i < np;) {
-            // grow [start, i) while it fits; always an even number of positions except for the last sub-batch
-            uint64_t j = i + 2 <= np ? i + 2 : np;
-            if (off[j] - off[start] + (j - start) * (cig_stride + 4) > budget_words && i > start) {
-                cuts.push_back(i);
-                max_sub_words = std::max(max_sub_words, off[i] - off[start]);
-                max_sub_tasks = std::max(max_sub_tasks, i - start);
-                start = i;
-                continue;
-            }
-            i = j;
+        // Sub-batches.  The positions are sorted longest first; cutting that list into contiguous pieces would make the first
+        // sub-batches all-long (a 40 GB piece of 5 kb pairs is ~1600 tasks: not even one wave of the persistent grid, and every
+        // task ends at the same time).  Instead the position PAIRS are dealt round-robin over K sub-batches: every sub-batch gets
+        // the same mix, still longest first inside, and its short pairs fill the SMs the long ones leave.
+        const uint64_t npairs = (np + 1) / 2;
+        auto cost = [&](uint64_t i) -> uint64_t { return i < np ? (off[i + 1] - off[i]) + cig_stride + 4 : 0; };
+        uint64_t total_cost = 0;
+        for (uint64_t i = 0; i < np; i++) total_cost += cost(i);
+        uint64_t K = std::max<uint64_t>(1, (total_cost + budget_words - 1) / budget_words);
+        static thread_local std::vector<uint64_t> sub_cost;
+        for (; K < npairs; K++) {
+            sub_cost.assign(K, 0);
+            for (uint64_t pr = 0; pr < npairs; pr++) sub_cost[pr % K] += cost(2 * pr) + cost(2 * pr + 1);
+            if (*std::max_element(sub_cost.begin(), sub_cost.end()) <= budget_words) break;
         }
-        cuts.push_back(np);
-        max_sub_words = std::max(max_sub_words, off[np] - off[start]);
-        max_sub_tasks = std::max<uint64_t>(max_sub_tasks, np - start);
+        K = std::min<uint64_t>(K, std::max<uint64_t>(npairs, 1));
+        cuts.push_back(0);
+        if (K > 1 && s->h_order.size() == np) {
+            static thread_local std::vector<uint32_t> order2, len2;
+            static thread_local std::vector<uint64_t> off2;
+            order2.clear(); len2.clear();
+            off2.assign(1, 0);
+            for (uint64_t k = 0; k < K; k++) {
+                for (uint64_t pr = k; pr < npairs; pr += K)
+                    for (uint64_t i = 2 * pr; i < 2 * pr + 2; i++) {
+                        order2.push_back(i < np ? s->h_order[i] : 0xffffffffu);  // an odd tail is padded: every sub-batch holds whole pairs
+                        off2.push_back(off2.back() + (i < np ? off[i + 1] - off[i] : 0));
+                    }
+                cuts.push_back(order2.size());
+            }
+            off.assign(off2.begin(), off2.end());
+            if ((rc = ensure(c, s->order2, (order2.size() + 2) * sizeof(uint32_t))) != CLQ_OK) return rc;
+            CU(c, cudaMemcpyAsync(s->order2.p, order2.data(), order2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+            p.order = (const uint32_t*)s->order2.p;
+        } else {
+            cuts.push_back(np);
+        }
+        const uint64_t npos2 = cuts.back();
+        max_sub_words = 0; max_sub_tasks = 0;
+        for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
+            max_sub_words = std::max(max_sub_words, off[cuts[ci + 1]] - off[cuts[ci]]);
+            max_sub_tasks = std::max(max_sub_tasks, cuts[ci + 1] - cuts[ci]);
+        }
         max_sub_tasks = (max_sub_tasks + 1) & ~1ull;
-        if ((rc = ensure(c, s->bits_off, ((size_t)np + 1) * sizeof(uint64_t))) != CLQ_OK) return rc;
-        CU(c, cudaMemcpyAsync(s->bits_off.p, off.data(), ((size_t)np + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
-        CU(c, cudaStreamSynchronize(s->stream));  // `off` is a reused host vector
+        if ((rc = ensure(c, s->bits_off, ((size_t)npos2 + 1) * sizeof(uint64_t))) != CLQ_OK) return rc;
+        CU(c, cudaMemcpyAsync(s->bits_off.p, off.data(), ((size_t)npos2 + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+        CU(c, cudaStreamSynchronize(s->stream));  // `off` / `order2` are reused host vectors
     } else {
         for (uint64_t b = 0; b < n_pos; b += sub) cuts.push_back(b);
         cuts.push_back(n_pos);
@@ -1137,9 +1176,12 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         const bool tb_pairs = pack_pairs || group_pairs;
         CU(c, cudaEventRecord(s->ev[3], s->stream));
         if (score_only) {
-            q.n_tasks = pack_pairs ? (n + 1) / 2 : n;
+            // positions, not reads: a host order that groups by reference holds padding positions
+            // (the adaptive kernel is traceback-only: a score-only launch of long pairs stays on the int32 kernel)
+            const bool sc_pairs = pack_pairs && !adapt;
+            q.n_tasks = (uint32_t)(sc_pairs ? (np + 1) / 2 : np);
             q.task_base = 0;
-            q.task_end = n;
+            q.task_end = (uint32_t)np;
             int g = grid_sc;
             if ((ce = launch_dp(false, q, &g, false)) != cudaSuccess)
                 return fail(c, CLQ_E_CUDA, std::string("score kernel: ") + cudaGetErrorString(ce));

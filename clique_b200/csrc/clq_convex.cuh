@@ -104,7 +104,11 @@ __global__ void __launch_bounds__(kThreads) convex_kernel(const KParams p, const
                 if (p.cand_mask && !((p.cand_mask[(size_t)ridx * p.mask_words + (ref >> 5)] >> (ref & 31)) & 1u)) valid = false;
             } else {
                 ridx = p.order ? p.order[p.task_base + task] : p.task_base + task;
-                ref = p.ref_of_read[ridx];
+                if (ridx == 0xffffffffu) {  // padding position of a reference group (host order / ref_scatter_kernel): nothing to align
+                    if (TB && gl == 0) { TbRec rec; rec.ridx = 0; rec.L1 = -1; rec.L2 = 0; rec.zK = 0; p.tb_rec[task] = rec; }
+                    valid = false;
+                } else
+                    ref = p.ref_of_read[ridx];
             }
         }
         int L1 = 0, L2 = 0;

@@ -11,6 +11,7 @@
 // into packed accumulators (low half = read A, high half = read B) and unzipped with PRMT into each read's row word.
 #pragma once
 
+#include <cstdio>
 #include <type_traits>
 
 #include "clq_kernels.cuh"
@@ -95,9 +96,10 @@ struct Canary {
 #endif
     }
     // call with full-warp convergence; `skip`: the task is redone elsewhere (its values do not matter)
-    __device__ __forceinline__ void report(bool active, bool skip) {
+    __device__ __forceinline__ void report(bool active, bool skip, int a = 0, int b = 0, int c = 0, int d = 0) {
 #if CLQ_PACK_CANARY
         const bool bad = active && !skip && ((mn & 0xffffu) < 64u || (mn >> 16) < 64u || (mx & 0xffffu) > 32767u || (mx >> 16) > 32767u);
+        if (bad) printf("canary: lane %d block %d min %u/%u max %u/%u ctx %d %d %d %d\n", (int)(threadIdx.x & 31), (int)blockIdx.x, mn & 0xffffu, mn >> 16, mx & 0xffffu, mx >> 16, a, b, c, d);
         const unsigned nbad = __popc(__ballot_sync(0xffffffffu, bad)), nact = __popc(__ballot_sync(0xffffffffu, active && !skip));
         if ((threadIdx.x & 31) == 0) { atomicAdd(&g_pack_canary[0], (unsigned long long)nact); if (nbad) atomicAdd(&g_pack_canary[1], (unsigned long long)nbad); }
 #endif
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
             __syncwarp();
         }
 
-        cy.report(anyrun, false);
+        cy.report(anyrun, false, L1, L2[0], L2[1], (int)(TB ? 1 : 0) | (RB ? 2 : 0) | (MADD ? 4 : 0) | (G << 8) | (slope << 16));
         // ---- final cells: score + start layer = LAST maximum of (M, E, F) per read ----
         if (RB) {
             const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (gw * G));

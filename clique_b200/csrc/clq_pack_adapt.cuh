@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 3) pack_adapt_kernel(const KParams p
         }
         const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (gw * G));
         const bool redo = anyrun && (__ballot_sync(FULL, fault) & gm) != 0u;
-        cy.report(anyrun, redo);  // a pair that is NOT redone must never have left the window: the guard band's soundness, checked
+        cy.report(anyrun, redo, L1, L2[0], L2[1], 0x1000 | G);  // a pair that is NOT redone must never have left the window: the guard band's soundness, checked
 
         // ---- final cells: score + start layer = LAST maximum of (M, E, F) per read ----
 #pragma unroll

@@ -27,7 +27,7 @@ run)
         timeout 120 python bench.py --workload $wl --steps ${AB_STEPS:-6} --warmup 3 --no-cpu-baseline --no-live-peak --no-extra 2>/dev/null | python -c '
 import sys, json
 d = json.loads(sys.stdin.readline())
-print("%s ms_per_step %.3f  reads/s %.4g  gcups %.1f  e2e %.4g  dp_kernel_ms %.3f  ok_reads %d" % (sys.argv[1], d["ms_per_step"], d["value"], d["gcups"], d["e2e"]["value"], d["roofline"]["kernel_ms"], d["config"]["status_ok_reads"]))' $wl
+print("%s ms_per_step %.3f  reads/s %.4g  gcups %.1f  e2e %.4g  dp_kernel_ms %.3f  ok_reads %d  sub_batches %s  pack_retries %s" % (sys.argv[1], d["ms_per_step"], d["value"], d["gcups"], d["e2e"]["value"], d["roofline"]["kernel_ms"], d["config"]["status_ok_reads"], d["config"].get("sub_batches"), d["config"].get("pack_retries")))' $wl
         done
     done ;;
 *) echo "usage: $0 build name=flags... | run name..."; exit 2 ;;
