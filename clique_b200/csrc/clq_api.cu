@@ -94,7 +94,11 @@ struct clq_ctx {
     bool rb_ok = false;              // rust-bio mode: the reference set fits the 16-row / 8-column profile
     uint8_t cls_rb[256] = {};        // rust-bio classes: 0 = 'N', 1 other, 2..7 reference bytes; row << 3; bit 7 = unscorable in a read
     DevBuf cls_lut_rb;
-    int64_t max_scratch_bytes = 40ll << 30;  // per slot: direction bits of one sub-batch
+    // Direction bits of one fill + walk round.  With the slot chain (serialize_slots, the default) the kernels of different slots
+    // never overlap, so ONE scratch serves every slot and can be large: a round must hold several waves of tasks, and a pair of
+    // 5 kb reads alone is 25 MB of bits and ~60 ms of one warp -- rounds shorter than that are bounded by their longest task.
+    int64_t max_scratch_bytes = 96ll << 30;
+    DevBuf sh_bits, sh_cig, sh_tbrec;        // the shared scratch (per-slot buffers are used instead when serialize_slots = 0)
     // Kernels of different slots are chained in submission order: every fill kernel is a persistent grid that fills the GPU, so
     // two launches sharing the SMs only finish together and leave the host nothing to overlap with.  With the chain slot B's
     // H2D copy runs under slot A's kernels, A finishes first, and its results are handled while B computes.
@@ -488,7 +492,7 @@ void clq_ctx_destroy(clq_ctx* c) {
             release(*b);
         if (s.h_counters) cudaFreeHost(s.h_counters);
     }
-    release(c->ref_bytes); release(c->ref_off); release(c->kmer_keys); release(c->kmer_owner); release(c->kmer_keys64); release(c->cls_lut); release(c->cls_lut_rb); release(c->tag_slot);
+    release(c->ref_bytes); release(c->ref_off); release(c->kmer_keys); release(c->kmer_owner); release(c->kmer_keys64); release(c->sh_bits); release(c->sh_cig); release(c->sh_tbrec); release(c->cls_lut); release(c->cls_lut_rb); release(c->tag_slot);
     delete c;
 }
 
@@ -1066,24 +1070,27 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         cuts.push_back(n_pos);
     }
     const uint64_t groups = (uint64_t)std::max(std::max(grid_tb, grid_sc), grid_retry) * (kThreads / 32) * GPW;
+    DevBuf& sbits = c->serialize ? c->sh_bits : s->bits;
+    DevBuf& scig = c->serialize ? c->sh_cig : s->cig_scratch;
+    DevBuf& stbrec = c->serialize ? c->sh_tbrec : s->tb_rec;
     if (!score_only && n) {
-        if ((rc = ensure(c, s->bits, max_sub_words * 4 + 64)) != CLQ_OK) return rc;
-        if ((rc = ensure(c, s->cig_scratch, max_sub_tasks * cig_stride * 4)) != CLQ_OK) return rc;
-        if ((rc = ensure(c, s->tb_rec, max_sub_tasks * sizeof(TbRec))) != CLQ_OK) return rc;
+        if ((rc = ensure(c, sbits, max_sub_words * 4 + 64)) != CLQ_OK) return rc;
+        if ((rc = ensure(c, scig, max_sub_tasks * cig_stride * 4)) != CLQ_OK) return rc;
+        if ((rc = ensure(c, stbrec, max_sub_tasks * sizeof(TbRec))) != CLQ_OK) return rc;
         if ((rc = ensure(c, s->cigar_pool, (size_t)c->lim.cigar_pool_ops * 4 + 16)) != CLQ_OK) return rc;
     }
     if ((rc = ensure(c, s->col_scratch, groups * col_stride * (adapt ? 20 : 16))) != CLQ_OK) return rc;  // pack_adapt_kernel keeps a fifth array (the bias of every row)
     if (adapt && (rc = ensure(c, s->retry_list, (max_sub_tasks + 2) * sizeof(uint32_t))) != CLQ_OK) return rc;
-    p.bits = (uint32_t*)s->bits.p;
+    p.bits = (uint32_t*)sbits.p;
     p.bits_stride = bits_stride;
     p.bits_off = var_slots ? (const uint64_t*)s->bits_off.p : nullptr;
-    p.cig_scratch = (uint32_t*)s->cig_scratch.p;
+    p.cig_scratch = (uint32_t*)scig.p;
     p.cig_stride = cig_stride;
     p.col_scratch = (int32_t*)s->col_scratch.p;
     p.col_stride = col_stride;
     p.cigar_pool = (uint32_t*)s->cigar_pool.p;
     p.cigar_cap = c->lim.cigar_pool_ops;
-    p.tb_rec = (TbRec*)s->tb_rec.p;
+    p.tb_rec = (TbRec*)stbrec.p;
     if (want_tags && n) {
         if ((rc = ensure(c, s->tags, (size_t)n * c->tag_stride)) != CLQ_OK) return rc;
         p.tag_slot = (const uint16_t*)c->tag_slot.p;

@@ -27,10 +27,13 @@
 
 namespace clq {
 
+#ifndef CLQ_ADAPT_MIN_BLOCKS
+#define CLQ_ADAPT_MIN_BLOCKS 3
+#endif
 constexpr int kAdaptBlock = 64;     // rows per slope block (>= G: every lane has switched to a block's slope before the next decision)
 constexpr int kAdaptSigmaMin = -16, kAdaptSigmaMax = 15, kAdaptTabs = 32;
 constexpr int kAdaptCentre = 16384;
-constexpr int kAdaptMaxRebias = 20000;  // |beta_s - beta_{s-1}| beyond this is treated as an overflow (keeps the re-bias wrap detectable)
+constexpr int kAdaptMaxRebias = 30000;  // |beta_s - beta_{s-1}| beyond this is treated as an overflow: with |d| <= 30000 a re-biased value that wraps lands outside [64, 32767] as s16 and is caught
 
 struct AdaptParams {
     int32_t guard;              // every cell of a lane-row lies within `guard` of the lane's first column in that row
@@ -45,7 +48,7 @@ __device__ __forceinline__ int lo16s(uint32_t w) { return (int)(int16_t)(w & 0xf
 __device__ __forceinline__ int hi16s(uint32_t w) { return (int)(int16_t)(w >> 16); }
 
 template <int G, int C>
-__global__ void __launch_bounds__(kThreads, 3) pack_adapt_kernel(const KParams p, const AdaptParams ap) {
+__global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_kernel(const KParams p, const AdaptParams ap) {
     static_assert(G >= 16 && C % 8 == 0 && !BitsLayout<G>::transposed, "long-read geometries only (row-per-step bit layout)");
     static_assert(kAdaptBlock >= G, "a block must be at least as long as the wavefront skew");
     extern __shared__ __align__(16) uint8_t smem_raw[];

@@ -75,13 +75,12 @@ while time.time() < t_end:
     sc = SC[int(rng.integers(0, len(SC)))]
     cfg = int(rng.choice([-1, -1, 0, 1, 2, 3, 4, 5]))
     al.set_option("force_cfg", cfg if mode != "convex" else min(cfg, 4))
-    al.set_option("no_pack", int(rng.random() < NO_PACK_P))
+    wopts = {"no_pack": int(rng.random() < NO_PACK_P)}
     if wide:  # sub-batches of the direction-bit scratch, int32 multi-reference traceback, generic kernels
-        al.set_option("max_scratch_bytes", int(rng.choice([40 << 30, 1 << 20, 16 << 20])))
-        al.set_option("no_group", int(rng.random() < 0.3))
-        al.set_option("force_generic", int(rng.random() < 0.15))
-        al.set_option("no_madd", int(rng.random() < 0.3))
-        al.set_option("no_adapt", int(rng.random() < 0.2))
+        wopts.update({"max_scratch_bytes": int(rng.choice([40 << 30, 1 << 20, 16 << 20])), "no_group": int(rng.random() < 0.3),
+                      "force_generic": int(rng.random() < 0.15), "no_madd": int(rng.random() < 0.3), "no_adapt": int(rng.random() < 0.2)})
+    for k_, v_ in wopts.items():
+        al.set_option(k_, v_)
     tags = bool(rng.random() < 0.5) and mode not in ("convex",)
     ctx = (it, mode, sc, cfg, nref, n, lmax, uniform)
     if only is not None and it not in only:
@@ -94,6 +93,8 @@ while time.time() < t_end:
             break
         continue
     first = True
+    if os.environ.get("CLQ_FUZZ_VERBOSE"):   # the context of every batch before it runs (to locate a crash)
+        print("batch", ctx, "reflens", [len(r) for r in refs], "readlens", [len(r) for r in reads][:30], "opts", wopts, flush=True)
     try:
         if mode == "rustbio":
             br = al.align_batch(qb, qo, RustBioScoring(), "fixed", "maxlen", fixed_ref=fixed, extract_tags=tags)
