@@ -989,7 +989,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     const uint64_t bits_stride = transposed ? (uint64_t)ns_max * ((L1max + G + 7) / 8) * G * (C / 8) * 8
                                             : ((uint64_t)ns_max * (L1max + G) * G * (C * bits_per_cell / 32) + 7) / 8 * 8;
     const uint32_t cig_stride = L1max + L2max + 8;
-    const uint32_t col_stride = L1max + 8;
+    const uint32_t col_stride = (L1max + 8 + 3) & ~3u;  // rows of the stripe-boundary column (F, E, M, B interleaved: 16-byte rows)
     // traceback scratch is per task of a sub-batch: direction bits + CIGAR scratch + walker record.  When the read lengths
     // vary (processing order = longest first) every position gets a slot of its own size and sub-batches are cut by bytes,
     // so a batch of mixed 300 bp - 5 kb reads is not split into tiny sub-batches sized for its longest pair.
@@ -1003,6 +1003,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     uint64_t sub = std::max<uint64_t>(2, std::min<uint64_t>(n_pos + 1, (uint64_t)c->max_scratch_bytes / per_task)) & ~1ull;  // even: PACK tasks are read pairs
     std::vector<uint64_t> cuts;          // sub-batch boundaries in processing positions
     const uint64_t np = s->have_order ? s->n_pos : n;  // processing positions of a host-ordered batch (incl. reference-group padding)
+    const uint32_t* order_tb = nullptr;
     const bool var_slots = !score_only && n && s->have_order && s->h_len.size() == np;
     uint64_t max_sub_words = sub * bits_stride, max_sub_tasks = sub;
     if (var_slots) {
@@ -1051,7 +1052,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
             off.assign(off2.begin(), off2.end());
             if ((rc = ensure(c, s->order2, (order2.size() + 2) * sizeof(uint32_t))) != CLQ_OK) return rc;
             CU(c, cudaMemcpyAsync(s->order2.p, order2.data(), order2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
-            p.order = (const uint32_t*)s->order2.p;
+            order_tb = (const uint32_t*)s->order2.p;  // the traceback stage walks the dealt order; a score stage keeps the upload's
         } else {
             cuts.push_back(np);
         }
@@ -1165,6 +1166,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         q.all_pairs = 0;
         q.ref_of_read = ref_of_read;
         q.task_counter = (unsigned int*)(ctr + 1);
+        if (order_tb) q.order = order_tb;
         if (group_pairs) {
             const uint32_t nb = c->n_refs + 1;
             if ((rc = ensure(c, s->ref_groups, (size_t)2 * nb * sizeof(uint32_t))) != CLQ_OK) return rc;

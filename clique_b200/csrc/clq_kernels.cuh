@@ -324,12 +324,13 @@ __device__ __forceinline__ void row_step_fast(int (&Eh)[C], int (&B)[C], const i
 
 // predicated global accesses for the stripe-boundary column (a branch around four loads / stores costs more issue slots in the
 // step loop than executing the address arithmetic on every lane)
-__device__ __forceinline__ int ldg_if_s32(const int32_t* ptr, bool cond, int keep) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.s32 %0, [%1];\n\t}" : "+r"(keep) : "l"(ptr), "r"((uint32_t)cond));
-    return keep;
+// the four values of one boundary-column row (F, E, M, B) sit side by side: one predicated 128-bit access per row
+__device__ __forceinline__ void ldg4_if_s32(const int32_t* ptr, bool cond, int& a, int& b, int& c, int& d) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.v4.s32 {%0, %1, %2, %3}, [%4];\n\t}"
+                 : "+r"(a), "+r"(b), "+r"(c), "+r"(d) : "l"(ptr), "r"((uint32_t)cond));
 }
-__device__ __forceinline__ void stg_if_s32(int32_t* ptr, bool cond, int v) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.s32 [%0], %1;\n\t}" ::"l"(ptr), "r"(v), "r"((uint32_t)cond) : "memory");
+__device__ __forceinline__ void stg4_if_s32(int32_t* ptr, bool cond, int a, int b, int c, int d) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.global.v4.s32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "r"((uint32_t)cond) : "memory");
 }
 
 template <int G, int C, bool TB, bool FIN, bool FAST, bool RB = false>
@@ -451,9 +452,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
             int oF = 0, oE = 0, oM = 0, oB = 0;
             // stripe boundary column (left edge of lane 0 when s > 0), prefetched one row ahead
             int nF = 0, nE = 0, nM = 0, nB = 0;
-            if (s > 0 && gl == 0 && act_s) {
-                nF = col_g[1]; nE = col_g[p.col_stride + 1]; nM = col_g[2 * p.col_stride + 1]; nB = col_g[3 * p.col_stride + 1];
-            }
+            if (s > 0 && gl == 0 && act_s) { const int4 v = *(const int4*)(col_g + 4); nF = v.x; nE = v.y; nM = v.z; nB = v.w; }  // row 1 of the boundary column
             int rnext = act_s ? ref_sm[0] : 0;  // every lane starts at row 1 (lane gl at step t = 1 + gl)
             // per-step conditions as single compares / loop-invariant flags (a compound condition is re-evaluated from its parts on
             // every step: predicates do not survive the row step)
@@ -482,8 +481,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
                     if (ld_col) { Fl = nF; El = nE; Ml = nM; Bl = nB; }
                     {
                         const bool nx = ld_col && x < L1;  // the next row's boundary values, one step ahead
-                        nF = ldg_if_s32(col_g + x + 1, nx, nF); nE = ldg_if_s32(col_g + p.col_stride + x + 1, nx, nE);
-                        nM = ldg_if_s32(col_g + 2 * p.col_stride + x + 1, nx, nM); nB = ldg_if_s32(col_g + 3 * p.col_stride + x + 1, nx, nB);
+                        ldg4_if_s32(col_g + 4 * (x + 1), nx, nF, nE, nM, nB);
                     }
                     const int r = rnext;
                     rnext = ref_sm[x < L1 ? x : L1 - 1];
@@ -524,8 +522,7 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
                         if (x == L1) { capM = 0; capE = 0; capF = 0; }
                     }
                     if (TB) bits_store<G, WPL>(tt_sm, bits_g, w, s, T, t, lane, gl, x == L1, nb);
-                    stg_if_s32(col_g + x, st_col, oF); stg_if_s32(col_g + p.col_stride + x, st_col, oE);
-                    stg_if_s32(col_g + 2 * p.col_stride + x, st_col, oM); stg_if_s32(col_g + 3 * p.col_stride + x, st_col, oB);
+                    stg4_if_s32(col_g + 4 * x, st_col, oF, oE, oM, oB);
                 }
             }
             __syncwarp();

@@ -80,6 +80,14 @@ __device__ __forceinline__ uint32_t ldg_if(const uint32_t* ptr, bool cond, uint3
 __device__ __forceinline__ void stg_if(uint32_t* ptr, bool cond, uint32_t v) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u32 [%0], %1;\n\t}" ::"l"(ptr), "r"(v), "r"((uint32_t)cond) : "memory");
 }
+// the four values of one boundary-column row (F, E, M, B) sit side by side: one 128-bit access per row
+__device__ __forceinline__ void ldg4_if(const uint32_t* ptr, bool cond, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+                 : "+r"(a), "+r"(b), "+r"(c), "+r"(d) : "l"(ptr), "r"((uint32_t)cond));
+}
+__device__ __forceinline__ void stg4_if(uint32_t* ptr, bool cond, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.global.v4.u32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "r"((uint32_t)cond) : "memory");
+}
 
 // -DCLQ_PACK_CANARY=1 (debug builds, tools/canary_gpu.sh): every value a PACK kernel stores (M, Eh, Fh, B of every cell) is
 // tracked per task; a task whose values left [64, 32767] WITHOUT being handed to the retry pass is counted here and reported by
@@ -381,9 +389,7 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
             uint32_t prevBl = dup16(((y0 == 0) ? 0 : sc.b0 + y0 * sc.b1) + bias);
             uint32_t oF = 0, oE = 0, oM = 0, oB = 0;
             uint32_t nF = 0, nE = 0, nM = 0, nB = 0;
-            if (s > 0 && gl == 0 && act_s) {
-                nF = col_g[1]; nE = col_g[p.col_stride + 1]; nM = col_g[2 * p.col_stride + 1]; nB = col_g[3 * p.col_stride + 1];
-            }
+            if (s > 0 && gl == 0 && act_s) { const uint4 v = *(const uint4*)(col_g + 4); nF = v.x; nE = v.y; nM = v.z; nB = v.w; }  // row 1 of the boundary column
             // per-step conditions as single integer compares (predicates do not survive the 900-instruction row step, so a
             // compound condition is re-evaluated from its parts every step)
             const uint32_t L1act = act_s ? (uint32_t)L1 : 0u;          // act  <=>  (unsigned)(x - 1) < L1act
@@ -431,8 +437,7 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
                         if (!SIMPLE) {
                             if (ld_col) { Fl = nF; El = nE; Ml = nM; Bl = nB; }  // selects; the next row's values are fetched one step ahead
                             const bool nx = ld_col && x < L1;
-                            nF = ldg_if(col_g + x + 1, nx, nF); nE = ldg_if(col_g + p.col_stride + x + 1, nx, nE);
-                            nM = ldg_if(col_g + 2 * p.col_stride + x + 1, nx, nM); nB = ldg_if(col_g + 3 * p.col_stride + x + 1, nx, nB);
+                            ldg4_if(col_g + 4 * (x + 1), nx, nF, nE, nM, nB);
                         }
                         rcur = ref_sm[x < L1 ? x : L1 - 1];  // class of row x + 1 (clamped on the last row: unused)
                         const uint32_t BlIn = Bl;
@@ -464,8 +469,7 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
                         }
                         if (TB) bits_store2<G, WPL>(tt_sm, bitsA, bitsB, wA, wB, stA, stB, s, T, t, lane, gl, x == L1, nb);
                         if (!SIMPLE) {
-                            stg_if(col_g + x, st_col, oF); stg_if(col_g + p.col_stride + x, st_col, oE);
-                            stg_if(col_g + 2 * p.col_stride + x, st_col, oM); stg_if(col_g + 3 * p.col_stride + x, st_col, oB);
+                            stg4_if(col_g + 4 * x, st_col, oF, oE, oM, oB);
                         }
                     }
                 } while (++t <= Tmax);

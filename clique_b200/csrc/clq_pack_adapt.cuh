@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
         uint32_t* bitsB = valid[1] ? p.bits + bits_slot(p.bits_off, p.bits_stride, p.task_base, 2 * task + 1) : nullptr;
         // the stored values this lane has seen: first column of every row (per half) + re-biased boundary values; and hard faults
         uint32_t seen_mn = dup16(kAdaptCentre), seen_mx = dup16(kAdaptCentre);
-        bool fault = false;
+        uint32_t fault = 0;  // reason bits: 1 boundary row, 2 first column, 4 re-bias too large, 8 stale cell, 16 watched values left the window
 
         for (int s = 0; s < NSmax; s++) {
             const bool act_s = anyrun && s < NS;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
             }
             {   // the boundary row itself must sit inside the guarded window
                 const int g_first = sc.b0 + (y0 + 1) * sc.b1 + beta0, g_last = sc.b0 + (y0 + C) * sc.b1 + beta0;
-                if (act_s && (min(g_first, g_last) < lo_lim || max(g_first, g_last) > hi_lim)) fault = true;
+                if (act_s && (min(g_first, g_last) < lo_lim || max(g_first, g_last) > hi_lim)) fault |= 1u;
             }
             uint32_t prevBl = dup16(((y0 == 0) ? 0 : sc.b0 + y0 * sc.b1) + beta0);
             uint32_t oF = 0, oE = 0, oM = 0, oB = 0;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
             const bool first_col = (gl == 0) && (s == 0);
             const bool ld_col = (gl == 0) && (s > 0) && act_s, st_col = (gl == G - 1) && (s < NS - 1) && act_s;
             if (ld_col) {
-                nF = col_g[1]; nE = col_g[p.col_stride + 1]; nM = col_g[2 * p.col_stride + 1]; nB = col_g[3 * p.col_stride + 1];
+                { const uint4 v = *(const uint4*)(col_g + 4); nF = v.x; nE = v.y; nM = v.z; nB = v.w; }
                 nBeta = (int)col_g[4 * p.col_stride + 1];
                 pBeta = (int)col_g[4 * p.col_stride + 0];  // beta_{s-1}(0), stored by the producer with row 1
             }
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
                     const uint32_t X1b = dup16(x1 + sg), X1M1 = dup16(x1 - 1 + sg), LEe = dup16(le + sgp);
                     if (first_col) {  // S[x,0] = (MAXNEG, g(x), g(x))
                         const int g = sc.b0 + x * sc.b1 + beta;
-                        if (g < lo_lim || g > hi_lim) fault = true;
+                        if (g < lo_lim || g > hi_lim) fault |= 2u;
                         Bl = dup16(g);
                         Fl = Bl + NX1;
                         El = Fl - (uint32_t)(sg * 0x10001);  // Eh' of row x carries beta(x - 1); (sg * 0x10001) mod 2^32 subtracts sg from both halves
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
                     if (ld_col) {
                         // inherit the boundary column of stripe s - 1, stored under ITS bias: re-bias to this stripe's
                         const int d = beta - nBeta, dE = beta_prev - pBeta;
-                        if (max(abs(d), abs(dE)) > kAdaptMaxRebias) fault = true;
+                        if (max(abs(d), abs(dE)) > kAdaptMaxRebias) fault |= 4u;
                         const uint32_t D = (uint32_t)(d * 0x10001), DE = (uint32_t)(dE * 0x10001);
                         Fl = nF + D; El = nE + DE; Ml = nM + D; Bl = nB + D;
                         seen_mn = vmin_s16x2(seen_mn, vmin_s16x2(Bl, vmin_s16x2(El, Fl)));
@@ -251,8 +251,7 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
                     }
                     {
                         const bool nx = ld_col && x < L1;
-                        nF = ldg_if(col_g + x + 1, nx, nF); nE = ldg_if(col_g + p.col_stride + x + 1, nx, nE);
-                        nM = ldg_if(col_g + 2 * p.col_stride + x + 1, nx, nM); nB = ldg_if(col_g + 3 * p.col_stride + x + 1, nx, nB);
+                        ldg4_if(col_g + 4 * (x + 1), nx, nF, nE, nM, nB);
                         nBeta = (int)ldg_if(col_g + 4 * p.col_stride + x + 1, nx, (uint32_t)nBeta);
                     }
                     const uint2 tr = *(const uint2*)(tab_sm + ((sg - kAdaptSigmaMin) * 16 + (int)rcur) * 8);
@@ -281,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
                             if (sa) { cap[0] = set_lo(cap[0], b0v); cap[1] = set_lo(cap[1], e0); cap[2] = set_lo(cap[2], f0); }
                             if (sb) { cap[0] = set_hi(cap[0], b0v); cap[1] = set_hi(cap[1], e0); cap[2] = set_hi(cap[2], f0); }
                         }
-                        if (b0v < lo_lim || b0v > hi_lim) fault = true;
+                        if (b0v < lo_lim || b0v > hi_lim) fault |= 8u;
                     }
                     // overflow watch: the first stored B of this lane-row (padding halves neutralised)
                     {
@@ -291,8 +290,7 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
                     }
                     if (stA) row_store<G, WPL>(bitsA, wA, s, T, t, gl, nb);
                     if (stB) row_store<G, WPL>(bitsB, wB, s, T, t, gl, nb);
-                    stg_if(col_g + x, st_col, oF); stg_if(col_g + p.col_stride + x, st_col, oE);
-                    stg_if(col_g + 2 * p.col_stride + x, st_col, oM); stg_if(col_g + 3 * p.col_stride + x, st_col, oB);
+                    stg4_if(col_g + 4 * x, st_col, oF, oE, oM, oB);
                     stg_if(col_g + 4 * p.col_stride + x, st_col, (uint32_t)beta);
                     if (x == 1) stg_if(col_g + 4 * p.col_stride, st_col, (uint32_t)beta0);
                 }
@@ -325,10 +323,13 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
         // ---- did every stored value stay inside the guarded window? (per group; padding halves were neutralised) ----
         {
             const int mn = min(lo16s(seen_mn), hi16s(seen_mn)), mx = max(lo16s(seen_mx), hi16s(seen_mx));
-            if (mn < lo_lim || mx > hi_lim) fault = true;
+            if (mn < lo_lim || mx > hi_lim) fault |= 16u;
+#if CLQ_PACK_CANARY
+            if (fault && anyrun) printf("adapt retry: reason %u lane %d L1 %d L2 %d %d seen %d..%d limits %d..%d\n", fault, gl, L1, L2[0], L2[1], mn, mx, lo_lim, hi_lim);
+#endif
         }
         const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (gw * G));
-        const bool redo = anyrun && (__ballot_sync(FULL, fault) & gm) != 0u;
+        const bool redo = anyrun && (__ballot_sync(FULL, fault != 0u) & gm) != 0u;
         cy.report(anyrun, redo, L1, L2[0], L2[1], 0x1000 | G);  // a pair that is NOT redone must never have left the window: the guard band's soundness, checked
 
         // ---- final cells: score + start layer = LAST maximum of (M, E, F) per read ----
