@@ -245,8 +245,9 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
                         if (max(abs(d), abs(dE)) > kAdaptMaxRebias) fault |= 4u;
                         const uint32_t D = (uint32_t)(d * 0x10001), DE = (uint32_t)(dE * 0x10001);
                         Fl = nF + D; El = nE + DE; Ml = nM + D; Bl = nB + D;
-                        seen_mn = vmin_s16x2(seen_mn, vmin_s16x2(Bl, vmin_s16x2(El, Fl)));
-                        seen_mx = vmax_s16x2(seen_mx, vmax_s16x2(Bl, vmax_s16x2(Ml, Fl)));
+                        // (only the halves that hold real cells in this stripe: the padded partner of an odd pair drifts freely)
+                        seen_mn = vmin_s16x2(seen_mn, (vmin_s16x2(Bl, vmin_s16x2(El, Fl)) & real_mask) | neutral);
+                        seen_mx = vmax_s16x2(seen_mx, (vmax_s16x2(Bl, vmax_s16x2(Ml, Fl)) & real_mask) | neutral);
                         pBeta = nBeta;
                     }
                     {
