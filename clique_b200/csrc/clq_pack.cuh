@@ -98,9 +98,12 @@ __device__ __forceinline__ void stg4_if(uint32_t* ptr, bool cond, uint32_t a, ui
 __device__ unsigned long long g_pack_canary[2];  // [0] tasks checked, [1] violations
 struct Canary {
     uint32_t mn = 0xffffffffu, mx = 0u;
-    __device__ __forceinline__ void see(uint32_t v) {
+    int nA = 1 << 30, nB = 1 << 30;  // columns j < nA / nB of this lane hold real cells of read A / B (static PACK: the window proof
+                                     // covers padding columns too; the adaptive kernel only guards real cells, padding may wrap)
+    __device__ __forceinline__ void see(uint32_t v, int j) {
 #if CLQ_PACK_CANARY
-        mn = __vminu2(mn, v); mx = __vmaxu2(mx, v);
+        const uint32_t w = (j < nA ? (v & 0xffffu) : 0x4000u) | (j < nB ? (v & 0xffff0000u) : 0x40000000u);
+        mn = __vminu2(mn, w); mx = __vmaxu2(mx, w);
 #endif
     }
     // call with full-warp convergence; `skip`: the task is redone elsewhere (its values do not matter)
@@ -190,7 +193,7 @@ __device__ __forceinline__ void pack_row_blocks(uint32_t (&Eh)[C], uint32_t (&B)
                 Eh[j] = Ehn;
                 B[j] = Bn;
                 Fh = Fhn; Ehl = Ehn; Ml = Mv; Bl = Bn;
-                if (CLQ_PACK_CANARY) { cy.see(Mv); cy.see(Ehn); cy.see(Fhn); cy.see(Bn); }
+                if (CLQ_PACK_CANARY) { cy.see(Mv, j); cy.see(Ehn, j); cy.see(Fhn, j); cy.see(Bn, j); }
                 if (LAST) {
                     if (ownA && j == jA) { cap[0] = set_lo(cap[0], get_lo(Mv)); cap[1] = set_lo(cap[1], get_lo(Ehn)); cap[2] = set_lo(cap[2], get_lo(Fhn)); }
                     if (ownB && j == jB) { cap[0] = set_hi(cap[0], get_hi(Mv)); cap[1] = set_hi(cap[1], get_hi(Ehn)); cap[2] = set_hi(cap[2], get_hi(Fhn)); }

@@ -166,6 +166,8 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
             const int Cs = (s == NS - 1) ? CsL : C;
             const int nb = Cs >> 3;
             const int y0 = s * W + gl * Cs;
+            cy.nA = run[0] ? max(0, min(Cs, L2[0] - y0)) : 0;  // canary builds: only real cells are guarded
+            cy.nB = run[1] ? max(0, min(Cs, L2[1] - y0)) : 0;
             // beta_s(0): the boundary row g(y) of this stripe is centred on the window
             const int ymid = s * W + min(W, max(L2m - s * W, 1)) / 2;
             int beta = kAdaptCentre - (sc.b0 + ymid * sc.b1);
