@@ -28,7 +28,7 @@
 namespace clq {
 
 #ifndef CLQ_ADAPT_MIN_BLOCKS
-#define CLQ_ADAPT_MIN_BLOCKS 3
+#define CLQ_ADAPT_MIN_BLOCKS 2  // 255 registers: at 168 (3 CTAs/SM) the compiler re-derives ~230 instructions of loop-invariant state per step (C5 335 vs 322 ms)
 #endif
 constexpr int kAdaptBlock = 64;     // rows per slope block (>= G: every lane has switched to a block's slope before the next decision)
 constexpr int kAdaptSigmaMin = -16, kAdaptSigmaMax = 15, kAdaptTabs = 32;
