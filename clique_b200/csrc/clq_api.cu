@@ -23,6 +23,7 @@ namespace {
 #ifndef CLQ_LEAN
 #define CLQ_LEAN 0
 #endif
+#define CLQ_LEAN_NO8 0
 #if CLQ_LEAN
 #define CLQ_FULL_CASE(n, stmt)
 #else
@@ -85,6 +86,7 @@ struct clq_ctx {
     int no_pack = 0;                 // option "no_pack": never take the s16x2 PACK kernels
     int no_madd = 0;                 // option "no_madd": PACK kernels without the static row slope (M step on the ALU pipe)
     int no_adapt = 0;                // option "no_adapt": long pairs beyond the static 15-bit window stay on the int32 kernels
+    int no_long8 = 0;                // option "no_long8": long reads keep the geometry their length picks instead of (8,40) with column stripes
     int adapt_guard = 0;             // option "adapt_guard" (tests): overrides the guard band of pack_adapt_kernel; a huge value forces every pair through the retry pass
     int no_group = 0;                // option "no_group": multi-reference traceback stays on the int32 kernels (no bucketing by reference)
     int force_generic = 0;           // option "force_generic": never take the FAST (PRMT/DPX) kernel variant
@@ -227,9 +229,10 @@ cudaError_t launch_adapt_one(const KParams& p, const AdaptParams& ap, int sm_cou
     return cudaGetLastError();
 }
 
-// adaptive-bias PACK: long-read geometries only
+// adaptive-bias PACK: (8,40) with column stripes by default, the long-read geometries by force_cfg
 cudaError_t launch_adapt(int cfg, const KParams& p, const AdaptParams& ap, int sm, size_t smem, cudaStream_t st, int* grid, bool q) {
     switch (cfg) {
+        case 2: return launch_adapt_one<8, 40>(p, ap, sm, smem, st, grid, q);
         CLQ_FULL_CASE(3, return (launch_adapt_one<16, 24>(p, ap, sm, smem, st, grid, q)))
         CLQ_FULL_CASE(4, return (launch_adapt_one<32, 16>(p, ap, sm, smem, st, grid, q)))
         default: return launch_adapt_one<32, 32>(p, ap, sm, smem, st, grid, q);
@@ -506,6 +509,7 @@ int32_t clq_set_option(clq_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "no_pack")) { c->no_pack = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_madd")) { c->no_madd = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_adapt")) { c->no_adapt = (int)value; return CLQ_OK; }
+    if (!strcmp(key, "no_long8")) { c->no_long8 = (int)value; return CLQ_OK; }
     if (!strcmp(key, "adapt_guard")) { c->adapt_guard = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_group")) { c->no_group = (int)value; return CLQ_OK; }
     if (!strcmp(key, "serialize_slots")) { c->serialize = (int)value; return CLQ_OK; }
@@ -856,60 +860,79 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         if (c->force_cfg >= 0 && c->force_cfg < kNumCvxCfgs) cfg = c->force_cfg;
         if (CLQ_LEAN && cfg != 0) cfg = 3;
     } else if (CLQ_LEAN && cfg != 2) cfg = kNumCfgs - 1;
+    const uint32_t L1max = c->max_ref_len, L2max = s->max_len;
+    // ---- which kernel family, on which geometry ----
+    // s16x2 PACK kernels: two reads per lane group.  Needs the FAST preconditions plus a proof that every cell value of
+    // this batch fits a 15-bit window: B >= 2*g(0) + (L1+L2)*e (the all-gap corner path), everything else is within a gap
+    // open / one substitution of B, and nothing exceeds max(match, special) * min(L1, L2).  Pairs beyond the static window
+    // (long reads) take the adaptive-bias kernel + int32 retry pass (clq_pack_adapt.cuh): traceback stage only, pair mode.
+    // Pair mode needs one reference for both reads of a task: a single-reference panel, or a fixed assignment that the upload
+    // grouped by reference (every group padded to whole pairs).
+    const bool pairs_ok = c->n_refs == 1 || (s->order_by_ref && search == CLQ_SEARCH_FIXED);
+    struct Plan { bool pack = false, madd = false, adapt = false; PackParams pkp = {}; AdaptParams adp = {}; };
+    auto plan_for = [&](int cfgx) -> Plan {
+        Plan pl;
+        if (convex) return pl;
+        const int Gx = kCfgs[cfgx].G, Cx = kCfgs[cfgx].C, Wx = Gx * Cx;
+        if (fast && !c->no_pack && n) {
+            const int64_t smin = std::min<int64_t>(std::min(sc.match, sc.mismatch), std::min(sc.special, 0));
+            const int64_t smax = std::max<int64_t>(std::max(sc.match, sc.special), 0);
+            const int64_t low = 2ll * sc.b0 + (int64_t)(L1max + L2max + Wx) * sc.b1 + 2ll * sc.oe_in - 1 + smin - 16;
+            const int64_t high = smax * std::min<int64_t>(L1max, L2max) - sc.oe_in + 16;
+            if (sc.b1 <= 0 && high - low + 128 <= 32767) {
+                pl.pack = true;
+                pl.pkp.bias = (int32_t)(64 - low);
+                // static row slope (MADD kernels, clq_pack.cuh): row x stored with x * slope more, slope = -min(substitution score, 0), so
+                // that the profile bytes are >= 0 and M = diag + m is a plain add.  Needs L1 * slope more head-room (Eh' of row 0 sits
+                // one slope lower) and bytes that still fit int8.
+                const int64_t slope = -smin;
+                // (short-read geometries only: on the long-read ones, 168 registers at 3 CTAs/SM, the two extra constants cost more
+                // than the ALU-pipe relief gains -- C3 1485 -> 1452 GCUPS with it)
+                if (!rb && !c->no_madd && Gx <= 8 && slope > 0 && smax + slope <= 127 && high + slope * (int64_t)L1max - (low - slope) + 128 <= 32767) {
+                    pl.madd = true;
+                    pl.pkp.slope = (int32_t)slope;
+                    pl.pkp.bias = (int32_t)(64 - (low - slope));
+                }
+            }
+        }
+        if (fast && !rb && !pl.pack && !c->no_pack && !c->no_adapt && !score_only && n && (Gx >= 16 || cfgx == 2) && sc.b1 <= 0 &&
+            search == CLQ_SEARCH_FIXED && pairs_ok) {
+            const int smin = std::min(std::min(sc.match, sc.mismatch), sc.special), smax = std::max(std::max(sc.match, sc.special), 0);
+            // adjacent cells of a row differ by at most smax - 2 * x1 (clq_pack_adapt.cuh); a lane holds C columns, E / F / M sit within a few opens of B
+            const int guard = c->adapt_guard > 0 ? c->adapt_guard : (Cx + 4) * (smax - 2 * sc.oe_in) + 64;
+            if (fits8(smax + kAdaptSigmaMax) && fits8(smin + kAdaptSigmaMin) && sc.oe_in >= -512 && (c->adapt_guard > 0 || 2 * guard + 64 + 16384 <= 32767)) {
+                pl.adapt = true;
+                pl.adp.guard = guard;
+            }
+        }
+        return pl;
+    };
+    Plan plan = convex ? Plan() : plan_for(cfg);
+    // Long reads: the s16x2 kernels run fastest on the SHORT-read geometry (8,40) with as many column stripes as the read needs
+    // (C3: 1870 GCUPS on (8,40) with four stripes against 1511 on (32,32); all 8 lanes of a group busy, MADD, 2 CTAs/SM with 255
+    // registers).  Taken when every stage of the launch stays on the s16x2 family; the int32 kernels prefer the wide geometries.
+    if (!convex && c->force_cfg < 0 && !CLQ_LEAN_NO8 && !c->no_long8 && cfg > 2 && fast && n) {
+        const Plan p2 = plan_for(2);
+        const bool tb_on_pack = score_only || pairs_ok || (p2.pack && !s->have_order && c->n_refs > 1 && !c->no_group);
+        if ((p2.pack && tb_on_pack) || p2.adapt) { cfg = 2; plan = p2; }
+    }
     const int G = convex ? kCvxCfgs[cfg].G : kCfgs[cfg].G, C = convex ? kCvxCfgs[cfg].C : kCfgs[cfg].C, W = G * C, GPW = 32 / G;
     const int bits_per_cell = convex ? 8 : 4;
-    const uint32_t L1max = c->max_ref_len, L2max = s->max_len;
     const uint32_t ns_max = std::max<uint32_t>(1, (L2max + W - 1) / W);
     const uint32_t ref_sm_stride = (L1max + 15) / 16 * 16 + 16;
     // + per-warp transposition buffers of the direction bits (C/8 KiB per warp, twice for the PACK kernels); the
     // convex kernels keep the plain row layout
-    const size_t smem = (size_t)(kThreads / 32) * GPW * ref_sm_stride + (fast ? kLutBytes + kTabBytes : 0) + ((!convex && G <= kTransposeMaxG) ? (size_t)(kThreads / 32) * (C / 8) * 1024 * 2 : 0);
+    const size_t tt_bytes = (!convex && G <= kTransposeMaxG) ? (size_t)(kThreads / 32) * (C / 8) * 1024 * 2 : 0;
+    const size_t smem = (size_t)(kThreads / 32) * GPW * ref_sm_stride + (fast ? kLutBytes + kTabBytes : 0) + tt_bytes;
     if (smem > 200 * 1024) return fail(c, CLQ_E_LIMIT, "references too long for this geometry's shared-memory staging");
-    const size_t smem_adapt = (size_t)(kThreads / 32) * GPW * ref_sm_stride + kLutBytes + (size_t)kAdaptTabs * kTabBytes;  // pack_adapt_kernel: one profile table per slope
-    // s16x2 PACK kernels: two reads per lane group.  Needs the FAST preconditions plus a proof that every cell value of
-    // this batch fits a 15-bit window: B >= 2*g(0) + (L1+L2)*e (the all-gap corner path), everything else is within a gap
-    // open / one substitution of B, and nothing exceeds max(match, special) * min(L1, L2).
-    PackParams pkp = {};
-    bool pack = false, madd = false;
-    if (fast && !convex && !c->no_pack && n) {
-        const int64_t smin = std::min<int64_t>(std::min(sc.match, sc.mismatch), std::min(sc.special, 0));
-        const int64_t smax = std::max<int64_t>(std::max(sc.match, sc.special), 0);
-        const int64_t low = 2ll * sc.b0 + (int64_t)(L1max + L2max + W) * sc.b1 + 2ll * sc.oe_in - 1 + smin - 16;
-        const int64_t high = smax * std::min<int64_t>(L1max, L2max) - sc.oe_in + 16;
-        if (sc.b1 <= 0 && high - low + 128 <= 32767) {
-            pack = true;
-            pkp.bias = (int32_t)(64 - low);
-            // static row slope (MADD kernels, clq_pack.cuh): row x stored with x * slope more, slope = -min(substitution score, 0), so
-            // that the profile bytes are >= 0 and M = diag + m is a plain add.  Needs L1 * slope more head-room (Eh' of row 0 sits
-            // one slope lower) and bytes that still fit int8.
-            const int64_t slope = -smin;
-            // (short-read geometries only: on the long-read ones, 168 registers at 3 CTAs/SM, the two extra constants cost more
-            // than the ALU-pipe relief gains -- C3 1485 -> 1452 GCUPS with it)
-            if (!rb && !c->no_madd && G <= 8 && slope > 0 && smax + slope <= 127 && high + slope * (int64_t)L1max - (low - slope) + 128 <= 32767) {
-                madd = true;
-                pkp.slope = (int32_t)slope;
-                pkp.bias = (int32_t)(64 - (low - slope));
-            }
-        }
-    }
+    const size_t smem_adapt = (size_t)(kThreads / 32) * GPW * ref_sm_stride + kLutBytes + (size_t)kAdaptTabs * kTabBytes + tt_bytes;  // pack_adapt_kernel: one profile table per slope
+    PackParams pkp = plan.pkp;
+    bool pack = plan.pack;
+    const bool madd = plan.madd;
     if (convex && !c->no_pack && n) pack = cvx_window(W, &pkp.bias);  // two-piece affine: same proof with the gap states of both pieces
-    // Pairs beyond the static window (long reads): s16x2 with an adaptive per-row bias, overflow detection and an int32 retry pass
-    // (clq_pack_adapt.cuh).  Traceback stage only, pair mode: one reference, or a fixed assignment the upload grouped by reference.
-    AdaptParams adp = {};
-    bool adapt = false;
-    if (fast && !convex && !rb && !pack && !c->no_pack && !c->no_adapt && !score_only && n && G >= 16 && sc.b1 <= 0 && search == CLQ_SEARCH_FIXED &&
-        (c->n_refs == 1 || s->order_by_ref)) {
-        const int smin = std::min(std::min(sc.match, sc.mismatch), sc.special), smax = std::max(std::max(sc.match, sc.special), 0);
-        // adjacent cells of a row differ by at most smax - 2 * x1 (clq_pack_adapt.cuh); a lane holds C columns, E / F / M sit within a few opens of B
-        const int guard = c->adapt_guard > 0 ? c->adapt_guard : (C + 4) * (smax - 2 * sc.oe_in) + 64;
-        if (fits8(smax + kAdaptSigmaMax) && fits8(smin + kAdaptSigmaMin) && sc.oe_in >= -512 && (c->adapt_guard > 0 || 2 * guard + 64 + 16384 <= 32767)) {
-            adapt = true;
-            adp.guard = guard;
-        }
-    }
-    // pair mode needs one reference for both reads of a task: a single-reference panel, or a fixed assignment that the upload
-    // grouped by reference (every group padded to whole pairs)
-    const bool pack_pairs = (pack && (c->n_refs == 1 || (s->order_by_ref && search == CLQ_SEARCH_FIXED))) || adapt;
+    AdaptParams adp = plan.adp;
+    const bool adapt = plan.adapt;
+    const bool pack_pairs = (pack && pairs_ok) || adapt;
     // multi-reference batches: the traceback stage buckets the reads by reference on the device (ref_scatter_kernel) so that
     // the two reads of a PACK task share theirs; only with the natural read order (uniform lengths, uniform scratch slots)
     const bool group_pairs = pack && !pack_pairs && !score_only && !s->have_order && n > 0 && c->n_refs > 1 && !c->no_group;

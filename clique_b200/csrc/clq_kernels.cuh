@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
         int c = yy - 1;
         const int s = c / W;
         c -= s * W;
-        const int cs = (G >= 16 && s == sL && CsL > 0) ? CsL : C;
+        const int cs = (s == sL && CsL > 0) ? CsL : C;  // the narrow last stripe of a multi-stripe task (fill kernels leave CsL = C, sL = 0 otherwise)
         const int ln = c / cs, j = c - ln * cs;
         shift = 28 - 4 * (j & 7);
         return bits_index<G, WPL>(s, T, xx + ln, ln, j >> 3);
@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
         int c = yy - 1;
         const int s = c / W;
         c -= s * W;
-        const int cs = (G >= 16 && s == sL && CsL > 0) ? CsL : C;
+        const int cs = (s == sL && CsL > 0) ? CsL : C;  // the narrow last stripe of a multi-stripe task (fill kernels leave CsL = C, sL = 0 otherwise)
         const int ln = c / cs, j = c - ln * cs;
         asm volatile("prefetch.global.L1 [%0];" ::"l"(bits_g + bits_index<G, WPL>(s, T, xx + ln, ln, j >> 3)));
     };

@@ -336,7 +336,9 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
         const int L2m = max(run[0] ? L2[0] : 0, run[1] ? L2[1] : 0);
         const int NS = anyrun ? (L2m + W - 1) / W : 0;
         // narrow last stripe of the PAIR: both reads share the lane mapping, so the longer one sets the width
-        const bool narrow = G >= 16 && NS - 1 <= kMaxNarrowStripe;
+        // (short-read geometries: only when the task spans several stripes -- long reads on (8,40) -- so that the single-stripe fast
+        // path keeps its compile-time column count)
+        const bool narrow = (G >= 16 || NS > 1) && NS - 1 <= kMaxNarrowStripe;
         const int CsL = (anyrun && narrow) ? narrow_cols<G>(L2m - (NS - 1) * W, C) : C;
         int K[2], NSh[2], lLh[2], jLh[2];
 #pragma unroll
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
             const bool act_s = anyrun && s < NS;
             const bool ownA = run[0] && s == NSh[0] - 1 && gl == lLh[0];
             const bool ownB = run[1] && s == NSh[1] - 1 && gl == lLh[1];
-            const int Cs = (G >= 16 && s == NS - 1) ? CsL : C;  // compile-time C for the short-read geometries
+            const int Cs = (s == NS - 1) ? CsL : C;  // CsL == C unless the last stripe is narrow
             const int nb = Cs >> 3;
             const int y0 = s * W + gl * Cs;
             uint32_t Eh[C], B[C], sel[C];
@@ -410,6 +412,7 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
             uint32_t rcur = act_s ? (uint32_t)ref_sm[0] : 0u;
             auto steps = [&](auto simple_tag) {
                 constexpr bool SIMPLE = decltype(simple_tag)::value;
+                const int nbx = SIMPLE ? C / 8 : nb;  // the single-stripe fast path runs all C / 8 blocks: no per-block branch
                 uint32_t gB = dup16(sc.b0 + bias);  // lane 0 of stripe 0: g(x) + bias, advanced by one row per step (x = t there)
                 int t = 1;
                 if (Tmax >= 1) do {
@@ -446,9 +449,9 @@ __global__ void __launch_bounds__(kThreads, pack_min_blocks<G, C, TB>()) pack_ke
                         const uint32_t BlIn = Bl;
                         // the capture variant only runs on the lane(s) that own column L2, at their last row: once per task
                         if (x == xcap)
-                            pack_row_step<C, TB, true, RB, MADD>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, LEe, X1b, ownA, jLh[0], ownB, jLh[1], cap, nb, cy);
+                            pack_row_step<C, TB, true, RB, MADD>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, LEe, X1b, ownA, jLh[0], ownB, jLh[1], cap, nbx, cy);
                         else
-                            pack_row_step<C, TB, false, RB, MADD>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, LEe, X1b, ownA, jLh[0], ownB, jLh[1], cap, nb, cy);
+                            pack_row_step<C, TB, false, RB, MADD>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, LEe, X1b, ownA, jLh[0], ownB, jLh[1], cap, nbx, cy);
                         prevBl = BlIn;
                         oF = Fl; oE = El; oM = Ml; oB = Bl;
                         if (!SIMPLE) {

@@ -19,8 +19,10 @@
 // reads that drift apart, since both halves share one bias -- is handed to the int32 kernel through the retry list: its
 // records are written by that kernel, bit-exact either way.
 //
-// Pair mode only (two reads against one reference; the host orders reads so that pairs share theirs), traceback only, long-read
-// geometries (G >= 16, row-per-step bit layout).  Same direction bits, same slots, same walker as pack_kernel.
+// Pair mode only (two reads against one reference; the host orders reads so that pairs share theirs), traceback only.  Same
+// direction bits, same slots, same walker as pack_kernel.  Runs on (8,40) with as many column stripes as the read needs: the
+// short-read geometry keeps 8 of 8 lanes busy and is 24 % faster on 1 kb reads than (32,32) even with four stripes (measured,
+// profiles/geometry_sweep_r02_s13.txt).
 #pragma once
 
 #include "clq_pack.cuh"
@@ -49,7 +51,7 @@ __device__ __forceinline__ int hi16s(uint32_t w) { return (int)(int16_t)(w >> 16
 
 template <int G, int C>
 __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_kernel(const KParams p, const AdaptParams ap) {
-    static_assert(G >= 16 && C % 8 == 0 && !BitsLayout<G>::transposed, "long-read geometries only (row-per-step bit layout)");
+    static_assert(C % 8 == 0, "C must be a multiple of 8");
     static_assert(kAdaptBlock >= G, "a block must be at least as long as the wavefront skew");
     extern __shared__ __align__(16) uint8_t smem_raw[];
     // [0,256) class LUT, [256, 256 + 32 * 128) one profile table per slope, then the reference rows
@@ -71,6 +73,8 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
     const int wpb = blockDim.x >> 5;
     const uint32_t ggid = (blockIdx.x * wpb + warp) * GPW + gw;
     uint8_t* ref_sm = smem + (size_t)(warp * GPW + gw) * p.ref_sm_stride;
+    // per-warp transposition buffers (read A, read B) of the direction bits for the time-transposed layout (G <= 8), after the reference rows
+    uint32_t* tt_sm = reinterpret_cast<uint32_t*>(smem + (size_t)wpb * GPW * p.ref_sm_stride) + (size_t)warp * (2 * WPL * 256);
     uint32_t* col_g = (uint32_t*)p.col_scratch + (size_t)ggid * 5 * p.col_stride;  // F, E, M, B of the boundary column + beta per row
     const clq_affine_t sc = p.sc;
     const int x1 = sc.oe_in, le = sc.e_in;
@@ -291,8 +295,7 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
                         seen_mn = vmin_s16x2(seen_mn, b0w);
                         seen_mx = vmax_s16x2(seen_mx, b0w);
                     }
-                    if (stA) row_store<G, WPL>(bitsA, wA, s, T, t, gl, nb);
-                    if (stB) row_store<G, WPL>(bitsB, wB, s, T, t, gl, nb);
+                    bits_store2<G, WPL>(tt_sm, bitsA, bitsB, wA, wB, stA, stB, s, T, t, lane, gl, x == L1, nb);
                     stg4_if(col_g + 4 * x, st_col, oF, oE, oM, oB);
                     stg_if(col_g + 4 * p.col_stride + x, st_col, (uint32_t)beta);
                     if (x == 1) stg_if(col_g + 4 * p.col_stride, st_col, (uint32_t)beta0);

@@ -787,9 +787,25 @@ def test_adaptive_pack_long_reads():
         want = O.align_batch(rb, ro, qb, qo, sc, search="fixed", fixed_ref=fixed, band_mode="readlen", threads=8)
         br = al2.align_batch(qb, qo, AffineScoring(*sc), "fixed", "readlen", fixed_ref=fixed, with_stats=True)
         assert br.stats["variant"] & 64, "long pairs should take the adaptive s16x2 kernel"
+        assert (br.stats["variant"] >> 8) == 2, "by default on the (8,40) geometry with column stripes"
         compare(br, want, len(reads), "adaptive")
         natural = br.stats["pack_retries"]
         assert natural < len(reads), "most pairs must stay on the s16x2 kernel"
+        for cfg in (3, 4, 5):   # the same kernel on the long-read geometries (row-per-step bit layout)
+            al2.set_option("force_cfg", cfg)
+            try:
+                brc = al2.align_batch(qb, qo, AffineScoring(*sc), "fixed", "readlen", fixed_ref=fixed, with_stats=True)
+            finally:
+                al2.set_option("force_cfg", -1)
+            assert brc.stats["variant"] & 64 and (brc.stats["variant"] >> 8) == cfg
+            compare(brc, want, len(reads), "adaptive cfg %d" % cfg)
+        al2.set_option("no_long8", 1)   # the geometry the read length picks
+        try:
+            brl = al2.align_batch(qb, qo, AffineScoring(*sc), "fixed", "readlen", fixed_ref=fixed, with_stats=True)
+        finally:
+            al2.set_option("no_long8", 0)
+        assert brl.stats["variant"] & 64 and (brl.stats["variant"] >> 8) == 5
+        compare(brl, want, len(reads), "adaptive, no_long8")
         # every pair through the retry pass: a guard wider than the window makes each task report an overflow
         al2.set_option("adapt_guard", 20000)
         try:
