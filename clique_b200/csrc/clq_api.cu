@@ -925,12 +925,14 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     const size_t tt_bytes = (!convex && G <= kTransposeMaxG) ? (size_t)(kThreads / 32) * (C / 8) * 1024 * 2 : 0;
     const size_t smem = (size_t)(kThreads / 32) * GPW * ref_sm_stride + (fast ? kLutBytes + kTabBytes : 0) + tt_bytes;
     if (smem > 200 * 1024) return fail(c, CLQ_E_LIMIT, "references too long for this geometry's shared-memory staging");
-    const size_t smem_adapt = (size_t)(kThreads / 32) * GPW * ref_sm_stride + kLutBytes + (size_t)kAdaptTabs * kTabBytes + tt_bytes;  // pack_adapt_kernel: one profile table per slope
+    const uint32_t ref_stride_adapt = ((L1max + 1) / 2 + 15) / 16 * 16 + 16;  // pack_adapt_kernel stages two reference classes per byte
+    const size_t smem_adapt = (size_t)(kThreads / 32) * GPW * ref_stride_adapt + kLutBytes + (size_t)kAdaptTabs * kTabBytes + tt_bytes;  // pack_adapt_kernel: one profile table per slope
     PackParams pkp = plan.pkp;
     bool pack = plan.pack;
     const bool madd = plan.madd;
     if (convex && !c->no_pack && n) pack = cvx_window(W, &pkp.bias);  // two-piece affine: same proof with the gap states of both pieces
     AdaptParams adp = plan.adp;
+    adp.ref_stride = ref_stride_adapt;
     const bool adapt = plan.adapt;
     const bool pack_pairs = (pack && pairs_ok) || adapt;
     // multi-reference batches: the traceback stage buckets the reads by reference on the device (ref_scatter_kernel) so that
@@ -1244,7 +1246,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
                 s->stats.launches++;
                 s->stats.dp_launches++;
                 s->stats.sub_batches++;
-                if (adapt) {
+                if (adapt && !(c->debug_flags & 2)) {
                     // pairs that left the guarded window are redone by the int32 kernel, which writes their records, walker records and
                     // direction bits into the same slots (same geometry); the number of tasks is read on the device
                     KParams q2 = q;

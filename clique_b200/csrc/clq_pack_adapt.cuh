@@ -42,6 +42,8 @@ struct AdaptParams {
     uint32_t* retry_list;       // sub-batch positions (2 * task, 2 * task + 1) of the pairs the int32 kernel must redo
     unsigned int* retry_count;  // reset per sub-batch
     unsigned int* retry_total;  // per launch (statistics)
+    uint32_t ref_stride;        // bytes of shared memory per staged reference row: TWO reference classes per byte (a 5 kb
+                                // amplicon is 2.5 KB per lane group, 40 KB per CTA on (8,40): two CTAs per SM instead of one)
 };
 
 __device__ __forceinline__ uint32_t vmin_s16x2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
@@ -72,9 +74,9 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
     const int gl = lane % G, gw = lane / G;
     const int wpb = blockDim.x >> 5;
     const uint32_t ggid = (blockIdx.x * wpb + warp) * GPW + gw;
-    uint8_t* ref_sm = smem + (size_t)(warp * GPW + gw) * p.ref_sm_stride;
+    uint8_t* ref_sm = smem + (size_t)(warp * GPW + gw) * ap.ref_stride;
     // per-warp transposition buffers (read A, read B) of the direction bits for the time-transposed layout (G <= 8), after the reference rows
-    uint32_t* tt_sm = reinterpret_cast<uint32_t*>(smem + (size_t)wpb * GPW * p.ref_sm_stride) + (size_t)warp * (2 * WPL * 256);
+    uint32_t* tt_sm = reinterpret_cast<uint32_t*>(smem + (size_t)wpb * GPW * ap.ref_stride) + (size_t)warp * (2 * WPL * 256);
     uint32_t* col_g = (uint32_t*)p.col_scratch + (size_t)ggid * 5 * p.col_stride;  // F, E, M, B of the boundary column + beta per row
     const clq_affine_t sc = p.sc;
     const int x1 = sc.oe_in, le = sc.e_in;
@@ -132,7 +134,10 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
         }
         const bool anyrun = run[0] || run[1];
         if (anyrun && ref != staged_ref) {
-            for (int i = gl; i < L1; i += G) ref_sm[i] = (lut_sm[refp[i]] >> 3) & 15;
+            for (int b = gl; 2 * b < L1; b += G) {  // two classes per byte, low nibble first
+                const uint32_t c0 = (lut_sm[refp[2 * b]] >> 3) & 15, c1 = (2 * b + 1 < L1) ? (lut_sm[refp[2 * b + 1]] >> 3) & 15 : 0u;
+                ref_sm[b] = (uint8_t)(c0 | (c1 << 4));
+            }
             staged_ref = ref;
         }
         __syncwarp();
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
             const bool realA = run[0] && y0 + 1 <= L2[0], realB = run[1] && y0 + 1 <= L2[1];
             const uint32_t real_mask = (realA ? 0x0000ffffu : 0u) | (realB ? 0xffff0000u : 0u);
             const uint32_t neutral = dup16(kAdaptCentre) & ~real_mask;
-            uint32_t rcur = act_s ? (uint32_t)ref_sm[0] : 0u;
+            uint32_t rcur = act_s ? (uint32_t)ref_sm[0] & 15u : 0u;
             // slope schedule: rows <= blk_end take sig_cur, later rows sig_next (decided at step blk_end, one block ahead)
             int sig_cur = 0, sig_next = 0, sig_prev_row = 0, blk_end = kAdaptBlock;
             int ctr_prev = kAdaptCentre, sig_last = 0;  // controller state (uniform over the group)
@@ -262,7 +267,7 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
                         nBeta = (int)ldg_if(col_g + 4 * p.col_stride + x + 1, nx, (uint32_t)nBeta);
                     }
                     const uint2 tr = *(const uint2*)(tab_sm + ((sg - kAdaptSigmaMin) * 16 + (int)rcur) * 8);
-                    rcur = ref_sm[x < L1 ? x : L1 - 1];
+                    { const int xi = x < L1 ? x : L1 - 1; rcur = ((uint32_t)ref_sm[xi >> 1] >> ((xi & 1) << 2)) & 15u; }
                     const uint32_t BlIn = Bl;
                     if (x == xcap) {
                         pack_row_step<C, true, true, false, false>(Eh, B, sel, wA, wB, Fl, El, Ml, Bl, prevBl, tr.x, tr.y, LE, X1, X1M1, LEe, X1b, ownA, jLh[0], ownB, jLh[1], cap, nb, cy);
@@ -335,7 +340,8 @@ __global__ void __launch_bounds__(kThreads, CLQ_ADAPT_MIN_BLOCKS) pack_adapt_ker
 #endif
         }
         const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (gw * G));
-        const bool redo = anyrun && (__ballot_sync(FULL, fault != 0u) & gm) != 0u;
+        const unsigned faulted = __ballot_sync(FULL, fault != 0u);  // every lane votes (an idle group must not skip the warp-wide vote)
+        const bool redo = anyrun && (faulted & gm) != 0u;
         cy.report(anyrun, redo, L1, L2[0], L2[1], 0x1000 | G);  // a pair that is NOT redone must never have left the window: the guard band's soundness, checked
 
         // ---- final cells: score + start layer = LAST maximum of (M, E, F) per read ----

@@ -699,9 +699,11 @@ def _edge_reads(rng, ref, L):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("scoring,bit", [((100.0, -90.0, 90.0, -20.0, -2.0, 1.0), 2),    # plain PACK <-> int32 FAST (slope 90 + 100 > 127: no MADD)
-                                          ((60.0, -60.0, 60.0, -20.0, -2.0, 1.0), 32)])  # PACK with the static row slope <-> plain PACK
-def test_pack_window_edge(al, scoring, bit):
+@pytest.mark.parametrize("scoring,bit,no_adapt", [
+    ((100.0, -90.0, 90.0, -20.0, -2.0, 1.0), 2 | 64, 0),    # static-window PACK (2) <-> adaptive-bias PACK (2 | 64) (slope 90 + 100 > 127: no MADD)
+    ((100.0, -90.0, 90.0, -20.0, -2.0, 1.0), 2, 1),         # static-window PACK <-> int32 FAST (adaptive kernel switched off)
+    ((60.0, -60.0, 60.0, -20.0, -2.0, 1.0), 32, 0)])        # PACK with the static row slope <-> plain PACK
+def test_pack_window_edge(al, scoring, bit, no_adapt, request):
     """Deterministic inputs AT the switch point of the 15-bit window proof (clq_api.cu): for consecutive read lengths around the
     length where the host stops taking the s16x2 kernel (or its sloped variant), reads at both ends of the score range must be
     bit-exact on either side.  A silent 16-bit wrap at the edge is exactly what random fuzzing can miss."""
@@ -709,6 +711,8 @@ def test_pack_window_edge(al, scoring, bit):
     seen = set()
     flips = 0
     prev = None
+    al.set_option("no_adapt", no_adapt)
+    request.addfinalizer(lambda: al.set_option("no_adapt", 0))
     for L in range(246, 316):
         ref = rand_seq(rng, L)
         # cheap scan: one launch of two reads tells which kernel family the host takes for this length
@@ -717,7 +721,7 @@ def test_pack_window_edge(al, scoring, bit):
         al.set_references(rm)
         qb, qo = pack_reads(probe)
         br = al.align_batch(qb, qo, AffineScoring(*scoring), "fixed", "readlen", fixed_ref=np.zeros(2, np.int32), with_stats=True)
-        cur = bool(br.stats["variant"] & bit)
+        cur = (br.stats["variant"] & bit) == 2 if bit & 64 else bool(br.stats["variant"] & bit)
         if prev is not None and cur != prev:
             flips += 1
             for LL in (L - 2, L - 1, L, L + 1):   # two lengths on each side of the switch
@@ -725,7 +729,8 @@ def test_pack_window_edge(al, scoring, bit):
                 reads = _edge_reads(rng, ref2, LL)
                 b2, want = run_both(al, [ref2], reads, scoring, "fixed", "readlen", fixed_ref=np.zeros(len(reads), np.int32))
                 compare(b2, want, len(reads), ("edge", scoring[0], LL))
-                seen.add((LL, bool(al.stats(0)["variant"] & bit)))
+                v = al.stats(0)["variant"]
+                seen.add((LL, (v & bit) == 2 if bit & 64 else bool(v & bit)))
         prev = cur
     assert flips == 1, "the switch point must lie inside the scanned range exactly once"
     assert {v for _, v in seen} == {True, False}, seen
