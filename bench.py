@@ -248,7 +248,7 @@ def run_config(args, workload, n, search, convex, rustbio, steps, warmup, e2e_ch
         assert c["search"] == "fixed" and not convex, "--rustbio is the single-reference branch"
         sci = RustBioScoring()   # Aligner.launch adds CLQ_RUSTBIO for this scoring type
         c["band"] = "maxlen"
-    for opt in ("force_cfg", "force_generic", "debug_flags", "no_pack", "no_madd", "no_adapt", "no_long8"):     # experiment knobs, e.g. CLQ_FORCE_CFG=3
+    for opt in ("force_cfg", "force_generic", "debug_flags", "no_pack", "no_madd", "no_adapt", "no_long8", "no_overlap", "max_scratch_bytes"):     # experiment knobs, e.g. CLQ_FORCE_CFG=3
         if os.environ.get("CLQ_" + opt.upper()):
             al.set_option(opt, int(os.environ["CLQ_" + opt.upper()]))
     score_only = bool(int(os.environ.get("CLQ_SCORE_ONLY", "0")))

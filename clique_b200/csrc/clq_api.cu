@@ -42,6 +42,8 @@ struct DevBuf {
 
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // overlapped sub-batches (clq_launch): odd sub-batches run here, in the other half of the scratch
+    cudaEvent_t fork = nullptr, join = nullptr;
     cudaEvent_t ev[6] = {};
     cudaEvent_t done = nullptr;      // recorded after the last kernel of a launch (see clq_ctx::last_done)
     DevBuf read_bytes, read_off, fixed_ref, order, results, scores, cand_mask, single_ref, ref_of_read, votes;
@@ -50,7 +52,8 @@ struct Slot {
     std::vector<int32_t> h_ref;      // fixed_ref in processing order (same condition, when given)
     std::vector<uint32_t> h_order;   // the processing order itself (read index per position, 0xffffffff = padding)
     DevBuf order2;                   // the order of one launch after its sub-batches were dealt (clq_launch)
-    DevBuf counters;                 // [0..3] task counters (u32, padded to 8 B each), [4] cigar cursor, [5] cells
+    DevBuf counters;                 // [0..3] task counters (u32, padded to 8 B each), [4] cigar cursor, [5] cells, [6] retry count, [7] retries of
+                                     // the launch, [8..10] fill / retry task counters and retry count of the sub-batches on stream2
     unsigned long long* h_counters = nullptr;  // pinned mirror
     uint32_t n_reads = 0;
     uint64_t n_read_bytes = 0;
@@ -86,6 +89,7 @@ struct clq_ctx {
     int no_pack = 0;                 // option "no_pack": never take the s16x2 PACK kernels
     int no_madd = 0;                 // option "no_madd": PACK kernels without the static row slope (M step on the ALU pipe)
     int no_adapt = 0;                // option "no_adapt": long pairs beyond the static 15-bit window stay on the int32 kernels
+    int no_overlap = 0;              // option "no_overlap": sub-batches run one after the other (dealt round-robin) instead of two at a time
     int no_long8 = 0;                // option "no_long8": long reads keep the geometry their length picks instead of (8,40) with column stripes
     int adapt_guard = 0;             // option "adapt_guard" (tests): overrides the guard band of pack_adapt_kernel; a huge value forces every pair through the retry pass
     int no_group = 0;                // option "no_group": multi-reference traceback stays on the int32 kernels (no bucketing by reference)
@@ -473,11 +477,14 @@ int32_t clq_ctx_create(int32_t device, const clq_limits_t* limits, clq_ctx** out
     c->slots.resize(c->lim.n_slots);
     for (auto& s : c->slots) {
         if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { clq_ctx_destroy(c); return CLQ_E_CUDA; }
+        if (cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking) != cudaSuccess) { clq_ctx_destroy(c); return CLQ_E_CUDA; }
+        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) { clq_ctx_destroy(c); return CLQ_E_CUDA; }
+        if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) { clq_ctx_destroy(c); return CLQ_E_CUDA; }
         for (auto& e : s.ev)
             if (cudaEventCreate(&e) != cudaSuccess) { clq_ctx_destroy(c); return CLQ_E_CUDA; }
         if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) { clq_ctx_destroy(c); return CLQ_E_CUDA; }
         if (cudaHostAlloc((void**)&s.h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) { clq_ctx_destroy(c); return CLQ_E_CUDA; }
-        if (ensure(c, s.counters, 8 * sizeof(unsigned long long)) != CLQ_OK) { clq_ctx_destroy(c); return CLQ_E_NOMEM; }
+        if (ensure(c, s.counters, 16 * sizeof(unsigned long long)) != CLQ_OK) { clq_ctx_destroy(c); return CLQ_E_NOMEM; }
     }
     *out = c;
     return CLQ_OK;
@@ -488,6 +495,9 @@ void clq_ctx_destroy(clq_ctx* c) {
     cudaSetDevice(c->device);
     for (auto& s : c->slots) {
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+        if (s.stream2) { cudaStreamSynchronize(s.stream2); cudaStreamDestroy(s.stream2); }
+        if (s.fork) cudaEventDestroy(s.fork);
+        if (s.join) cudaEventDestroy(s.join);
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
         if (s.done) cudaEventDestroy(s.done);
         for (DevBuf* b : {&s.read_bytes, &s.read_off, &s.fixed_ref, &s.order, &s.results, &s.scores, &s.cand_mask, &s.single_ref,
@@ -509,6 +519,7 @@ int32_t clq_set_option(clq_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "no_pack")) { c->no_pack = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_madd")) { c->no_madd = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_adapt")) { c->no_adapt = (int)value; return CLQ_OK; }
+    if (!strcmp(key, "no_overlap")) { c->no_overlap = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_long8")) { c->no_long8 = (int)value; return CLQ_OK; }
     if (!strcmp(key, "adapt_guard")) { c->adapt_guard = (int)value; return CLQ_OK; }
     if (!strcmp(key, "no_group")) { c->no_group = (int)value; return CLQ_OK; }
@@ -914,7 +925,10 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     if (!convex && c->force_cfg < 0 && !CLQ_LEAN_NO8 && !c->no_long8 && cfg > 2 && fast && n) {
         const Plan p2 = plan_for(2);
         const bool tb_on_pack = score_only || pairs_ok || (p2.pack && !s->have_order && c->n_refs > 1 && !c->no_group);
-        if ((p2.pack && tb_on_pack) || p2.adapt) { cfg = 2; plan = p2; }
+        // (the adaptive-bias kernel stays on the geometry the length picks: both reach the same cells/s on 5 kb pairs, but a pair
+        // takes ~4x longer on one 8-lane group than on a 32-lane one, and the bits of the 4736 pairs in flight on (8,40) do not
+        // fit the scratch -- C5 60k reads: 232 ms on (8,40), 212 ms on (32,32), both with overlapped sub-batches)
+        if (p2.pack && tb_on_pack) { cfg = 2; plan = p2; }
     }
     const int G = convex ? kCvxCfgs[cfg].G : kCfgs[cfg].G, C = convex ? kCvxCfgs[cfg].C : kCfgs[cfg].C, W = G * C, GPW = 32 / G;
     const int bits_per_cell = convex ? 8 : 4;
@@ -940,23 +954,24 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     const bool group_pairs = pack && !pack_pairs && !score_only && !s->have_order && n > 0 && c->n_refs > 1 && !c->no_group;
     const uint64_t n_pos = group_pairs ? (((uint64_t)n + c->n_refs + 2) & ~1ull) : (s->have_order ? s->n_pos : n);  // processing positions incl. group padding
     uint32_t madd_tab[32] = {};  // the MADD kernels take the profile table with the row slope already added (every byte >= 0)
+    cudaStream_t dp_stream = s->stream;  // the stream launch_dp queues on (odd overlapped sub-batches: stream2)
     auto launch_dp = [&](bool tb, const KParams& kp, int* grid, bool query) -> cudaError_t {
         if (convex) {
             if (pack && !kp.all_pairs && (pack_pairs || (tb && group_pairs)))  // the convex PACK kernel is pair-mode only
-                return tb ? launch_cvx_pack<true>(cfg, kp, cp, pkp, c->sm_count, smem, s->stream, grid, query) : launch_cvx_pack<false>(cfg, kp, cp, pkp, c->sm_count, smem, s->stream, grid, query);
-            return tb ? launch_cvx<true>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query) : launch_cvx<false>(cfg, kp, cp, c->sm_count, smem, s->stream, grid, query);
+                return tb ? launch_cvx_pack<true>(cfg, kp, cp, pkp, c->sm_count, smem, dp_stream, grid, query) : launch_cvx_pack<false>(cfg, kp, cp, pkp, c->sm_count, smem, dp_stream, grid, query);
+            return tb ? launch_cvx<true>(cfg, kp, cp, c->sm_count, smem, dp_stream, grid, query) : launch_cvx<false>(cfg, kp, cp, c->sm_count, smem, dp_stream, grid, query);
         }
-        if (adapt && tb && !kp.all_pairs) return launch_adapt(cfg, kp, adp, c->sm_count, smem_adapt, s->stream, grid, query);
+        if (adapt && tb && !kp.all_pairs) return launch_adapt(cfg, kp, adp, c->sm_count, smem_adapt, dp_stream, grid, query);
         if (pack && (kp.all_pairs || pack_pairs || (tb && group_pairs))) {
-            if (rb) return launch_pack<true, true>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query);
+            if (rb) return launch_pack<true, true>(cfg, kp, pkp, c->sm_count, smem, dp_stream, grid, query);
             if (madd) {
                 KParams km = kp;
                 memcpy(km.tab, madd_tab, sizeof(madd_tab));
-                return tb ? launch_pack<true, false, true>(cfg, km, pkp, c->sm_count, smem, s->stream, grid, query) : launch_pack<false, false, true>(cfg, km, pkp, c->sm_count, smem, s->stream, grid, query);
+                return tb ? launch_pack<true, false, true>(cfg, km, pkp, c->sm_count, smem, dp_stream, grid, query) : launch_pack<false, false, true>(cfg, km, pkp, c->sm_count, smem, dp_stream, grid, query);
             }
-            return tb ? launch_pack<true>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query) : launch_pack<false>(cfg, kp, pkp, c->sm_count, smem, s->stream, grid, query);
+            return tb ? launch_pack<true>(cfg, kp, pkp, c->sm_count, smem, dp_stream, grid, query) : launch_pack<false>(cfg, kp, pkp, c->sm_count, smem, dp_stream, grid, query);
         }
-        return launch_any(cfg, tb, fin, fast, rb && tb, kp, c->sm_count, smem, s->stream, grid, query);
+        return launch_any(cfg, tb, fin, fast, rb && tb, kp, c->sm_count, smem, dp_stream, grid, query);
     };
 
     KParams p = {};
@@ -1029,6 +1044,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     std::vector<uint64_t> cuts;          // sub-batch boundaries in processing positions
     const uint64_t np = s->have_order ? s->n_pos : n;  // processing positions of a host-ordered batch (incl. reference-group padding)
     const uint32_t* order_tb = nullptr;
+    bool overlap = false;  // sub-batches two at a time: even ones on the slot's stream, odd ones on stream2, each stream its half of the scratch
     const bool var_slots = !score_only && n && s->have_order && s->h_len.size() == np;
     uint64_t max_sub_words = sub * bits_stride, max_sub_tasks = sub;
     if (var_slots) {
@@ -1061,7 +1077,23 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
         }
         K = std::min<uint64_t>(K, std::max<uint64_t>(npairs, 1));
         cuts.push_back(0);
-        if (K > 1 && s->h_order.size() == np) {
+        if (K > 1 && !c->no_overlap) {
+            // Overlapped sub-batches: the positions stay in their order (longest reference, then longest read first) and are cut
+            // into contiguous pieces of HALF the scratch budget; piece k runs on stream k % 2 in scratch half k % 2, so the
+            // persistent CTAs a piece frees while its last pairs finish are taken by the next piece at once.  The whole launch
+            // then behaves like one longest-first task list: the 5 kb pairs (one pair: ~100 ms on one lane group) all start in
+            // the first pieces, and the launch ends on short pairs.  (A dealt sequence of sub-batches pays that critical path once
+            // per sub-batch: C5 271 ms dealt, 2 sub-batches.)
+            overlap = true;
+            const uint64_t half = budget_words / 2;
+            uint64_t acc = 0;
+            for (uint64_t pr = 0; pr < npairs; pr++) {
+                const uint64_t cst = cost(2 * pr) + cost(2 * pr + 1);
+                if (acc && acc + cst > half) { cuts.push_back(2 * pr); acc = 0; }
+                acc += cst;
+            }
+            cuts.push_back(np);
+        } else if (K > 1 && s->h_order.size() == np) {
             static thread_local std::vector<uint32_t> order2, len2;
             static thread_local std::vector<uint64_t> off2;
             order2.clear(); len2.clear();
@@ -1099,14 +1131,17 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     DevBuf& sbits = c->serialize ? c->sh_bits : s->bits;
     DevBuf& scig = c->serialize ? c->sh_cig : s->cig_scratch;
     DevBuf& stbrec = c->serialize ? c->sh_tbrec : s->tb_rec;
+    const size_t nh = overlap ? 2 : 1;
+    const size_t half_bits = (size_t)max_sub_words * 4, half_cig = ((size_t)max_sub_tasks * cig_stride * 4 + 15) & ~(size_t)15, half_tbrec = (size_t)max_sub_tasks * sizeof(TbRec);
+    const size_t half_col = (size_t)groups * col_stride * (adapt ? 20 : 16), half_retry = (((size_t)max_sub_tasks + 2) * sizeof(uint32_t) + 15) & ~(size_t)15;
     if (!score_only && n) {
-        if ((rc = ensure(c, sbits, max_sub_words * 4 + 64)) != CLQ_OK) return rc;
-        if ((rc = ensure(c, scig, max_sub_tasks * cig_stride * 4)) != CLQ_OK) return rc;
-        if ((rc = ensure(c, stbrec, max_sub_tasks * sizeof(TbRec))) != CLQ_OK) return rc;
+        if ((rc = ensure(c, sbits, nh * half_bits + 64)) != CLQ_OK) return rc;
+        if ((rc = ensure(c, scig, nh * half_cig)) != CLQ_OK) return rc;
+        if ((rc = ensure(c, stbrec, nh * half_tbrec)) != CLQ_OK) return rc;
         if ((rc = ensure(c, s->cigar_pool, (size_t)c->lim.cigar_pool_ops * 4 + 16)) != CLQ_OK) return rc;
     }
-    if ((rc = ensure(c, s->col_scratch, groups * col_stride * (adapt ? 20 : 16))) != CLQ_OK) return rc;  // pack_adapt_kernel keeps a fifth array (the bias of every row)
-    if (adapt && (rc = ensure(c, s->retry_list, (max_sub_tasks + 2) * sizeof(uint32_t))) != CLQ_OK) return rc;
+    if ((rc = ensure(c, s->col_scratch, nh * half_col)) != CLQ_OK) return rc;  // pack_adapt_kernel keeps a fifth array (the bias of every row)
+    if (adapt && (rc = ensure(c, s->retry_list, nh * half_retry)) != CLQ_OK) return rc;
     p.bits = (uint32_t*)sbits.p;
     p.bits_stride = bits_stride;
     p.bits_off = var_slots ? (const uint64_t*)s->bits_off.p : nullptr;
@@ -1131,7 +1166,7 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
     s->stats.dp_launches = 0;
     s->n_dp = 0;
     if (c->serialize && c->last_done && c->last_done != s->done) CU(c, cudaStreamWaitEvent(s->stream, c->last_done, 0));
-    CU(c, cudaMemsetAsync(s->counters.p, 0, 8 * sizeof(unsigned long long), s->stream));
+    CU(c, cudaMemsetAsync(s->counters.p, 0, 16 * sizeof(unsigned long long), s->stream));
     CU(c, cudaEventRecord(s->ev[0], s->stream));
 
     const int32_t* ref_of_read = nullptr;
@@ -1223,21 +1258,37 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
             s->stats.dp_launches++;
         } else {
             // fill (direction bits into the sub-batch's slots) then walk (one thread per pair), sub-batch by sub-batch
+            if (overlap) {
+                CU(c, cudaEventRecord(s->fork, s->stream));
+                CU(c, cudaStreamWaitEvent(s->stream2, s->fork, 0));
+            }
             for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
                 const uint64_t base = cuts[ci];
                 const uint32_t cnt = (uint32_t)(cuts[ci + 1] - base);
                 if (!cnt) continue;
+                const size_t h = overlap ? (ci & 1) : 0;   // scratch half + stream of this sub-batch
+                cudaStream_t st = h ? s->stream2 : s->stream;
+                dp_stream = st;
+                unsigned long long* c_fill = ctr + (h ? 8 : 1);
+                unsigned long long* c_retry = ctr + (h ? 9 : 2);
+                unsigned long long* c_count = ctr + (h ? 10 : 6);
                 q.n_tasks = tb_pairs ? (cnt + 1) / 2 : cnt;
                 q.task_base = (uint32_t)base;
                 q.task_end = (uint32_t)(base + cnt);
-                if (base) CU(c, cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned long long), s->stream));
-                if (adapt) {  // retry pass bookkeeping: its task counter (ctr[2]) and the number of listed positions (ctr[6])
-                    if (base) {
-                        CU(c, cudaMemsetAsync(ctr + 2, 0, sizeof(unsigned long long), s->stream));
-                        CU(c, cudaMemsetAsync(ctr + 6, 0, sizeof(unsigned long long), s->stream));
+                q.task_counter = (unsigned int*)c_fill;
+                q.bits = (uint32_t*)((char*)sbits.p + h * half_bits);
+                q.cig_scratch = (uint32_t*)((char*)scig.p + h * half_cig);
+                q.tb_rec = (TbRec*)((char*)stbrec.p + h * half_tbrec);
+                q.col_scratch = (int32_t*)((char*)s->col_scratch.p + h * half_col);
+                const bool again = ci >= nh;  // this half's counters were used by an earlier sub-batch (same stream: ordered)
+                if (again) CU(c, cudaMemsetAsync(c_fill, 0, sizeof(unsigned long long), st));
+                if (adapt) {  // retry pass bookkeeping: its task counter and the number of listed positions
+                    if (again) {
+                        CU(c, cudaMemsetAsync(c_retry, 0, sizeof(unsigned long long), st));
+                        CU(c, cudaMemsetAsync(c_count, 0, sizeof(unsigned long long), st));
                     }
-                    adp.retry_list = (uint32_t*)s->retry_list.p;
-                    adp.retry_count = (unsigned int*)(ctr + 6);
+                    adp.retry_list = (uint32_t*)((char*)s->retry_list.p + h * half_retry);
+                    adp.retry_count = (unsigned int*)c_count;
                     adp.retry_total = (unsigned int*)(ctr + 7);
                 }
                 int g = grid_tb;
@@ -1250,21 +1301,26 @@ int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags
                     // pairs that left the guarded window are redone by the int32 kernel, which writes their records, walker records and
                     // direction bits into the same slots (same geometry); the number of tasks is read on the device
                     KParams q2 = q;
-                    q2.retry_list = (const uint32_t*)s->retry_list.p;
-                    q2.n_tasks_dev = (const unsigned int*)(ctr + 6);
+                    q2.retry_list = adp.retry_list;
+                    q2.n_tasks_dev = (const unsigned int*)c_count;
                     q2.n_tasks = 0;
-                    q2.task_counter = (unsigned int*)(ctr + 2);
+                    q2.task_counter = (unsigned int*)c_retry;
                     int g2 = grid_retry;
-                    if ((ce = launch_any(cfg, true, false, true, false, q2, c->sm_count, smem, s->stream, &g2, false)) != cudaSuccess)
+                    if ((ce = launch_any(cfg, true, false, true, false, q2, c->sm_count, smem, st, &g2, false)) != cudaSuccess)
                         return fail(c, CLQ_E_CUDA, std::string("retry kernel: ") + cudaGetErrorString(ce));
                     s->stats.launches++;
                     s->stats.dp_launches++;
                 }
                 if (!(c->debug_flags & 1)) {
-                    if ((ce = convex ? launch_cvx_walk(cfg, q, tb_pairs ? 2 * q.n_tasks : cnt, s->stream) : launch_walk(cfg, q, tb_pairs ? 2 * q.n_tasks : cnt, s->stream)) != cudaSuccess)
+                    if ((ce = convex ? launch_cvx_walk(cfg, q, tb_pairs ? 2 * q.n_tasks : cnt, st) : launch_walk(cfg, q, tb_pairs ? 2 * q.n_tasks : cnt, st)) != cudaSuccess)
                         return fail(c, CLQ_E_CUDA, std::string("walk kernel: ") + cudaGetErrorString(ce));
                     s->stats.launches++;
                 }
+            }
+            dp_stream = s->stream;
+            if (overlap) {
+                CU(c, cudaEventRecord(s->join, s->stream2));
+                CU(c, cudaStreamWaitEvent(s->stream, s->join, 0));
             }
         }
         CU(c, cudaEventRecord(s->ev[4], s->stream));

@@ -792,11 +792,11 @@ def test_adaptive_pack_long_reads():
         want = O.align_batch(rb, ro, qb, qo, sc, search="fixed", fixed_ref=fixed, band_mode="readlen", threads=8)
         br = al2.align_batch(qb, qo, AffineScoring(*sc), "fixed", "readlen", fixed_ref=fixed, with_stats=True)
         assert br.stats["variant"] & 64, "long pairs should take the adaptive s16x2 kernel"
-        assert (br.stats["variant"] >> 8) == 2, "by default on the (8,40) geometry with column stripes"
+        assert (br.stats["variant"] >> 8) == 5, "on the geometry the read length picks"
         compare(br, want, len(reads), "adaptive")
         natural = br.stats["pack_retries"]
         assert natural < len(reads), "most pairs must stay on the s16x2 kernel"
-        for cfg in (3, 4, 5):   # the same kernel on the long-read geometries (row-per-step bit layout)
+        for cfg in (2, 3, 4):   # the same kernel on (8,40) with column stripes (time-transposed bit layout) and the other long-read geometries
             al2.set_option("force_cfg", cfg)
             try:
                 brc = al2.align_batch(qb, qo, AffineScoring(*sc), "fixed", "readlen", fixed_ref=fixed, with_stats=True)
@@ -827,13 +827,17 @@ def test_adaptive_pack_long_reads():
         assert not (br3.stats["variant"] & 64)
         compare(br3, want, len(reads), "int32")
         # sub-batching of the direction-bit scratch (several fill / retry / walk rounds)
-        al2.set_option("max_scratch_bytes", 16 << 20)
-        try:
-            br4 = al2.align_batch(qb, qo, AffineScoring(*sc), "fixed", "readlen", fixed_ref=fixed, with_stats=True)
-        finally:
-            al2.set_option("max_scratch_bytes", 40 << 30)
-        assert br4.stats["sub_batches"] > 1 and br4.stats["variant"] & 64
-        compare(br4, want, len(reads), "adaptive, sub-batched")
+        # (two at a time on two streams, each in its half of the scratch; or one after the other, dealt round-robin)
+        for no_overlap in (0, 1):
+            al2.set_option("max_scratch_bytes", 16 << 20)
+            al2.set_option("no_overlap", no_overlap)
+            try:
+                br4 = al2.align_batch(qb, qo, AffineScoring(*sc), "fixed", "readlen", fixed_ref=fixed, with_stats=True)
+            finally:
+                al2.set_option("max_scratch_bytes", 40 << 30)
+                al2.set_option("no_overlap", 0)
+            assert br4.stats["sub_batches"] > 2 and br4.stats["variant"] & 64, br4.stats
+            compare(br4, want, len(reads), "adaptive, sub-batched, no_overlap=%d" % no_overlap)
         # single reference, uniform read length (no host order at all)
         al2.set_references(ReferenceManager([Reference(refs[0], b"r0")]))
         uni = [(mutate(rng, refs[0], 0.05) + rand_seq(rng, 2600))[:2600] for _ in range(11)]

@@ -14,7 +14,7 @@ from clique_b200 import AffineScoring, Aligner, Reference, ReferenceManager, Rus
 from clique_b200.aligner import pack_reads
 
 def reset():
-    for k, v in (("force_cfg", -1), ("no_pack", 0), ("max_scratch_bytes", 40 << 30), ("no_group", 0), ("force_generic", 0), ("no_madd", 0), ("no_adapt", 0), ("no_long8", 0)):
+    for k, v in (("force_cfg", -1), ("no_pack", 0), ("max_scratch_bytes", 40 << 30), ("no_group", 0), ("force_generic", 0), ("no_madd", 0), ("no_adapt", 0), ("no_long8", 0), ("no_overlap", 0)):
         al.set_option(k, v)
 
 
@@ -79,7 +79,7 @@ while time.time() < t_end:
     if wide:  # sub-batches of the direction-bit scratch, int32 multi-reference traceback, generic kernels
         wopts.update({"max_scratch_bytes": int(rng.choice([40 << 30, 1 << 20, 16 << 20])), "no_group": int(rng.random() < 0.3),
                       "force_generic": int(rng.random() < 0.15), "no_madd": int(rng.random() < 0.3), "no_adapt": int(rng.random() < 0.2),
-                      "no_long8": int(rng.random() < 0.3)})
+                      "no_long8": int(rng.random() < 0.3), "no_overlap": int(rng.random() < 0.3)})
     for k_, v_ in wopts.items():
         al.set_option(k_, v_)
     tags = bool(rng.random() < 0.5) and mode not in ("convex",)
