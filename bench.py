@@ -401,11 +401,11 @@ def sorted_c5_stream(n):
 # the other north_star configs (BASELINE.json configs[2..4]) as short passes inside the same bench line: (key, workload, search,
 # convex, reads per GPU per step, oracle-checked reads)
 EXTRA_CONFIGS = [
-    ("C3", "C3", "", False, 40_000, 96),
+    ("C3", "C3", "", False, 100_000, 96),
     ("C3_convex", "C3", "", True, 40_000, 48),
     ("C4_exhaustive", "C4", "exhaustive", False, 50_000, 48),
     ("C4_quick", "C4", "quick", False, 400_000, 2048),
-    ("C5", "C5", "", False, 30_000, 24),
+    ("C5", "C5", "", False, 60_000, 24),
 ]
 
 

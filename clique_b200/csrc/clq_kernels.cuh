@@ -585,6 +585,30 @@ __global__ void __launch_bounds__(kThreads, (FAST && TB && C >= 32) ? 3 : 1) got
 #endif
 constexpr int kWalkPrefetch = CLQ_WALK_PREFETCH;  // steps ahead along the diagonal (0 = off)
 
+// The walker's load of a direction-bit word.  CLQ_WALK_L2_HINT = 64 / 128 / 256 adds the L2 prefetch-size hint: a miss then
+// brings the aligned 64 / 128 / 256 bytes around the sector into L2 in one DRAM access.  Within one block of 8 steps a diagonal
+// path reads two neighbouring sectors (words k and k - 1 of its lane), so the second one is then an L2 hit.
+#ifndef CLQ_WALK_L2_HINT
+#define CLQ_WALK_L2_HINT 0
+#endif
+__device__ __forceinline__ uint32_t ld_bits(const uint32_t* p) {
+#if CLQ_WALK_L2_HINT == 64
+    uint32_t v;
+    asm("ld.global.nc.L2::64B.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#elif CLQ_WALK_L2_HINT == 128
+    uint32_t v;
+    asm("ld.global.nc.L2::128B.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#elif CLQ_WALK_L2_HINT == 256
+    uint32_t v;
+    asm("ld.global.nc.L2::256B.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 // perform_3d_global_traceback (alignment/alignment_matrix.rs:941-1086) + simplify_cigar_string (alignment_manager.rs:386-423)
 // over the direction bits gotoh_kernel<.., TB=true, ..> stored.  One thread per pair: the walk is a chain of dependent
 // loads (one 32-byte sector per step), so it is spread over as many threads as there are pairs in the sub-batch.
@@ -663,7 +687,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
     auto nibble = [&](int xx, int yy) -> uint32_t {
         int shift;
         const size_t idx = locate(xx, yy, shift);
-        if (!WARP) return (__ldg(bits_g + idx) >> shift) & 15u;
+        if (!WARP) return (ld_bits(bits_g + idx) >> shift) & 15u;
         const int d = win_x - xx;   // every lane walks the same path: all of this is warp-uniform
         uint32_t v = 0;
         bool hit = false;
@@ -679,7 +703,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const TbRec* recs, uint32_t n
                 int sh;
                 const size_t pi = locate(px, py, sh);
                 win_idx = (uint32_t)pi;
-                win_word = __ldg(bits_g + pi);
+                win_word = ld_bits(bits_g + pi);
             }
             v = __shfl_sync(FULL, win_word, 0);
         }
