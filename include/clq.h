@@ -193,7 +193,20 @@ int32_t clq_download(clq_ctx* ctx, int32_t slot);
 int32_t clq_sync(clq_ctx* ctx, int32_t slot);
 int32_t clq_slot_stats(clq_ctx* ctx, int32_t slot, clq_stats_t* out);
 
-/* tuning knob for experiments: 0 = automatic kernel geometry */
+/* Tuning / experiment knobs.  Except "debug_flags" none of them changes a result (every kernel family is bit-exact against the
+ * oracle); they pick which family runs, for A/B measurements and the parity tests.  Unknown keys return CLQ_E_INVALID.
+ *   "max_scratch_bytes"  traceback scratch per context (direction bits + CIGAR scratch), >= 1 MiB; a batch whose bits exceed it
+ *                        runs as several fill + walk rounds (default 96 GiB)
+ *   "force_cfg"          wavefront geometry 0..5 = (8,16) (8,24) (8,40) (16,24) (32,16) (32,32); -1 = picked from the read lengths
+ *   "force_generic"      1 = generic int32 kernels even when the FAST / s16x2 preconditions hold
+ *   "no_pack" / "no_madd" / "no_adapt"   1 = without the s16x2 kernels / their static-row-slope form / the adaptive-bias form
+ *   "adapt_guard"        guard band of the adaptive-bias kernel in score units (0 = derived from the scoring)
+ *   "no_long8"           1 = long reads keep the geometry their length picks instead of (8,40) with column stripes
+ *   "no_overlap"         1 = sub-batches run one after the other (dealt round-robin) instead of two at a time on two streams
+ *   "no_group"           1 = multi-reference traceback without the on-device bucketing by reference (int32 kernels)
+ *   "serialize_slots"    1 = launches of different stream slots are chained and share one scratch (default), 0 = per-slot scratch
+ *   "debug_flags"        measurement only, results incomplete: 1 = skip the traceback walk (no CIGARs), 2 = skip the int32 retry
+ *                        pass behind the adaptive-bias kernel */
 int32_t clq_set_option(clq_ctx* ctx, const char* key, int64_t value);
 
 #ifdef __cplusplus
