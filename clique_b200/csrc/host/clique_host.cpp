@@ -487,6 +487,7 @@ ReadBatch::~ReadBatch() {
 
 void ReadBatch::clear() {
     n_ = 0;
+    n_first = 0xffffffffu;
     off_[0] = 0;
     name_bytes_.clear();
     name_off_.assign(1, 0);
@@ -522,6 +523,20 @@ bool ReadBatch::assign_span(const uint8_t* bytes, const uint64_t* off, uint64_t 
     else std::fill(fixed_, fixed_ + n, -1);
     name_off_.assign((size_t)n + 1, 0);
     n_ = (uint32_t)n;
+    return true;
+}
+
+bool ReadBatch::append_span(const uint8_t* bytes, const uint64_t* off, uint64_t lo, uint64_t hi, const int32_t* fixed_ref) {
+    const uint64_t n = hi - lo, nb = off[hi] - off[lo], have = off_[n_];
+    if (n_ + n > max_reads_ || have + nb > max_bytes_) return false;
+    if (nb) std::memcpy(bytes_ + have, bytes + off[lo], nb);
+    const uint64_t base = off[lo];
+    for (uint64_t i = 1; i <= n; i++) off_[n_ + i] = have + (off[lo + i] - base);
+    if (fixed_ref) std::memcpy(fixed_ + n_, fixed_ref + lo, n * sizeof(int32_t));
+    else std::fill(fixed_ + n_, fixed_ + n_ + n, -1);
+    name_off_.resize((size_t)(n_ + n) + 1, 0);
+    if (n_first == 0xffffffffu) { n_first = n_; second_index = lo; }
+    n_ += (uint32_t)n;
     return true;
 }
 
@@ -1175,6 +1190,87 @@ struct IdxQueue {
 };
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------ SpanClaimer
+// Claims of align_reads_span.  One pair of cursors over the whole span ([front, back) is what is left): a claim takes up to a full
+// batch, but with several devices never more than 1 / (2 * devices) of the bytes that are left (guided self-scheduling), so the
+// last batches are small and the devices drain together.  On a length-sorted stream (the reads at one end much longer than at
+// the other) a claim takes half of its bytes from the LONG end and fills up from the short end: a launch of only-long pairs runs
+// in whole waves of the persistent grid (1184 pairs of 5 kb, ~50 ms each, whatever the batch holds), a mixed one back-fills the
+// last wave with its short pairs, and the cheap short reads are what is left for the small claims at the end.
+SpanClaimer::SpanClaimer(const uint64_t* off, uint64_t n, size_t n_devices, int claimers_per_device, uint64_t max_reads,
+                         uint64_t max_read_bytes, ReadSpan::Order order)
+    : off_(off), nd_(std::max<size_t>(n_devices, 1)), nf_(std::max(claimers_per_device, 1)), max_reads_(std::max<uint64_t>(max_reads, 1)),
+      max_bytes_(std::max<uint64_t>(max_read_bytes, 1)), back_(n), order_(order) {
+    const uint64_t m = std::min<uint64_t>(4096, n / 8);
+    double head = 0.0, tail = 0.0;
+    if (m) {
+        head = (double)(off[m] - off[0]) / (double)m;
+        tail = (double)(off[n] - off[n - m]) / (double)m;
+    }
+    const bool skewed = m && (tail > 1.5 * head || head > 1.5 * tail);
+    long_at_back_ = tail >= head;
+    if (order_ == ReadSpan::Order::Auto) order_ = skewed ? ReadSpan::Order::TwoEnded : ReadSpan::Order::Front;
+}
+
+// reads taken from one end of [front, back) within a byte and a read budget
+uint64_t SpanClaimer::fit_front(uint64_t bytes_budget, uint64_t reads_budget) const {
+    const uint64_t* first = off_ + front_ + 1;
+    const uint64_t* last = off_ + back_ + 1;
+    const uint64_t n = (uint64_t)(std::upper_bound(first, last, off_[front_] + bytes_budget) - first);
+    return std::min<uint64_t>(n, std::min<uint64_t>(reads_budget, back_ - front_));
+}
+
+uint64_t SpanClaimer::fit_back(uint64_t bytes_budget, uint64_t reads_budget) const {
+    const uint64_t* first = off_ + front_;
+    const uint64_t* last = off_ + back_ + 1;
+    const uint64_t floor_off = off_[back_] > bytes_budget ? off_[back_] - bytes_budget : 0;
+    const uint64_t i = front_ + (uint64_t)(std::lower_bound(first, last, floor_off) - first);  // first read boundary >= floor_off
+    return std::min<uint64_t>(back_ - std::min(i, back_), std::min<uint64_t>(reads_budget, back_ - front_));
+}
+
+bool SpanClaimer::claim(uint64_t& lo, uint64_t& hi, uint64_t& lo2, uint64_t& hi2) {
+    std::lock_guard<std::mutex> g(mu_);
+    lo2 = hi2 = 0;
+    if (front_ >= back_) return false;
+    const uint64_t min_claim = std::min<uint64_t>(max_reads_, 4096);
+    const uint64_t left_bytes = off_[back_] - off_[front_];
+    // one device: nothing to balance, full batches.  Several: a claim is at most half of an equal share of what is left
+    const uint64_t share = nd_ > 1 ? left_bytes / (2 * nd_) : left_bytes;
+    const uint64_t want_bytes = std::min<uint64_t>(max_bytes_, std::max<uint64_t>(share, 1));
+    // ramp-up: the first claims are small (32 Ki reads, doubling per round of claims) so that every GPU starts computing
+    // after about a millisecond of staging instead of after a whole batch
+    const uint64_t round = n_claims_++ / (uint64_t)(nd_ * (size_t)nf_);
+    const uint64_t max_n = std::min<uint64_t>(max_reads_, 32768ull << std::min<uint64_t>(round, 10));
+    const bool from_back = order_ != ReadSpan::Order::Front && long_at_back_;
+    auto fit_long = [&](uint64_t bb, uint64_t rb) { return from_back ? fit_back(bb, rb) : fit_front(bb, rb); };
+    auto fit_short = [&](uint64_t bb, uint64_t rb) { return from_back ? fit_front(bb, rb) : fit_back(bb, rb); };
+    auto take_long = [&](uint64_t n, uint64_t& a, uint64_t& b) { if (from_back) { a = back_ - n; b = back_; back_ -= n; } else { a = front_; b = front_ + n; front_ += n; } };
+    auto take_short = [&](uint64_t n, uint64_t& a, uint64_t& b) { if (from_back) { a = front_; b = front_ + n; front_ += n; } else { a = back_ - n; b = back_; back_ -= n; } };
+    if (order_ == ReadSpan::Order::TwoEnded) {
+        uint64_t nl = fit_long(std::max<uint64_t>(want_bytes / 2, 1), max_n);
+        if (nl == 0) nl = 1;  // at least the longest read (alone if it is larger than a whole batch: the caller reports CLQ_READ_TOO_LONG)
+        take_long(nl, lo, hi);
+        const uint64_t long_bytes = off_[hi] - off_[lo];
+        if (front_ < back_ && long_bytes <= max_bytes_ && nl < max_n) {
+            // the rest of the byte budget from the short end; a tiny claim (the end of the stream) is topped up to min_claim reads,
+            // within 1 MiB (by reads alone the top-up would eat the short end and leave the expensive reads for the last claims)
+            uint64_t ns = fit_short(want_bytes > long_bytes ? want_bytes - long_bytes : 0, max_n - nl);
+            const uint64_t tiny = std::min<uint64_t>(max_bytes_, 1ull << 20);
+            if (nl + ns < min_claim && nl < std::min<uint64_t>(min_claim, max_n) && long_bytes < tiny)
+                ns = std::max(ns, fit_short(tiny - long_bytes, std::min<uint64_t>(min_claim, max_n) - nl));
+            if (ns) take_short(ns, lo2, hi2);
+        }
+        return true;
+    }
+    // one-ended claims (front to back, or longest first): at least min_claim reads when they fit
+    const uint64_t by_bytes = fit_long(want_bytes, max_n);
+    const uint64_t cap_bytes = fit_long(max_bytes_, max_n);
+    uint64_t n = std::max<uint64_t>(by_bytes, std::min<uint64_t>(min_claim, cap_bytes));
+    if (n == 0) n = 1;  // a read larger than a whole batch: handed over alone, the caller reports CLQ_READ_TOO_LONG
+    take_long(n, lo, hi);
+    return true;
+}
+
 SpanStats ShardedAligner::align_reads_span(const ReadSpan& span, const AffineScoring& scoring, bool fast_lookup, SpanOutput& out,
                                            int fillers_per_device, bool extract_tags, bool rust_bio) {
     SpanStats stats;
@@ -1214,36 +1310,8 @@ SpanStats ShardedAligner::align_reads_span(const ReadSpan& span, const AffineSco
     const auto t0 = std::chrono::steady_clock::now();
     stats.total.setup_seconds = std::chrono::duration<double>(t0 - tsetup).count();
 
-    // one cursor over the whole span: a claim takes up to a full batch, but with several devices never more than 1 / (2 * devices)
-    // of what is left (guided self-scheduling), so the last batches are small and the devices drain together even on
-    // length-sorted input
-    std::mutex claim_mu;
-    uint64_t cursor = 0, n_claims = 0;
-    const uint64_t min_claim = std::min<uint64_t>(opt.max_reads, 4096);
-    auto claim = [&](uint64_t& lo, uint64_t& hi) -> bool {
-        std::lock_guard<std::mutex> g(claim_mu);
-        if (cursor >= span.n) return false;
-        lo = cursor;
-        const uint64_t left_bytes = span.off[span.n] - span.off[lo];
-        // one device: nothing to balance, full batches.  Several: a claim is at most half of an equal share of what is left
-        const uint64_t share = nd > 1 ? left_bytes / (2 * nd) : left_bytes;
-        uint64_t want_bytes = std::min<uint64_t>(opt.max_read_bytes, std::max<uint64_t>(share, 1));
-        // last read whose end stays within want_bytes (binary search over the offsets), at least min_claim reads when they fit
-        const uint64_t* first = span.off + lo + 1;
-        const uint64_t* last = span.off + span.n + 1;
-        uint64_t by_bytes = (uint64_t)(std::upper_bound(first, last, span.off[lo] + want_bytes) - first);
-        uint64_t cap_bytes = (uint64_t)(std::upper_bound(first, last, span.off[lo] + opt.max_read_bytes) - first);
-        uint64_t n = std::max<uint64_t>(by_bytes, std::min<uint64_t>(min_claim, cap_bytes));
-        n = std::min<uint64_t>(n, std::min<uint64_t>(opt.max_reads, span.n - lo));
-        // ramp-up: the first claims are small (32 Ki reads, doubling per round of claims) so that every GPU starts computing
-        // after about a millisecond of staging instead of after a whole batch
-        const uint64_t round = n_claims++ / (uint64_t)(nd * (size_t)nf);
-        n = std::min<uint64_t>(n, 32768ull << std::min<uint64_t>(round, 10));
-        if (n == 0) n = 1;  // a read larger than a whole batch: handed over alone, reported CLQ_READ_TOO_LONG below
-        hi = lo + n;
-        cursor = hi;
-        return true;
-    };
+    SpanClaimer claimer(span.off, span.n, nd, nf, opt.max_reads, opt.max_read_bytes, span.order);
+    auto claim = [&](uint64_t& lo, uint64_t& hi, uint64_t& lo2, uint64_t& hi2) { return claimer.claim(lo, hi, lo2, hi2); };
 
     std::mutex stat_mu, pool_mu;
     std::exception_ptr err;
@@ -1258,8 +1326,8 @@ SpanStats ShardedAligner::align_reads_span(const ReadSpan& span, const AffineSco
         Dev& D = *devs[d];
         double secs = 0.0;
         try {
-            uint64_t lo, hi;
-            while (!failed && claim(lo, hi)) {
+            uint64_t lo, hi, lo2, hi2;
+            while (!failed && claim(lo, hi, lo2, hi2)) {
                 int b;
                 if (!D.free_q.pop(b)) break;
                 const auto f0 = std::chrono::steady_clock::now();
@@ -1270,9 +1338,10 @@ SpanStats ShardedAligner::align_reads_span(const ReadSpan& span, const AffineSco
                     D.free_q.push(b);
                     std::lock_guard<std::mutex> g(stat_mu);
                     stats.total.reads += hi - lo; stats.total.dropped += hi - lo;
-                    continue;
+                    continue;   // (such a claim is a single read and has no second range)
                 }
                 rbuf.first_index = lo;
+                if (hi2 > lo2 && !rbuf.append_span(span.bytes, span.off, lo2, hi2, span.fixed_ref)) fail(CLQ_E_STATE, "align_reads_span: a two-ended claim does not fit its batch");
                 secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - f0).count();
                 D.ready_q.push(b);
             }
@@ -1303,15 +1372,17 @@ SpanStats ShardedAligner::align_reads_span(const ReadSpan& span, const AffineSco
             }
             if (base + v.cigar_used > out.cigar_cap || base + v.cigar_used > 0xffffffffull) fail(CLQ_E_LIMIT, "align_reads_span: the caller's CIGAR pool is too small");
             if (v.cigar_used) std::memcpy(out.cigar_pool + base, v.cigar_pool, v.cigar_used * sizeof(uint32_t));
-            clq_result_t* dst = out.results + first;
+            // a batch is one range of the input, or two (a two-ended claim): reads 0 .. n1-1 and n1 .. n-1
+            const uint64_t n1 = std::min<uint64_t>(v.batch->n_first, n), second = v.batch->second_index;
             for (uint64_t i = 0; i < n; i++) {
                 clq_result_t r = v.results[i];
                 r.cigar_off += (uint32_t)base;
-                dst[i] = r;
+                out.results[i < n1 ? first + i : second + (i - n1)] = r;
                 (r.status == CLQ_OK ? aligned : dropped)++;
             }
             if (out.tags && v.tags && v.tag_stride) {
-                std::memcpy(out.tags + first * v.tag_stride, v.tags, n * v.tag_stride);
+                std::memcpy(out.tags + first * v.tag_stride, v.tags, n1 * v.tag_stride);
+                if (n > n1) std::memcpy(out.tags + second * v.tag_stride, v.tags + n1 * v.tag_stride, (n - n1) * v.tag_stride);
             }
             sink_secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
             reads += n; batches++;

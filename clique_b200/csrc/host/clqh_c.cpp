@@ -1,6 +1,8 @@
 // clqh_c.cpp -- a thin extern "C" view of the pure host functions of include/clique_host.hpp, so that the CPU test suite
 // (ctypes) can check them against the oracle and the reference's golden vectors without a GPU.  Not part of the drop-in
 // boundary (that is include/clq.h); declared in include/clqh.h.
+#include <cstdlib>
+#include <cctype>
 #include <cstring>
 
 #include "../../../include/clique_host.hpp"
@@ -262,6 +264,18 @@ int32_t clqh_align_reads_span(const int32_t* devices, uint32_t n_devices, const 
         sh.set_references(ReferenceManager(std::move(refs)));
         ReadSpan span;
         span.bytes = read_bytes; span.off = read_off; span.n = n_reads; span.fixed_ref = fixed_ref;
+        // experiment knobs of this test / bench view (the C++ API takes them as ReadSpan::order and Aligner::ctx() options)
+        if (const char* e = std::getenv("CLQ_SPAN_ORDER")) {
+            const std::string v(e);
+            span.order = v == "front" ? ReadSpan::Order::Front : v == "longest" ? ReadSpan::Order::LongestFirst : v == "two" ? ReadSpan::Order::TwoEnded : ReadSpan::Order::Auto;
+        }
+        for (const char* key : {"serialize_slots", "max_scratch_bytes", "no_overlap"}) {
+            std::string envn = "CLQ_SPAN_";
+            for (const char* c = key; *c; c++) envn += (char)std::toupper((unsigned char)*c);
+            if (const char* e = std::getenv(envn.c_str()))
+                for (size_t k = 0; k < sh.n_devices(); k++)
+                    if (clq_set_option(sh.aligner(k).ctx(), key, std::atoll(e)) != CLQ_OK) throw ClqError(CLQ_E_INVALID, std::string("bad ") + envn);
+        }
         SpanOutput out;
         out.results = static_cast<clq_result_t*>(results);
         out.cigar_pool = cigar_pool;
@@ -287,6 +301,19 @@ int32_t clqh_align_reads_span(const int32_t* devices, uint32_t n_devices, const 
         if (err && err_cap) { std::strncpy(err, e.what(), err_cap - 1); err[err_cap - 1] = 0; }
         return CLQ_E_INVALID;
     }
+}
+
+uint64_t clqh_span_claims(const uint64_t* read_off, uint64_t n_reads, uint32_t n_devices, int32_t claimers_per_device, uint64_t max_reads,
+                          uint64_t max_read_bytes, int32_t order, uint64_t* claims, uint64_t cap, int32_t* resolved_order) {
+    const ReadSpan::Order ord = order == 1 ? ReadSpan::Order::Front : order == 2 ? ReadSpan::Order::LongestFirst : order == 3 ? ReadSpan::Order::TwoEnded : ReadSpan::Order::Auto;
+    SpanClaimer cl(read_off, n_reads, n_devices, claimers_per_device, max_reads, max_read_bytes, ord);
+    if (resolved_order) *resolved_order = cl.order() == ReadSpan::Order::Front ? 1 : cl.order() == ReadSpan::Order::LongestFirst ? 2 : cl.order() == ReadSpan::Order::TwoEnded ? 3 : 0;
+    uint64_t k = 0, lo, hi, lo2, hi2;
+    while (cl.claim(lo, hi, lo2, hi2)) {
+        if (claims && k < cap) { claims[4 * k] = lo; claims[4 * k + 1] = hi; claims[4 * k + 2] = lo2; claims[4 * k + 3] = hi2; }
+        k++;
+    }
+    return k;
 }
 
 }  // extern "C"

@@ -253,6 +253,9 @@ public:
     /// replaces the batch by reads [lo, hi) of a caller-owned span (bytes + offsets, any host memory): one memcpy of the bytes,
     /// offsets rebased, unnamed reads, no qualities.  false when the range exceeds the batch's capacity.
     bool assign_span(const uint8_t* bytes, const uint64_t* off, uint64_t lo, uint64_t hi, const int32_t* fixed_ref);
+    /// appends reads [lo, hi) of the same span behind the ones assign_span put there (a batch made of two ranges of the input:
+    /// reads 0 .. n_first-1 are input reads first_index + i, the others second_index + (i - n_first)).  false when it does not fit.
+    bool append_span(const uint8_t* bytes, const uint64_t* off, uint64_t lo, uint64_t hi, const int32_t* fixed_ref);
     uint32_t size() const { return n_; }
     uint32_t capacity() const { return max_reads_; }
     uint64_t byte_capacity() const { return max_bytes_; }
@@ -268,6 +271,8 @@ public:
     const int32_t* fixed_ref() const { return fixed_; }
     int32_t* fixed_ref_mut() { return fixed_; }
     uint64_t first_index = 0;  // index of read 0 in the whole input
+    uint64_t second_index = 0; // index of read n_first in the whole input (batches of two ranges, see append_span)
+    uint32_t n_first = 0xffffffffu;  // reads of the first range (0xffffffff: the whole batch is one range)
 
 private:
     uint32_t max_reads_, n_ = 0;
@@ -432,6 +437,33 @@ struct ReadSpan {
     const uint64_t* off = nullptr;
     uint64_t n = 0;
     const int32_t* fixed_ref = nullptr;
+    /// how align_reads_span cuts batches from the span.  Auto: front to back, unless the reads at one end are much longer than
+    /// at the other (a length-sorted stream); then every batch takes its long reads from that end and fills up with short ones
+    /// from the other, so that each launch holds the mix of long and short pairs the persistent grid needs to stay full.
+    enum class Order { Auto, Front, LongestFirst, TwoEnded };
+    Order order = Order::Auto;
+};
+
+/// The batch cutter of ShardedAligner::align_reads_span (thread-safe; pure host logic, see clique_host.cpp).  A claim is one range
+/// [lo, hi) of the span plus, for a two-ended claim on a length-sorted stream, a second range [lo2, hi2) (empty otherwise).
+class SpanClaimer {
+public:
+    SpanClaimer(const uint64_t* off, uint64_t n, size_t n_devices, int claimers_per_device, uint64_t max_reads, uint64_t max_read_bytes,
+                ReadSpan::Order order = ReadSpan::Order::Auto);
+    bool claim(uint64_t& lo, uint64_t& hi, uint64_t& lo2, uint64_t& hi2);
+    ReadSpan::Order order() const { return order_; }  // what Auto resolved to
+
+private:
+    uint64_t fit_front(uint64_t bytes_budget, uint64_t reads_budget) const;
+    uint64_t fit_back(uint64_t bytes_budget, uint64_t reads_budget) const;
+    const uint64_t* off_;
+    size_t nd_;
+    int nf_;
+    uint64_t max_reads_, max_bytes_;
+    uint64_t front_ = 0, back_, n_claims_ = 0;
+    ReadSpan::Order order_;
+    bool long_at_back_ = true;
+    std::mutex mu_;
 };
 
 /// Caller-owned result arrays of ShardedAligner::align_reads_span, in input order: results[i] for read i (cigar_off indexes

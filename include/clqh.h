@@ -79,6 +79,14 @@ int32_t clqh_align_reads_span(const int32_t* devices, uint32_t n_devices, const 
                               uint32_t* cigar_pool, uint64_t cigar_cap, uint64_t* cigar_used, int32_t* scale, double* stats, char* err,
                               size_t err_cap);
 
+
+/* The batch cutter of align_reads_span (clique::SpanClaimer, pure host logic: no CUDA device needed): replays the claims a
+ * single thread would get over a span with the given read offsets.  order: 0 auto, 1 front to back, 2 longest first, 3 two-ended.
+ * claims[4 * k .. 4 * k + 3] = lo, hi, lo2, hi2 of claim k (lo2 == hi2: one range).  Returns the number of claims (those
+ * beyond `cap` are counted, not stored); *resolved_order (nullable) = what auto resolved to. */
+uint64_t clqh_span_claims(const uint64_t* read_off, uint64_t n_reads, uint32_t n_devices, int32_t claimers_per_device, uint64_t max_reads,
+                          uint64_t max_read_bytes, int32_t order, uint64_t* claims, uint64_t cap, int32_t* resolved_order);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ SYMBOLS = ["clqh_extract_tagged_sequences", "clqh_reverse_complement", "clqh_f64
            "clqh_simplify_cigar", "clqh_from_cigar", "clqh_sam_line", "clqh_merge_reads_by_concatenation",
            "clqh_combine_phred_scores", "clqh_alignment_rate_and_consensus", "clqh_merge_read_pairs_by_alignment",
            "clqh_find_greedy_non_overlapping_segments", "clqh_orient_by_longest_segment", "clqh_bam_file", "clqh_extend_hit",
-           "clqh_align_reads_span"]
+           "clqh_align_reads_span", "clqh_span_claims"]
 
 
 @pytest.fixture(scope="module")
@@ -690,3 +690,81 @@ def test_clq_align_bam_output(H, tmp_path):
         assert text.rstrip("\n").split("\n") == head
         assert brefs == [(n.decode(), len(r)) for n, r in zip(names, refs)]
         assert [r[0] for r in recs] == sam, extra
+
+
+# ------------------------------------------------------------------------------------------------ the span dispatcher's batch cutter (CPU)
+def span_claims(H, lens, n_devices, max_reads, max_bytes, order=0, claimers=2):
+    off = np.zeros(len(lens) + 1, np.uint64)
+    off[1:] = np.cumsum(np.asarray(lens, dtype=np.uint64))
+    H.clqh_span_claims.restype = C.c_uint64
+    H.clqh_span_claims.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p]
+    cap = len(lens) + 16
+    out = np.zeros(4 * cap, np.uint64)
+    res = C.c_int32(-1)
+    k = int(H.clqh_span_claims(off.ctypes.data, len(lens), n_devices, claimers, max_reads, max_bytes, order, out.ctypes.data, cap, C.byref(res)))
+    assert k <= cap
+    return [tuple(int(v) for v in out[4 * i:4 * i + 4]) for i in range(k)], res.value, off
+
+
+def check_partition(claims, off, n, max_reads, max_bytes):
+    """every read in exactly one claim, every claim within the batch capacity (a single oversize read may stand alone)"""
+    seen = np.zeros(n, np.int32)
+    for lo, hi, lo2, hi2 in claims:
+        assert lo < hi and lo2 <= hi2
+        seen[lo:hi] += 1
+        seen[lo2:hi2] += 1
+        reads = (hi - lo) + (hi2 - lo2)
+        nbytes = int(off[hi] - off[lo]) + int(off[hi2] - off[lo2])
+        assert reads <= max_reads
+        assert nbytes <= max_bytes or reads == 1
+    assert (seen == 1).all()
+
+
+def test_span_claims_uniform_stream_goes_front_to_back(H):
+    lens = [300] * 100_000
+    claims, order, off = span_claims(H, lens, 2, 1 << 16, 1 << 26)
+    assert order == 1
+    check_partition(claims, off, len(lens), 1 << 16, 1 << 26)
+    assert all(lo2 == hi2 for _, _, lo2, hi2 in claims)
+    assert [c[0] for c in claims] == sorted(c[0] for c in claims)       # contiguous, in input order
+    assert claims[-1][1] == len(lens)
+    sizes = [hi - lo for lo, hi, _, _ in claims]
+    assert max(sizes[len(sizes) // 2:]) <= max(sizes[:len(sizes) // 2])  # guided: the claims shrink towards the end
+
+
+@pytest.mark.parametrize("ascending", [True, False])
+@pytest.mark.parametrize("n_devices", [1, 2, 8])
+def test_span_claims_sorted_stream_mixes_both_ends(H, ascending, n_devices):
+    rng = np.random.default_rng(5 + n_devices)
+    lens = np.sort(rng.choice([300, 450, 700, 1000, 1500, 2200, 3300, 5000], size=60_000))
+    if not ascending:
+        lens = lens[::-1]
+    max_reads, max_bytes = 1 << 15, 1 << 26
+    claims, order, off = span_claims(H, lens, n_devices, max_reads, max_bytes)
+    assert order == 3                                                     # auto -> two-ended
+    check_partition(claims, off, len(lens), max_reads, max_bytes)
+    two = [c for c in claims if c[3] > c[2]]
+    assert len(two) >= len(claims) // 2
+    lo, hi, lo2, hi2 = claims[0]
+    long_mean = float(np.mean(lens[lo:hi])), float(np.mean(lens[lo2:hi2]))
+    assert long_mean[0] >= 4000 and long_mean[1] <= 1000                  # first claim: longest reads + shortest reads
+    # cost (cells ~ len^2) of the claims decreases overall: the cheap reads are what is left for the end
+    cost = [float((lens[a:b].astype(np.float64) ** 2).sum() + (lens[c:d].astype(np.float64) ** 2).sum()) for a, b, c, d in claims]
+    assert cost[0] >= cost[-1] and sum(cost[:len(cost) // 2]) > sum(cost[len(cost) // 2:])
+
+
+def test_span_claims_explicit_orders_and_oversize_read(H):
+    lens = np.sort(np.random.default_rng(9).integers(100, 4000, size=20_000))
+    for order in (1, 2, 3):
+        claims, res, off = span_claims(H, lens, 4, 4096, 1 << 22, order=order)
+        assert res == order
+        check_partition(claims, off, len(lens), 4096, 1 << 22)
+    longest_first, _, _ = span_claims(H, lens, 4, 4096, 1 << 22, order=2)
+    assert longest_first[0][1] == len(lens) and all(c[2] == c[3] for c in longest_first)
+    # one read larger than a whole batch is handed over alone (the dispatcher reports it CLQ_READ_TOO_LONG)
+    lens2 = [200] * 5000 + [1 << 20] + [200] * 5000
+    for order in (0, 1, 2, 3):
+        claims, _, off = span_claims(H, lens2, 2, 4096, 1 << 18, order=order)
+        check_partition(claims, off, len(lens2), 4096, 1 << 18)
+        assert any(hi - lo == 1 and lo == 5000 and lo2 == hi2 for lo, hi, lo2, hi2 in claims)
+    assert span_claims(H, [], 2, 4096, 1 << 18)[0] == []
