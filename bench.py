@@ -229,7 +229,8 @@ def oracle_parity(c, res, ns, convex=False, rustbio=False, threads=None):
     return {"checked_reads": ns, "mismatches": bad, "oracle_seconds": dt, "oracle_cells": int(out["cells"])}
 
 
-def run_config(args, workload, n, search, convex, rustbio, steps, warmup, e2e_chunks, rank, local_rank, world, barrier, clock_device=None):
+def run_config(args, workload, n, search, convex, rustbio, steps, warmup, e2e_chunks, rank, local_rank, world, barrier, clock_device=None,
+               packed2_e2e=False):
     """Device-resident and end-to-end passes of one workload on this rank's GPU; max over ranks of the timings."""
     import torch
     import torch.distributed as dist
@@ -349,8 +350,43 @@ def run_config(args, workload, n, search, convex, rustbio, steps, warmup, e2e_ch
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t[0]) / steps
+
+    # ---------------- the same stream with the chunks 2-bit packed (clq_submit_packed2): a quarter of the read bytes on the wire ----------------
+    packed = None
+    if packed2_e2e:
+        plain_chunks = chunks
+        t0 = time.perf_counter()
+        pchunks, n_exc = [], 0
+        for rb, off, fr in plain_chunks:
+            words = al.alloc_pinned((len(rb) + 15) // 16 + 4, np.uint32)
+            pk = al.pack_reads(rb, len(rb), out_words=words)
+            n_exc += len(pk.exc_pos)
+            pchunks.append((pk, off, fr))
+        pack_s = time.perf_counter() - t0          # host packing pass, one thread (reported, not inside the packed timer)
+        chunks = pchunks
+        h2d_p, d2h_p, _ = e2e_step(collect=True)
+        for _ in range(warmup):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(steps)
+        barrier()
+        p_ms = 1e3 * (time.perf_counter() - t0)
+        t = torch.tensor([p_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # results of the packed route against the device-resident ASCII launch above, record for record
+        al.submit(0, pchunks[0][0], pchunks[0][1], sci, c["search"], c["band"], fixed_ref=pchunks[0][2])
+        rp = al.wait(0, copy=True)
+        k0 = len(pchunks[0][1]) - 1
+        same = bool((rp.score_scaled == res.score_scaled[:k0]).all() and (rp.cigar_len == res.cigar_len[:k0]).all()
+                    and (rp.status == res.status[:k0]).all() and (rp.ref_index == res.ref_index[:k0]).all()
+                    and all(np.array_equal(rp.cigar(i), res.cigar(i)) for i in range(0, k0, max(1, k0 // 2000))))
+        packed = {"ms": float(t[0]) / steps, "h2d": int(h2d_p), "d2h": int(d2h_p), "exceptions": int(n_exc), "same": same,
+                  "host_pack_gb_s_one_thread": total_bytes / pack_s / 1e9}
+        chunks = plain_chunks
     al.close()
-    return {"c": c, "n": n, "total_bytes": total_bytes, "res": res, "n_ok": n_ok, "ms_per_step": ms_per_step, "wall_ms": wall_ms,
+    return {"packed2": packed, "c": c, "n": n, "total_bytes": total_bytes, "res": res, "n_ok": n_ok, "ms_per_step": ms_per_step, "wall_ms": wall_ms,
             "dp_ms": float(np.mean(dp_ms)), "launches": int(launches), "cells": int(cells), "variant": int(variant), "clk": clk,
             "e2e_ms": e2e_ms, "h2d": int(h2d), "d2h": int(d2h), "nch": nch, "pack_retries": int(pack_retries), "sub_batches": int(sub_batches)}
 
@@ -429,6 +465,7 @@ def main():
     ap.add_argument("--extra-steps", type=int, default=3)
     ap.add_argument("--no-api", action="store_true", help="skip the C++ align_reads loop measurements (e2e_api, sharded)")
     ap.add_argument("--sharded-reads-per-gpu", type=int, default=30_000)
+    ap.add_argument("--no-packed2", action="store_true", help="skip the 2-bit packed upload measurements (e2e_packed2, e2e_api_packed2)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
@@ -451,7 +488,7 @@ def main():
         torch.cuda.synchronize()
 
     r = run_config(args, args.workload, n, args.search, args.convex, args.rustbio, args.steps, args.warmup, args.e2e_chunks,
-                   rank, local_rank, world, barrier, clock_device=dev)
+                   rank, local_rank, world, barrier, clock_device=dev, packed2_e2e=not args.no_packed2)
     c, res, cells, variant, total_bytes = r["c"], r["res"], r["cells"], r["variant"], r["total_bytes"]
     ms_per_step, e2e_ms = r["ms_per_step"], r["e2e_ms"]
     value = n * n_gpus / (ms_per_step / 1e3)
@@ -488,7 +525,7 @@ def main():
                 extras[key] = ent
 
     # ---------------- the product's own batch loop (C++ host layer), fed from unpinned memory ----------------
-    e2e_api, sharded = None, None
+    e2e_api, sharded, e2e_api_packed2 = None, None, None
     if not args.no_api and not args.convex and not args.rustbio:
         try:
             rep = max(1, min(8, 4_000_000 // max(n, 1)))
@@ -508,6 +545,25 @@ def main():
                               "to the caller's arrays; staging copy + H2D + kernels + D2H + copy-out inside the timer; one stream of %d x the step's reads (third pass reported)" % rep}
         except Exception as e:  # noqa: BLE001
             e2e_api = {"error": "%s: %s" % (type(e).__name__, e)}
+        if not args.no_packed2 and e2e_api and "error" not in e2e_api:
+            # the same loop with AlignerOptions::pack2_upload: the filler threads also pack the staged batch (inside the timer)
+            try:
+                os.environ["CLQ_SPAN_PACK2"] = "1"
+                br_p, st_p = api_pass(c, [dev], n, passes=3, repeat=rep, fillers=4)
+                barrier()
+                t = torch.tensor([st_p["seconds"]], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                p_s = float(t[0])
+                same_p = bool((br_p.score_scaled == br_api.score_scaled).all() and (br_p.cigar_len == br_api.cigar_len).all() and (br_p.status == br_api.status).all()
+                              and all(np.array_equal(br_p.cigar(i), br_api.cigar(i)) for i in range(0, n * rep, max(1, n * rep // 4000))))
+                e2e_api_packed2 = {"value": n * rep * n_gpus / p_s, "unit": "reads/s", "ms_per_step": 1e3 * p_s / rep, "fill_thread_seconds": st_p["fill_seconds"],
+                                   "fillers_per_device": 4, "identical_to_ascii_upload_results": same_p,
+                                   "how": "as e2e_api with AlignerOptions::pack2_upload: 4 filler threads stage AND 2-bit pack each batch (ReadBatch::pack2), clq_submit_packed2"}
+            except Exception as e:  # noqa: BLE001
+                e2e_api_packed2 = {"error": "%s: %s" % (type(e).__name__, e)}
+            finally:
+                os.environ.pop("CLQ_SPAN_PACK2", None)
         if world > 1:
             # one read stream sharded over all GPUs of the box by the product dispatcher, from ONE process (rank 0); the other
             # ranks wait on the host (gloo), their GPUs idle
@@ -573,6 +629,15 @@ def main():
             line["roofline"]["ncu"] = ncu
         if e2e_api:
             line["e2e_api"] = e2e_api
+        if r.get("packed2"):
+            pk = r["packed2"]
+            line["e2e_packed2"] = {"value": n * n_gpus / (pk["ms"] / 1e3), "unit": "reads/s", "ms_per_step": pk["ms"], "h2d_bytes_per_step": pk["h2d"],
+                                   "d2h_bytes_per_step": pk["d2h"], "exception_bytes": pk["exceptions"], "identical_to_ascii_upload_results": pk["same"],
+                                   "host_pack_gb_s_one_thread": pk["host_pack_gb_s_one_thread"],
+                                   "how": "as e2e, chunks shipped 2-bit packed (clq_submit_packed2: 0.25 B per base + exception list, expanded on the "
+                                          "device by unpack2_kernel); packed ahead of the timer by clq_pack2, whose one-thread rate is reported"}
+        if e2e_api_packed2:
+            line["e2e_api_packed2"] = e2e_api_packed2
         if sharded:
             line["sharded"] = sharded
         if extras:

@@ -8,9 +8,9 @@ There is no CPU fallback: importing works anywhere, running an alignment needs t
 from ._lib import (CLQ_OK, READ_TOO_LONG, SCORING_NOT_REPRESENTABLE, TRACEBACK_DIVERGED, CIGAR_POOL_FULL, NO_CANDIDATE,
                    ClqError, Limits, load_library, library_path)
 from .aligner import (AffineScoring, ConvexScoring, TwoPieceScoring, RustBioScoring, AlignmentResult, AlignmentWithRef, Aligner, BatchResult, Reference,
-                      ReferenceManager, ShardedAligner, cigar_to_string)
+                      ReferenceManager, ShardedAligner, cigar_to_string, PackedReads, pack_reads_2bit)
 
 __all__ = ["AffineScoring", "ConvexScoring", "TwoPieceScoring", "RustBioScoring", "AlignmentResult", "AlignmentWithRef", "Aligner", "BatchResult", "Reference",
-           "ReferenceManager", "ShardedAligner", "cigar_to_string", "ClqError", "Limits", "load_library",
+           "ReferenceManager", "ShardedAligner", "cigar_to_string", "PackedReads", "pack_reads_2bit", "ClqError", "Limits", "load_library",
            "library_path", "CLQ_OK", "READ_TOO_LONG", "SCORING_NOT_REPRESENTABLE", "TRACEBACK_DIVERGED",
            "CIGAR_POOL_FULL", "NO_CANDIDATE"]

@@ -16,7 +16,7 @@ SCORE_ONLY, CONVEX, EXTRACT_TAGS, RUSTBIO = 1 << 4, 1 << 5, 1 << 6, 1 << 7
 SYMBOLS = ["clq_version", "clq_strerror", "clq_device_count", "clq_affine_from_f64", "clq_host_alloc", "clq_host_free",
            "clq_ctx_create", "clq_ctx_destroy", "clq_ctx_last_error", "clq_refs_set", "clq_kmer_index_set", "clq_submit",
            "clq_wait", "clq_upload", "clq_launch", "clq_download", "clq_sync", "clq_slot_stats", "clq_set_option",
-           "clq_tags_download", "clq_rustbio_scoring"]
+           "clq_tags_download", "clq_rustbio_scoring", "clq_pack2", "clq_upload_packed2", "clq_submit_packed2"]
 
 
 class ClqError(RuntimeError):
@@ -94,6 +94,11 @@ def load_library():
     L.clq_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     L.clq_rustbio_scoring.argtypes = [C.c_int32] * 4 + [C.POINTER(AffineInt)]
     L.clq_tags_download.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
+    L.clq_pack2.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.clq_upload_packed2.argtypes = [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_uint64, C.c_void_p]
+    L.clq_submit_packed2.argtypes = [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double]
     for name in SYMBOLS:
         f = getattr(L, name)
         if f.restype is C.c_int:

@@ -275,6 +275,47 @@ def pack_reads(reads):
     return (data if data.size else np.zeros(1, np.uint8)), off
 
 
+@dataclass
+class PackedReads:
+    """A batch in the 2-bit form of clq_upload_packed2 (include/clq.h): A C G T = 0 1 2 3, base i in bits 2 (i % 16) of
+    words[i // 16]; bytes outside that alphabet as (exc_pos, exc_byte), ascending."""
+    words: np.ndarray
+    exc_pos: np.ndarray
+    exc_byte: np.ndarray
+    n_bytes: int
+
+    def unpack(self) -> np.ndarray:
+        """Host-side inverse (tests / tools): what unpack2_kernel + patch2_kernel leave in the device's read buffer."""
+        w = np.ascontiguousarray(self.words[:(self.n_bytes + 15) // 16], dtype=np.uint32)
+        codes = (w[:, None] >> (2 * np.arange(16, dtype=np.uint32))[None, :]) & 3
+        out = np.frombuffer(b"ACGT", np.uint8)[codes.reshape(-1)][:self.n_bytes].copy()
+        out[self.exc_pos.astype(np.int64)] = self.exc_byte
+        return out
+
+
+def pack_reads_2bit(read_bytes, n_bytes=None, out_words=None, lib=None) -> PackedReads:
+    """clq_pack2 (host only, no GPU needed): raw ASCII batch bytes -> PackedReads."""
+    lib = lib or L.load_library()
+    rb = np.ascontiguousarray(read_bytes, dtype=np.uint8)
+    nb = int(rb.size if n_bytes is None else n_bytes)
+    if nb > rb.size:
+        raise ClqError(L.E_INVALID, "n_bytes exceeds the buffer")
+    nw = (nb + 15) // 16
+    words = out_words if out_words is not None else np.zeros(max(nw, 1), np.uint32)
+    if words.dtype != np.uint32 or words.size < nw or not words.flags.c_contiguous:
+        raise ClqError(L.E_INVALID, "out_words must be a contiguous uint32 array of (n_bytes + 15) // 16 words")
+    cap = max(64, nb // 64)
+    while True:
+        pos, byt, ne = np.zeros(cap, np.uint64), np.zeros(cap, np.uint8), C.c_uint64()
+        rc = lib.clq_pack2(rb.ctypes.data, nb, words.ctypes.data, pos.ctypes.data, byt.ctypes.data, cap, C.byref(ne))
+        if rc == L.E_LIMIT:   # *n_exc tells the capacity the list needs
+            cap = int(ne.value)
+            continue
+        if rc != L.CLQ_OK:
+            raise ClqError(rc, "clq_pack2")
+        return PackedReads(words, pos[:ne.value], byt[:ne.value], nb)
+
+
 _RESULT_DT = np.dtype([("score_scaled", "<i4"), ("ref_index", "<u4"), ("cigar_off", "<u4"), ("cigar_len", "<u4"),
                        ("status", "<u4"), ("matches", "<u4"), ("mismatches", "<u4")])
 
@@ -363,14 +404,33 @@ class Aligner:
             f |= L.SCORE_ONLY
         return f
 
-    def upload(self, slot, read_bytes, read_off, fixed_ref=None):
+    def pack_reads(self, read_bytes, n_bytes=None, out_words=None) -> "PackedReads":
+        """clq_pack2: the batch's bytes as a 2-bit stream + exception list (host only).  `out_words`: a (pinned) uint32 buffer
+        to pack into."""
+        return pack_reads_2bit(read_bytes, n_bytes, out_words, self.lib)
+
+    def upload(self, slot, read_bytes, read_off, fixed_ref=None, packed2=False):
+        """clq_upload; `read_bytes` may be a PackedReads (or raw bytes with packed2=True, packed here): clq_upload_packed2."""
         n = len(read_off) - 1
         fr = None
         if fixed_ref is not None:
             fr = np.ascontiguousarray(fixed_ref, dtype=np.int32)
-        rb = np.ascontiguousarray(read_bytes, dtype=np.uint8)
         ro = np.ascontiguousarray(read_off, dtype=np.uint64)
-        self._check(self.lib.clq_upload(self.ctx, slot, n, rb.ctypes.data, ro.ctypes.data, fr.ctypes.data if fr is not None else None))
+        frp = fr.ctypes.data if fr is not None else None
+        if packed2 and not isinstance(read_bytes, PackedReads):
+            read_bytes = self.pack_reads(read_bytes, int(ro[-1]) if n else 0)
+        if isinstance(read_bytes, PackedReads):
+            pk = read_bytes
+            if n and int(ro[-1]) > pk.n_bytes:
+                raise ClqError(L.E_INVALID, "read offsets run past the packed stream")
+            ne = len(pk.exc_pos)
+            self._check(self.lib.clq_upload_packed2(self.ctx, slot, n, pk.words.ctypes.data, ro.ctypes.data,
+                                                    pk.exc_pos.ctypes.data if ne else None, pk.exc_byte.ctypes.data if ne else None,
+                                                    ne, frp))
+            self._pending[slot] = [n, None, (pk, ro, fr)]
+            return
+        rb = np.ascontiguousarray(read_bytes, dtype=np.uint8)
+        self._check(self.lib.clq_upload(self.ctx, slot, n, rb.ctypes.data, ro.ctypes.data, frp))
         self._pending[slot] = [n, None, (rb, ro, fr)]
 
     def launch(self, slot, scoring, search="fixed", band="readlen", score_only=False, threshold=0.90, extract_tags=False):
@@ -395,9 +455,9 @@ class Aligner:
         return {k: getattr(st, k) for k, _ in L.Stats._fields_}
 
     def submit(self, slot, read_bytes, read_off, scoring, search="fixed", band="readlen", fixed_ref=None, score_only=False,
-               threshold=0.90, extract_tags=False):
-        """clq_submit: asynchronous H2D + kernels + D2H on the slot's stream."""
-        self.upload(slot, read_bytes, read_off, fixed_ref)
+               threshold=0.90, extract_tags=False, packed2=False):
+        """clq_submit (clq_submit_packed2 for a PackedReads batch): asynchronous H2D + kernels + D2H on the slot's stream."""
+        self.upload(slot, read_bytes, read_off, fixed_ref, packed2)
         self.launch(slot, scoring, search, band, score_only, threshold, extract_tags)
         self._check(self.lib.clq_download(self.ctx, slot))
 
@@ -424,8 +484,8 @@ class Aligner:
         return out
 
     def align_batch(self, read_bytes, read_off, scoring, search="fixed", band="readlen", fixed_ref=None, score_only=False,
-                    threshold=0.90, with_stats=False, extract_tags=False) -> BatchResult:
-        self.submit(0, read_bytes, read_off, scoring, search, band, fixed_ref, score_only, threshold, extract_tags)
+                    threshold=0.90, with_stats=False, extract_tags=False, packed2=False) -> BatchResult:
+        self.submit(0, read_bytes, read_off, scoring, search, band, fixed_ref, score_only, threshold, extract_tags, packed2)
         return self.wait(0, with_stats=with_stats)
 
     # ---- the reference's call surface ----

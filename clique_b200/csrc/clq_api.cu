@@ -13,6 +13,7 @@
 #include "clq_pack.cuh"
 #include "clq_convex_pack.cuh"
 #include "clq_pack_adapt.cuh"
+#include "clq_reads2bit.cuh"
 
 using namespace clq;
 
@@ -63,6 +64,7 @@ struct Slot {
                                      // number of positions with 0xffffffff) so that the reads of a PACK pair share theirs
     uint32_t n_pos = 0;              // processing positions incl. that padding (== n_reads otherwise)
     DevBuf retry_list;               // pack_adapt_kernel -> int32 retry pass
+    DevBuf packed2, exc_pos, exc_byte;  // clq_upload_packed2: the 2-bit stream and its exception list before the expansion
     int state = 0;  // 0 empty, 1 uploaded, 2 launched, 3 downloaded
     uint32_t flags = 0;
     clq_stats_t stats = {};
@@ -501,7 +503,7 @@ void clq_ctx_destroy(clq_ctx* c) {
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
         if (s.done) cudaEventDestroy(s.done);
         for (DevBuf* b : {&s.read_bytes, &s.read_off, &s.fixed_ref, &s.order, &s.results, &s.scores, &s.cand_mask, &s.single_ref,
-                          &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.tb_rec, &s.bits_off, &s.tags, &s.ref_groups, &s.retry_list, &s.order2, &s.counters})
+                          &s.ref_of_read, &s.votes, &s.cigar_pool, &s.bits, &s.cig_scratch, &s.col_scratch, &s.tb_rec, &s.bits_off, &s.tags, &s.ref_groups, &s.retry_list, &s.packed2, &s.exc_pos, &s.exc_byte, &s.order2, &s.counters})
             release(*b);
         if (s.h_counters) cudaFreeHost(s.h_counters);
     }
@@ -678,14 +680,27 @@ int32_t clq_kmer_index_set(clq_ctx* c, uint32_t k, uint32_t skip) {
     return CLQ_OK;
 }
 
-int32_t clq_upload(clq_ctx* c, int32_t slot, uint32_t n_reads, const uint8_t* read_bytes, const uint64_t* read_off,
-                   const int32_t* fixed_ref) {
+}  // extern "C"
+
+namespace {
+
+// the 2-bit form of a batch (clq_upload_packed2); null = raw ASCII bytes
+struct Packed2Src {
+    const uint32_t* words;
+    const uint64_t* exc_pos;
+    const uint8_t* exc_byte;
+    uint64_t n_exc;
+};
+
+int32_t upload_common(clq_ctx* c, int32_t slot, uint32_t n_reads, const uint8_t* read_bytes, const uint64_t* read_off,
+                      const int32_t* fixed_ref, const Packed2Src* pk) {
     Slot* s = get_slot(c, slot);
     if (!s || (n_reads && (!read_off))) return CLQ_E_INVALID;
     if (n_reads > c->lim.max_reads) return fail(c, CLQ_E_LIMIT, "too many reads for one batch");
     const uint64_t total = n_reads ? read_off[n_reads] - read_off[0] : 0;
     if (total > c->lim.max_read_bytes) return fail(c, CLQ_E_LIMIT, "read bytes exceed limit");
-    if (total && !read_bytes) return CLQ_E_INVALID;
+    if (total && !(pk ? (const void*)pk->words : (const void*)read_bytes)) return CLQ_E_INVALID;
+    if (pk && pk->n_exc && (!pk->exc_pos || !pk->exc_byte)) return CLQ_E_INVALID;
     if (n_reads && read_off[0] != 0) return fail(c, CLQ_E_INVALID, "read_off[0] must be 0");
     CU(c, cudaSetDevice(c->device));
     int32_t rc;
@@ -773,9 +788,29 @@ int32_t clq_upload(clq_ctx* c, int32_t slot, uint32_t n_reads, const uint8_t* re
         }
     }
     uint64_t h2d = 0;
-    if (total) {
+    if (total && !pk) {
         CU(c, cudaMemcpyAsync(s->read_bytes.p, read_bytes + read_off[0], total, cudaMemcpyHostToDevice, s->stream));
         h2d += total;
+    }
+    if (total && pk) {
+        // 2-bit stream + exception list -> the same ASCII read buffer (clq_reads2bit.cuh); everything behind it is shared
+        const uint64_t n_words = (total + 15) / 16;
+        if ((rc = ensure(c, s->packed2, ((n_words + 3) / 4) * 16)) != CLQ_OK) return rc;
+        CU(c, cudaMemcpyAsync(s->packed2.p, pk->words, n_words * 4, cudaMemcpyHostToDevice, s->stream));
+        h2d += n_words * 4;
+        const uint64_t n_vec = (n_words + 3) / 4;
+        const unsigned grid = (unsigned)std::min<uint64_t>((n_vec + 255) / 256, (uint64_t)c->sm_count * 8);
+        clq::unpack2_kernel<<<grid, 256, 0, s->stream>>>((const uint4*)s->packed2.p, (uint4*)s->read_bytes.p, n_words);
+        if (pk->n_exc) {
+            if ((rc = ensure(c, s->exc_pos, pk->n_exc * sizeof(uint64_t))) != CLQ_OK) return rc;
+            if ((rc = ensure(c, s->exc_byte, pk->n_exc)) != CLQ_OK) return rc;
+            CU(c, cudaMemcpyAsync(s->exc_pos.p, pk->exc_pos, pk->n_exc * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+            CU(c, cudaMemcpyAsync(s->exc_byte.p, pk->exc_byte, pk->n_exc, cudaMemcpyHostToDevice, s->stream));
+            h2d += pk->n_exc * 9;
+            const unsigned g2 = (unsigned)std::min<uint64_t>((pk->n_exc + 255) / 256, (uint64_t)c->sm_count * 8);
+            clq::patch2_kernel<<<g2, 256, 0, s->stream>>>((uint8_t*)s->read_bytes.p, (const uint64_t*)s->exc_pos.p, (const uint8_t*)s->exc_byte.p, pk->n_exc, total);
+        }
+        CU(c, cudaGetLastError());
     }
     if (n_reads) {
         CU(c, cudaMemcpyAsync(s->read_off.p, read_off, ((size_t)n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
@@ -796,6 +831,79 @@ int32_t clq_upload(clq_ctx* c, int32_t slot, uint32_t n_reads, const uint8_t* re
     s->stats.h2d_bytes = h2d;
     s->state = 1;
     return CLQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t clq_upload(clq_ctx* c, int32_t slot, uint32_t n_reads, const uint8_t* read_bytes, const uint64_t* read_off,
+                   const int32_t* fixed_ref) {
+    return upload_common(c, slot, n_reads, read_bytes, read_off, fixed_ref, nullptr);
+}
+
+int32_t clq_upload_packed2(clq_ctx* c, int32_t slot, uint32_t n_reads, const uint32_t* packed, const uint64_t* read_off,
+                           const uint64_t* exc_pos, const uint8_t* exc_byte, uint64_t n_exc, const int32_t* fixed_ref) {
+    const Packed2Src pk{packed, exc_pos, exc_byte, n_exc};
+    return upload_common(c, slot, n_reads, nullptr, read_off, fixed_ref, &pk);
+}
+
+// Host side of the 2-bit form (no CUDA call): A C G T -> 0 1 2 3, base i in bits 2 (i % 16) of word i / 16; every other byte
+// is stored as code 0 and listed (position, byte) in ascending position order.
+int32_t clq_pack2(const uint8_t* bytes, uint64_t n_bytes, uint32_t* packed, uint64_t* exc_pos, uint8_t* exc_byte, uint64_t exc_cap,
+                  uint64_t* n_exc) {
+    if ((n_bytes && (!bytes || !packed)) || !n_exc) return CLQ_E_INVALID;
+    static const struct Lut {
+        uint8_t v[256];
+        Lut() {
+            for (int i = 0; i < 256; i++) v[i] = 0x80;
+            v['A'] = 0; v['C'] = 1; v['G'] = 2; v['T'] = 3;
+        }
+    } lut;
+    uint64_t ne = 0;
+    bool overflow = false;
+    const uint64_t n_words = (n_bytes + 15) / 16;
+    // 8 bases at a time in a 64-bit register: code = ((b >> 1) ^ (b >> 2)) & 3 maps A C G T to 0 1 2 3; the chunk is plain iff
+    // rebuilding the four letters from the codes ('A' + 2 lo + 6 hi + 11 (lo & hi), no carry between bytes) gives it back
+    const uint64_t K01 = 0x0101010101010101ull;
+    auto pack8 = [&](const uint8_t* q, uint32_t& out) -> bool {
+        uint64_t x;
+        std::memcpy(&x, q, 8);
+        uint64_t t = ((x >> 1) ^ (x >> 2)) & (3 * K01);
+        const uint64_t lo = t & K01, hi = (t >> 1) & K01;
+        const uint64_t e = 0x41 * K01 + 2 * lo + 6 * hi + 11 * (lo & hi);
+        t = (t | (t >> 6)) & 0x000f000f000f000full;
+        t = (t | (t >> 12)) & 0x000000ff000000ffull;
+        t = (t | (t >> 24)) & 0xffffull;
+        out = (uint32_t)t;
+        return e == x;
+    };
+    for (uint64_t w = 0; w < n_words; w++) {
+        const uint64_t b0 = w * 16;
+        const unsigned m = (unsigned)std::min<uint64_t>(16, n_bytes - b0);
+        if (m == 16) {
+            uint32_t l, h;
+            const bool okl = pack8(bytes + b0, l), okh = pack8(bytes + b0 + 8, h);
+            if (okl && okh) { packed[w] = l | (h << 16); continue; }
+        }
+        uint32_t word = 0, flags = 0;
+        for (unsigned k = 0; k < m; k++) {
+            const uint32_t code = lut.v[bytes[b0 + k]];
+            word |= (code & 3u) << (2 * k);
+            flags |= code;
+        }
+        if (flags & 0x80u) {
+            for (unsigned k = 0; k < m; k++)
+                if (lut.v[bytes[b0 + k]] & 0x80u) {
+                    if (ne < exc_cap && exc_pos && exc_byte) { exc_pos[ne] = b0 + k; exc_byte[ne] = bytes[b0 + k]; }
+                    else overflow = true;
+                    ne++;
+                }
+        }
+        packed[w] = word;
+    }
+    *n_exc = ne;  // on CLQ_E_LIMIT: the capacity the list needs
+    return overflow ? CLQ_E_LIMIT : CLQ_OK;
 }
 
 int32_t clq_launch(clq_ctx* c, int32_t slot, const void* scoring, uint32_t flags, double match_threshold) {
@@ -1426,6 +1534,15 @@ int32_t clq_submit(clq_ctx* c, int32_t slot, uint32_t n_reads, const uint8_t* re
                    const int32_t* fixed_ref, const void* scoring, uint32_t flags, double match_threshold) {
     int32_t rc;
     if ((rc = clq_upload(c, slot, n_reads, read_bytes, read_off, fixed_ref)) != CLQ_OK) return rc;
+    if ((rc = clq_launch(c, slot, scoring, flags, match_threshold)) != CLQ_OK) return rc;
+    return clq_download(c, slot);
+}
+
+int32_t clq_submit_packed2(clq_ctx* c, int32_t slot, uint32_t n_reads, const uint32_t* packed, const uint64_t* read_off,
+                           const uint64_t* exc_pos, const uint8_t* exc_byte, uint64_t n_exc, const int32_t* fixed_ref,
+                           const void* scoring, uint32_t flags, double match_threshold) {
+    int32_t rc;
+    if ((rc = clq_upload_packed2(c, slot, n_reads, packed, read_off, exc_pos, exc_byte, n_exc, fixed_ref)) != CLQ_OK) return rc;
     if ((rc = clq_launch(c, slot, scoring, flags, match_threshold)) != CLQ_OK) return rc;
     return clq_download(c, slot);
 }

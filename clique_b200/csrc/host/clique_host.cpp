@@ -480,13 +480,31 @@ ReadBatch::ReadBatch(uint32_t max_reads, uint64_t max_bytes) : max_reads_(max_re
 }
 
 ReadBatch::~ReadBatch() {
+    if (words_) clq_host_free(words_);
     clq_host_free(bytes_);
     clq_host_free(off_);
     clq_host_free(fixed_);
 }
 
+void ReadBatch::pack2() const {
+    if (packed_) return;
+    if (!words_) words_ = pinned<uint32_t>((size_t)((max_bytes_ + 15) / 16) + 4);
+    const uint64_t nb = off_[n_];
+    uint64_t ne = 0;
+    if (exc_pos_.size() < 1024) { exc_pos_.resize(1024); exc_byte_.resize(1024); }
+    int32_t rc = clq_pack2(bytes_, nb, words_, exc_pos_.data(), exc_byte_.data(), exc_pos_.size(), &ne);
+    if (rc == CLQ_E_LIMIT) {  // ne = the capacity the list needs
+        exc_pos_.resize((size_t)ne); exc_byte_.resize((size_t)ne);
+        rc = clq_pack2(bytes_, nb, words_, exc_pos_.data(), exc_byte_.data(), exc_pos_.size(), &ne);
+    }
+    if (rc != CLQ_OK) fail(rc, "clq_pack2");
+    exc_pos_.resize((size_t)ne); exc_byte_.resize((size_t)ne);
+    packed_ = true;
+}
+
 void ReadBatch::clear() {
     n_ = 0;
+    packed_ = false;
     n_first = 0xffffffffu;
     off_[0] = 0;
     name_bytes_.clear();
@@ -497,6 +515,7 @@ void ReadBatch::clear() {
 
 bool ReadBatch::push(const char* name, size_t name_len, const uint8_t* seq, size_t n, const uint8_t* qual, int32_t fixed_ref) {
     if (n_ >= max_reads_ || off_[n_] + n > max_bytes_) return false;
+    packed_ = false;
     if (n) std::memcpy(bytes_ + off_[n_], seq, n);
     if (qual) {
         if (!have_quals_) { quals_.assign((size_t)off_[n_], (uint8_t)'H'); have_quals_ = true; }
@@ -529,6 +548,7 @@ bool ReadBatch::assign_span(const uint8_t* bytes, const uint64_t* off, uint64_t 
 bool ReadBatch::append_span(const uint8_t* bytes, const uint64_t* off, uint64_t lo, uint64_t hi, const int32_t* fixed_ref) {
     const uint64_t n = hi - lo, nb = off[hi] - off[lo], have = off_[n_];
     if (n_ + n > max_reads_ || have + nb > max_bytes_) return false;
+    packed_ = false;
     if (nb) std::memcpy(bytes_ + have, bytes + off[lo], nb);
     const uint64_t base = off[lo];
     for (uint64_t i = 1; i <= n; i++) off_[n_ + i] = have + (off[lo + i] - base);
@@ -860,7 +880,15 @@ uint32_t Aligner::search_flags(bool fast_lookup) const {
 
 void Aligner::submit(int slot, const ReadBatch& b, const clq_affine_t& sc, uint32_t flags, double threshold) {
     const bool fixed = (flags & CLQ_SEARCH_MASK) == CLQ_SEARCH_FIXED;
-    check(clq_submit(ctx_, slot, b.size(), b.bytes(), b.offsets(), fixed ? b.fixed_ref() : nullptr, &sc, flags, threshold), "clq_submit");
+    if (opt_.pack2_upload) {
+        b.pack2();  // no-op when a filler thread already packed the batch
+        const auto& ep = b.exception_positions();
+        check(clq_submit_packed2(ctx_, slot, b.size(), b.packed_words(), b.offsets(), ep.empty() ? nullptr : ep.data(),
+                                 ep.empty() ? nullptr : b.exception_bytes().data(), ep.size(), fixed ? b.fixed_ref() : nullptr, &sc, flags, threshold),
+              "clq_submit_packed2");
+    } else {
+        check(clq_submit(ctx_, slot, b.size(), b.bytes(), b.offsets(), fixed ? b.fixed_ref() : nullptr, &sc, flags, threshold), "clq_submit");
+    }
     flags_[slot] = flags;
     scale_[slot] = sc.scale;
 }
@@ -1342,6 +1370,7 @@ SpanStats ShardedAligner::align_reads_span(const ReadSpan& span, const AffineSco
                 }
                 rbuf.first_index = lo;
                 if (hi2 > lo2 && !rbuf.append_span(span.bytes, span.off, lo2, hi2, span.fixed_ref)) fail(CLQ_E_STATE, "align_reads_span: a two-ended claim does not fit its batch");
+                if (opt.pack2_upload) rbuf.pack2();  // on the filler thread, so that the packing pass scales with fillers_per_device
                 secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - f0).count();
                 D.ready_q.push(b);
             }

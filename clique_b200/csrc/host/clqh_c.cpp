@@ -257,6 +257,7 @@ int32_t clqh_align_reads_span(const int32_t* devices, uint32_t n_devices, const 
         opt.cigar_ops_per_read = o->cigar_ops_per_read;
         opt.n_slots = o->n_slots;
         opt.max_refs = std::max<uint32_t>(64, n_refs);
+        if (const char* e = std::getenv("CLQ_SPAN_PACK2")) opt.pack2_upload = std::atoi(e) != 0;  // bench / test view of AlignerOptions::pack2_upload
         ShardedAligner sh(std::vector<int>(devices, devices + n_devices), opt);
         std::vector<Reference> refs;
         for (uint32_t r = 0; r < n_refs; r++)

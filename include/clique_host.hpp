@@ -270,6 +270,14 @@ public:
     const uint64_t* offsets() const { return off_; }
     const int32_t* fixed_ref() const { return fixed_; }
     int32_t* fixed_ref_mut() { return fixed_; }
+    /// 2-bit form of the staged bytes (clq_pack2 into a page-locked word buffer, allocated on first use) for
+    /// clq_submit_packed2: a quarter of the H2D bytes; the ASCII bytes stay for the sinks (SAM SEQ, tags).  Call it once the
+    /// batch is complete (after any read_mut); clear() / push / assign_span drop it.
+    void pack2() const;
+    bool packed() const { return packed_; }
+    const uint32_t* packed_words() const { return words_; }
+    const std::vector<uint64_t>& exception_positions() const { return exc_pos_; }
+    const std::vector<uint8_t>& exception_bytes() const { return exc_byte_; }
     uint64_t first_index = 0;  // index of read 0 in the whole input
     uint64_t second_index = 0; // index of read n_first in the whole input (batches of two ranges, see append_span)
     uint32_t n_first = 0xffffffffu;  // reads of the first range (0xffffffff: the whole batch is one range)
@@ -284,6 +292,10 @@ private:
     std::vector<size_t> name_off_;
     Bytes quals_;
     bool have_quals_ = false;
+    mutable uint32_t* words_ = nullptr;
+    mutable std::vector<uint64_t> exc_pos_;
+    mutable std::vector<uint8_t> exc_byte_;
+    mutable bool packed_ = false;
 };
 
 class Aligner;
@@ -335,6 +347,8 @@ struct AlignerOptions {
     uint64_t max_ref_bytes = 1u << 26;
     uint32_t cigar_ops_per_read = 32;
     uint32_t n_slots = 2;               // stream slots: batch k+1 uploads while batch k computes
+    bool pack2_upload = false;          // ship batches 2-bit packed (ReadBatch::pack2 + clq_submit_packed2): 0.25 B per base on the
+                                        // wire for one more host pass over the staged bytes; results are identical
 };
 
 /// the source side of the batch loop: fill `batch` (already cleared), return false once the input is exhausted

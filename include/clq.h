@@ -193,6 +193,24 @@ int32_t clq_download(clq_ctx* ctx, int32_t slot);
 int32_t clq_sync(clq_ctx* ctx, int32_t slot);
 int32_t clq_slot_stats(clq_ctx* ctx, int32_t slot, clq_stats_t* out);
 
+/* 2-bit packed read ingestion -- the "2-bit packing" of the host layer BASELINE.json's north_star (1) names; the reference keeps
+ * reads as raw bytes (Vec<u8>, read_strategies/sequence_layout.rs) and match_mismatch compares them byte for byte, case included
+ * (alignment/scoring_functions.rs:100-102), so the packed form carries an exception list and is expanded on the device into
+ * the same ASCII buffer clq_upload fills: results are identical to clq_submit's on the same reads.
+ *   clq_pack2            host only, no CUDA call: A C G T -> 0 1 2 3, base i of the concatenated batch in bits 2 (i % 16) of
+ *                        packed[i / 16] ((n_bytes + 15) / 16 words); every other byte (N, IUPAC, lower case) is stored as 0 and
+ *                        listed as (exc_pos, exc_byte) in ascending position order.  *n_exc = number of exceptions; returns
+ *                        CLQ_E_LIMIT when exc_cap is too small (*n_exc then tells the capacity needed; packed is complete).
+ *   clq_upload_packed2 / clq_submit_packed2   as clq_upload / clq_submit with the batch in that form; read_off are base offsets
+ *                        (read_off[0] == 0).  H2D traffic: 0.25 B per base + 9 B per exception instead of 1 B per base. */
+int32_t clq_pack2(const uint8_t* bytes, uint64_t n_bytes, uint32_t* packed, uint64_t* exc_pos, uint8_t* exc_byte, uint64_t exc_cap,
+                  uint64_t* n_exc);
+int32_t clq_upload_packed2(clq_ctx* ctx, int32_t slot, uint32_t n_reads, const uint32_t* packed, const uint64_t* read_off,
+                           const uint64_t* exc_pos, const uint8_t* exc_byte, uint64_t n_exc, const int32_t* fixed_ref);
+int32_t clq_submit_packed2(clq_ctx* ctx, int32_t slot, uint32_t n_reads, const uint32_t* packed, const uint64_t* read_off,
+                           const uint64_t* exc_pos, const uint8_t* exc_byte, uint64_t n_exc, const int32_t* fixed_ref,
+                           const void* scoring, uint32_t flags, double match_threshold);
+
 /* Tuning / experiment knobs.  Except "debug_flags" none of them changes a result (every kernel family is bit-exact against the
  * oracle); they pick which family runs, for A/B measurements and the parity tests.  Unknown keys return CLQ_E_INVALID.
  *   "max_scratch_bytes"  traceback scratch per context (direction bits + CIGAR scratch), >= 1 MiB; a batch whose bits exceed it

@@ -144,4 +144,12 @@ extern "C" {
     pub fn clq_sync(ctx: *mut clq_ctx, slot: i32) -> i32;
     pub fn clq_slot_stats(ctx: *mut clq_ctx, slot: i32, out: *mut clq_stats_t) -> i32;
     pub fn clq_set_option(ctx: *mut clq_ctx, key: *const c_char, value: i64) -> i32;
+    // 2-bit packed read ingestion (host packer + the packed forms of clq_upload / clq_submit)
+    pub fn clq_pack2(bytes: *const u8, n_bytes: u64, packed: *mut u32, exc_pos: *mut u64, exc_byte: *mut u8, exc_cap: u64,
+                     n_exc: *mut u64) -> i32;
+    pub fn clq_upload_packed2(ctx: *mut clq_ctx, slot: i32, n_reads: u32, packed: *const u32, read_off: *const u64,
+                              exc_pos: *const u64, exc_byte: *const u8, n_exc: u64, fixed_ref: *const i32) -> i32;
+    pub fn clq_submit_packed2(ctx: *mut clq_ctx, slot: i32, n_reads: u32, packed: *const u32, read_off: *const u64,
+                              exc_pos: *const u64, exc_byte: *const u8, n_exc: u64, fixed_ref: *const i32,
+                              scoring: *const c_void, flags: u32, match_threshold: f64) -> i32;
 }

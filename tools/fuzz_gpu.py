@@ -94,11 +94,12 @@ while time.time() < t_end:
             break
         continue
     first = True
+    p2 = ((it * 2654435761) >> 7) % 3 == 0   # every third batch or so ships 2-bit packed (clq_submit_packed2); no draw from rng
     if os.environ.get("CLQ_FUZZ_VERBOSE"):   # the context of every batch before it runs (to locate a crash)
         print("batch", ctx, "reflens", [len(r) for r in refs], "readlens", [len(r) for r in reads][:30], "opts", wopts, flush=True)
     try:
         if mode == "rustbio":
-            br = al.align_batch(qb, qo, RustBioScoring(), "fixed", "maxlen", fixed_ref=fixed, extract_tags=tags)
+            br = al.align_batch(qb, qo, RustBioScoring(), "fixed", "maxlen", fixed_ref=fixed, extract_tags=tags, packed2=p2)
             for i, rd in enumerate(reads):
                 w = O.rustbio_global(refs[fixed[i]], rd)
                 st = int(br.status[i])
@@ -115,7 +116,7 @@ while time.time() < t_end:
                 continue
             cv = TwoPieceScoring(10, -9, 9, -20, -2, -40, -1)
             ocv = O.Convex(10, -9, 9, -20, -2, -40, -1, -100000)
-            br = al.align_batch(qb, qo, cv, "fixed", "readlen", fixed_ref=fixed)
+            br = al.align_batch(qb, qo, cv, "fixed", "readlen", fixed_ref=fixed, packed2=p2)
             for i, rd in enumerate(reads):
                 w = O.convex_align_pair(refs[fixed[i]], rd, ocv)
                 if int(br.status[i]) != 0 or int(br.score_scaled[i]) != w["score"] or br.cigar_string(i) != O.cigar_str(w["cigar"]):
@@ -129,7 +130,7 @@ while time.time() < t_end:
             search = mode if mode in ("exhaustive", "quick") else "fixed"
             if mode == "bandk":
                 band = int(rng.choice([1, 3, 10, 50, 400]))
-            br = al.align_batch(qb, qo, AffineScoring(*sc), search, band, fixed_ref=fixed if search == "fixed" else None, extract_tags=tags)
+            br = al.align_batch(qb, qo, AffineScoring(*sc), search, band, fixed_ref=fixed if search == "fixed" else None, extract_tags=tags, packed2=p2)
             want = O.align_batch(rb, ro, qb, qo, sc, search=search, fixed_ref=fixed if search == "fixed" else None,
                                  band_mode="k" if mode == "bandk" else band, band_k=band if mode == "bandk" else 0, threads=16,
                                  traceback_all=False)
