@@ -15,6 +15,10 @@
 #include "clq_pack_adapt.cuh"
 #include "clq_reads2bit.cuh"
 
+namespace clq {
+size_t pack2_plain_run(const uint8_t* bytes, size_t n_words, uint32_t* packed);  // clq_pack2_host.cpp
+}
+
 using namespace clq;
 
 namespace {
@@ -863,29 +867,14 @@ int32_t clq_pack2(const uint8_t* bytes, uint64_t n_bytes, uint32_t* packed, uint
     uint64_t ne = 0;
     bool overflow = false;
     const uint64_t n_words = (n_bytes + 15) / 16;
-    // 8 bases at a time in a 64-bit register: code = ((b >> 1) ^ (b >> 2)) & 3 maps A C G T to 0 1 2 3; the chunk is plain iff
-    // rebuilding the four letters from the codes ('A' + 2 lo + 6 hi + 11 (lo & hi), no carry between bytes) gives it back
-    const uint64_t K01 = 0x0101010101010101ull;
-    auto pack8 = [&](const uint8_t* q, uint32_t& out) -> bool {
-        uint64_t x;
-        std::memcpy(&x, q, 8);
-        uint64_t t = ((x >> 1) ^ (x >> 2)) & (3 * K01);
-        const uint64_t lo = t & K01, hi = (t >> 1) & K01;
-        const uint64_t e = 0x41 * K01 + 2 * lo + 6 * hi + 11 * (lo & hi);
-        t = (t | (t >> 6)) & 0x000f000f000f000full;
-        t = (t | (t >> 12)) & 0x000000ff000000ffull;
-        t = (t | (t >> 24)) & 0xffffull;
-        out = (uint32_t)t;
-        return e == x;
-    };
-    for (uint64_t w = 0; w < n_words; w++) {
+    const uint64_t n_full = n_bytes / 16;
+    uint64_t w = 0;
+    while (w < n_words) {
+        if (w < n_full) w += clq::pack2_plain_run(bytes + 16 * w, (size_t)(n_full - w), packed + w);  // runs of plain ACGT words (clq_pack2_host.cpp)
+        if (w >= n_words) break;
+        // a word holding other bytes, or the partial last word
         const uint64_t b0 = w * 16;
         const unsigned m = (unsigned)std::min<uint64_t>(16, n_bytes - b0);
-        if (m == 16) {
-            uint32_t l, h;
-            const bool okl = pack8(bytes + b0, l), okh = pack8(bytes + b0 + 8, h);
-            if (okl && okh) { packed[w] = l | (h << 16); continue; }
-        }
         uint32_t word = 0, flags = 0;
         for (unsigned k = 0; k < m; k++) {
             const uint32_t code = lut.v[bytes[b0 + k]];
@@ -901,6 +890,7 @@ int32_t clq_pack2(const uint8_t* bytes, uint64_t n_bytes, uint32_t* packed, uint
                 }
         }
         packed[w] = word;
+        w++;
     }
     *n_exc = ne;  // on CLQ_E_LIMIT: the capacity the list needs
     return overflow ? CLQ_E_LIMIT : CLQ_OK;

@@ -175,6 +175,14 @@ impl ReadBatch {
     }
 }
 
+/// Exception list of a 2-bit packed batch (`Context::submit_packed2`): positions and bytes of everything that is not an
+/// upper-case `ACGT`; reused across batches, must outlive the batch's `wait`.
+#[derive(Default)]
+pub struct Packed2Exceptions {
+    pub pos: Vec<u64>,
+    pub byte: Vec<u8>,
+}
+
 /// What to run on a batch: the `flags` word of `clq_submit`.
 #[derive(Clone, Copy, Debug)]
 pub struct Mode {
@@ -351,6 +359,46 @@ impl Context {
             unsafe {
                 clq_submit(self.raw, slot as i32, b.n as u32, b.bytes.as_ptr(), b.off.as_ptr(), fixed,
                            scoring as *const clq_affine_t as *const c_void, mode.flags, mode.match_threshold)
+            },
+            self.raw,
+        )?;
+        let sub = Submitted { n: b.n, scale: scoring.scale, tags: mode.flags & CLQ_EXTRACT_TAGS != 0 };
+        self.slots[slot].in_flight = Some(sub);
+        Ok(())
+    }
+
+    /// `submit` with the batch shipped 2-bit packed (`clq_pack2` + `clq_submit_packed2`): the host packs the staged bytes into
+    /// `words` (a pinned buffer of at least `(bytes + 15) / 16` u32, owned by the caller and kept alive until `wait`), bytes
+    /// outside `ACGT` travel in an exception list.  A quarter of the H2D bytes for one more host pass; identical results.
+    pub fn submit_packed2(&mut self, slot: usize, scoring: &clq_affine_t, mode: Mode, words: &mut [u32], exc: &mut Packed2Exceptions) -> Result<()> {
+        if self.slots[slot].in_flight.is_some() {
+            return Err(Error { code: CLQ_E_STATE, message: strerror(CLQ_E_STATE) });
+        }
+        let b = &self.slots[slot].batch;
+        if words.len() < (b.used + 15) / 16 {
+            return Err(Error { code: CLQ_E_INVALID, message: strerror(CLQ_E_INVALID) });
+        }
+        let mut n_exc: u64 = 0;
+        loop {
+            let rc = unsafe {
+                clq_pack2(b.bytes.as_ptr(), b.used as u64, words.as_mut_ptr(), exc.pos.as_mut_ptr(), exc.byte.as_mut_ptr(),
+                          exc.pos.len() as u64, &mut n_exc)
+            };
+            if rc == CLQ_E_LIMIT {
+                // n_exc = the capacity the list needs
+                exc.pos.resize(n_exc as usize, 0);
+                exc.byte.resize(n_exc as usize, 0);
+                continue;
+            }
+            check(rc, self.raw)?;
+            break;
+        }
+        let fixed = if b.has_fixed { b.fixed.as_ptr() } else { ptr::null() };
+        let (ep, eb) = if n_exc > 0 { (exc.pos.as_ptr(), exc.byte.as_ptr()) } else { (ptr::null(), ptr::null()) };
+        check(
+            unsafe {
+                clq_submit_packed2(self.raw, slot as i32, b.n as u32, words.as_ptr(), b.off.as_ptr(), ep, eb, n_exc, fixed,
+                                   scoring as *const clq_affine_t as *const c_void, mode.flags, mode.match_threshold)
             },
             self.raw,
         )?;

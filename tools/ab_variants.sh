@@ -14,7 +14,7 @@ build)
         name=${v%%=*}; flags=${v#*=}
         echo "== $name: $flags"
         (cd clique_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $flags \
-            -shared -o ../../tools/_v/libclq_$name.so clq_api.cu -lcudart)
+            -shared -o ../../tools/_v/libclq_$name.so clq_api.cu clq_pack2_host.cpp -lcudart)
     done ;;
 run)
     cp clique_b200/libclq.so tools/_v/.in_tree.so
