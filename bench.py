@@ -488,7 +488,7 @@ def main():
         torch.cuda.synchronize()
 
     r = run_config(args, args.workload, n, args.search, args.convex, args.rustbio, args.steps, args.warmup, args.e2e_chunks,
-                   rank, local_rank, world, barrier, clock_device=dev, packed2_e2e=not args.no_packed2)
+                   rank, local_rank, world, barrier, clock_device=dev, packed2_e2e=(not args.no_packed2 and world == 1))   # side measurement: N = 1 only
     c, res, cells, variant, total_bytes = r["c"], r["res"], r["cells"], r["variant"], r["total_bytes"]
     ms_per_step, e2e_ms = r["ms_per_step"], r["e2e_ms"]
     value = n * n_gpus / (ms_per_step / 1e3)
@@ -545,7 +545,7 @@ def main():
                               "to the caller's arrays; staging copy + H2D + kernels + D2H + copy-out inside the timer; one stream of %d x the step's reads (third pass reported)" % rep}
         except Exception as e:  # noqa: BLE001
             e2e_api = {"error": "%s: %s" % (type(e).__name__, e)}
-        if not args.no_packed2 and e2e_api and "error" not in e2e_api:
+        if not args.no_packed2 and world == 1 and e2e_api and "error" not in e2e_api:
             # the same loop with AlignerOptions::pack2_upload: the filler threads also pack the staged batch (inside the timer)
             try:
                 os.environ["CLQ_SPAN_PACK2"] = "1"
