@@ -183,3 +183,25 @@ def test_packed_large_batch_grid_stride():
     plain_reads[::7] = False
     assert np.all(pk.score_scaled[plain_reads] == (10 * (L1 - 1) - 9) * pk.scale)
     assert np.all(pk.mismatches[plain_reads] == 1) and np.all(pk.matches[plain_reads] == L1 - 1)
+
+
+def test_pack2_round_trip_property():
+    """any byte string survives pack -> unpack (the exception list carries whatever the 2-bit alphabet cannot), and the
+    packer's fast bodies (AVX2 / SWAR, plain runs of 16-base words) agree with the per-byte restatement at every alignment"""
+    from hypothesis import given, settings, strategies as st
+
+    dna = st.lists(st.sampled_from(list(b"ACGT")), min_size=0, max_size=200).map(bytes)
+    junk = st.binary(min_size=0, max_size=6)
+    pieces = st.lists(st.one_of(dna, dna, junk), min_size=0, max_size=12).map(b"".join)
+
+    @settings(max_examples=300, deadline=None)
+    @given(pieces, st.integers(0, 15))
+    def check(data, shift):
+        buf = np.frombuffer(b"A" * shift + data, np.uint8)[shift:]     # also from unaligned addresses
+        pk = pack_reads_2bit(buf if buf.size else np.zeros(1, np.uint8), buf.size)
+        w, pos, byt = np_pack(buf)
+        assert np.array_equal(pk.words[:w.size], w)
+        assert np.array_equal(pk.exc_pos, pos) and np.array_equal(pk.exc_byte, byt)
+        assert np.array_equal(pk.unpack(), buf)
+
+    check()
