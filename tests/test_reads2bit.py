@@ -205,3 +205,11 @@ def test_pack2_round_trip_property():
         assert np.array_equal(pk.unpack(), buf)
 
     check()
+
+
+def test_packed_entry_points_reject_a_null_context():
+    """no GPU needed: the packed upload validates like clq_upload (CLQ_E_INVALID, no crash)"""
+    lib = L.load_library()
+    w, off = np.zeros(4, np.uint32), np.zeros(2, np.uint64)
+    assert lib.clq_upload_packed2(None, 0, 1, w.ctypes.data, off.ctypes.data, None, None, 0, None) == L.E_INVALID
+    assert lib.clq_submit_packed2(None, 0, 1, w.ctypes.data, off.ctypes.data, None, None, 0, None, None, 0, 0.9) == L.E_INVALID
