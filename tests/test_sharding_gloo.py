@@ -25,6 +25,16 @@ def _worker(rank, world, port, tmp):
     lo, hi = bounds[rank], bounds[rank + 1]
     off = c["read_off"][lo:hi + 1] - c["read_off"][lo]
     qb = c["read_bytes"][int(c["read_off"][lo]):int(c["read_off"][hi])]
+    if rank == 1 and len(qb):
+        # this rank ships its shard 2-bit packed (clq_pack2, host only): the packed form of a shard is self-contained (its own
+        # base offsets from 0, whatever byte of the whole stream it starts at) and expands to the same bytes
+        from clique_b200 import pack_reads_2bit
+        qb = qb.copy()
+        qb[5::97] = ord("N")                       # bytes outside the 2-bit alphabet travel in the exception list
+        c["read_bytes"][int(c["read_off"][lo]):int(c["read_off"][hi])] = qb   # (the full run on rank 0 repeats this edit below)
+        pk = pack_reads_2bit(qb, int(off[-1]))
+        assert pk.words.nbytes <= (len(qb) + 15) // 16 * 4 + 4 and len(pk.exc_pos) > 0
+        qb = pk.unpack()
     out = O.align_batch(rb, ro, qb if len(qb) else np.zeros(1, np.uint8), off, c["scoring"], search="fixed",
                         fixed_ref=c["fixed_ref"][lo:hi], band_mode="readlen", threads=2)
     mine = BatchResult(1, out["score"].astype(np.int64), out["ref_index"], out["cigar_off"].astype(np.uint32), out["cigar_len"],
@@ -34,6 +44,8 @@ def _worker(rank, world, port, tmp):
     dist.barrier()
     if rank == 0:
         allr = concat_results(gathered)
+        l1, h1 = int(c["read_off"][bounds[1]]), int(c["read_off"][bounds[2]])
+        c["read_bytes"][l1:h1][5::97] = ord("N")   # rank 1's shard as rank 1 aligned it
         full = O.align_batch(rb, ro, c["read_bytes"], c["read_off"], c["scoring"], search="fixed", fixed_ref=c["fixed_ref"],
                              band_mode="readlen", threads=2)
         ok = (allr.score_scaled == full["score"]).all() and (allr.cigar_len == full["cigar_len"]).all()
